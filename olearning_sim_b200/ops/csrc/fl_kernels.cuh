@@ -1,0 +1,578 @@
+// fl_kernels.cuh — the non-GEMM device code of a federated round:
+//   ingest_u8          uint8 NHWC client samples  -> normalised bf16, horizontally unrolled conv1 operand
+//   bcast_scatter      global model (optionally pulled from the owning peer GPU over NVLink) -> packed
+//                      per-client replicas: fp32 master rows + bf16 tensor-core operand copies
+//   head_fc_xent       fused classifier head: FC forward, softmax-xent, FC backward, SGD on FC + conv2 bias,
+//                      un-pool / ReLU-backward into the conv2 pre-activation gradient
+//   fedavg_partial     masked, sample-count-weighted partial sums of client deltas  (on-GPU level of the reduce)
+//   fedavg_finish      cross-GPU pull of the partials (P2P loads), normalise, server SGD/Adam, write new shard
+//   deviceflow_mask    counter-based (Philox4x32-10) per-round participation / drop sampling
+//   peer_barrier       device-side barrier over flags in peer-mapped memory
+//
+// Reference parity: model broadcast = per-actor model-file download (ols_core/taskMgr/utils/
+// utils_run_task.py:327-397); update reduce = DeviceFlow sorter/dispatcher message path
+// (ols_core/deviceflow/non_grpc/sorter.py:37-91, dispatcher.py:84-242); sampling/drops =
+// ols_core/deviceflow/non_grpc/strategy.py:275-311 and dispatcher.py:103-109.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace flk {
+
+// ---------------------------------------------------------------------------------------------
+// CNN-2 packed parameter layout (floats per client).  Shared with python (ops/layout.py).
+// ---------------------------------------------------------------------------------------------
+struct Cnn2Layout {
+  static constexpr int W1 = 0;                 // [32][5][16]   cout, kh, (kw*3+c ; 15 used, 1 pad)
+  static constexpr int B1 = 2560;              // [32]
+  static constexpr int W2 = 2592;              // [64][25][32]  cout, kh*5+kw, cin
+  static constexpr int B2 = 53792;             // [64]
+  static constexpr int WFC = 53856;            // [10][4096]    class, (ph*8+pw)*64+ch
+  static constexpr int BFC = 94816;            // [10] (+6 pad)
+  static constexpr int P = 94832;
+  static constexpr int W1_N = 2560, W2_N = 51200, WFC_N = 40960;
+};
+
+constexpr int kMaxPeers = 8;
+struct PeerPtrs {
+  void* p[kMaxPeers];
+};
+
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float bf2f(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+// uint8 [N][32][32][3]  ->  bf16 [N][32][32][16] with channel = kw*3+c holding x[h][w+kw-2][c] (zero outside).
+// The 5 horizontal taps of conv1 are unrolled into the channel dim once at upload time, so conv1 runs as a
+// 5-tap (vertical) implicit GEMM with K=16 per tap instead of wasting 13/16 of a K=16 MMA on 3 channels.
+__global__ void ingest_u8_kernel(const uint8_t* __restrict__ src, __nv_bfloat16* __restrict__ dst, size_t npix) {
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= npix) return;
+  const int w = i & 31;
+  const uint8_t* row = src + (i - w) * 3;
+  __align__(16) __nv_bfloat16 v[16];
+#pragma unroll
+  for (int kw = 0; kw < 5; ++kw) {
+    const int ww = w + kw - 2;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float f = 0.f;
+      if (ww >= 0 && ww < 32) f = (static_cast<float>(row[ww * 3 + c]) * (1.f / 255.f) - 0.5f) * 2.f;
+      v[kw * 3 + c] = __float2bfloat16_rn(f);
+    }
+  }
+  v[15] = __float2bfloat16_rn(0.f);
+  uint4* o = reinterpret_cast<uint4*>(dst + i * 16);
+  o[0] = reinterpret_cast<uint4*>(v)[0];
+  o[1] = reinterpret_cast<uint4*>(v)[1];
+}
+
+// ---------------------------------------------------------------------------------------------
+// bcast_scatter: one pass that (a) pulls each parameter shard from its owner GPU (peer-mapped pointer; the
+// owner of element i is i / shard_len), (b) refreshes the local copy of the global model, and (c) fans the
+// values out into every local client replica row (fp32 master) plus the bf16 operand copies in the layouts
+// the tensor-core kernels consume.  With one GPU the "pull" is a local read.
+// ---------------------------------------------------------------------------------------------
+struct BcastParams {
+  PeerPtrs global_peers;        // float* [P] on each rank (symmetric)
+  int nranks, rank;
+  int shard_len;                // elements per owner shard (P padded / nranks)
+  float* global_local;          // [P] local copy (FedProx anchor, checkpoint source)
+  float* master;                // [C][P]
+  int num_clients;
+  const uint8_t* participate;   // [C] or nullptr — only refresh clients sampled for this round
+  __nv_bfloat16* w1_fwd;        // [C][2560]
+  __nv_bfloat16* w2_fwd;        // [C][51200]
+  __nv_bfloat16* w2_dgrad;      // [C][25*32][64]
+  int P;
+};
+
+__global__ void bcast_scatter_cnn2_kernel(const BcastParams p) {
+  using L = Cnn2Layout;
+  // each thread owns 4 consecutive parameters; blockIdx.y strides over clients
+  const int i4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i4 >= p.P) return;
+  const int owner = min(i4 / p.shard_len, p.nranks - 1);
+  const float4 v = *reinterpret_cast<const float4*>(static_cast<const float*>(p.global_peers.p[owner]) + i4);
+  if (blockIdx.y == 0) *reinterpret_cast<float4*>(p.global_local + i4) = v;
+  const float vv[4] = {v.x, v.y, v.z, v.w};
+  for (int c = blockIdx.y; c < p.num_clients; c += gridDim.y) {
+    if (p.participate && !p.participate[c]) continue;
+    *reinterpret_cast<float4*>(p.master + (size_t)c * p.P + i4) = v;
+    if (i4 < L::B1) {
+      uint2 o;
+      __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+      o.x = *reinterpret_cast<uint32_t*>(&a); o.y = *reinterpret_cast<uint32_t*>(&b);
+      *reinterpret_cast<uint2*>(p.w1_fwd + (size_t)c * L::W1_N + i4) = o;
+    } else if (i4 >= L::W2 && i4 < L::B2) {
+      const int j = i4 - L::W2;
+      uint2 o;
+      __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+      o.x = *reinterpret_cast<uint32_t*>(&a); o.y = *reinterpret_cast<uint32_t*>(&b);
+      *reinterpret_cast<uint2*>(p.w2_fwd + (size_t)c * L::W2_N + j) = o;
+      // dgrad copy [tap][cin][cout]
+      const int cout = j / 800, rem = j % 800;   // rem = tap*32 + cin (4 consecutive cin)
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        p.w2_dgrad[(size_t)c * L::W2_N + (size_t)(rem + e) * 64 + cout] = __float2bfloat16_rn(vv[e]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fused classifier head.  One CTA per client, 256 threads.  BATCH=32 samples, K=4096 features, 10 classes.
+// ---------------------------------------------------------------------------------------------
+struct HeadParams {
+  int num_clients;
+  const uint8_t* active;
+  const __nv_bfloat16* p2;      // [C*32][8][8][64]  pooled conv2 activations
+  const uint8_t* code2;         // same shape
+  const int32_t* labels;        // [C][label_stride]
+  int label_stride, label_off;  // this step's batch = labels[c][label_off .. +32)
+  float* master;                // [C][P]
+  const float* global_w;        // [P] FedProx anchor or nullptr
+  int P;
+  float lr, mu;
+  __nv_bfloat16* dy2;           // [C*32][16][16][64]  grad wrt conv2 pre-pool output
+  float* loss_sum;              // [C]  += mean loss of this step
+  int32_t* nonfinite;           // [C]  set to 1 when the loss is not finite (poisoned client)
+  float* logits_out;            // optional [C][32][10] (tests)
+  int apply_update;             // 0 => gradient-check mode (no parameter update)
+  float* dwfc_out;              // optional [C][10*4096+16] raw FC grads (tests)
+  float* db2_out;               // optional [C][64]
+};
+
+constexpr int kHeadThreads = 256;
+constexpr int kHeadSmem = (10 * 4096 + 32 * 10 + 32 * 10 + 64 + 16) * 4;
+
+__global__ void __launch_bounds__(kHeadThreads, 1) head_fc_xent_kernel(const HeadParams p) {
+  using L = Cnn2Layout;
+  extern __shared__ float hs[];
+  float* Ws = hs;                    // [10][4096]
+  float* logit = Ws + 10 * 4096;     // [32][10]
+  float* dlog = logit + 320;         // [32][10]
+  float* db2 = dlog + 320;           // [64]
+  float* misc = db2 + 64;            // [16]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  for (int c = blockIdx.x; c < p.num_clients; c += gridDim.x) {
+    if (p.active && !p.active[c]) continue;
+    float* wm = p.master + (size_t)c * p.P;
+    for (int i = tid * 4; i < L::WFC_N; i += kHeadThreads * 4)
+      *reinterpret_cast<float4*>(Ws + i) = *reinterpret_cast<const float4*>(wm + L::WFC + i);
+    if (tid < 64) db2[tid] = 0.f;
+    __syncthreads();
+
+    // ---- logits
+    const __nv_bfloat16* x = p.p2 + (size_t)c * 32 * 4096;
+    for (int si = 0; si < 4; ++si) {
+      const int s = warp * 4 + si;
+      float acc[10];
+#pragma unroll
+      for (int j = 0; j < 10; ++j) acc[j] = 0.f;
+      for (int k = lane * 8; k < 4096; k += 256) {
+        const uint4 xv = *reinterpret_cast<const uint4*>(x + (size_t)s * 4096 + k);
+        const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w};
+        float xf[8];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { xf[2 * e] = __uint_as_float(xw[e] << 16); xf[2 * e + 1] = __uint_as_float(xw[e] & 0xFFFF0000u); }
+#pragma unroll
+        for (int j = 0; j < 10; ++j) {
+          const float4 w0 = *reinterpret_cast<const float4*>(Ws + j * 4096 + k);
+          const float4 w1 = *reinterpret_cast<const float4*>(Ws + j * 4096 + k + 4);
+          acc[j] += xf[0] * w0.x + xf[1] * w0.y + xf[2] * w0.z + xf[3] * w0.w + xf[4] * w1.x + xf[5] * w1.y +
+                    xf[6] * w1.z + xf[7] * w1.w;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 10; ++j) {
+        float v = acc[j];
+        v += __shfl_xor_sync(0xffffffffu, v, 16); v += __shfl_xor_sync(0xffffffffu, v, 8);
+        v += __shfl_xor_sync(0xffffffffu, v, 4);  v += __shfl_xor_sync(0xffffffffu, v, 2);
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        if (lane == 0) logit[s * 10 + j] = v + wm[L::BFC + j];
+      }
+    }
+    __syncthreads();
+
+    // ---- softmax cross-entropy, dlogits = (p - onehot)/B
+    if (tid < 32) {
+      const int s = tid;
+      const int y = p.labels[(size_t)c * p.label_stride + p.label_off + s];
+      float mx = -1e30f;
+#pragma unroll
+      for (int j = 0; j < 10; ++j) mx = fmaxf(mx, logit[s * 10 + j]);
+      float e[10], sum = 0.f;
+#pragma unroll
+      for (int j = 0; j < 10; ++j) { e[j] = __expf(logit[s * 10 + j] - mx); sum += e[j]; }
+      const float inv = 1.f / sum;
+      float loss = 0.f;
+#pragma unroll
+      for (int j = 0; j < 10; ++j) {
+        const float pj = e[j] * inv;
+        if (j == y) loss = -(logit[s * 10 + j] - mx - __logf(sum));
+        dlog[s * 10 + j] = (pj - (j == y ? 1.f : 0.f)) * (1.f / 32.f);
+      }
+      if (p.logits_out) {
+#pragma unroll
+        for (int j = 0; j < 10; ++j) p.logits_out[((size_t)c * 32 + s) * 10 + j] = logit[s * 10 + j];
+      }
+      float ls = loss;
+      ls += __shfl_xor_sync(0xffffffffu, ls, 16); ls += __shfl_xor_sync(0xffffffffu, ls, 8);
+      ls += __shfl_xor_sync(0xffffffffu, ls, 4);  ls += __shfl_xor_sync(0xffffffffu, ls, 2);
+      ls += __shfl_xor_sync(0xffffffffu, ls, 1);
+      if (tid == 0) {
+        const float m = ls * (1.f / 32.f);
+        p.loss_sum[c] += m;
+        if (!(fabsf(m) < 3.0e38f)) p.nonfinite[c] = 1;   // catches NaN and Inf
+      }
+    }
+    __syncthreads();
+
+    // ---- backward: dW_fc, dP2 -> un-pool -> dY2_pre, db2, db_fc ; SGD on W_fc
+    const uint8_t* code = p.code2 + (size_t)c * 32 * 4096;
+    __nv_bfloat16* dy = p.dy2 + (size_t)c * 32 * 16 * 16 * 64;
+    const float* wg = p.global_w;
+    for (int it = 0; it < 8; ++it) {
+      const int k = (it * kHeadThreads + tid) * 2;       // two consecutive features (same pooled pixel)
+      float w0[10], w1[10], g0[10], g1[10];
+#pragma unroll
+      for (int j = 0; j < 10; ++j) { w0[j] = Ws[j * 4096 + k]; w1[j] = Ws[j * 4096 + k + 1]; g0[j] = 0.f; g1[j] = 0.f; }
+      const int pix = k >> 6, ch = k & 63, ph = pix >> 3, pw = pix & 7;
+      float dbl0 = 0.f, dbl1 = 0.f;
+      for (int s = 0; s < 32; ++s) {
+        const uint32_t xr = *reinterpret_cast<const uint32_t*>(x + (size_t)s * 4096 + k);
+        const float x0 = __uint_as_float(xr << 16), x1 = __uint_as_float(xr & 0xFFFF0000u);
+        const uint16_t cr = *reinterpret_cast<const uint16_t*>(code + (size_t)s * 4096 + k);
+        float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+        for (int j = 0; j < 10; ++j) {
+          const float dl = dlog[s * 10 + j];
+          d0 += dl * w0[j]; d1 += dl * w1[j];
+          g0[j] += dl * x0; g1[j] += dl * x1;
+        }
+        d0 = x0 > 0.f ? d0 : 0.f; d1 = x1 > 0.f ? d1 : 0.f;
+        dbl0 += d0; dbl1 += d1;
+        const int c0 = cr & 0xFF, c1 = cr >> 8;
+#pragma unroll
+        for (int pos = 0; pos < 4; ++pos) {
+          const size_t o = (((size_t)s * 16 + (2 * ph + (pos >> 1))) * 16 + (2 * pw + (pos & 1))) * 64 + ch;
+          __nv_bfloat162 ov = __floats2bfloat162_rn(c0 == pos ? d0 : 0.f, c1 == pos ? d1 : 0.f);
+          *reinterpret_cast<__nv_bfloat162*>(dy + o) = ov;
+        }
+      }
+      atomicAdd(&db2[ch], dbl0);
+      atomicAdd(&db2[ch + 1], dbl1);
+      if (p.dwfc_out) {
+#pragma unroll
+        for (int j = 0; j < 10; ++j) {
+          p.dwfc_out[(size_t)c * (L::WFC_N + 16) + j * 4096 + k] = g0[j];
+          p.dwfc_out[(size_t)c * (L::WFC_N + 16) + j * 4096 + k + 1] = g1[j];
+        }
+      }
+      if (p.apply_update) {
+#pragma unroll
+        for (int j = 0; j < 10; ++j) {
+          float a = w0[j], b = w1[j];
+          float ga = g0[j], gb = g1[j];
+          if (wg) { ga += p.mu * (a - wg[L::WFC + j * 4096 + k]); gb += p.mu * (b - wg[L::WFC + j * 4096 + k + 1]); }
+          a -= p.lr * ga; b -= p.lr * gb;
+          *reinterpret_cast<float2*>(wm + L::WFC + j * 4096 + k) = make_float2(a, b);
+        }
+      }
+    }
+    __syncthreads();
+    if (tid < 10) {
+      float g = 0.f;
+      for (int s = 0; s < 32; ++s) g += dlog[s * 10 + tid];
+      if (p.dwfc_out) p.dwfc_out[(size_t)c * (L::WFC_N + 16) + L::WFC_N + tid] = g;
+      if (p.apply_update) {
+        float b = wm[L::BFC + tid];
+        if (wg) g += p.mu * (b - wg[L::BFC + tid]);
+        wm[L::BFC + tid] = b - p.lr * g;
+      }
+    }
+    if (tid >= 64 && tid < 128) {
+      const int ch = tid - 64;
+      float g = db2[ch];
+      if (p.db2_out) p.db2_out[(size_t)c * 64 + ch] = g;
+      if (p.apply_update) {
+        float b = wm[L::B2 + ch];
+        if (wg) g += p.mu * (b - wg[L::B2 + ch]);
+        wm[L::B2 + ch] = b - p.lr * g;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// FedAvg reduce, level 1 (on-GPU): partial[g][i] = sum_{c in group g} a_c * (master[c][i] - global[i]),
+// a_c = participate_c * arrived_c * finite_c * n_c.  Streaming, HBM-bound; float4 per thread.
+// Also produces wsum[g] = sum a_c (thread 0 of block x==0) and per-class success / failed counters.
+// ---------------------------------------------------------------------------------------------
+struct PartialParams {
+  const float* master;      // [C][P]
+  const float* global_w;    // [P]
+  const float* weight;      // [C] effective aggregation weight a_c (0 => masked)
+  const int32_t* nonfinite; // [C] or nullptr (1 => client poisoned; treated as weight 0)
+  int num_clients, P, groups;
+  float* partial;           // [groups][P]
+  float* wsum;              // [groups]
+};
+
+__global__ void fedavg_partial_kernel(const PartialParams p) {
+  const int i4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  const int g = blockIdx.y;
+  const int per = (p.num_clients + p.groups - 1) / p.groups;
+  const int c0 = g * per, c1 = min(c0 + per, p.num_clients);
+  if (i4 < p.P) {
+    const float4 gw = *reinterpret_cast<const float4*>(p.global_w + i4);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    float asum = 0.f;
+#pragma unroll 4
+    for (int c = c0; c < c1; ++c) {
+      float a = __ldg(&p.weight[c]);
+      if (p.nonfinite && __ldg(&p.nonfinite[c])) a = 0.f;
+      if (a == 0.f) continue;
+      const float4 w = __ldcs(reinterpret_cast<const float4*>(p.master + (size_t)c * p.P + i4));
+      acc.x += a * (w.x - gw.x); acc.y += a * (w.y - gw.y); acc.z += a * (w.z - gw.z); acc.w += a * (w.w - gw.w);
+      asum += a;
+    }
+    *reinterpret_cast<float4*>(p.partial + (size_t)g * p.P + i4) = acc;
+    if (i4 == 0) p.wsum[g] = asum;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Device-side barrier across ranks: flags live in peer-mapped memory (one uint32 per (dst, src) pair).
+// Every rank writes `epoch` into slot [rank] of every peer's flag array, then waits until all of its own
+// slots reached `epoch`.  Bounded spin -> trap, so a dead peer fails the launch instead of hanging the box.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void peer_barrier(const PeerPtrs& flags, int nranks, int rank, uint32_t epoch) {
+  // caller: a single CTA-wide call; thread r (< nranks) signals peer r and waits on local slot r
+  __syncthreads();
+  if ((int)threadIdx.x < nranks) {
+    __threadfence_system();
+    st_release_sys(static_cast<uint32_t*>(flags.p[threadIdx.x]) + rank, epoch);
+    const uint32_t* mine = static_cast<const uint32_t*>(flags.p[rank]) + threadIdx.x;
+    uint32_t spins = 0;
+    while (ld_acquire_sys(mine) < epoch) {
+      if (++spins > (1u << 28)) { __trap(); }
+    }
+  }
+  __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------------
+// FedAvg reduce, level 2 + server optimiser, fused with the cross-GPU transfer: the owner of a parameter
+// shard pulls every peer's partial sums for that shard straight out of peer HBM (P2P loads over NVLink,
+// no NCCL, no staging copy), normalises by the global weight sum, applies server SGD(momentum)/Adam and
+// writes the new global shard in place.  Grid barrier at entry (partials ready) and exit (shard published).
+// ---------------------------------------------------------------------------------------------
+struct FinishParams {
+  PeerPtrs partial_peers;   // float* [groups][P] per rank
+  PeerPtrs wsum_peers;      // float* [groups] per rank
+  PeerPtrs flags;           // uint32* [kMaxPeers] per rank
+  int nranks, rank, groups, P, shard_len;
+  uint32_t epoch;
+  float* global_w;          // [P] on this rank (symmetric; peers pull from it in bcast_scatter)
+  float* opt_m;             // [shard_len] momentum / Adam m   (owner shard only)
+  float* opt_v;             // [shard_len] Adam v
+  int opt;                  // 0 = plain averaging (server lr), 1 = SGD momentum, 2 = Adam
+  float server_lr, beta1, beta2, eps;
+  int step;                 // Adam step (1-based)
+  float* stats;             // [4]: total weight, |delta|^2 of owned shard, participants(unused), spare
+  uint32_t* arrive_ctr;     // [2] zero-initialised scratch for the intra-grid barriers
+};
+
+__device__ __forceinline__ void grid_gate(uint32_t* ctr, uint32_t nblocks) {
+  // lightweight one-shot "all CTAs arrived" (all CTAs are co-resident: grid <= #SMs)
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(ctr, 1u);
+    uint32_t spins = 0;
+    while (atomicAdd(ctr, 0u) < nblocks) { if (++spins > (1u << 28)) __trap(); }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+__global__ void fedavg_finish_kernel(const FinishParams p) {
+  // entry barrier: every rank's partials are complete & visible
+  if (p.nranks > 1) {
+    if (blockIdx.x == 0) peer_barrier(p.flags, p.nranks, p.rank, p.epoch * 2 + 1);
+    grid_gate(p.arrive_ctr + 0, gridDim.x);
+  }
+  float wtot = 0.f;
+  for (int r = 0; r < p.nranks; ++r) {
+    const float* ws = static_cast<const float*>(p.wsum_peers.p[r]);
+    for (int g = 0; g < p.groups; ++g) wtot += ws[g];
+  }
+  const float inv = wtot > 0.f ? 1.f / wtot : 0.f;
+  const int s0 = p.rank * p.shard_len;
+  const int s1 = min(s0 + p.shard_len, p.P);
+  float dn = 0.f;
+  for (int i4 = s0 + (blockIdx.x * blockDim.x + threadIdx.x) * 4; i4 < s1; i4 += gridDim.x * blockDim.x * 4) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int r = 0; r < p.nranks; ++r) {
+      const float* pp = static_cast<const float*>(p.partial_peers.p[r]);
+      for (int g = 0; g < p.groups; ++g) {
+        const float4 v = *reinterpret_cast<const float4*>(pp + (size_t)g * p.P + i4);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+    }
+    float d[4] = {acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv};   // averaged client delta (pseudo-gradient = -d)
+    float4 w = *reinterpret_cast<const float4*>(p.global_w + i4);
+    float wv[4] = {w.x, w.y, w.z, w.w};
+    const int li = i4 - s0;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float upd;
+      if (p.opt == 0) {
+        upd = p.server_lr * d[e];
+      } else if (p.opt == 1) {
+        const float m = p.beta1 * p.opt_m[li + e] + d[e];
+        p.opt_m[li + e] = m;
+        upd = p.server_lr * m;
+      } else {
+        const float m = p.beta1 * p.opt_m[li + e] + (1.f - p.beta1) * d[e];
+        const float v = p.beta2 * p.opt_v[li + e] + (1.f - p.beta2) * d[e] * d[e];
+        p.opt_m[li + e] = m; p.opt_v[li + e] = v;
+        const float mh = m / (1.f - __powf(p.beta1, (float)p.step));
+        const float vh = v / (1.f - __powf(p.beta2, (float)p.step));
+        upd = p.server_lr * mh / (sqrtf(vh) + p.eps);
+      }
+      if (wtot <= 0.f) upd = 0.f;     // nobody arrived this round: keep the model
+      wv[e] += upd;
+      dn += upd * upd;
+    }
+    *reinterpret_cast<float4*>(p.global_w + i4) = make_float4(wv[0], wv[1], wv[2], wv[3]);
+  }
+  // stats
+  dn += __shfl_xor_sync(0xffffffffu, dn, 16); dn += __shfl_xor_sync(0xffffffffu, dn, 8);
+  dn += __shfl_xor_sync(0xffffffffu, dn, 4);  dn += __shfl_xor_sync(0xffffffffu, dn, 2);
+  dn += __shfl_xor_sync(0xffffffffu, dn, 1);
+  if ((threadIdx.x & 31) == 0 && dn != 0.f) atomicAdd(&p.stats[1], dn);
+  if (blockIdx.x == 0 && threadIdx.x == 0) p.stats[0] = wtot;
+  // exit barrier: new shard visible to every peer before anyone starts the next broadcast pull
+  if (p.nranks > 1) {
+    grid_gate(p.arrive_ctr + 1, gridDim.x);
+    if (blockIdx.x == 0) peer_barrier(p.flags, p.nranks, p.rank, p.epoch * 2 + 2);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// DeviceFlow sampler: Philox4x32-10 keyed by (seed), counter (round, client, stream, 0).
+// Bit-identical to olearning_sim_b200.deviceflow.philox (CPU) so a trace replays the same on either side.
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                       uint32_t k0, uint32_t k1, uint32_t out[4]) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint64_t p0 = (uint64_t)M0 * c0, p1 = (uint64_t)M1 * c2;
+    const uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0, hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += W0; k1 += W1;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+struct MaskParams {
+  int num_clients;
+  int client_base;                 // global id of local client 0 (so every rank draws the same stream per client)
+  uint32_t seed_lo, seed_hi, round;
+  const float* p_online;           // [C] probability that the client is online / sampled this round (or nullptr => 1)
+  float drop_probability;          // DeviceFlow drop_simulation.drop_probability: update lost in flight
+  const int32_t* arrive_tick;      // [C] or nullptr: dispatch slot of the client's update from the flow schedule (-1 = never)
+  int32_t max_tick;                // updates with tick > max_tick are late -> discarded (clean_remain_message)
+  const int32_t* n_samples;        // [C]
+  const int32_t* local_steps;      // [C] heterogeneous local-step budget
+  int max_steps;
+  uint8_t* participate;            // [C] 1 => trains this round
+  uint8_t* step_active;            // [max_steps][C]  1 => client runs local step s
+  float* agg_weight;               // [C] n_c if the update arrives, else 0
+  int32_t* counters;               // [4]: participants, dropped, late, arrived
+};
+
+__global__ void deviceflow_mask_kernel(const MaskParams p) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= p.num_clients) return;
+  uint32_t r[4];
+  philox4x32_10(p.round, (uint32_t)(p.client_base + c), 0u, 0u, p.seed_lo, p.seed_hi, r);
+  const float u_on = (r[0] >> 8) * (1.f / 16777216.f);
+  const float u_drop = (r[1] >> 8) * (1.f / 16777216.f);
+  const float pon = p.p_online ? p.p_online[c] : 1.f;
+  const bool part = u_on < pon;
+  // reference semantics: forwarded iff random() > p  (p==1 drops everything, p==0 keeps everything)
+  const bool dropped = part && (p.drop_probability >= 1.f || (p.drop_probability > 0.f && !(u_drop > p.drop_probability)));
+  bool late = false;
+  if (part && !dropped && p.arrive_tick) { const int t = p.arrive_tick[c]; late = (t < 0) || (t > p.max_tick); }
+  const bool arrived = part && !dropped && !late;
+  p.participate[c] = part ? 1 : 0;
+  const int steps = p.local_steps ? min(p.local_steps[c], p.max_steps) : p.max_steps;
+  for (int s = 0; s < p.max_steps; ++s) p.step_active[(size_t)s * p.num_clients + c] = (part && s < steps) ? 1 : 0;
+  p.agg_weight[c] = arrived ? (float)p.n_samples[c] : 0.f;
+  if (part) atomicAdd(&p.counters[0], 1);
+  if (dropped) atomicAdd(&p.counters[1], 1);
+  if (late) atomicAdd(&p.counters[2], 1);
+  if (arrived) atomicAdd(&p.counters[3], 1);
+}
+
+// Rate-curve integration (DeviceFlow specific_interval): area of max(f,0)-clipped trapezoids per 1-second bin.
+// `y` holds f sampled at 101 points per bin (bins*100+1 samples are NOT shared between bins to match the
+// reference's per-bin linspace exactly).  out[b] = sum_j 0.5*(y[j]+y[j-1])/100 over segments with positive area.
+__global__ void rate_curve_area_kernel(const float* __restrict__ y, float* __restrict__ area, int bins) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= bins) return;
+  const float* yy = y + (size_t)b * 101;
+  float a = 0.f;
+  for (int j = 1; j <= 100; ++j) {
+    const float s = 0.5f * (yy[j] + yy[j - 1]) * 0.01f;
+    if (s > 0.f) a += s;
+  }
+  area[b] = a;
+}
+
+// Generic per-client SGD / FedProx step on packed rows (used by the non-fused model families):
+//   w_c <- w_c - lr * (g_c + mu * (w_c - w_g)),  skipped where step_active[c] == 0
+__global__ void client_sgd_kernel(float* __restrict__ w, const float* __restrict__ g, const float* __restrict__ wg,
+                                  const uint8_t* __restrict__ active, int num_clients, int P, float lr, float mu,
+                                  float momentum, float* __restrict__ mom) {
+  const int i4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  const int c = blockIdx.y;
+  if (i4 >= P || c >= num_clients) return;
+  if (active && !active[c]) return;
+  const size_t o = (size_t)c * P + i4;
+  float4 wv = *reinterpret_cast<float4*>(w + o);
+  const float4 gv = *reinterpret_cast<const float4*>(g + o);
+  float gg[4] = {gv.x, gv.y, gv.z, gv.w};
+  float ww[4] = {wv.x, wv.y, wv.z, wv.w};
+  if (wg) {
+    const float4 a = *reinterpret_cast<const float4*>(wg + i4);
+    gg[0] += mu * (ww[0] - a.x); gg[1] += mu * (ww[1] - a.y); gg[2] += mu * (ww[2] - a.z); gg[3] += mu * (ww[3] - a.w);
+  }
+  if (mom) {
+    float4 mv = *reinterpret_cast<float4*>(mom + o);
+    float mm[4] = {mv.x, mv.y, mv.z, mv.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { mm[e] = momentum * mm[e] + gg[e]; gg[e] = mm[e]; }
+    *reinterpret_cast<float4*>(mom + o) = make_float4(mm[0], mm[1], mm[2], mm[3]);
+  }
+#pragma unroll
+  for (int e = 0; e < 4; ++e) ww[e] -= lr * gg[e];
+  *reinterpret_cast<float4*>(w + o) = make_float4(ww[0], ww[1], ww[2], ww[3]);
+}
+
+}  // namespace flk

@@ -1,0 +1,197 @@
+"""ctypes binding of the sm_100a kernel library (``csrc/api.cu``).
+
+Every function takes torch CUDA tensors, passes raw device pointers and the *current* torch CUDA stream, and
+raises ``NativeError`` on a non-zero return code.  There is deliberately **no** eager fallback here: on a GPU box
+a missing library is an error (``require()``), so a silent PyTorch path can never masquerade as the product.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import torch
+
+from . import build as _build
+from .layout import CNN2
+
+_lib: Optional[C.CDLL] = None
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+def available() -> bool:
+    return torch.cuda.is_available() and (_build.LIB.exists() or _build._nvcc() is not None)
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        path = _build.build()
+        _lib = C.CDLL(str(path))
+        _lib.olsb_last_error.restype = C.c_char_p
+        _lib.olsb_philox_host.restype = None
+    return _lib
+
+
+def require() -> C.CDLL:
+    if not torch.cuda.is_available():
+        raise NativeError("CUDA device required for the native sm_100a path")
+    l = lib()
+    _ck(l.olsb_init())
+    return l
+
+
+def _ck(rc: int) -> None:
+    if rc != 0:
+        msg = lib().olsb_last_error().decode(errors="replace")
+        raise NativeError(f"native call failed rc={rc}: {msg}")
+
+
+def _p(t: Optional[torch.Tensor]) -> C.c_void_p:
+    if t is None:
+        return C.c_void_p(0)
+    assert t.is_cuda and t.is_contiguous(), "native ops need contiguous CUDA tensors"
+    return C.c_void_p(t.data_ptr())
+
+
+def _stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr_array(ptrs: Sequence[int]):
+    arr = (C.c_void_p * len(ptrs))(*[C.c_void_p(int(p)) for p in ptrs])
+    return arr
+
+
+def num_sms() -> int:
+    require()
+    return lib().olsb_num_sms()
+
+
+# --------------------------------------------------------------------------------------------------
+def ingest_u8(src_u8: torch.Tensor, dst_x5: torch.Tensor) -> None:
+    """uint8 [N,32,32,3] -> bf16 [N,32,32,16] (normalised, kw-unrolled)."""
+    n = src_u8.shape[0]
+    assert src_u8.dtype == torch.uint8 and dst_x5.dtype == torch.bfloat16
+    assert tuple(dst_x5.shape) == (n, 32, 32, 16)
+    _ck(require().olsb_ingest_u8(_p(src_u8), _p(dst_x5), C.c_longlong(n), _stream()))
+
+
+def conv1_fwd(x5, x_n_stride, x_n_off, w1_fwd, master, num_clients, active, p1, code1, nsplit=0):
+    _ck(require().olsb_conv1_fwd(_p(x5), C.c_longlong(x5.shape[0]), C.c_int(x_n_stride), C.c_int(x_n_off), _p(w1_fwd),
+                                 _p(master), C.c_longlong(master.shape[1]), C.c_int(num_clients), _p(active), _p(p1),
+                                 _p(code1), C.c_int(nsplit), _stream()))
+
+
+def conv2_fwd(p1, w2_fwd, master, num_clients, active, p2, code2, nsplit=0):
+    _ck(require().olsb_conv2_fwd(_p(p1), _p(w2_fwd), _p(master), C.c_longlong(master.shape[1]), C.c_int(num_clients),
+                                 _p(active), _p(p2), _p(code2), C.c_int(nsplit), _stream()))
+
+
+def conv2_dgrad(dy2, w2_dgrad, master, global_w, num_clients, active, p1, code1, dy1, lr, mu, dbias_out=None,
+                nsplit=0):
+    _ck(require().olsb_conv2_dgrad(_p(dy2), _p(w2_dgrad), _p(master), _p(global_w), C.c_longlong(master.shape[1]),
+                                   C.c_int(num_clients), _p(active), _p(p1), _p(code1), _p(dy1), C.c_float(lr),
+                                   C.c_float(mu), _p(dbias_out), C.c_int(nsplit), _stream()))
+
+
+def conv2_wgrad(p1, dy2, master, global_w, num_clients, active, w2_fwd, w2_dgrad, lr, mu, grad_out=None):
+    _ck(require().olsb_conv2_wgrad(_p(p1), _p(dy2), _p(master), _p(global_w), C.c_longlong(master.shape[1]),
+                                   C.c_int(num_clients), _p(active), _p(w2_fwd), _p(w2_dgrad), C.c_float(lr),
+                                   C.c_float(mu), _p(grad_out), _stream()))
+
+
+def conv1_wgrad(x5, x_n_stride, x_n_off, dy1, master, global_w, num_clients, active, w1_fwd, lr, mu, grad_out=None):
+    _ck(require().olsb_conv1_wgrad(_p(x5), C.c_longlong(x5.shape[0]), C.c_int(x_n_stride), C.c_int(x_n_off), _p(dy1),
+                                   _p(master), _p(global_w), C.c_longlong(master.shape[1]), C.c_int(num_clients),
+                                   _p(active), _p(w1_fwd), C.c_float(lr), C.c_float(mu), _p(grad_out), _stream()))
+
+
+def head(num_clients, active, p2, code2, labels, label_off, master, global_w, lr, mu, dy2, loss_sum, nonfinite,
+         logits_out=None, apply_update=True, dwfc_out=None, db2_out=None):
+    assert labels.dtype == torch.int32
+    _ck(require().olsb_head(C.c_int(num_clients), _p(active), _p(p2), _p(code2), _p(labels),
+                            C.c_int(labels.shape[1]), C.c_int(label_off), _p(master), _p(global_w),
+                            C.c_longlong(master.shape[1]), C.c_float(lr), C.c_float(mu), _p(dy2), _p(loss_sum),
+                            _p(nonfinite), _p(logits_out), C.c_int(1 if apply_update else 0), _p(dwfc_out),
+                            _p(db2_out), _stream()))
+
+
+class Cnn2StepArgs(C.Structure):
+    _fields_ = [
+        ("x5", C.c_void_p), ("x_total", C.c_longlong), ("x_n_stride", C.c_int), ("x_n_off", C.c_int),
+        ("labels", C.c_void_p), ("label_stride", C.c_int), ("label_off", C.c_int),
+        ("master", C.c_void_p), ("global_w", C.c_void_p), ("P", C.c_longlong), ("C", C.c_int),
+        ("active", C.c_void_p),
+        ("w1_fwd", C.c_void_p), ("w2_fwd", C.c_void_p), ("w2_dgrad", C.c_void_p),
+        ("p1", C.c_void_p), ("code1", C.c_void_p), ("p2", C.c_void_p), ("code2", C.c_void_p),
+        ("dy2", C.c_void_p), ("dy1", C.c_void_p),
+        ("loss_sum", C.c_void_p), ("nonfinite", C.c_void_p),
+        ("lr", C.c_float), ("mu", C.c_float), ("use_prox", C.c_int), ("nsplit", C.c_int),
+    ]
+
+
+def cnn2_local_step(args: Cnn2StepArgs) -> None:
+    _ck(require().olsb_cnn2_local_step(C.byref(args), _stream()))
+
+
+KERNELS_PER_LOCAL_STEP = 6
+
+
+# --------------------------------------------------------------------------------------------------
+def bcast_scatter_cnn2(global_peer_ptrs: Sequence[int], rank: int, shard_len: int, global_local, master,
+                       participate, w1_fwd, w2_fwd, w2_dgrad) -> None:
+    n = len(global_peer_ptrs)
+    _ck(require().olsb_bcast_scatter_cnn2(_ptr_array(global_peer_ptrs), C.c_int(n), C.c_int(rank),
+                                          C.c_int(shard_len), _p(global_local), _p(master),
+                                          C.c_int(master.shape[0]), _p(participate), _p(w1_fwd), _p(w2_fwd),
+                                          _p(w2_dgrad), _stream()))
+
+
+def fedavg_partial(master, global_w, weight, nonfinite, groups: int, partial, wsum) -> None:
+    c, p = master.shape
+    _ck(require().olsb_fedavg_partial(_p(master), _p(global_w), _p(weight), _p(nonfinite), C.c_int(c), C.c_int(p),
+                                      C.c_int(groups), _p(partial), _p(wsum), _stream()))
+
+
+def fedavg_finish(partial_peer_ptrs, wsum_peer_ptrs, flag_peer_ptrs, rank: int, groups: int, P: int, shard_len: int,
+                  epoch: int, global_w, opt_m, opt_v, opt: int, server_lr: float, beta1: float, beta2: float,
+                  eps: float, step: int, stats, arrive_ctr) -> None:
+    n = len(partial_peer_ptrs)
+    flags = _ptr_array(flag_peer_ptrs) if flag_peer_ptrs is not None else None
+    _ck(require().olsb_fedavg_finish(_ptr_array(partial_peer_ptrs), _ptr_array(wsum_peer_ptrs), flags, C.c_int(n),
+                                     C.c_int(rank), C.c_int(groups), C.c_int(P), C.c_int(shard_len),
+                                     C.c_uint(epoch), _p(global_w), _p(opt_m), _p(opt_v), C.c_int(opt),
+                                     C.c_float(server_lr), C.c_float(beta1), C.c_float(beta2), C.c_float(eps),
+                                     C.c_int(step), _p(stats), _p(arrive_ctr), _stream()))
+
+
+def deviceflow_mask(num_clients, client_base, seed, round_idx, p_online, drop_probability, arrive_tick, max_tick,
+                    n_samples, local_steps, max_steps, participate, step_active, agg_weight, counters) -> None:
+    _ck(require().olsb_deviceflow_mask(C.c_int(num_clients), C.c_int(client_base), C.c_ulonglong(seed),
+                                       C.c_uint(round_idx), _p(p_online), C.c_float(drop_probability),
+                                       _p(arrive_tick), C.c_int(max_tick), _p(n_samples), _p(local_steps),
+                                       C.c_int(max_steps), _p(participate), _p(step_active), _p(agg_weight),
+                                       _p(counters), _stream()))
+
+
+def rate_curve_area(y: torch.Tensor, area: torch.Tensor) -> None:
+    _ck(require().olsb_rate_curve_area(_p(y), _p(area), C.c_int(area.numel()), _stream()))
+
+
+def client_sgd(w, g, wg, active, lr, mu=0.0, momentum=0.0, mom=None) -> None:
+    c, p = w.shape
+    assert p % 4 == 0
+    _ck(require().olsb_client_sgd(_p(w), _p(g), _p(wg), _p(active), C.c_int(c), C.c_int(p), C.c_float(lr),
+                                  C.c_float(mu), C.c_float(momentum), _p(mom), _stream()))
+
+
+def philox_host(c0, c1, c2, c3, k0, k1):
+    out = (C.c_uint * 4)()
+    lib().olsb_philox_host(C.c_uint(c0), C.c_uint(c1), C.c_uint(c2), C.c_uint(c3), C.c_uint(k0), C.c_uint(k1), out)
+    return tuple(int(v) for v in out)
+
+
+assert CNN2.P % 4 == 0

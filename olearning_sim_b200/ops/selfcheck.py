@@ -1,0 +1,378 @@
+"""Numerics self-check of every CUDA kernel against the plain-PyTorch fp32 oracle.
+
+``python -m olearning_sim_b200.ops.selfcheck [--clients N] [--json out.json]`` runs all checks, prints one line per
+check and never stops at the first failure (a GPU call is expensive; we want the whole picture per run).  The same
+functions back ``tests/test_gpu_kernels.py``.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import sys
+import traceback
+from typing import Callable, Dict, List
+
+import torch
+import torch.nn.functional as F
+
+from . import native, reference
+from .layout import CNN2
+
+B = CNN2.BATCH
+
+
+def rel_err(a: torch.Tensor, b: torch.Tensor) -> float:
+    a = a.double().flatten()
+    b = b.double().flatten()
+    denom = b.norm().item()
+    return (a - b).norm().item() / (denom if denom > 0 else 1.0)
+
+
+def _rand_master(c: int, seed: int = 0, scale: float = 1.0) -> torch.Tensor:
+    rows = [CNN2.init(seed + i) for i in range(c)]
+    m = torch.stack(rows) * scale
+    return m.cuda()
+
+
+def _operand_copies(master: torch.Tensor):
+    c = master.shape[0]
+    L = CNN2
+    w1f = master[:, L.W1:L.W1 + L.W1_N].to(torch.bfloat16).contiguous()
+    w2 = master[:, L.W2:L.W2 + L.W2_N]
+    w2f = w2.to(torch.bfloat16).contiguous()
+    w2d = w2.reshape(c, 64, 800).transpose(1, 2).to(torch.bfloat16).contiguous()   # [C][tap*32+cin][cout]
+    return w1f, w2f, w2d
+
+
+def _conv_ref(x_nhwc: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None) -> torch.Tensor:
+    """per-client conv, x [C,B,H,W,Cin] fp32, w [C,Cout,Cin,5,5] -> [C,B,H,W,Cout]"""
+    c, b, h, ww, cin = x_nhwc.shape
+    cout = w.shape[1]
+    xg = x_nhwc.permute(1, 0, 4, 2, 3).reshape(b, c * cin, h, ww)
+    y = F.conv2d(xg, w.reshape(c * cout, cin, 5, 5), None if bias is None else bias.reshape(-1), padding=2, groups=c)
+    return y.reshape(b, c, cout, h, ww).permute(1, 0, 3, 4, 2).contiguous()
+
+
+def _pool_ref(a: torch.Tensor) -> torch.Tensor:
+    c, b, h, w, ch = a.shape
+    return a.reshape(c, b, h // 2, 2, w // 2, 2, ch).amax(dim=(3, 5))
+
+
+def _unpool_with_code(g: torch.Tensor, code: torch.Tensor) -> torch.Tensor:
+    """g, code [N,h,w,ch] -> [N,2h,2w,ch] placing g at the coded position."""
+    n, h, w, ch = g.shape
+    out = torch.zeros(n, h, 2, w, 2, ch, device=g.device, dtype=g.dtype)
+    for pos in range(4):
+        out[:, :, pos >> 1, :, pos & 1, :] = torch.where(code == pos, g, torch.zeros_like(g))
+    return out.reshape(n, 2 * h, 2 * w, ch)
+
+
+# --------------------------------------------------------------------------------------------------
+def check_ingest(c: int) -> Dict:
+    n = c * 4
+    x = torch.randint(0, 256, (n, 32, 32, 3), dtype=torch.uint8, device="cuda")
+    out = torch.empty(n, 32, 32, 16, dtype=torch.bfloat16, device="cuda")
+    native.ingest_u8(x, out)
+    ref = reference.ingest_ref(x).to(torch.bfloat16)
+    return {"err": rel_err(out.float(), ref.float()), "tol": 1e-6}
+
+
+def _make_x5(c: int, shard: int, seed: int = 1):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    x = torch.randint(0, 256, (c * shard, 32, 32, 3), dtype=torch.uint8, device="cuda", generator=g)
+    x5 = torch.empty(c * shard, 32, 32, 16, dtype=torch.bfloat16, device="cuda")
+    native.ingest_u8(x, x5)
+    return x, x5
+
+
+def check_conv1_fwd(c: int) -> Dict:
+    shard, off = 2 * B, B // 2
+    xu8, x5 = _make_x5(c, shard)
+    master = _rand_master(c)
+    w1f, _, _ = _operand_copies(master)
+    p1 = torch.zeros(c * B, 16, 16, 32, dtype=torch.bfloat16, device="cuda")
+    code1 = torch.full((c * B, 16, 16, 32), 9, dtype=torch.uint8, device="cuda")
+    native.conv1_fwd(x5, shard, off, w1f, master, c, None, p1, code1)
+    torch.cuda.synchronize()
+    x = reference.normalize_u8(xu8).reshape(c, shard, 32, 32, 3)[:, off:off + B].to(torch.bfloat16).float()
+    v = reference.cnn2_views(master)
+    a1 = F.relu(_conv_ref(x, v["w1"].to(torch.bfloat16).float(), v["b1"]))
+    ref = _pool_ref(a1).reshape(c * B, 16, 16, 32)
+    # code consistency: un-pooling the pooled value with the code must reproduce a1 at the argmax position
+    a1f = a1.reshape(c * B, 16, 2, 16, 2, 32)
+    pos_h = (code1 >> 1).long()
+    pos_w = (code1 & 1).long()
+    gathered = torch.gather(torch.gather(a1f, 2, pos_h[:, :, None, :, None, :].expand(-1, -1, 1, -1, 2, -1)), 4,
+                            pos_w[:, :, None, :, None, :].expand(-1, -1, 1, -1, 1, -1)).reshape(c * B, 16, 16, 32)
+    return {"err": rel_err(p1.float(), ref), "tol": 1e-2, "code_err": rel_err(gathered, ref),
+            "code_max": int(code1.max().item())}
+
+
+def check_conv2_fwd(c: int) -> Dict:
+    master = _rand_master(c)
+    _, w2f, _ = _operand_copies(master)
+    p1 = (torch.randn(c * B, 16, 16, 32, device="cuda").clamp_min(0)).to(torch.bfloat16)
+    p2 = torch.zeros(c * B, 8, 8, 64, dtype=torch.bfloat16, device="cuda")
+    code2 = torch.full((c * B, 8, 8, 64), 9, dtype=torch.uint8, device="cuda")
+    native.conv2_fwd(p1, w2f, master, c, None, p2, code2)
+    torch.cuda.synchronize()
+    v = reference.cnn2_views(master)
+    a2 = F.relu(_conv_ref(p1.float().reshape(c, B, 16, 16, 32), v["w2"].to(torch.bfloat16).float(), v["b2"]))
+    ref = _pool_ref(a2).reshape(c * B, 8, 8, 64)
+    return {"err": rel_err(p2.float(), ref), "tol": 1e-2, "code_max": int(code2.max().item())}
+
+
+def check_head(c: int) -> Dict:
+    master = _rand_master(c)
+    p2 = torch.randn(c * B, 8, 8, 64, device="cuda").clamp_min(0).to(torch.bfloat16)
+    code2 = torch.randint(0, 4, (c * B, 8, 8, 64), dtype=torch.uint8, device="cuda")
+    labels = torch.randint(0, 10, (c, 2 * B), dtype=torch.int32, device="cuda")
+    off = B // 2
+    dy2 = torch.zeros(c * B, 16, 16, 64, dtype=torch.bfloat16, device="cuda")
+    loss = torch.zeros(c, device="cuda")
+    nonf = torch.zeros(c, dtype=torch.int32, device="cuda")
+    logits = torch.zeros(c, B, 10, device="cuda")
+    dwfc = torch.zeros(c, CNN2.WFC_N + 16, device="cuda")
+    db2 = torch.zeros(c, 64, device="cuda")
+    m2 = master.clone()
+    native.head(c, None, p2, code2, labels, off, m2, None, 0.1, 0.0, dy2, loss, nonf, logits, False, dwfc, db2)
+    torch.cuda.synchronize()
+    v = reference.cnn2_views(master)
+    feat = p2.float().reshape(c, B, 4096).requires_grad_(True)
+    wfc = v["wfc"].clone().requires_grad_(True)
+    bfc = v["bfc"].clone().requires_grad_(True)
+    lg = torch.bmm(feat, wfc.transpose(1, 2)) + bfc[:, None, :]
+    y = labels[:, off:off + B].long()
+    l = F.cross_entropy(lg.reshape(c * B, 10), y.reshape(-1), reduction="none").reshape(c, B).mean(1)
+    l.sum().backward()
+    dfeat = torch.where(feat > 0, feat.grad, torch.zeros_like(feat.grad)).reshape(c * B, 8, 8, 64)
+    dy2_ref = _unpool_with_code(dfeat, code2)
+    res = {
+        "logits": rel_err(logits, lg.detach()), "loss": rel_err(loss, l.detach()),
+        "dwfc": rel_err(dwfc[:, :CNN2.WFC_N], wfc.grad.reshape(c, -1)),
+        "dbfc": rel_err(dwfc[:, CNN2.WFC_N:CNN2.WFC_N + 10], bfc.grad),
+        "dy2": rel_err(dy2.float(), dy2_ref), "db2": rel_err(db2, dfeat.reshape(c, -1, 64).sum(1)),
+        "unchanged": float((m2 - master).abs().max().item()),
+    }
+    res["err"] = max(res["logits"], res["loss"], res["dwfc"], res["dbfc"], res["dy2"], res["db2"])
+    res["tol"] = 1e-2
+    # update mode: w_fc' = w_fc - lr*g
+    m3 = master.clone()
+    native.head(c, None, p2, code2, labels, off, m3, None, 0.1, 0.0, dy2, loss, nonf, None, True, None, None)
+    torch.cuda.synchronize()
+    exp = master[:, CNN2.WFC:CNN2.WFC + CNN2.WFC_N] - 0.1 * wfc.grad.reshape(c, -1)
+    res["sgd"] = rel_err(m3[:, CNN2.WFC:CNN2.WFC + CNN2.WFC_N], exp)
+    res["err"] = max(res["err"], res["sgd"])
+    return res
+
+
+def check_conv2_dgrad(c: int) -> Dict:
+    master = _rand_master(c)
+    _, _, w2d = _operand_copies(master)
+    dy2 = (torch.randn(c * B, 16, 16, 64, device="cuda") * 0.1).to(torch.bfloat16)
+    p1 = torch.randn(c * B, 16, 16, 32, device="cuda").clamp_min(0).to(torch.bfloat16)
+    code1 = torch.randint(0, 4, (c * B, 16, 16, 32), dtype=torch.uint8, device="cuda")
+    dy1 = torch.zeros(c * B, 32, 32, 32, dtype=torch.bfloat16, device="cuda")
+    db1 = torch.zeros(c, 32, device="cuda")
+    native.conv2_dgrad(dy2, w2d, master, None, c, None, p1, code1, dy1, 0.1, 0.0, db1)
+    torch.cuda.synchronize()
+    v = reference.cnn2_views(master)
+    x = p1.float().reshape(c, B, 16, 16, 32).clone().requires_grad_(True)
+    y = _conv_ref(x, v["w2"].to(torch.bfloat16).float(), None)
+    y.backward(dy2.float().reshape(c, B, 16, 16, 64))
+    dp1 = torch.where(x > 0, x.grad, torch.zeros_like(x.grad)).reshape(c * B, 16, 16, 32)
+    dy1_ref = _unpool_with_code(dp1, code1)
+    return {"err": max(rel_err(dy1.float(), dy1_ref), rel_err(db1, dp1.reshape(c, -1, 32).sum(1))), "tol": 1.5e-2,
+            "dy1": rel_err(dy1.float(), dy1_ref), "db1": rel_err(db1, dp1.reshape(c, -1, 32).sum(1))}
+
+
+def check_conv2_wgrad(c: int) -> Dict:
+    master = _rand_master(c)
+    w1f, w2f, w2d = _operand_copies(master)
+    dy2 = (torch.randn(c * B, 16, 16, 64, device="cuda") * 0.1).to(torch.bfloat16)
+    p1 = torch.randn(c * B, 16, 16, 32, device="cuda").clamp_min(0).to(torch.bfloat16)
+    gout = torch.zeros(c, CNN2.W2_N, device="cuda")
+    native.conv2_wgrad(p1, dy2, master, None, c, None, w2f, w2d, 0.1, 0.0, gout)
+    torch.cuda.synchronize()
+    w = reference.cnn2_views(master)["w2"].clone().requires_grad_(True)
+    y = _conv_ref(p1.float().reshape(c, B, 16, 16, 32), w, None)
+    y.backward(dy2.float().reshape(c, B, 16, 16, 64))
+    gref = w.grad.permute(0, 1, 3, 4, 2).reshape(c, -1)       # cout, kh, kw, cin
+    res = {"err": rel_err(gout, gref), "tol": 1e-2}
+    # fused-update mode
+    m2 = master.clone()
+    native.conv2_wgrad(p1, dy2, m2, None, c, None, w2f, w2d, 0.1, 0.0, None)
+    torch.cuda.synchronize()
+    exp = master[:, CNN2.W2:CNN2.W2 + CNN2.W2_N] - 0.1 * gref
+    res["sgd"] = rel_err(m2[:, CNN2.W2:CNN2.W2 + CNN2.W2_N], exp)
+    res["w2f"] = rel_err(w2f.float(), exp.to(torch.bfloat16).float())
+    res["w2d"] = rel_err(w2d.float(), exp.reshape(c, 64, 800).transpose(1, 2).to(torch.bfloat16).float())
+    res["err"] = max(res["err"], res["sgd"], res["w2f"], res["w2d"])
+    return res
+
+
+def check_conv1_wgrad(c: int) -> Dict:
+    shard, off = 2 * B, B
+    xu8, x5 = _make_x5(c, shard, seed=5)
+    master = _rand_master(c)
+    w1f, _, _ = _operand_copies(master)
+    dy1 = (torch.randn(c * B, 32, 32, 32, device="cuda") * 0.1).to(torch.bfloat16)
+    gout = torch.zeros(c, CNN2.W1_N, device="cuda")
+    native.conv1_wgrad(x5, shard, off, dy1, master, None, c, None, w1f, 0.1, 0.0, gout)
+    torch.cuda.synchronize()
+    x = reference.normalize_u8(xu8).reshape(c, shard, 32, 32, 3)[:, off:off + B].to(torch.bfloat16).float()
+    w = reference.cnn2_views(master)["w1"].clone().requires_grad_(True)
+    y = _conv_ref(x, w, None)
+    y.backward(dy1.float().reshape(c, B, 32, 32, 32))
+    gref = torch.zeros(c, 32, 5, 16, device="cuda")
+    gref[..., :15] = w.grad.permute(0, 1, 3, 4, 2).reshape(c, 32, 5, 15)
+    return {"err": rel_err(gout, gref.reshape(c, -1)), "tol": 1e-2}
+
+
+def check_local_step(c: int) -> Dict:
+    """whole fused step (6 kernels) vs autograd SGD step on the same bf16-rounded operands"""
+    from ..engine.cnn2_native import Cnn2Workspace
+    shard = 2 * B
+    xu8, _ = _make_x5(c, shard, seed=11)
+    labels = torch.randint(0, 10, (c, shard), dtype=torch.int32, device="cuda")
+    ws = Cnn2Workspace(c, shard, device="cuda")
+    ws.load_data(xu8.reshape(c, shard, 32, 32, 3), labels)
+    g0 = CNN2.init(123).cuda()
+    ws.set_global(g0)
+    ws.broadcast()
+    lr = 0.05
+    ws.local_step(0, lr=lr)
+    torch.cuda.synchronize()
+    x = reference.normalize_u8(xu8).reshape(c, shard, 32, 32, 3)[:, :B]
+    flat0 = g0[None, :].repeat(c, 1)
+    new, loss = reference.cnn2_local_step(flat0, x, labels[:, :B], lr, emulate_bf16=True)
+    d_k = ws.master - flat0
+    d_r = new - flat0
+    res = {"loss": rel_err(ws.loss_sum, loss), "delta": rel_err(d_k, d_r), "tol": 6e-2}
+    res["err"] = max(res["loss"], res["delta"])
+    return res
+
+
+def check_reduce(c: int) -> Dict:
+    P = CNN2.P
+    master = torch.randn(c, P, device="cuda")
+    g = torch.randn(P, device="cuda")
+    w = torch.rand(c, device="cuda")
+    w[::3] = 0
+    nonf = torch.zeros(c, dtype=torch.int32, device="cuda")
+    if c > 1:
+        nonf[1] = 1
+    groups = 4
+    partial = torch.zeros(groups, P, device="cuda")
+    wsum = torch.zeros(groups, device="cuda")
+    native.fedavg_partial(master, g, w, nonf, groups, partial, wsum)
+    weff = torch.where(nonf > 0, torch.zeros_like(w), w)
+    dref, ws_ref = reference.fedavg_delta(master, g, weff)
+    res = {"partial": rel_err(partial.sum(0), dref), "wsum": abs(wsum.sum().item() - ws_ref)}
+    for opt in (0, 1, 2):
+        gw = g.clone()
+        m = torch.zeros(P, device="cuda")
+        v = torch.zeros(P, device="cuda")
+        stats = torch.zeros(4, device="cuda")
+        ctr = torch.zeros(2, dtype=torch.int32, device="cuda")
+        state: dict = {}
+        ref = g.clone()
+        for step in (1, 2):
+            native.fedavg_finish([partial.data_ptr()], [wsum.data_ptr()], None, 0, groups, P, P, step, gw, m, v, opt,
+                                 0.5, 0.9, 0.99, 1e-3, step, stats, ctr)
+            ref = reference.server_update(ref, dref, ws_ref, opt, state, 0.5, 0.9, 0.99, 1e-3)
+        torch.cuda.synchronize()
+        res[f"opt{opt}"] = rel_err(gw, ref)
+    res["err"] = max(res["partial"], res["opt0"], res["opt1"], res["opt2"])
+    res["tol"] = 1e-4
+    return res
+
+
+def check_bcast(c: int) -> Dict:
+    g = CNN2.init(7).cuda()
+    P = CNN2.P
+    master = torch.zeros(c, P, device="cuda")
+    gl = torch.zeros(P, device="cuda")
+    w1f = torch.zeros(c, CNN2.W1_N, dtype=torch.bfloat16, device="cuda")
+    w2f = torch.zeros(c, CNN2.W2_N, dtype=torch.bfloat16, device="cuda")
+    w2d = torch.zeros(c, CNN2.W2_N, dtype=torch.bfloat16, device="cuda")
+    native.bcast_scatter_cnn2([g.data_ptr()], 0, P, gl, master, None, w1f, w2f, w2d)
+    torch.cuda.synchronize()
+    e1, e2, e3 = _operand_copies(g[None, :].repeat(c, 1))
+    errs = [rel_err(master, g[None, :].repeat(c, 1)), rel_err(gl, g), rel_err(w1f.float(), e1.float()),
+            rel_err(w2f.float(), e2.float()), rel_err(w2d.float().reshape(c, -1), e3.float().reshape(c, -1))]
+    return {"err": max(errs), "tol": 1e-7, "parts": errs}
+
+
+def check_mask(c: int) -> Dict:
+    from ..deviceflow import philox
+    n = max(c, 257)
+    p_on = torch.rand(n, device="cuda")
+    ns = torch.randint(1, 100, (n,), dtype=torch.int32, device="cuda")
+    steps = torch.randint(1, 6, (n,), dtype=torch.int32, device="cuda")
+    part = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    act = torch.zeros(5, n, dtype=torch.uint8, device="cuda")
+    aw = torch.zeros(n, device="cuda")
+    cnt = torch.zeros(4, dtype=torch.int32, device="cuda")
+    native.deviceflow_mask(n, 1000, 0x1234567890ABCDEF, 3, p_on, 0.25, None, 0, ns, steps, 5, part, act, aw, cnt)
+    torch.cuda.synchronize()
+    ref = philox.round_mask(n, 1000, 0x1234567890ABCDEF, 3, p_on.cpu().numpy(), 0.25, None, 0, ns.cpu().numpy(),
+                            steps.cpu().numpy(), 5)
+    import numpy as np
+    ok = (np.array_equal(part.cpu().numpy(), ref["participate"]) and np.array_equal(act.cpu().numpy(), ref["step_active"])
+          and np.allclose(aw.cpu().numpy(), ref["agg_weight"]) and np.array_equal(cnt.cpu().numpy(), ref["counters"]))
+    return {"err": 0.0 if ok else 1.0, "tol": 0.5, "counters": cnt.cpu().tolist()}
+
+
+CHECKS: Dict[str, Callable[[int], Dict]] = {
+    "ingest": check_ingest, "conv1_fwd": check_conv1_fwd, "conv2_fwd": check_conv2_fwd, "head": check_head,
+    "conv2_dgrad": check_conv2_dgrad, "conv2_wgrad": check_conv2_wgrad, "conv1_wgrad": check_conv1_wgrad,
+    "bcast": check_bcast, "reduce": check_reduce, "mask": check_mask, "local_step": check_local_step,
+}
+
+
+def run_all(clients: List[int], only: List[str] | None = None) -> List[Dict]:
+    out = []
+    for name, fn in CHECKS.items():
+        if only and name not in only:
+            continue
+        for c in clients:
+            rec: Dict = {"check": name, "clients": c}
+            try:
+                torch.manual_seed(1234 + c)
+                r = fn(c)
+                rec.update(r)
+                rec["ok"] = bool(r["err"] <= r["tol"])
+            except Exception as e:  # noqa: BLE001 - report and continue
+                rec["ok"] = False
+                rec["exception"] = f"{type(e).__name__}: {e}"
+                rec["trace"] = traceback.format_exc(limit=4)
+                try:
+                    torch.cuda.synchronize()
+                except Exception as e2:  # sticky CUDA error: nothing else can run
+                    rec["fatal"] = str(e2)
+                    out.append(rec)
+                    print(json.dumps(rec), flush=True)
+                    return out
+            out.append(rec)
+            print(json.dumps({k: v for k, v in rec.items() if k != "trace"}), flush=True)
+    return out
+
+
+def main(argv=None) -> int:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--clients", type=int, nargs="*", default=[3, 160])
+    ap.add_argument("--only", nargs="*", default=None)
+    ap.add_argument("--json", default=None)
+    a = ap.parse_args(argv)
+    res = run_all(a.clients, a.only)
+    if a.json:
+        with open(a.json, "w") as f:
+            json.dump(res, f, indent=1)
+    bad = [r for r in res if not r["ok"]]
+    print(f"selfcheck: {len(res) - len(bad)}/{len(res)} ok")
+    return 1 if bad else 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,139 @@
+"""NVLink/NVSwitch communication runtime: symmetric heap + peer pointer exchange.
+
+One process per GPU (``torch.distributed`` is only the *bootstrap*: it carries 64-byte CUDA-IPC handles and
+small metadata; no tensor payload ever goes through NCCL on the product path).  Each rank allocates identical
+slabs with ``cudaMalloc`` (csrc/api.cu: olsb_sym_alloc), exports them with ``cudaIpcGetMemHandle`` and maps every
+peer's slab with ``cudaIpcOpenMemHandle``.  The fused kernels (``bcast_scatter``, ``fedavg_finish``) then receive
+``void* peer[nranks]`` and issue loads/stores on those pointers directly — the transfer *is* the kernel.
+
+Reference parity: replaces the Ray object store / Pulsar / S3 transports of the reference
+(ols_core/taskMgr/utils/utils_run_task.py:327-397, ols_core/deviceflow/non_grpc/message_producer.py:42-78).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional
+
+import torch
+import torch.distributed as dist
+
+_DTYPE_STR = {torch.float32: "<f4", torch.int32: "<i4", torch.uint8: "|u1", torch.bfloat16: None, torch.uint32: "<u4"}
+
+
+class _CudaBuffer:
+    """Minimal __cuda_array_interface__ holder so torch can wrap a raw device pointer without copying."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
+def wrap_device_ptr(ptr: int, nbytes: int, dtype: torch.dtype, shape, device) -> torch.Tensor:
+    raw = torch.as_tensor(_CudaBuffer(ptr, nbytes), device=device)
+    return raw.view(dtype).reshape(shape)
+
+
+@dataclass
+class SymBuffer:
+    name: str
+    nbytes: int
+    local_ptr: int
+    peer_ptrs: List[int]            # device pointers valid in THIS process for every rank's slab (self included)
+    tensors: Dict[str, torch.Tensor] = field(default_factory=dict)
+
+
+class SymmetricHeap:
+    """Per-process registry of symmetric slabs.  With world_size == 1 it degenerates to plain local allocations
+    (the same kernels run with ``nranks=1``)."""
+
+    def __init__(self, group: Optional["dist.ProcessGroup"] = None, device: Optional[torch.device] = None):
+        from ..ops import native
+        self._native = native
+        self._lib = native.require()
+        self.group = group
+        self.rank = dist.get_rank(group) if (dist.is_available() and dist.is_initialized()) else 0
+        self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+        self.device = device or torch.device("cuda", torch.cuda.current_device())
+        self.buffers: Dict[str, SymBuffer] = {}
+
+    # ---- allocation ------------------------------------------------------------------------------
+    def alloc(self, name: str, nbytes: int) -> SymBuffer:
+        nbytes = (nbytes + 255) // 256 * 256
+        p = C.c_void_p()
+        self._native._ck(self._lib.olsb_sym_alloc(C.c_ulonglong(nbytes), C.byref(p)))
+        local = int(p.value)
+        peers = [local]
+        if self.world > 1:
+            h = (C.c_ubyte * 64)()
+            self._native._ck(self._lib.olsb_ipc_get(C.c_void_p(local), h))
+            mine = torch.tensor(list(h), dtype=torch.uint8)
+            gathered: List[Optional[torch.Tensor]] = [None] * self.world
+            dist.all_gather_object(gathered, mine, group=self.group)
+            peers = []
+            for r, hb in enumerate(gathered):
+                if r == self.rank:
+                    peers.append(local)
+                    continue
+                arr = (C.c_ubyte * 64)(*[int(v) for v in hb.tolist()])
+                q = C.c_void_p()
+                self._native._ck(self._lib.olsb_ipc_open(arr, C.byref(q)))
+                peers.append(int(q.value))
+        buf = SymBuffer(name, nbytes, local, peers)
+        self.buffers[name] = buf
+        return buf
+
+    def tensor(self, name: str, dtype: torch.dtype, shape, peer: Optional[int] = None,
+               byte_offset: int = 0) -> torch.Tensor:
+        """View (a prefix of) a slab — the local one or a peer's — as a torch tensor."""
+        buf = self.buffers[name]
+        ptr = (buf.local_ptr if peer is None else buf.peer_ptrs[peer]) + byte_offset
+        numel = 1
+        for d in shape:
+            numel *= int(d)
+        nbytes = numel * torch.empty((), dtype=dtype).element_size()
+        assert byte_offset + nbytes <= buf.nbytes, "view exceeds the symmetric slab"
+        return wrap_device_ptr(ptr, nbytes, dtype, shape, self.device)
+
+    def barrier(self) -> None:
+        torch.cuda.synchronize(self.device)
+        if self.world > 1:
+            dist.barrier(group=self.group)
+
+    def close(self) -> None:
+        self.barrier()
+        for buf in self.buffers.values():
+            for r, p in enumerate(buf.peer_ptrs):
+                if r != self.rank:
+                    self._lib.olsb_ipc_close(C.c_void_p(p))
+            self._lib.olsb_sym_free(C.c_void_p(buf.local_ptr))
+        self.buffers.clear()
+
+
+def init_distributed(backend: Optional[str] = None) -> tuple[int, int, int]:
+    """Initialise torch.distributed from the torchrun environment (no-op for a single process).
+    Returns (rank, world_size, local_rank)."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29511")
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(local)
+            dist.init_process_group(backend, rank=rank, world_size=world, device_id=torch.device("cuda", local))
+        else:
+            dist.init_process_group(backend, rank=rank, world_size=world)
+    elif torch.cuda.is_available():
+        torch.cuda.set_device(local)
+    return rank, world, local
+
+
+def shard_range(total: int, parts: int, index: int) -> tuple[int, int]:
+    """Near-even contiguous split: floor(N/R) each, the first N mod R parts get one more — the reference's
+    client->actor sharding rule (ols_core/taskMgr/run_task.py:85-105)."""
+    base, rem = divmod(total, parts)
+    start = index * base + min(index, rem)
+    return start, start + base + (1 if index < rem else 0)
