@@ -1,0 +1,375 @@
+"""FedEngine — the public round-loop API of the simulator (one instance per rank / GPU).
+
+    eng = FedEngine(FedConfig(model="cnn2", num_clients=1024, local_steps=5), rank, world)
+    eng.load_synthetic()
+    for r in range(rounds):
+        res = eng.run_round(r)            # broadcast -> masked local training -> FedAvg reduce + server update
+
+It replaces the reference's ``RayRunner.run`` round loop + ``Actor.run`` client loop
+(ols_core/taskMgr/run_task.py:212-322, ols_core/taskMgr/utils/utils_run_task.py:481-577): clients are rows of packed
+device tensors sharded contiguously over ranks (``shard_range`` = run_task.py:85-105), DeviceFlow's
+online/offline/drop behaviour is a per-round mask (``deviceflow_mask_kernel`` / ``philox.round_mask``), the model
+"download" is ``bcast_scatter`` and the update path is ``fedavg_partial`` + ``fedavg_finish``.
+
+Backends:  ``native``  hand-written sm_100a kernels (CNN-2 family, CUDA only)
+           ``torch``   generic ``torch.func`` backend for every model family; CPU (gloo) or CUDA; collectives via
+                       ``torch.distributed`` — this is the library path / baseline, never the product path on GPU.
+"""
+from __future__ import annotations
+
+import math
+import time
+from dataclasses import asdict, dataclass, field
+from typing import Any, Dict, List, Optional
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from ..deviceflow import philox
+from ..models.zoo import ModelSpec, get_model
+from ..ops import reference
+from ..ops.layout import CNN2
+from ..parallel.comm import shard_range
+
+
+@dataclass
+class FedConfig:
+    model: str = "cnn2"
+    model_kwargs: Dict[str, Any] = field(default_factory=dict)
+    num_clients: int = 1024
+    local_steps: int = 5
+    batch: int = 32
+    shard: int = 64                  # samples per client
+    lr: float = 0.05
+    algorithm: str = "fedavg"        # fedavg | fedprox
+    mu: float = 0.0                  # FedProx proximal coefficient
+    server_opt: str = "avg"          # avg | momentum | adam
+    server_lr: float = 1.0
+    seed: int = 0
+    p_online: float = 1.0            # per-round probability that a client is online / sampled
+    drop_probability: float = 0.0    # DeviceFlow drop_simulation (update lost in flight)
+    hetero_steps: bool = False       # stragglers: per-client local-step budget in [1, local_steps]
+    backend: str = "auto"            # auto | native | torch
+    device: str = "auto"
+    use_cuda_graph: bool = True
+    dynamic_nums: int = 0            # tolerated failed clients per round (reference: dynamic_nums)
+
+    def __post_init__(self):
+        if self.algorithm == "fedprox" and self.mu <= 0:
+            self.mu = 0.01
+        if self.algorithm == "fedavg":
+            self.mu = 0.0
+
+
+@dataclass
+class RoundResult:
+    round: int
+    participants: int
+    dropped: int
+    late: int
+    arrived: int
+    failed: int
+    loss: float
+    client_steps: int
+    wall_s: float = 0.0
+    extras: Dict[str, Any] = field(default_factory=dict)
+
+
+def synthetic_client_data(model: str, client_ids: np.ndarray, shard: int, seed: int, spec: ModelSpec):
+    """Synthetic non-IID shards: client i draws labels from a 2-class-dominant distribution and inputs from a
+    label-dependent pattern, generated independently per *global* client id (any rank count sees the same data)."""
+    n = len(client_ids)
+    ncls = spec.num_classes
+    labels = np.empty((n, shard), np.int32)
+    if spec.input_dtype == torch.int64:
+        xs = np.empty((n, shard) + spec.input_shape, np.int64)
+    elif model in ("cnn2", "resnet18"):
+        xs = np.empty((n, shard, 32, 32, 3), np.uint8)
+    else:
+        xs = np.empty((n, shard) + spec.input_shape, np.float32)
+    for j, cid in enumerate(client_ids):
+        rng = np.random.default_rng([seed, int(cid)])
+        major = rng.choice(ncls, size=min(2, ncls), replace=False)
+        probs = np.full(ncls, 0.2 / max(ncls - len(major), 1))
+        probs[major] = 0.8 / len(major)
+        probs /= probs.sum()
+        y = rng.choice(ncls, size=shard, p=probs).astype(np.int32)
+        labels[j] = y
+        if xs.dtype == np.uint8:
+            base = rng.integers(0, 256, size=(shard, 32, 32, 3), dtype=np.uint8)
+            tint = ((y[:, None, None, None].astype(np.int32) * 23) % 97).astype(np.uint8)
+            xs[j] = (base // 2 + tint)
+        elif xs.dtype == np.int64:
+            xs[j] = rng.integers(0, 1000, size=(shard,) + spec.input_shape) + y[:, None] * 7
+        else:
+            xs[j] = rng.standard_normal((shard,) + spec.input_shape).astype(np.float32) + y[:, None] * 0.3
+    return xs, labels
+
+
+class FedEngine:
+    def __init__(self, cfg: FedConfig, rank: int = 0, world: int = 1, group: Optional[Any] = None):
+        self.cfg, self.rank, self.world, self.group = cfg, rank, world, group
+        dev = cfg.device
+        if dev == "auto":
+            dev = f"cuda:{torch.cuda.current_device()}" if torch.cuda.is_available() else "cpu"
+        self.device = torch.device(dev)
+        backend = cfg.backend
+        if backend == "auto":
+            backend = "native" if (self.device.type == "cuda" and cfg.model == "cnn2") else "torch"
+        if backend == "native" and (self.device.type != "cuda" or cfg.model != "cnn2"):
+            raise RuntimeError("the native backend needs CUDA and the cnn2 family")
+        self.backend = backend
+        self.spec = get_model(cfg.model, **cfg.model_kwargs)
+        self.c0, self.c1 = shard_range(cfg.num_clients, world, rank)
+        self.C = self.c1 - self.c0
+        self.client_ids = np.arange(self.c0, self.c1)
+        self.round_log: List[RoundResult] = []
+        self._graph = None
+        self._graph_key = None
+        # per-client static attributes
+        rng = np.random.default_rng([cfg.seed, 991])
+        all_steps = rng.integers(1, cfg.local_steps + 1, size=cfg.num_clients).astype(np.int32) if cfg.hetero_steps \
+            else np.full(cfg.num_clients, cfg.local_steps, np.int32)
+        self.local_steps_np = all_steps[self.c0:self.c1]
+        self.n_samples_np = np.full(self.C, cfg.shard, np.int32)
+        if backend == "native":
+            self._init_native()
+        else:
+            self._init_torch()
+
+    # ==================================================================================================
+    # native backend
+    # ==================================================================================================
+    def _init_native(self) -> None:
+        from ..parallel.comm import SymmetricHeap
+        from .cnn2_native import Cnn2Workspace
+        assert self.cfg.batch == CNN2.BATCH, f"native cnn2 kernels are compiled for batch {CNN2.BATCH}"
+        heap = SymmetricHeap(group=self.group, device=self.device)
+        self.ws = Cnn2Workspace(self.C, self.cfg.shard, device=self.device, heap=heap)
+        d = self.device
+        S = self.cfg.local_steps
+        self.p_online_t = torch.full((self.C,), float(self.cfg.p_online), device=d)
+        self.local_steps_t = torch.from_numpy(self.local_steps_np).to(d)
+        self.participate = torch.ones(self.C, dtype=torch.uint8, device=d)
+        self.step_active = torch.ones(S, self.C, dtype=torch.uint8, device=d)
+        self.agg_weight = torch.zeros(self.C, device=d)
+        self.counters = torch.zeros(4, dtype=torch.int32, device=d)
+        self.result_dev = torch.zeros(8, device=d)
+        self.result_host = torch.zeros(8).pin_memory()
+        self.ws.set_global(CNN2.init(self.cfg.seed))
+        self.P = CNN2.P
+
+    def _native_round_body(self, round_idx: int) -> None:
+        """All device work of one round on the current stream; no host synchronisation."""
+        from ..ops import native
+        cfg, ws = self.cfg, self.ws
+        ws.reset_round_stats()
+        native.deviceflow_mask(self.C, self.c0, cfg.seed, round_idx, self.p_online_t if cfg.p_online < 1.0 else None,
+                               cfg.drop_probability, None, 0, ws.n_samples, self.local_steps_t if cfg.hetero_steps else None,
+                               cfg.local_steps, self.participate, self.step_active, self.agg_weight, self.counters)
+        ws.kernel_launches += 1
+        need_mask = cfg.p_online < 1.0 or cfg.hetero_steps
+        ws.broadcast(self.participate if cfg.p_online < 1.0 else None)
+        for s in range(cfg.local_steps):
+            ws.local_step(s, lr=cfg.lr, mu=cfg.mu, active=self.step_active[s] if need_mask else None)
+        ws.reduce_and_update(self.agg_weight, opt=cfg.server_opt, server_lr=cfg.server_lr)
+
+    def _native_finish(self, round_idx: int) -> RoundResult:
+        ws = self.ws
+        # tiny result vector assembled on device, one D2H copy per round (the "loss or metric" read-back)
+        part = self.participate.float().sum()
+        loss = (ws.loss_sum * self.participate.float()).sum() / self.cfg.local_steps
+        self.result_dev[0] = loss
+        self.result_dev[1] = part
+        self.result_dev[2:6] = self.counters.float()
+        self.result_dev[6] = ws.nonfinite.float().sum()
+        self.result_dev[7] = self.step_active.float().sum()
+        self.result_host.copy_(self.result_dev, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        r = self.result_host
+        vals = torch.tensor([r[0], r[1], r[2], r[3], r[4], r[5], r[6], r[7]], dtype=torch.float64)
+        if self.world > 1:
+            t = vals.to(self.device)
+            dist.all_reduce(t, group=self.group)
+            vals = t.cpu()
+        part_n = int(vals[1].item())
+        return RoundResult(round=round_idx, participants=int(vals[2]), dropped=int(vals[3]), late=int(vals[4]),
+                           arrived=int(vals[5]), failed=int(vals[6]),
+                           loss=float(vals[0] / max(part_n, 1)), client_steps=int(vals[7]))
+
+    # ==================================================================================================
+    # generic torch backend (CPU/gloo or CUDA; library path)
+    # ==================================================================================================
+    def _init_torch(self) -> None:
+        from torch.func import functional_call, grad, vmap  # noqa: F401
+        d = self.device
+        self.P = self.spec.padded_params
+        g0 = self.spec.init(self.cfg.seed).to(d)
+        self.global_w = g0.clone()
+        self.master = g0[None, :].repeat(self.C, 1)
+        self.server_state: Dict[str, Any] = {}
+        self.loss_sum = torch.zeros(self.C, device=d)
+        self.x = None
+        self.y = None
+        spec = self.spec
+
+        def loss_fn(flat, x, y):
+            return spec.loss(flat, x, y)
+
+        self._grad_fn = vmap(grad(loss_fn, has_aux=False), in_dims=(0, 0, 0), randomness="different")
+        self._loss_fn = vmap(loss_fn, in_dims=(0, 0, 0))
+
+    def _torch_round(self, round_idx: int) -> RoundResult:
+        cfg = self.cfg
+        m = philox.round_mask(self.C, self.c0, cfg.seed, round_idx,
+                              np.full(self.C, cfg.p_online, np.float32) if cfg.p_online < 1.0 else None,
+                              cfg.drop_probability, None, 0, self.n_samples_np,
+                              self.local_steps_np if cfg.hetero_steps else None, cfg.local_steps)
+        d = self.device
+        part = torch.from_numpy(m["participate"].astype(bool)).to(d)
+        step_active = torch.from_numpy(m["step_active"].astype(bool)).to(d)
+        weight = torch.from_numpy(m["agg_weight"]).to(d)
+        # broadcast: refresh replicas of sampled clients
+        self.master = torch.where(part[:, None], self.global_w[None, :].expand_as(self.master), self.master)
+        self.loss_sum.zero_()
+        B = cfg.batch
+        for s in range(cfg.local_steps):
+            off = (s * B) % cfg.shard
+            xb, yb = self.x[:, off:off + B], self.y[:, off:off + B]
+            w = self.master
+            g = self._grad_fn(w, xb, yb)
+            with torch.no_grad():
+                self.loss_sum += self._loss_fn(w, xb, yb) * step_active[s]
+            if cfg.mu > 0:
+                g = g + cfg.mu * (w - self.global_w[None, :])
+            self.master = torch.where(step_active[s][:, None], w - cfg.lr * g, w)
+        finite = torch.isfinite(self.loss_sum)
+        weight = torch.where(finite, weight, torch.zeros_like(weight))
+        delta, wsum = reference.fedavg_delta(self.master, self.global_w, weight)
+        pack = torch.cat([delta, torch.tensor([wsum], device=d, dtype=delta.dtype)])
+        stats = torch.tensor([float((self.loss_sum * part).sum() / cfg.local_steps), float(part.sum()),
+                              *[float(v) for v in m["counters"]], float((~finite).sum()), float(step_active.sum())],
+                             dtype=torch.float64)
+        if self.world > 1:
+            dist.all_reduce(pack, group=self.group)
+            st = stats.to(d) if d.type == "cuda" else stats
+            dist.all_reduce(st, group=self.group)
+            stats = st.cpu()
+        self.global_w = reference.server_update(self.global_w, pack[:-1], float(pack[-1]), cfg.server_opt,
+                                                self.server_state, cfg.server_lr)
+        n = max(int(stats[1]), 1)
+        return RoundResult(round=round_idx, participants=int(stats[2]), dropped=int(stats[3]), late=int(stats[4]),
+                           arrived=int(stats[5]), failed=int(stats[6]), loss=float(stats[0]) / n,
+                           client_steps=int(stats[7]))
+
+    # ==================================================================================================
+    # public API
+    # ==================================================================================================
+    def load_synthetic(self) -> None:
+        xs, ys = synthetic_client_data(self.cfg.model, self.client_ids, self.cfg.shard, self.cfg.seed, self.spec)
+        self.load_client_data(xs, ys)
+
+    def load_client_data(self, xs: np.ndarray, labels: np.ndarray) -> None:
+        """xs: uint8 NHWC [C, shard, 32,32,3] for the image families, float/int arrays otherwise."""
+        self.host_x = torch.from_numpy(np.ascontiguousarray(xs))
+        self.host_y = torch.from_numpy(np.ascontiguousarray(labels))
+        if self.device.type == "cuda":
+            self.host_x = self.host_x.pin_memory()
+            self.host_y = self.host_y.pin_memory()
+        if self.backend == "native":
+            self.ws.load_data(self.host_x.to(self.device, non_blocking=True), self.host_y.to(self.device))
+        else:
+            x = self.host_x.to(self.device)
+            if x.dtype == torch.uint8:
+                x = reference.normalize_u8(x).permute(0, 1, 4, 2, 3).contiguous()   # C,S,3,32,32
+            self.x, self.y = x, self.host_y.to(self.device)
+
+    def stream_inputs(self, stream: Optional["torch.cuda.Stream"] = None) -> int:
+        """End-to-end mode: (re)upload this round's client samples and labels from pinned host memory and ingest
+        them (native: uint8 -> bf16 operand layout on the GPU).  Returns the bytes copied host->device."""
+        nbytes = self.host_x.numel() * self.host_x.element_size() + self.host_y.numel() * self.host_y.element_size()
+        if self.backend == "native":
+            if not hasattr(self, "_stage_x"):
+                self._stage_x = torch.empty_like(self.host_x, device=self.device)
+            self._stage_x.copy_(self.host_x, non_blocking=True)
+            self.ws.labels.copy_(self.host_y, non_blocking=True)
+            self.ws.ingest_slice(self._stage_x.reshape(-1, 32, 32, 3), 0)
+        else:
+            x = self.host_x.to(self.device, non_blocking=True)
+            if x.dtype == torch.uint8:
+                x = reference.normalize_u8(x).permute(0, 1, 4, 2, 3).contiguous()
+            self.x, self.y = x, self.host_y.to(self.device, non_blocking=True)
+        return nbytes
+
+    def run_round(self, round_idx: int, stream_inputs: bool = False) -> RoundResult:
+        t0 = time.perf_counter()
+        if stream_inputs:
+            h2d = self.stream_inputs()
+        if self.backend == "native":
+            self._native_round_body(round_idx)
+            res = self._native_finish(round_idx)
+        else:
+            res = self._torch_round(round_idx)
+        res.wall_s = time.perf_counter() - t0
+        if stream_inputs:
+            res.extras["h2d_bytes"] = h2d
+            res.extras["d2h_bytes"] = 32 if self.backend == "native" else 64
+        self.round_log.append(res)
+        return res
+
+    def enqueue_round(self, round_idx: int) -> None:
+        """Device-only enqueue of a round (no host read-back) — used by the device-timed benchmark."""
+        assert self.backend == "native"
+        self._native_round_body(round_idx)
+
+    def global_model(self) -> torch.Tensor:
+        return self.ws.get_global() if self.backend == "native" else self.global_w
+
+    def set_global_model(self, flat: torch.Tensor) -> None:
+        if self.backend == "native":
+            self.ws.set_global(flat)
+        else:
+            self.global_w = flat.to(self.device).clone()
+
+    def evaluate(self) -> Dict[str, float]:
+        """Mean loss / accuracy of the current global model over every local client's shard."""
+        g = self.global_model()
+        if self.backend == "native":
+            x = reference.normalize_u8(self.host_x.to(self.device)[:, :CNN2.BATCH])
+            losses, logits = reference.cnn2_loss(g[None, :].repeat(self.C, 1), x, self.host_y.to(self.device)[:, :CNN2.BATCH])
+            acc = (logits.argmax(-1) == self.host_y.to(self.device)[:, :CNN2.BATCH]).float().mean()
+            out = torch.tensor([losses.mean().item(), acc.item(), 1.0], dtype=torch.float64)
+        else:
+            B = self.cfg.batch
+            w = g[None, :].expand(self.C, -1)
+            l = self._loss_fn(w, self.x[:, :B], self.y[:, :B]).mean()
+            out = torch.tensor([l.item(), float("nan"), 1.0], dtype=torch.float64)
+        if self.world > 1:
+            t = out.to(self.device) if self.device.type == "cuda" else out
+            dist.all_reduce(t, group=self.group)
+            out = t.cpu()
+        return {"loss": float(out[0] / out[2]), "acc": float(out[1] / out[2])}
+
+    def kernel_launches(self) -> int:
+        return self.ws.kernel_launches if self.backend == "native" else 0
+
+    def state_dict(self) -> Dict[str, Any]:
+        sd = {"config": asdict(self.cfg), "global": self.global_model().detach().cpu(), "rounds_done": len(self.round_log)}
+        if self.backend == "native":
+            sd["opt_m"], sd["opt_v"] = self.ws.opt_m.cpu(), self.ws.opt_v.cpu()
+            sd["server_step"] = self.ws.server_step
+        else:
+            sd["server_state"] = {k: (v.cpu() if torch.is_tensor(v) else v) for k, v in self.server_state.items()}
+        return sd
+
+    def load_state_dict(self, sd: Dict[str, Any]) -> None:
+        self.set_global_model(sd["global"])
+        if self.backend == "native":
+            self.ws.opt_m.copy_(sd["opt_m"]); self.ws.opt_v.copy_(sd["opt_v"]); self.ws.server_step = sd["server_step"]
+        else:
+            self.server_state = {k: (v.to(self.device) if torch.is_tensor(v) else v) for k, v in sd.get("server_state", {}).items()}
+
+    def close(self) -> None:
+        if self.backend == "native":
+            self.ws.close()
