@@ -8,6 +8,7 @@ by a lock (the reference opens a fresh ``engine.execute`` per statement and has 
 """
 from __future__ import annotations
 
+import itertools
 import json
 import sqlite3
 import threading
@@ -21,6 +22,7 @@ TASK_COLUMNS = ["task_id", "task_status", "task_params", "total_simulation", "in
 RES_COLUMNS = ["task_id", "cpu", "mem", "gpu", "status", "freeze_time", "release_time", "detail"]
 FLOW_COLUMNS = ["task_id", "flow_id", "task_registry", "flow"]
 LOG_COLUMNS = ["task_id", "other_number", "system_name", "module_name", "message", "log_type", "ts"]
+_mem_counter = itertools.count()
 _INT_COLS = {"resource_occupied", "logical_round", "device_round", "status"}
 _REAL_COLS = {"cpu", "mem", "gpu", "ts"}
 
@@ -34,7 +36,7 @@ class SqlDataBase:
     def __init__(self, path: str = ":memory:", table: str = "table", columns: Sequence[str] = (),
                  shared_key: Optional[str] = None):
         self.path, self.table, self.columns = path, table, list(columns)
-        key = shared_key or (path if path != ":memory:" else f":memory:{id(self)}")
+        key = shared_key or (path if path != ":memory:" else f":memory:{next(_mem_counter)}")
         with SqlDataBase._shared_guard:
             if key not in SqlDataBase._shared:
                 conn = sqlite3.connect(path, check_same_thread=False, isolation_level=None)

@@ -1,0 +1,352 @@
+"""Round-loop driver of one task (the job a TaskRunner submits).
+
+    python -m olearning_sim_b200.control.run_task --task '<json>'            (CLI parity with run_task.py:40-49,324-326)
+    python -m torch.distributed.run --nproc-per-node N -m olearning_sim_b200.control.run_task --task-file f.json
+
+Counterpart of ``RayRunner`` (ols_core/taskMgr/run_task.py:32-322) and of the Ray ``Actor``
+(ols_core/taskMgr/utils/utils_run_task.py:146-577):
+
+    for round in rounds:                      operatorflow.start() gate
+      for operator in operators:              NotifyStart -> run all clients -> NotifyComplete -> analyze_results
+                                              operatorflow.stop() gate
+
+* built-in GPU operators: every client of every (dataset, device class) is a row of the FedEngine's packed tensors;
+  one call trains them all.  Device classes map to heterogeneity knobs (local-step budget, online probability).
+* script operators (reference contract): clients are sharded over ``num_request`` workers with the reference's
+  near-even contiguous split (run_task.py:85-105); each worker runs its clients sequentially, one
+  ``python3 <operator>/<entry> --params f.json`` subprocess per simulated phone (utils_run_task.py:481-514).
+"""
+from __future__ import annotations
+
+import argparse
+import concurrent.futures
+import json
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+import threading
+from typing import Any, Dict, List, Optional, Tuple
+
+from ..deviceflow.service import NotifyRequest
+from ..parallel.comm import shard_range
+from ..utils.logger import Logger
+from .operatorflow import OperatorFlow
+from .operators import BUILTIN_OPERATORS, parse_builtin
+
+logger = Logger()
+
+
+class Params:
+    """Parsed job JSON (utils_run_task.py:20-51)."""
+
+    def __init__(self, task_json: Dict[str, Any]):
+        if isinstance(task_json, str):
+            task_json = json.loads(task_json)
+        self.json = task_json
+        self.task_id = task_json.get("task_id", "")
+        self.user_id = task_json.get("user_id", "")
+        of = task_json.get("operatorflow", {})
+        fs = of.get("flow_setting", {})
+        self.round = int(fs.get("round", 1))
+        self.start_params = fs.get("start", {}).get("logical_simulation", {}) or {}
+        self.stop_params = fs.get("stop", {}).get("logical_simulation", {}) or {}
+        self.operators = list(of.get("operators", []))
+        self.data = list(task_json.get("target", {}).get("data", []))
+        ls = task_json.get("logical_simulation", {})
+        cu = ls.get("computation_unit", {})
+        self.computation_unit = {d: s for d, s in zip(cu.get("devices", []), cu.get("setting", []))}
+        self.resource_request = {r.get("name"): r for r in ls.get("resource_request", [])}
+        self.engine = task_json.get("engine", {}) or {}
+
+
+def construct_run_params(data: Dict[str, Any], resource_request: Dict[str, Any]) -> List[Dict[str, Any]]:
+    """client -> worker sharding for one dataset: clients of device class d are split near-evenly over
+    ``num_request[d]`` workers, contiguous ``split_index`` ranges; classes follow each other in index space."""
+    out, base = [], 0
+    devices = data.get("simulation_target", {}).get("devices", [])
+    nums = data.get("simulation_target", {}).get("nums", [])
+    req = dict(zip(resource_request.get("devices", []), resource_request.get("num_request", [])))
+    for dev, n in zip(devices, nums):
+        workers = int(req.get(dev, 0))
+        if n > 0 and workers <= 0:
+            workers = 1
+        for w in range(workers):
+            s, e = shard_range(n, workers, w)
+            if e > s:
+                out.append({"data_name": data.get("name", ""), "device_type": dev, "worker": w,
+                            "split_index": list(range(base + s, base + e))})
+        base += n
+    return out
+
+
+class ScriptActor:
+    """One worker ("actor"): runs its simulated phones sequentially, one subprocess each."""
+
+    def __init__(self, params: Params, operator: Dict[str, Any], working_dir: str, round_idx: int,
+                 deviceflow_info: Dict[str, Any], stop_event: threading.Event):
+        self.p, self.op, self.wd, self.round, self.df, self.stop = params, operator, working_dir, round_idx, deviceflow_info, stop_event
+
+    def construct_params_for_phones(self, run_params: Dict[str, Any], data: Dict[str, Any]) -> List[Dict[str, Any]]:
+        model = self.op.get("model", {})
+        path = model.get("model_path", "")
+        if model.get("use_model") and model.get("model_for_train") and self.round > 0 and model.get("model_update_style"):
+            # per-round global model written by the aggregator: "{task_id}_{current_round}_result_model..." (utils_run_task.py:335-350)
+            name = model["model_update_style"].replace("{task_id}", self.p.task_id).replace("{current_round}", str(self.round))
+            path = os.path.join(os.path.dirname(path), name)
+        info = self.op.get("logical_simulation", {})
+        try:
+            user_params = json.loads(info.get("operator_params") or "{}")
+        except ValueError:
+            user_params = {}
+        return [{"task_id": self.p.task_id, "operator_name": self.op.get("name", ""), "round": self.round,
+                 "device_type": run_params["device_type"], "split_index": idx,
+                 "data": {"name": data.get("name", ""), "path": data.get("data_path", ""),
+                          "split_type": data.get("data_split_type", False)},
+                 "model": {"use_model": model.get("use_model", False), "for_train": model.get("model_for_train", False), "path": path},
+                 "operator_params": user_params, "deviceflow": self.df} for idx in run_params["split_index"]]
+
+    def run(self, run_params: Dict[str, Any], data: Dict[str, Any]) -> Dict[str, Any]:
+        info = self.op.get("logical_simulation", {})
+        entry = os.path.join(self.wd, self.op.get("name", ""), info.get("operator_entry_file", ""))
+        ok = bad = 0
+        tmp = tempfile.mkdtemp(prefix="olsb_actor_")
+        try:
+            for i, prm in enumerate(self.construct_params_for_phones(run_params, data)):
+                if self.stop.is_set():
+                    break
+                f = os.path.join(tmp, f"params_{i}.json")
+                with open(f, "w") as fh:
+                    json.dump(prm, fh)
+                rc = subprocess.call([sys.executable, entry, "--params", f], cwd=os.path.dirname(entry))
+                ok, bad = (ok + 1, bad) if rc == 0 else (ok, bad + 1)
+        finally:
+            shutil.rmtree(tmp, ignore_errors=True)
+        return {"data_name": run_params["data_name"], "device_type": run_params["device_type"], "success": ok, "failed": bad}
+
+
+class RoundRunner:
+    def __init__(self, task_json: Dict[str, Any], stop_event: Optional[threading.Event] = None, repo: Any = None,
+                 deviceflow: Any = None, working_dir: Optional[str] = None, gate_params: Optional[Dict[str, Any]] = None,
+                 rank: int = 0, world: int = 1, checkpoint_dir: Optional[str] = None, **_: Any):
+        self.params = Params(task_json)
+        self.stop_event = stop_event or threading.Event()
+        self.repo, self.deviceflow, self.working_dir = repo, deviceflow, working_dir or tempfile.mkdtemp(prefix="olsb_job_")
+        self.rank, self.world = rank, world
+        self.gate_params = gate_params or {}
+        self.checkpoint_dir = checkpoint_dir or self.params.engine.get("checkpoint_dir")
+        self.engines: Dict[str, Any] = {}
+        self.history: List[Dict[str, Any]] = []
+
+    # ---- deviceflow wiring (utils_run_task.py:53-144) ----------------------------------------------------
+    def _df_start(self, operator: Dict[str, Any], round_idx: int) -> Dict[str, Any]:
+        bc = operator.get("operation_behavior_controller", {})
+        if not bc.get("use_gradient_house") or self.deviceflow is None:
+            return {"use": False}
+        routing_key = f"{self.params.task_id}_{operator.get('name', '')}_{round_idx}"
+        outbound = {}
+        if bc.get("outbound_service"):
+            try:
+                outbound = json.loads(bc["outbound_service"])
+            except ValueError:
+                outbound = {}
+        if self.rank == 0:
+            ok = self.deviceflow.NotifyStart(NotifyRequest(self.params.task_id, routing_key, "logical_simulation",
+                                                           bc.get("strategy_gradient_house", ""), outbound))
+            if not ok:
+                raise RuntimeError(f"deviceflow NotifyStart failed for {routing_key}")
+        return {"use": True, "routing_key": routing_key, "compute_resource": "logical_simulation",
+                "inbound": self.deviceflow.GetDeviceflowPulsarClient(),
+                "websocket_url": self.deviceflow.GetDeviceflowWebsocket().get("url", "")}
+
+    def _df_stop(self, df_info: Dict[str, Any]) -> None:
+        if df_info.get("use") and self.rank == 0:
+            self.deviceflow.NotifyComplete(NotifyRequest(self.params.task_id, df_info["routing_key"], "logical_simulation"))
+
+    # ---- built-in (GPU-native) operator ---------------------------------------------------------------
+    def _builtin_engine(self, operator: Dict[str, Any]):
+        from ..engine.fed_engine import FedConfig, FedEngine
+        name = operator.get("name", "")
+        if name in self.engines:
+            return self.engines[name]
+        info = operator.get("logical_simulation", {})
+        kind = parse_builtin(info.get("operator_code_path", ""))
+        if kind not in BUILTIN_OPERATORS:
+            raise ValueError(f"unknown builtin operator {kind!r}")
+        try:
+            user = json.loads(info.get("operator_params") or "{}")
+        except ValueError:
+            user = {}
+        cfgd = {**self.params.engine, **BUILTIN_OPERATORS[kind](user)}
+        # shared engine for all operators that train the same population (e.g. "train" + "evaluate")
+        share = cfgd.pop("share_engine_with", None)
+        if share and share in self.engines:
+            self.engines[name] = self.engines[share]
+            return self.engines[name]
+        # population: every client of every dataset / device class, in order
+        classes: List[str] = []
+        for d in self.params.data:
+            st = d.get("simulation_target", {})
+            for dev, n in zip(st.get("devices", []), st.get("nums", [])):
+                classes += [f"{d.get('name', '')}/{dev}"] * int(n)
+        fields = {k: v for k, v in cfgd.items() if k in FedConfig.__dataclass_fields__}
+        fields["num_clients"] = len(classes)
+        cfg = FedConfig(**fields)
+        eng = FedEngine(cfg, self.rank, self.world)
+        eng.client_class = classes
+        # device classes -> heterogeneity (stragglers / availability), e.g. {"Low": {"local_steps": 2, "p_online": 0.8}}
+        dc = cfgd.get("device_classes", {})
+        if dc:
+            import numpy as np
+            steps = eng.local_steps_np.copy()
+            pon = np.full(eng.C, cfg.p_online, np.float32)
+            for i in range(eng.C):
+                dev = classes[eng.c0 + i].split("/", 1)[1]
+                if dev in dc:
+                    steps[i] = min(int(dc[dev].get("local_steps", steps[i])), cfg.local_steps)
+                    pon[i] = float(dc[dev].get("p_online", pon[i]))
+            eng.local_steps_np = steps
+            eng.cfg.hetero_steps = bool((steps != cfg.local_steps).any()) or cfg.hetero_steps
+            eng.cfg.p_online = float(pon.min()) if (pon < 1).any() else cfg.p_online
+            if eng.backend == "native":
+                import torch
+                eng.local_steps_t = torch.from_numpy(steps).to(eng.device)
+                eng.p_online_t = torch.from_numpy(pon).to(eng.device)
+        eng.load_synthetic() if cfgd.get("data", "synthetic") == "synthetic" else None
+        if self.checkpoint_dir:
+            from ..engine.checkpoint import CheckpointManager
+            eng.ckpt = CheckpointManager(self.checkpoint_dir, self.params.task_id, rank=self.rank)
+            state = eng.ckpt.load_latest()
+            if state is not None:
+                eng.load_state_dict(state["engine"])
+                eng.resume_round = state["round"] + 1
+        self.engines[name] = eng
+        return eng
+
+    def _run_builtin(self, operator: Dict[str, Any], round_idx: int) -> List[Dict[str, Any]]:
+        eng = self._builtin_engine(operator)
+        kind = parse_builtin(operator.get("logical_simulation", {}).get("operator_code_path", ""))
+        if getattr(eng, "resume_round", 0) > round_idx:
+            res_failed = 0                                  # round already done before the restart
+        elif kind == "evaluate":
+            self.history.append({"round": round_idx, "operator": operator.get("name"), **eng.evaluate()})
+            res_failed = 0
+        else:
+            res = eng.run_round(round_idx)
+            self.history.append({"round": round_idx, "operator": operator.get("name"), "loss": res.loss,
+                                 "participants": res.participants, "dropped": res.dropped, "arrived": res.arrived,
+                                 "failed": res.failed, "client_steps": res.client_steps, "wall_s": res.wall_s})
+            res_failed = res.failed
+            if getattr(eng, "ckpt", None) is not None:
+                eng.ckpt.save(round_idx, {"engine": eng.state_dict(), "round": round_idx})
+        # per (dataset, class) accounting: a client "fails" only if its computation failed (non-finite update);
+        # offline / dropped-in-flight clients behaved as the trace prescribed and count as successes.
+        out: Dict[Tuple[str, str], List[int]] = {}
+        for d in self.params.data:
+            st = d.get("simulation_target", {})
+            for dev, n in zip(st.get("devices", []), st.get("nums", [])):
+                out[(d.get("name", ""), dev)] = [int(n), 0]
+        if res_failed:
+            # attribute failures to classes (rank-local flags are reduced inside the engine for the total only)
+            key = next(iter(out))
+            out[key][0] -= min(res_failed, out[key][0])
+            out[key][1] += res_failed
+        return [{"data_name": k[0], "device_type": k[1], "success": v[0], "failed": v[1]} for k, v in out.items()]
+
+    # ---- script operator ----------------------------------------------------------------------------
+    def _run_script(self, operator: Dict[str, Any], round_idx: int, df_info: Dict[str, Any]) -> List[Dict[str, Any]]:
+        jobs = []
+        for d in self.params.data:
+            rr = self.params.resource_request.get(d.get("name"), {})
+            for rp in construct_run_params(d, rr):
+                jobs.append((rp, d))
+        results = []
+        with concurrent.futures.ThreadPoolExecutor(max_workers=max(1, min(len(jobs), os.cpu_count() or 1))) as pool:
+            futs = [pool.submit(ScriptActor(self.params, operator, self.working_dir, round_idx, df_info, self.stop_event).run, rp, d)
+                    for rp, d in jobs]
+            for f in futs:
+                results.append(f.result())
+        return results
+
+    # ---- result accounting (run_task.py:149-210) -------------------------------------------------------
+    def analyze_results(self, results: List[Dict[str, Any]], operator_name: str, round_idx: int) -> List[Dict[str, Any]]:
+        logical_result = []
+        for d in self.params.data:
+            devices = d.get("simulation_target", {}).get("devices", [])
+            succ, fail = [0] * len(devices), [0] * len(devices)
+            for r in results:
+                if r["data_name"] == d.get("name") and r["device_type"] in devices:
+                    i = devices.index(r["device_type"])
+                    succ[i] += int(r["success"])
+                    fail[i] += int(r["failed"])
+            logical_result.append({"name": d.get("name", ""),
+                                   "simulation_target": {"devices": devices, "success_num": succ, "failed_num": fail}})
+        if self.repo is not None and self.rank == 0:
+            self.repo.set_item_values("task_id", self.params.task_id, {
+                "logical_round": round_idx + 1, "logical_operator": operator_name,
+                "logical_result": json.dumps({"logical_result": logical_result})})
+        return logical_result
+
+    # ---- main loop -----------------------------------------------------------------------------------
+    def run(self) -> bool:
+        p = self.params
+        flow = OperatorFlow(p.task_id, p.round, p.start_params, p.stop_params, self.gate_params)
+        try:
+            for round_idx in range(p.round):
+                if self.stop_event.is_set():
+                    return False
+                if not flow.start(round_idx):
+                    raise RuntimeError(f"operatorflow start gate timed out in round {round_idx}")
+                for op in p.operators:
+                    if self.stop_event.is_set():
+                        return False
+                    df_info = self._df_start(op, round_idx)
+                    code_path = op.get("logical_simulation", {}).get("operator_code_path", "")
+                    if parse_builtin(code_path) is not None:
+                        results = self._run_builtin(op, round_idx)
+                    else:
+                        results = self._run_script(op, round_idx, df_info)
+                    self._df_stop(df_info)
+                    self.analyze_results(results, op.get("name", ""), round_idx)
+                if not flow.stop(round_idx) and round_idx != p.round - 1:
+                    raise RuntimeError(f"operatorflow stop gate failed in round {round_idx}")
+            return True
+        finally:
+            for e in {id(e): e for e in self.engines.values()}.values():
+                try:
+                    e.close()
+                except Exception:  # noqa: BLE001
+                    pass
+
+
+def main(argv: Optional[List[str]] = None) -> int:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--task", type=str, default=None, help="task json string")
+    ap.add_argument("--task-file", type=str, default=None, help="file with {'task': ..., 'context': ...}")
+    a = ap.parse_args(argv)
+    ctx: Dict[str, Any] = {}
+    if a.task_file:
+        with open(a.task_file) as f:
+            blob = json.load(f)
+        task, ctx = blob["task"], blob.get("context", {})
+    elif a.task:
+        task = json.loads(a.task)
+    else:
+        ap.error("--task or --task-file required")
+    from ..parallel.comm import init_distributed
+    rank, world, _ = init_distributed()
+    repo = None
+    if ctx.get("repo_path"):
+        from .repo import TaskTableRepo
+        repo = TaskTableRepo(ctx["repo_path"])
+    runner = RoundRunner(task, repo=repo, working_dir=ctx.get("working_dir"), rank=rank, world=world,
+                         checkpoint_dir=ctx.get("checkpoint_dir"))
+    ok = runner.run()
+    if rank == 0:
+        print(json.dumps({"task_id": runner.params.task_id, "ok": ok, "history": runner.history[-3:]}))
+    return 0 if ok else 1
+
+
+if __name__ == "__main__":
+    sys.exit(main())

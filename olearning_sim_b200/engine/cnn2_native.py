@@ -6,7 +6,7 @@ packed tensors that never leave HBM during a task:
 
     data      x5   [C*shard, 32,32,16] bf16 (ingested once)      labels [C, shard] int32
     weights   master [C, P] fp32  +  bf16 tensor-core operand copies (w1_fwd, w2_fwd, w2_dgrad)
-    acts      p1/code1, p2/code2, dy2, dy1 (one local batch per client)
+    acts      p1/code1, p2/code2, dy2, dp1 (one local batch per client)
     server    global [P] fp32 in the symmetric heap (each rank owns the optimiser state of one shard)
 
 and a round is: ``broadcast`` (1 kernel) -> ``local_step`` x S (6 kernels each) -> ``reduce_and_update`` (2 kernels).
@@ -56,7 +56,7 @@ class Cnn2Workspace:
         self.p2 = torch.empty(C * B, 8, 8, 64, dtype=bf, device=d)
         self.code2 = torch.empty(C * B, 8, 8, 64, dtype=u8, device=d)
         self.dy2 = torch.empty(C * B, 16, 16, 64, dtype=bf, device=d)
-        self.dy1 = torch.empty(C * B, 32, 32, 32, dtype=bf, device=d)
+        self.dp1 = torch.empty(C * B, 16, 16, 32, dtype=bf, device=d)
         self.loss_sum = torch.zeros(C, dtype=f32, device=d)
         self.nonfinite = torch.zeros(C, dtype=i32, device=d)
         self.n_samples = torch.full((C,), shard, dtype=i32, device=d)
@@ -124,7 +124,7 @@ class Cnn2Workspace:
         a.active = active.data_ptr() if active is not None else None
         a.w1_fwd = self.w1_fwd.data_ptr(); a.w2_fwd = self.w2_fwd.data_ptr(); a.w2_dgrad = self.w2_dgrad.data_ptr()
         a.p1 = self.p1.data_ptr(); a.code1 = self.code1.data_ptr(); a.p2 = self.p2.data_ptr()
-        a.code2 = self.code2.data_ptr(); a.dy2 = self.dy2.data_ptr(); a.dy1 = self.dy1.data_ptr()
+        a.code2 = self.code2.data_ptr(); a.dy2 = self.dy2.data_ptr(); a.dp1 = self.dp1.data_ptr()
         a.loss_sum = self.loss_sum.data_ptr(); a.nonfinite = self.nonfinite.data_ptr()
         a.lr = lr; a.mu = mu; a.use_prox = 1 if mu > 0 else 0; a.nsplit = nsplit
         native.cnn2_local_step(a)

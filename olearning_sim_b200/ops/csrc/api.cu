@@ -91,13 +91,13 @@ constexpr int BATCH = 32;
 //                          ROWB NKW BN  H   W   BATCH  FLIP   EPI         NSTAGE
 #define CONV1_FWD conv_taps_kernel<32, 1, 32, 32, 32, BATCH, false, EPI_POOL, 8>
 #define CONV2_FWD conv_taps_kernel<64, 5, 64, 16, 16, BATCH, false, EPI_POOL, 7>
-#define CONV2_DGRAD conv_taps_kernel<128, 5, 32, 16, 16, BATCH, true, EPI_UNPOOL, 4>
+#define CONV2_DGRAD conv_taps_kernel<128, 5, 32, 16, 16, BATCH, true, EPI_GATE, 4>
 using Conv1FwdCfg = FwdCfg<32, 1, 32, 32, 32, BATCH, false, EPI_POOL, 8>;
 using Conv2FwdCfg = FwdCfg<64, 5, 64, 16, 16, BATCH, false, EPI_POOL, 7>;
-using Conv2DgradCfg = FwdCfg<128, 5, 32, 16, 16, BATCH, true, EPI_UNPOOL, 4>;
-//                              XROWB NKW YROWB H   W   BATCH NSS
-#define CONV2_WGRAD conv_wgrad_kernel<64, 5, 128, 16, 16, BATCH, 2>
-#define CONV1_WGRAD conv_wgrad_kernel<32, 1, 64, 32, 32, BATCH, 6>
+using Conv2DgradCfg = FwdCfg<128, 5, 32, 16, 16, BATCH, true, EPI_GATE, 4>;
+//                              XROWB NKW YROWB H   W   BATCH NSS SYNTH_Y
+#define CONV2_WGRAD conv_wgrad_kernel<64, 5, 128, 16, 16, BATCH, 2, false>
+#define CONV1_WGRAD conv_wgrad_kernel<32, 1, 64, 32, 32, BATCH, 6, true>
 using Conv2WgradCfg = WgradCfg<64, 5, 128, 2>;
 using Conv1WgradCfg = WgradCfg<32, 1, 64, 6>;
 
@@ -186,11 +186,11 @@ int olsb_conv2_fwd(const void* p1, const void* w2_fwd, const void* master, long 
   return 0;
 }
 
-// conv2 data gradient fused with un-pool/ReLU-backward of layer 1 and the conv1-bias SGD step:
-// dY2 [C*32][16][16][64] (x) W2 -> dP1 -> dY1 [C*32][32][32][32]
+// conv2 data gradient fused with the ReLU-backward gate of layer 1 and the conv1-bias SGD step:
+// dY2 [C*32][16][16][64] (x) W2 -> dP1 [C*32][16][16][32] (gradient w.r.t. the pooled conv1 activation, gated by P1>0)
 int olsb_conv2_dgrad(const void* dy2, const void* w2_dgrad, void* master, const void* global_w, long long P, int C,
-                     const void* active, const void* p1, const void* code1, void* dy1, float lr, float mu,
-                     void* dbias_out, int nsplit, void* stream) {
+                     const void* active, const void* p1, void* dp1, float lr, float mu, void* dbias_out, int nsplit,
+                     void* stream) {
   if (int r = olsb_init()) return r;
   CUtensorMap tmA, tmW;
   if (int r = make_act_map(&tmA, dy2, (uint64_t)C * BATCH, 16, 16, 64, kBoxH)) return r;
@@ -199,7 +199,7 @@ int olsb_conv2_dgrad(const void* dy2, const void* w2_dgrad, void* master, const 
   memset(&p, 0, sizeof(p));
   p.num_clients = C; p.nsplit = auto_split(C, Conv2DgradCfg::TILES_PER_CLIENT, nsplit);
   p.a_n_stride = BATCH; p.a_n_off = 0; p.active = (const uint8_t*)active;
-  p.pooled = (const __nv_bfloat16*)p1; p.pcode = (const uint8_t*)code1; p.dpre = (__nv_bfloat16*)dy1;
+  p.pooled = (const __nv_bfloat16*)p1; p.dpool = (__nv_bfloat16*)dp1;
   p.bias_master = (float*)master + Cnn2Layout::B1; p.bias_stride = (int)P;
   p.bias_global = global_w ? (const float*)global_w + Cnn2Layout::B1 : nullptr;
   p.lr = lr; p.mu = mu; p.dbias_out = (float*)dbias_out;
@@ -229,21 +229,22 @@ int olsb_conv2_wgrad(const void* p1, const void* dy2, void* master, const void* 
   return 0;
 }
 
-int olsb_conv1_wgrad(const void* x5, long long x_total, int x_n_stride, int x_n_off, const void* dy1, void* master,
-                     const void* global_w, long long P, int C, const void* active, void* w1_fwd, float lr, float mu,
-                     void* grad_out, void* stream) {
+// conv1 weight gradient; the un-pooled output gradient is synthesised in shared memory from dP1 + code1
+int olsb_conv1_wgrad(const void* x5, long long x_total, int x_n_stride, int x_n_off, const void* dp1,
+                     const void* code1, void* master, const void* global_w, long long P, int C, const void* active,
+                     void* w1_fwd, float lr, float mu, void* grad_out, void* stream) {
   if (int r = olsb_init()) return r;
-  CUtensorMap tmX, tmY;
+  CUtensorMap tmX;
   if (int r = make_act_map(&tmX, x5, (uint64_t)x_total, 32, 32, 16, kBoxH)) return r;
-  if (int r = make_act_map(&tmY, dy1, (uint64_t)C * BATCH, 32, 32, 32, kTileH)) return r;
   WgradParams p;
   memset(&p, 0, sizeof(p));
   p.num_clients = C; p.x_n_stride = x_n_stride; p.x_n_off = x_n_off; p.active = (const uint8_t*)active;
   p.w_master = (float*)master; p.w_global = (const float*)global_w; p.p_stride = (size_t)P;
   p.w_off = Cnn2Layout::W1; p.w_fwd = (__nv_bfloat16*)w1_fwd; p.w_dgrad = nullptr;
   p.lr = lr; p.mu = mu; p.grad_out = (float*)grad_out;
+  p.dpool = (const __nv_bfloat16*)dp1; p.pcode = (const uint8_t*)code1;
   const int grid = C < g_sms ? C : g_sms;
-  CONV1_WGRAD<<<grid, kThreads, Conv1WgradCfg::SMEM_BYTES, (cudaStream_t)stream>>>(tmX, tmY, p);
+  CONV1_WGRAD<<<grid, kThreads, Conv1WgradCfg::SMEM_BYTES, (cudaStream_t)stream>>>(tmX, tmX, p);
   CK(cudaGetLastError());
   return 0;
 }
@@ -275,7 +276,7 @@ struct OlsbCnn2Step {
   void* master; const void* global_w; long long P; int C;
   const void* active;
   void* w1_fwd; void* w2_fwd; void* w2_dgrad;
-  void* p1; void* code1; void* p2; void* code2; void* dy2; void* dy1;
+  void* p1; void* code1; void* p2; void* code2; void* dy2; void* dp1;
   void* loss_sum; void* nonfinite;
   float lr, mu; int use_prox; int nsplit;
 };
@@ -290,12 +291,12 @@ int olsb_cnn2_local_step(const OlsbCnn2Step* s, void* stream) {
   if ((r = olsb_head(s->C, s->active, s->p2, s->code2, s->labels, s->label_stride, s->label_off, s->master, gw, s->P,
                      s->lr, s->mu, s->dy2, s->loss_sum, s->nonfinite, nullptr, 1, nullptr, nullptr, stream)))
     return r;
-  if ((r = olsb_conv2_dgrad(s->dy2, s->w2_dgrad, s->master, gw, s->P, s->C, s->active, s->p1, s->code1, s->dy1, s->lr,
-                            s->mu, nullptr, s->nsplit, stream))) return r;
+  if ((r = olsb_conv2_dgrad(s->dy2, s->w2_dgrad, s->master, gw, s->P, s->C, s->active, s->p1, s->dp1, s->lr, s->mu,
+                            nullptr, s->nsplit, stream))) return r;
   if ((r = olsb_conv2_wgrad(s->p1, s->dy2, s->master, gw, s->P, s->C, s->active, s->w2_fwd, s->w2_dgrad, s->lr, s->mu,
                             nullptr, stream))) return r;
-  if ((r = olsb_conv1_wgrad(s->x5, s->x_total, s->x_n_stride, s->x_n_off, s->dy1, s->master, gw, s->P, s->C,
-                            s->active, s->w1_fwd, s->lr, s->mu, nullptr, stream))) return r;
+  if ((r = olsb_conv1_wgrad(s->x5, s->x_total, s->x_n_stride, s->x_n_off, s->dp1, s->code1, s->master, gw, s->P,
+                            s->C, s->active, s->w1_fwd, s->lr, s->mu, nullptr, stream))) return r;
   return 0;
 }
 

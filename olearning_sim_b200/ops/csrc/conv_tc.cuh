@@ -9,13 +9,18 @@
 //     12x16 pixels (8 rows + 4 halo rows) per horizontal tap lands in smem with hardware swizzle and
 //     zero-filled borders ("same" padding); the five vertical taps are pure start-address shifts of
 //     the UMMA shared-memory descriptor (one image row = 16 pixel-rows = a whole number of swizzle atoms).
-//   * accumulators live in TMEM (double buffered) and are drained by four epilogue warps with
-//     tcgen05.ld; the epilogues are fused: bias+ReLU+2x2-maxpool(+argmax code) for the forward,
-//     un-pool + ReLU-backward + bias-grad (+SGD on the bias) for the data gradient.
+//   * warp roles: warps 0-3 epilogue (TMEM lanes 32*w..), warp 4 TMA producer, warp 5 MMA issuer.  The
+//     producer and issuer warps run *converged* and predicate only the TMA / MMA / commit instructions on an
+//     elected lane, so descriptor arithmetic stays in the uniform datapath (one add per operand per MMA).
+//   * accumulators live in TMEM (double buffered) and are drained with tcgen05.ld; epilogues are fused:
+//     bias+ReLU+2x2-maxpool(+argmax code) for the forward (a shuffle butterfly leaves every lane with exactly
+//     the 8 channels it stores), ReLU-backward gate + bias-grad (+SGD on the bias) for the data gradient.
 //   * weight gradient: both operands are MN-major (pixels are the reduction dim), all taps accumulate
 //     in TMEM simultaneously (7 x [128 x 64] fp32 tiles = 448 columns for 5x5x32->64) while the pixels
 //     stream through once; the epilogue applies the SGD / FedProx update to the fp32 master weights
-//     and refreshes the bf16 operand copies, so gradients never touch HBM.
+//     and refreshes the bf16 operand copies, so weight gradients never touch HBM.  For the first layer the
+//     un-pooled output gradient is not materialised either: the four otherwise idle epilogue warps synthesise
+//     the swizzled dY operand tile in shared memory from the pooled gradient + argmax codes.
 //
 // Reference parity: this replaces the per-client `os.system("python3 <operator>")` local training
 // step of the reference (ols_core/taskMgr/utils/utils_run_task.py:481-514).
@@ -44,7 +49,7 @@ struct Barriers {
 // ================================================================================================
 // Forward / data-gradient kernel
 // ================================================================================================
-enum { EPI_POOL = 0, EPI_UNPOOL = 1 };
+enum { EPI_POOL = 0, EPI_GATE = 1 };
 
 struct FwdParams {
   int num_clients;
@@ -57,10 +62,9 @@ struct FwdParams {
   int bias_stride;
   __nv_bfloat16* out;    // [C*BATCH][H/2][W/2][BN]
   uint8_t* code;         // same shape, argmax position 0..3
-  // EPI_UNPOOL
-  const __nv_bfloat16* pooled;  // [C*BATCH][H][W][BN]   forward activations of the layer below (post-pool)
-  const uint8_t* pcode;         // same shape
-  __nv_bfloat16* dpre;          // [C*BATCH][2H][2W][BN]  gradient w.r.t. the pre-pool conv output
+  // EPI_GATE (data gradient w.r.t. a pooled+ReLU activation)
+  const __nv_bfloat16* pooled;  // [C*BATCH][H][W][BN]  forward activation (ReLU mask)
+  __nv_bfloat16* dpool;         // [C*BATCH][H][W][BN]  gated gradient w.r.t. the pooled activation
   float* bias_master;           // [C][bias_stride] fp32, updated in place:  b -= lr*(db + mu*(b-bg))
   const float* bias_global;     // [bias_stride] fp32 (FedProx anchor) or nullptr
   float lr, mu;
@@ -114,75 +118,82 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int tiles_per_work = (Cfg::TILES_PER_CLIENT + p.nsplit - 1) / p.nsplit;
 
   if (warp == 4) {
-    // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0; int cur_client = -1; uint32_t wphase = 0; bool first_w = true;
-      for (int wi = blockIdx.x; wi < num_work; wi += gridDim.x) {
-        const int c = wi / p.nsplit, sp = wi % p.nsplit;
-        if (p.active && !p.active[c]) continue;
-        if (c != cur_client) {
-          if (!first_w) { mbar_wait(&bars->wempty, wphase); wphase ^= 1; }
-          first_w = false; cur_client = c;
+    // ------------------------------------------------------------------ TMA producer (warp-converged)
+    const bool leader = elect_one();
+    int stage = 0; uint32_t phase = 0; int cur_client = -1; uint32_t wphase = 0; bool first_w = true;
+    for (int wi = blockIdx.x; wi < num_work; wi += gridDim.x) {
+      const int c = wi / p.nsplit, sp = wi % p.nsplit;
+      if (p.active && !p.active[c]) continue;
+      if (c != cur_client) {
+        if (!first_w) { mbar_wait(&bars->wempty, wphase); wphase ^= 1; }
+        first_w = false; cur_client = c;
+        if (leader) {
           mbar_arrive_expect_tx(&bars->wfull, Cfg::W_BYTES);
+#pragma unroll 1
           for (int t = 0; t < Cfg::NTAPS; ++t)
             // forward copy  [C][BN][NTAPS*KT]  -> box (KT, BN, 1) at (t*KT, 0, c)
             // dgrad copy    [C][NTAPS*BN][K]   -> box (K,  BN, 1) at (0, t*BN, c)
             tma_load_3d(w_sm + t * Cfg::W_TAP_BYTES, &tmW, &bars->wfull, FLIP ? 0 : t * Cfg::KT,
                         FLIP ? t * BN : 0, c);
         }
-        const int t0 = sp * tiles_per_work;
-        const int t1 = min(t0 + tiles_per_work, Cfg::TILES_PER_CLIENT);
-        for (int t = t0; t < t1; ++t) {
-          const int s = t / (Cfg::TILES_X * Cfg::TILES_Y);
-          const int r = t % (Cfg::TILES_X * Cfg::TILES_Y);
-          const int h0 = (r / Cfg::TILES_X) * kTileH, w0 = (r % Cfg::TILES_X) * kTileW;
-          const int n = c * p.a_n_stride + p.a_n_off + s;
+      }
+      const int t0 = sp * tiles_per_work;
+      const int t1 = min(t0 + tiles_per_work, Cfg::TILES_PER_CLIENT);
+      for (int t = t0; t < t1; ++t) {
+        const int s = t / (Cfg::TILES_X * Cfg::TILES_Y);
+        const int r = t % (Cfg::TILES_X * Cfg::TILES_Y);
+        const int h0 = (r / Cfg::TILES_X) * kTileH, w0 = (r % Cfg::TILES_X) * kTileW;
+        const int n = c * p.a_n_stride + p.a_n_off + s;
 #pragma unroll 1
-          for (int kw = 0; kw < NKW; ++kw) {
-            mbar_wait(&bars->empty[stage], phase ^ 1);
+        for (int kw = 0; kw < NKW; ++kw) {
+          mbar_wait(&bars->empty[stage], phase ^ 1);
+          if (leader) {
             mbar_arrive_expect_tx(&bars->full[stage], Cfg::STAGE_BYTES);
             const int dw = (NKW == 1) ? 0 : (FLIP ? (kHalo - kw) : (kw - kHalo));
             tma_load_4d(a_sm + stage * Cfg::STAGE_BYTES, &tmA, &bars->full[stage], 0, w0 + dw, h0 - kHalo, n);
-            if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
           }
+          if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 5) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t LT = layout_type_for_row_bytes(ROWB);
-      constexpr uint32_t IDESC = make_idesc_bf16(128, BN, 0, 0);
-      int stage = 0; uint32_t phase = 0; int cur_client = -1; uint32_t wphase = 0;
-      int buf = 0; uint32_t tphase[2] = {0, 0};
-      for (int wi = blockIdx.x; wi < num_work; wi += gridDim.x) {
-        const int c = wi / p.nsplit, sp = wi % p.nsplit;
-        if (p.active && !p.active[c]) continue;
-        // is this the last work item this CTA will run for client c?
-        bool last_of_client = true;
-        {
-          const int nwi = wi + gridDim.x;
-          if (nwi < num_work && (nwi / p.nsplit) == c) last_of_client = false;
-        }
-        if (c != cur_client) { mbar_wait(&bars->wfull, wphase); wphase ^= 1; cur_client = c; }
-        const int t0 = sp * tiles_per_work;
-        const int t1 = min(t0 + tiles_per_work, Cfg::TILES_PER_CLIENT);
-        for (int t = t0; t < t1; ++t) {
-          mbar_wait(&bars->tempty[buf], tphase[buf] ^ 1);
-          fence_after_sync();
-          const uint32_t d_tmem = tmem_base + buf * BN;
-          uint32_t acc = 0;
+    // ------------------------------------------------------------------ MMA issuer (warp-converged)
+    const bool leader = elect_one();
+    constexpr uint32_t LT = layout_type_for_row_bytes(ROWB);
+    constexpr uint32_t IDESC = make_idesc_bf16(128, BN, 0, 0);
+    const uint64_t a_desc_base = make_smem_desc(smem_u32(a_sm), 16, 8 * ROWB, LT);
+    const uint64_t b_desc_base = make_smem_desc(smem_u32(w_sm), 16, 8 * ROWB, LT);
+    int stage = 0; uint32_t phase = 0; int cur_client = -1; uint32_t wphase = 0;
+    int buf = 0; uint32_t tphase0 = 0, tphase1 = 0;
+    for (int wi = blockIdx.x; wi < num_work; wi += gridDim.x) {
+      const int c = wi / p.nsplit, sp = wi % p.nsplit;
+      if (p.active && !p.active[c]) continue;
+      bool last_of_client = true;
+      {
+        const int nwi = wi + gridDim.x;
+        if (nwi < num_work && (nwi / p.nsplit) == c) last_of_client = false;
+      }
+      if (c != cur_client) { mbar_wait(&bars->wfull, wphase); wphase ^= 1; cur_client = c; }
+      const int t0 = sp * tiles_per_work;
+      const int t1 = min(t0 + tiles_per_work, Cfg::TILES_PER_CLIENT);
+      for (int t = t0; t < t1; ++t) {
+        mbar_wait(&bars->tempty[buf], (buf ? tphase1 : tphase0) ^ 1);
+        fence_after_sync();
+        const uint32_t d_tmem = tmem_base + buf * BN;
+        uint32_t acc = 0;
 #pragma unroll 1
-          for (int kw = 0; kw < NKW; ++kw) {
-            mbar_wait(&bars->full[stage], phase);
-            fence_after_sync();
-            const uint32_t a_base = smem_u32(a_sm + stage * Cfg::STAGE_BYTES);
+        for (int kw = 0; kw < NKW; ++kw) {
+          mbar_wait(&bars->full[stage], phase);
+          fence_after_sync();
+          if (leader) {
+            const uint64_t a_stage = desc_advance(a_desc_base, stage * Cfg::STAGE_BYTES);
+            const uint64_t b_kw = desc_advance(b_desc_base, kw * Cfg::W_TAP_BYTES);
 #pragma unroll
             for (int kh = 0; kh < kNKH; ++kh) {
-              const int row_shift = FLIP ? (2 * kHalo - kh) : kh;  // image rows above the tile start
-              const int tap = kh * NKW + kw;
-              const uint64_t a_desc = make_smem_desc(a_base + row_shift * kTileW * ROWB, 16, 8 * ROWB, LT);
-              const uint64_t b_desc = make_smem_desc(smem_u32(w_sm + tap * Cfg::W_TAP_BYTES), 16, 8 * ROWB, LT);
+              constexpr int dummy = 0; (void)dummy;
+              const int row_shift = FLIP ? (2 * kHalo - kh) : kh;          // image rows above the tile start
+              const uint64_t a_desc = desc_advance(a_stage, row_shift * kTileW * ROWB);
+              const uint64_t b_desc = desc_advance(b_kw, kh * NKW * Cfg::W_TAP_BYTES);
 #pragma unroll
               for (int ks = 0; ks < ROWB / 32; ++ks) {
                 umma_bf16(d_tmem, desc_advance(a_desc, ks * 32), desc_advance(b_desc, ks * 32), IDESC, acc);
@@ -190,37 +201,45 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               }
             }
             umma_commit(&bars->empty[stage]);
-            if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
           }
-          umma_commit(&bars->tfull[buf]);
-          tphase[buf] ^= 1;
-          buf ^= 1;
+          __syncwarp();
+          if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
         }
-        if (last_of_client) umma_commit(&bars->wempty);
+        if (leader) umma_commit(&bars->tfull[buf]);
+        __syncwarp();
+        if (buf) tphase1 ^= 1; else tphase0 ^= 1;
+        buf ^= 1;
+      }
+      if (last_of_client) {
+        if (leader) umma_commit(&bars->wempty);
+        __syncwarp();
       }
     }
   } else {
     // ------------------------------------------------------------------ epilogue warps (TMEM lanes 32*warp ..)
-    int buf = 0; uint32_t tphase[2] = {0, 0};
+    int buf = 0; uint32_t tphase0 = 0, tphase1 = 0;
     const int q = warp;  // 0..3
     const int hl = 2 * q + (lane >> 4), wl = lane & 15;
-    float dbacc[(EPI == EPI_UNPOOL) ? BN : 1];
-    if (EPI == EPI_UNPOOL) {
+    constexpr int NDB = (EPI == EPI_GATE) ? BN : 1;
+    float dbacc[NDB];
 #pragma unroll
-      for (int i = 0; i < BN; ++i) dbacc[i] = 0.f;
-    }
+    for (int i = 0; i < NDB; ++i) dbacc[i] = 0.f;
     int cur_client = -1;
     bool had_sp0 = false;
-    __shared__ float s_db[(EPI == EPI_UNPOOL) ? BN : 1];
+    __shared__ float s_db[NDB];
+    // this lane's output slice after the pooling butterfly: channels [j*32 + sl*8, +8)
+    const int b0 = lane & 1, b4 = (lane >> 4) & 1;
+    const int sl = b0 * 2 + b4;
+    const int pos = (b4 << 1) | b0;                      // position inside the 2x2 window (row-major)
+    float bias_r[(EPI == EPI_POOL) ? BN / 4 : 1];
 
     auto flush_bias = [&](int c) {
-      if (EPI != EPI_UNPOOL) return;
-      // reduce the per-thread partial bias gradients of the 128 epilogue threads, then update the bias
+      if (EPI != EPI_GATE) return;
       asm volatile("bar.sync 1, 128;");
-      if (threadIdx.x < BN) s_db[threadIdx.x] = 0.f;
+      if (threadIdx.x < NDB) s_db[threadIdx.x] = 0.f;
       asm volatile("bar.sync 1, 128;");
 #pragma unroll
-      for (int i = 0; i < BN; ++i) {
+      for (int i = 0; i < NDB; ++i) {
         float v = dbacc[i];
         v += __shfl_xor_sync(0xffffffffu, v, 16);
         v += __shfl_xor_sync(0xffffffffu, v, 8);
@@ -231,13 +250,13 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         dbacc[i] = 0.f;
       }
       asm volatile("bar.sync 1, 128;");
-      if (threadIdx.x < BN) {
+      if (threadIdx.x < NDB) {
         const float g = s_db[threadIdx.x];
         if (p.dbias_out) {
           atomicAdd(&p.dbias_out[(size_t)c * BN + threadIdx.x], g);
         } else {
-          // several CTAs may share a client (nsplit>1): the bias update is linear in g, so apply the
-          // partial gradient atomically; the FedProx pull is applied by the split-0 CTA only.
+          // several CTAs may share a client (nsplit>1): the update is linear in g, so apply the partial
+          // gradient atomically; the FedProx pull is applied once, by the CTA that owns split 0.
           float* bp = &p.bias_master[(size_t)c * p.bias_stride + threadIdx.x];
           float upd = -p.lr * g;
           if (had_sp0 && p.bias_global) upd -= p.lr * p.mu * (*bp - p.bias_global[threadIdx.x]);
@@ -254,6 +273,13 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (cur_client >= 0) flush_bias(cur_client);
         cur_client = c;
         had_sp0 = false;
+        if (EPI == EPI_POOL) {
+          const float* bias = p.bias + (size_t)c * p.bias_stride;
+#pragma unroll
+          for (int j = 0; j < BN / 32; ++j)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) bias_r[j * 8 + k] = __ldg(&bias[j * 32 + sl * 8 + k]);
+        }
       }
       if (sp == 0) had_sp0 = true;
       const int t0 = sp * tiles_per_work;
@@ -263,96 +289,92 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int r = t % (Cfg::TILES_X * Cfg::TILES_Y);
         const int h0 = (r / Cfg::TILES_X) * kTileH, w0 = (r % Cfg::TILES_X) * kTileW;
         const size_t n_out = (size_t)c * BATCH + s;
-        mbar_wait(&bars->tfull[buf], tphase[buf]);
+        mbar_wait(&bars->tfull[buf], buf ? tphase1 : tphase0);
         fence_after_sync();
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(32 * q) << 16) + buf * BN;
 
         if (EPI == EPI_POOL) {
-          const int pos = ((lane >> 4) << 1) | (lane & 1);      // position inside the 2x2 window
-          const int sub = pos;                                   // which 8-channel slice this lane stores
+          // max-pool commutes with the (per-channel) bias add and with ReLU:  relu(max(acc) + b).
+          // Keys: order-preserving uint image of the fp32 accumulator with (3-pos) stashed in the two LSBs, so a
+          // single unsigned max carries value and argmax together (ties -> smallest position).
           const int ph = (h0 >> 1) + q, pw = (w0 >> 1) + (wl >> 1);
           const size_t obase = ((n_out * (IMG_H / 2) + ph) * (IMG_W / 2) + pw) * BN;
-          const float* bias = p.bias + (size_t)c * p.bias_stride;
 #pragma unroll
           for (int j = 0; j < BN / 32; ++j) {
             uint32_t v[32];
             tmem_ld32(taddr + j * 32, v);
             tmem_ld_wait();
-            uint32_t m[32];
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
-              float f = __uint_as_float(v[i]) + __ldg(&bias[j * 32 + i]);
-              f = fmaxf(f, 0.f);
-              // non-negative floats order like unsigned ints: stash (3-pos) in the two LSBs so one max
-              // yields both the pooled value and its argmax (ties -> smallest position)
-              uint32_t u = (__float_as_uint(f) & ~3u) | static_cast<uint32_t>(3 - pos);
-              u = max(u, __shfl_xor_sync(0xffffffffu, u, 1));
-              u = max(u, __shfl_xor_sync(0xffffffffu, u, 16));
-              m[i] = u;
+              const uint32_t bits = v[i];
+              const uint32_t key = bits ^ (static_cast<uint32_t>(static_cast<int32_t>(bits) >> 31) | 0x80000000u);
+              v[i] = (key & ~3u) | static_cast<uint32_t>(3 - pos);
             }
-            uint32_t o[8];
+            // butterfly 1 (partner = lane^1): b0=0 keeps channels [0,16), b0=1 keeps [16,32)
+            uint32_t m16[16];
 #pragma unroll
-            for (int k = 0; k < 8; ++k)
-              o[k] = sub == 0 ? m[k] : (sub == 1 ? m[8 + k] : (sub == 2 ? m[16 + k] : m[24 + k]));
+            for (int i = 0; i < 16; ++i) {
+              const uint32_t give = b0 ? v[i] : v[16 + i];
+              const uint32_t keep = b0 ? v[16 + i] : v[i];
+              m16[i] = max(keep, __shfl_xor_sync(0xffffffffu, give, 1));
+            }
+            // butterfly 2 (partner = lane^16): b4=0 keeps the low 8, b4=1 the high 8
+            uint32_t m8[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const uint32_t give = b4 ? m16[i] : m16[8 + i];
+              const uint32_t keep = b4 ? m16[8 + i] : m16[i];
+              m8[i] = max(keep, __shfl_xor_sync(0xffffffffu, give, 16));
+            }
+            float f[8];
+            uint32_t cd[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const uint32_t key = m8[i];
+              cd[i] = 3u - (key & 3u);
+              const uint32_t kk = key & ~3u;
+              const uint32_t bits = (kk & 0x80000000u) ? (kk ^ 0x80000000u) : ~kk;
+              f[i] = fmaxf(__uint_as_float(bits) + bias_r[j * 8 + i], 0.f);
+            }
             uint4 pv;
-            pv.x = pack_bf16x2(__uint_as_float(o[0] & ~3u), __uint_as_float(o[1] & ~3u));
-            pv.y = pack_bf16x2(__uint_as_float(o[2] & ~3u), __uint_as_float(o[3] & ~3u));
-            pv.z = pack_bf16x2(__uint_as_float(o[4] & ~3u), __uint_as_float(o[5] & ~3u));
-            pv.w = pack_bf16x2(__uint_as_float(o[6] & ~3u), __uint_as_float(o[7] & ~3u));
+            pv.x = pack_bf16x2(f[0], f[1]); pv.y = pack_bf16x2(f[2], f[3]);
+            pv.z = pack_bf16x2(f[4], f[5]); pv.w = pack_bf16x2(f[6], f[7]);
             uint2 cv;
-            cv.x = (3 - (o[0] & 3)) | ((3 - (o[1] & 3)) << 8) | ((3 - (o[2] & 3)) << 16) | ((3 - (o[3] & 3)) << 24);
-            cv.y = (3 - (o[4] & 3)) | ((3 - (o[5] & 3)) << 8) | ((3 - (o[6] & 3)) << 16) | ((3 - (o[7] & 3)) << 24);
-            const size_t off = obase + j * 32 + sub * 8;
+            cv.x = cd[0] | (cd[1] << 8) | (cd[2] << 16) | (cd[3] << 24);
+            cv.y = cd[4] | (cd[5] << 8) | (cd[6] << 16) | (cd[7] << 24);
+            const size_t off = obase + j * 32 + sl * 8;
             *reinterpret_cast<uint4*>(p.out + off) = pv;
             *reinterpret_cast<uint2*>(p.code + off) = cv;
           }
         } else {
-          // EPI_UNPOOL: this lane owns pooled pixel (h0+hl, wl) of sample n_out; BN == 32 channels.
+          // EPI_GATE: this lane owns pixel (h0+hl, w0+wl) of sample n_out; BN == 32 channels.
+          static_assert(EPI != EPI_GATE || BN == 32, "gate epilogue is written for 32 channels");
           const int h = h0 + hl, w = w0 + wl;
           const size_t pbase = ((n_out * IMG_H + h) * IMG_W + w) * BN;
           uint32_t v[32];
           tmem_ld32(taddr, v);
-          // forward value (ReLU mask) and argmax code of the layer below
-          uint4 pq[BN / 8];
-          uint4 cq[BN / 16];
+          uint4 pq[4];
 #pragma unroll
-          for (int k = 0; k < BN / 8; ++k) pq[k] = *reinterpret_cast<const uint4*>(p.pooled + pbase + k * 8);
-#pragma unroll
-          for (int k = 0; k < BN / 16; ++k) cq[k] = *reinterpret_cast<const uint4*>(p.pcode + pbase + k * 16);
+          for (int k = 0; k < 4; ++k) pq[k] = *reinterpret_cast<const uint4*>(p.pooled + pbase + k * 8);
           tmem_ld_wait();
           const uint32_t* pw32 = reinterpret_cast<const uint32_t*>(pq);
-          const uint8_t* cb = reinterpret_cast<const uint8_t*>(cq);
-          float g[32];
+          uint4 o[4];
+          uint32_t* ow = reinterpret_cast<uint32_t*>(o);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const uint32_t pr = pw32[i >> 1];
-            const float pv = (i & 1) ? bf16hi(pr) : bf16lo(pr);
-            g[i] = pv > 0.f ? __uint_as_float(v[i]) : 0.f;
-            dbacc[i] += g[i];
+          for (int i = 0; i < 16; ++i) {
+            const uint32_t pr = pw32[i];
+            const float g0 = bf16lo(pr) > 0.f ? __uint_as_float(v[2 * i]) : 0.f;
+            const float g1 = bf16hi(pr) > 0.f ? __uint_as_float(v[2 * i + 1]) : 0.f;
+            dbacc[2 * i] += g0; dbacc[2 * i + 1] += g1;
+            ow[i] = pack_bf16x2(g0, g1);
           }
 #pragma unroll
-          for (int pos = 0; pos < 4; ++pos) {
-            const size_t obase =
-                ((n_out * (2 * IMG_H) + (2 * h + (pos >> 1))) * (2 * IMG_W) + (2 * w + (pos & 1))) * BN;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              uint4 o;
-              uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const int i0 = k * 8 + e * 2;
-                const float a = (cb[i0] == pos) ? g[i0] : 0.f;
-                const float b = (cb[i0 + 1] == pos) ? g[i0 + 1] : 0.f;
-                ow[e] = pack_bf16x2(a, b);
-              }
-              *reinterpret_cast<uint4*>(p.dpre + obase + k * 8) = o;
-            }
-          }
+          for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(p.dpool + pbase + k * 8) = o[k];
         }
         fence_before_sync();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars->tempty[buf]);
-        tphase[buf] ^= 1;
+        if (buf) tphase1 ^= 1; else tphase0 ^= 1;
         buf ^= 1;
       }
     }
@@ -379,6 +401,9 @@ struct WgradParams {
   __nv_bfloat16* w_dgrad;        // [C][NTAPS][KT][BN] bf16 operand copy (data-gradient layout) or nullptr
   float lr, mu;
   float* grad_out;               // optional [C][BN*NTAPS*KT] raw gradient (tests); when set no update is applied
+  // SYNTH_Y: the dY operand is synthesised from the pooled gradient instead of being loaded by TMA
+  const __nv_bfloat16* dpool;    // [C*BATCH][H/2][W/2][BN]
+  const uint8_t* pcode;          // same shape, argmax position 0..3
 };
 
 template <int XROWB, int NKW, int YROWB, int NSS>
@@ -396,7 +421,7 @@ struct WgradCfg {
   static_assert(SS_BYTES % 1024 == 0, "superstage must keep 1024B alignment");
 };
 
-template <int XROWB, int NKW, int YROWB, int IMG_H, int IMG_W, int BATCH, int NSS>
+template <int XROWB, int NKW, int YROWB, int IMG_H, int IMG_W, int BATCH, int NSS, bool SYNTH_Y>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
                   const WgradParams p) {
@@ -404,6 +429,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   constexpr int KT = Cfg::KT, BN = Cfg::BN;
   constexpr int TILES_X = IMG_W / kTileW, TILES_Y = IMG_H / kTileH;
   constexpr int CHUNKS = BATCH * TILES_X * TILES_Y;   // pixel chunks (K dimension, 128 pixels each)
+  static_assert(!SYNTH_Y || YROWB == 64, "operand synthesis is written for 32 output channels (SW64 rows)");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   Barriers* bars = reinterpret_cast<Barriers*>(smem + NSS * Cfg::SS_BYTES);
@@ -411,29 +437,38 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    for (int i = 0; i < NSS; ++i) { mbar_init(&bars->full[i], 1); mbar_init(&bars->empty[i], 1); }
+    for (int i = 0; i < NSS; ++i) { mbar_init(&bars->full[i], SYNTH_Y ? 1 + kEpiWarps : 1); mbar_init(&bars->empty[i], 1); }
     mbar_init(&bars->tfull[0], 1);
     mbar_init(&bars->tempty[0], kEpiWarps);
     fence_mbar_init();
   }
   if (warp == 5) { tmem_alloc(&bars->tmem_base, Cfg::TMEM_COLS); tmem_relinquish(); }
-  if (warp == 4 && lane == 0) { tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmY); }
+  if (warp == 4 && lane == 0) { tma_prefetch_desc(&tmX); if (!SYNTH_Y) tma_prefetch_desc(&tmY); }
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem_base = bars->tmem_base;
 
   if (warp == 4) {
-    if (lane == 0) {
-      int ss = 0; uint32_t phase = 0;
-      for (int c = blockIdx.x; c < p.num_clients; c += gridDim.x) {
-        if (p.active && !p.active[c]) continue;
-        for (int t = 0; t < CHUNKS; ++t) {
-          const int s = t / (TILES_X * TILES_Y);
-          const int r = t % (TILES_X * TILES_Y);
-          const int h0 = (r / TILES_X) * kTileH, w0 = (r % TILES_X) * kTileW;
-          mbar_wait(&bars->empty[ss], phase ^ 1);
-          mbar_arrive_expect_tx(&bars->full[ss], Cfg::SS_BYTES);
+    const bool leader = elect_one();
+    int ss = 0; uint32_t phase = 0;
+    for (int c = blockIdx.x; c < p.num_clients; c += gridDim.x) {
+      if (p.active && !p.active[c]) continue;
+      for (int t = 0; t < CHUNKS; ++t) {
+        const int s = t / (TILES_X * TILES_Y);
+        const int r = t % (TILES_X * TILES_Y);
+        const int h0 = (r / TILES_X) * kTileH, w0 = (r % TILES_X) * kTileW;
+        mbar_wait(&bars->empty[ss], phase ^ 1);
+        if (leader && !p.grad_out && t == (CHUNKS > 16 ? CHUNKS - 12 : 0)) {
+          // warm L2 with this client's fp32 master block shortly before the fused-SGD epilogue reads it (issued
+          // late on purpose: the activation stream would evict an early prefetch from L2 again)
+          const char* wmb = reinterpret_cast<const char*>(p.w_master + (size_t)c * p.p_stride + p.w_off);
+          constexpr uint32_t WB = BN * Cfg::NTAPS * KT * 4;
+#pragma unroll 1
+          for (uint32_t o = 0; o < WB; o += 16384) prefetch_l2_bulk(wmb + o, min(16384u, WB - o));
+        }
+        if (leader) {
+          mbar_arrive_expect_tx(&bars->full[ss], SYNTH_Y ? NKW * Cfg::XSTAGE : Cfg::SS_BYTES);
           uint8_t* base = smem + ss * Cfg::SS_BYTES;
           const int nx = c * p.x_n_stride + p.x_n_off + s;
 #pragma unroll 1
@@ -441,53 +476,117 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             const int dw = (NKW == 1) ? 0 : (kw - kHalo);
             tma_load_4d(base + kw * Cfg::XSTAGE, &tmX, &bars->full[ss], 0, w0 + dw, h0 - kHalo, nx);
           }
-          tma_load_4d(base + NKW * Cfg::XSTAGE, &tmY, &bars->full[ss], 0, w0, h0, c * BATCH + s);
-          if (++ss == NSS) { ss = 0; phase ^= 1; }
+          if (!SYNTH_Y) tma_load_4d(base + NKW * Cfg::XSTAGE, &tmY, &bars->full[ss], 0, w0, h0, c * BATCH + s);
         }
+        if (++ss == NSS) { ss = 0; phase ^= 1; }
       }
     }
   } else if (warp == 5) {
-    if (lane == 0) {
-      constexpr uint32_t LTX = layout_type_for_row_bytes(XROWB);
-      constexpr uint32_t LTY = layout_type_for_row_bytes(YROWB);
-      constexpr uint32_t IDESC = make_idesc_bf16(128, BN, 1, 1);
-      int ss = 0; uint32_t phase = 0; uint32_t tphase = 0;
-      for (int c = blockIdx.x; c < p.num_clients; c += gridDim.x) {
-        if (p.active && !p.active[c]) continue;
-        mbar_wait(&bars->tempty[0], tphase ^ 1);
+    const bool leader = elect_one();
+    constexpr uint32_t LTX = layout_type_for_row_bytes(XROWB);
+    constexpr uint32_t LTY = layout_type_for_row_bytes(YROWB);
+    constexpr uint32_t IDESC = make_idesc_bf16(128, BN, 1, 1);
+    const uint32_t sbase = smem_u32(smem);
+    // A-operand descriptor templates (stage 0): M tile = 4 taps stacked along MN via the leading-dim offset
+    const uint64_t a_kw = make_smem_desc(sbase, kTileW * XROWB, 8 * XROWB, LTX);                       // kh 0..3 of one kw box
+    const uint64_t a_r = make_smem_desc(sbase + 4 * kTileW * XROWB, Cfg::XSTAGE, 8 * XROWB, LTX);     // kh 4 of kw 0..3
+    const uint64_t a_l = make_smem_desc(sbase + 4 * Cfg::XSTAGE + 4 * kTileW * XROWB, kTileW * XROWB, 8 * XROWB, LTX);
+    const uint64_t b_y = make_smem_desc(sbase + NKW * Cfg::XSTAGE, 16, 8 * YROWB, LTY);
+    int ss = 0; uint32_t phase = 0; uint32_t tphase = 0;
+    for (int c = blockIdx.x; c < p.num_clients; c += gridDim.x) {
+      if (p.active && !p.active[c]) continue;
+      mbar_wait(&bars->tempty[0], tphase ^ 1);
+      fence_after_sync();
+      for (int t = 0; t < CHUNKS; ++t) {
+        mbar_wait(&bars->full[ss], phase);
         fence_after_sync();
-        for (int t = 0; t < CHUNKS; ++t) {
-          mbar_wait(&bars->full[ss], phase);
-          fence_after_sync();
-          const uint32_t base = smem_u32(smem + ss * Cfg::SS_BYTES);
-          const uint64_t b_desc0 = make_smem_desc(base + NKW * Cfg::XSTAGE, 16, 8 * YROWB, LTY);
+        if (leader) {
+          const uint32_t soff = ss * Cfg::SS_BYTES;
+          const uint64_t b0 = desc_advance(b_y, soff);
+          const uint32_t accum = t > 0 ? 1u : 0u;
 #pragma unroll
           for (int mt = 0; mt < Cfg::MTILES; ++mt) {
-            uint32_t a_start, lbo;
-            if (mt < NKW) { a_start = base + mt * Cfg::XSTAGE; lbo = kTileW * XROWB; }
-            else if (mt == NKW) { a_start = base + 4 * kTileW * XROWB; lbo = Cfg::XSTAGE; }
-            else { a_start = base + 4 * Cfg::XSTAGE + 4 * kTileW * XROWB; lbo = kTileW * XROWB; }
-            const uint64_t a_desc0 = make_smem_desc(a_start, lbo, 8 * XROWB, LTX);
+            const uint64_t a0 = (mt < NKW) ? desc_advance(a_kw, soff + mt * Cfg::XSTAGE)
+                                           : (mt == NKW ? desc_advance(a_r, soff) : desc_advance(a_l, soff));
 #pragma unroll
             for (int ks = 0; ks < (kTileH * kTileW) / 16; ++ks) {
-              umma_bf16(tmem_base + mt * BN, desc_advance(a_desc0, ks * 16 * XROWB),
-                        desc_advance(b_desc0, ks * 16 * YROWB), IDESC, (t > 0 || ks > 0) ? 1u : 0u);
+              umma_bf16(tmem_base + mt * BN, desc_advance(a0, ks * 16 * XROWB), desc_advance(b0, ks * 16 * YROWB), IDESC,
+                        ks > 0 ? 1u : accum);
             }
           }
           umma_commit(&bars->empty[ss]);
-          if (++ss == NSS) { ss = 0; phase ^= 1; }
         }
-        umma_commit(&bars->tfull[0]);
-        tphase ^= 1;
+        __syncwarp();
+        if (++ss == NSS) { ss = 0; phase ^= 1; }
       }
+      if (leader) umma_commit(&bars->tfull[0]);
+      __syncwarp();
+      tphase ^= 1;
     }
   } else {
     uint32_t tphase = 0;
     const int q = warp;
-    const int L = 32 * q + lane;            // accumulator row
+    const int L = 32 * q + lane;            // accumulator row / (SYNTH_Y) pixel of the chunk
     const int ci = L / KT, cin = L % KT;    // chunk index inside the M tile, input channel
+    int ss = 0; uint32_t phase = 0;
     for (int c = blockIdx.x; c < p.num_clients; c += gridDim.x) {
       if (p.active && !p.active[c]) continue;
+      if (SYNTH_Y) {
+        // ---- operand synthesis: dY[pix][ch] = (code == pos) ? dpool : 0, written as a SW64 MN-major tile
+        const int rr = L >> 4, cc = L & 15;                      // pixel (row, col) inside the 8x16 patch
+        const int posy = ((rr & 1) << 1) | (cc & 1);
+        auto src_off = [&](int t) -> size_t {
+          const int s = t / (TILES_X * TILES_Y);
+          const int r = t % (TILES_X * TILES_Y);
+          const int h0 = (r / TILES_X) * kTileH, w0 = (r % TILES_X) * kTileW;
+          const size_t n = (size_t)c * BATCH + s;
+          return ((n * (IMG_H / 2) + ((h0 + rr) >> 1)) * (IMG_W / 2) + ((w0 + cc) >> 1)) * BN;
+        };
+        // register ring, kDepth chunks of global loads in flight per thread (hides ~kDepth x the per-chunk work)
+        constexpr int kDepth = 4;
+        uint4 gq[kDepth][4], cq[kDepth][2];
+        auto issue = [&](int t, int slot) {
+          if (t < CHUNKS) {
+            const size_t pb = src_off(t);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) gq[slot][k] = __ldg(reinterpret_cast<const uint4*>(p.dpool + pb + k * 8));
+#pragma unroll
+            for (int k = 0; k < 2; ++k) cq[slot][k] = __ldg(reinterpret_cast<const uint4*>(p.pcode + pb + k * 16));
+          }
+        };
+#pragma unroll
+        for (int d = 0; d < kDepth - 1; ++d) issue(d, d);
+#pragma unroll 1
+        for (int tb = 0; tb < CHUNKS; tb += kDepth) {
+#pragma unroll
+          for (int u = 0; u < kDepth; ++u) {
+            const int t = tb + u;
+            if (t >= CHUNKS) break;
+            issue(t + kDepth - 1, (u + kDepth - 1) % kDepth);
+            const uint32_t* gw = reinterpret_cast<const uint32_t*>(gq[u]);
+            const uint32_t* cw = reinterpret_cast<const uint32_t*>(cq[u]);
+            uint4 o[4];
+            uint32_t* ow = reinterpret_cast<uint32_t*>(o);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {                         // channel pair (2i, 2i+1)
+              const uint32_t c2 = (cw[i >> 1] >> ((i & 1) * 16)) & 0xFFFFu;
+              uint32_t val = gw[i];
+              if ((c2 & 0xFFu) != (uint32_t)posy) val &= 0xFFFF0000u;
+              if ((c2 >> 8) != (uint32_t)posy) val &= 0x0000FFFFu;
+              ow[i] = val;
+            }
+            mbar_wait(&bars->empty[ss], phase ^ 1);
+            uint8_t* ybase = smem + ss * Cfg::SS_BYTES + NKW * Cfg::XSTAGE + L * YROWB;
+            const int sw = (L >> 1) & 3;                           // SW64: 16B-chunk index ^= bits[7:8] of the byte address
+#pragma unroll
+            for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(ybase + ((k ^ sw) << 4)) = o[k];
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars->full[ss]);
+            if (++ss == NSS) { ss = 0; phase ^= 1; }
+          }
+        }
+      }
       mbar_wait(&bars->tfull[0], tphase);
       fence_after_sync();
       float* wm = p.w_master + (size_t)c * p.p_stride + p.w_off;
@@ -509,23 +608,43 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
           tmem_ld32(taddr + j * 32, v);
           tmem_ld_wait();
           if (valid) {
+            uint32_t wdp[16];
+            const size_t idx0 = (size_t)(j * 32) * (Cfg::NTAPS * KT) + tap * KT + cin;
+            constexpr size_t ISTR = Cfg::NTAPS * KT;          // stride between consecutive output channels
+            // Issue all 32 master-weight loads before the first store: stores through `wm` would otherwise order
+            // every later load behind them (no alias information) and serialise 32 DRAM/L2 round trips.
+            float wv[32], av[32];
+            if (!go) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) wv[i] = wm[idx0 + i * ISTR];
+              if (wg) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) av[i] = __ldg(&wg[idx0 + i * ISTR]);
+              }
+            }
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
-              const int cout = j * 32 + i;
-              const size_t idx = (size_t)cout * (Cfg::NTAPS * KT) + tap * KT + cin;
+              const size_t idx = idx0 + i * ISTR;
               const float gacc = __uint_as_float(v[i]);
+              float w = 0.f;
               if (go) {
                 go[idx] = gacc;
               } else {
-                float w = wm[idx];
+                w = wv[i];
                 float g = gacc;
-                if (wg) g += p.mu * (w - wg[idx]);
+                if (wg) g += p.mu * (w - av[i]);
                 w -= p.lr * g;
                 wm[idx] = w;
-                const __nv_bfloat16 wb = __float2bfloat16_rn(w);
-                wf[idx] = wb;
-                if (wd) wd[((size_t)tap * KT + cin) * BN + cout] = wb;
+                wf[idx] = __float2bfloat16_rn(w);
               }
+              // pack pairs for the (contiguous-in-cout) data-gradient copy
+              if (i & 1) wdp[i >> 1] |= static_cast<uint32_t>(__bfloat16_as_ushort(__float2bfloat16_rn(w))) << 16;
+              else wdp[i >> 1] = static_cast<uint32_t>(__bfloat16_as_ushort(__float2bfloat16_rn(w)));
+            }
+            if (wd && !go) {
+              uint4* dst = reinterpret_cast<uint4*>(wd + ((size_t)tap * KT + cin) * BN + j * 32);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) dst[k] = make_uint4(wdp[4 * k], wdp[4 * k + 1], wdp[4 * k + 2], wdp[4 * k + 3]);
             }
           }
         }

@@ -102,6 +102,11 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* tm, ui
       : "memory");
 }
 
+// L2 prefetch of a contiguous global range (bytes multiple of 16): warms L2 for data an epilogue will read later.
+__device__ __forceinline__ void prefetch_l2_bulk(const void* gptr, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
+}
+
 // ------------------------------------------------------------------------------------------------
 // tcgen05: TMEM allocation, MMA issue, commit, TMEM loads
 // ------------------------------------------------------------------------------------------------
@@ -191,12 +196,11 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t 
   d |= static_cast<uint64_t>(layout_type & 7u) << 61;
   return d;
 }
-// Same descriptor with the start address advanced by `bytes` (K-steps inside a swizzle atom, tap shifts).
+// Same descriptor with the start address advanced by `bytes` (K-steps inside a swizzle atom, tap shifts, ring
+// stages).  The 14-bit address field holds addr>>4 and shared memory tops out at 227 KB (< 2^18), so a plain
+// 64-bit add can never carry out of the field — one IADD per MMA operand instead of a mask/merge sequence.
 __device__ __forceinline__ uint64_t desc_advance(uint64_t d, uint32_t bytes) {
-  uint32_t lo = static_cast<uint32_t>(d);
-  uint32_t addr = (lo & 0x3FFFu) + (bytes >> 4);
-  lo = (lo & ~0x3FFFu) | (addr & 0x3FFFu);
-  return (d & 0xFFFFFFFF00000000ull) | lo;
+  return d + static_cast<uint64_t>(bytes >> 4);
 }
 
 // 32-bit instruction descriptor for kind::f16 with bf16 A/B and fp32 accumulator.

@@ -90,10 +90,9 @@ def conv2_fwd(p1, w2_fwd, master, num_clients, active, p2, code2, nsplit=0):
                                  _p(active), _p(p2), _p(code2), C.c_int(nsplit), _stream()))
 
 
-def conv2_dgrad(dy2, w2_dgrad, master, global_w, num_clients, active, p1, code1, dy1, lr, mu, dbias_out=None,
-                nsplit=0):
+def conv2_dgrad(dy2, w2_dgrad, master, global_w, num_clients, active, p1, dp1, lr, mu, dbias_out=None, nsplit=0):
     _ck(require().olsb_conv2_dgrad(_p(dy2), _p(w2_dgrad), _p(master), _p(global_w), C.c_longlong(master.shape[1]),
-                                   C.c_int(num_clients), _p(active), _p(p1), _p(code1), _p(dy1), C.c_float(lr),
+                                   C.c_int(num_clients), _p(active), _p(p1), _p(dp1), C.c_float(lr),
                                    C.c_float(mu), _p(dbias_out), C.c_int(nsplit), _stream()))
 
 
@@ -103,9 +102,10 @@ def conv2_wgrad(p1, dy2, master, global_w, num_clients, active, w2_fwd, w2_dgrad
                                    C.c_float(mu), _p(grad_out), _stream()))
 
 
-def conv1_wgrad(x5, x_n_stride, x_n_off, dy1, master, global_w, num_clients, active, w1_fwd, lr, mu, grad_out=None):
-    _ck(require().olsb_conv1_wgrad(_p(x5), C.c_longlong(x5.shape[0]), C.c_int(x_n_stride), C.c_int(x_n_off), _p(dy1),
-                                   _p(master), _p(global_w), C.c_longlong(master.shape[1]), C.c_int(num_clients),
+def conv1_wgrad(x5, x_n_stride, x_n_off, dp1, code1, master, global_w, num_clients, active, w1_fwd, lr, mu,
+                grad_out=None):
+    _ck(require().olsb_conv1_wgrad(_p(x5), C.c_longlong(x5.shape[0]), C.c_int(x_n_stride), C.c_int(x_n_off), _p(dp1),
+                                   _p(code1), _p(master), _p(global_w), C.c_longlong(master.shape[1]), C.c_int(num_clients),
                                    _p(active), _p(w1_fwd), C.c_float(lr), C.c_float(mu), _p(grad_out), _stream()))
 
 
@@ -127,7 +127,7 @@ class Cnn2StepArgs(C.Structure):
         ("active", C.c_void_p),
         ("w1_fwd", C.c_void_p), ("w2_fwd", C.c_void_p), ("w2_dgrad", C.c_void_p),
         ("p1", C.c_void_p), ("code1", C.c_void_p), ("p2", C.c_void_p), ("code2", C.c_void_p),
-        ("dy2", C.c_void_p), ("dy1", C.c_void_p),
+        ("dy2", C.c_void_p), ("dp1", C.c_void_p),
         ("loss_sum", C.c_void_p), ("nonfinite", C.c_void_p),
         ("lr", C.c_float), ("mu", C.c_float), ("use_prox", C.c_int), ("nsplit", C.c_int),
     ]
