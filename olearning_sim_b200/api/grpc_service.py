@@ -1,0 +1,170 @@
+"""gRPC façade with the reference's service and method names, and ``SimulatorSession`` to host them.
+
+Services / methods (ols_core/proto/*.proto):
+
+    TaskMgr                          submitTask stopTask getTaskStatus getTaskQueue changeScheduler
+    ResourceMgr                      getClusterAvailableResource getClusterResourceDetail requestClusterResource
+                                     releaseClusterResource getClusterTotalResource getResource requestResource
+                                     releaseResource getVMResource getPhoneResource getTotalResource
+    TaskOperatorOrientedDeviceFlow   GetDeviceflowPulsarClient GetDeviceflowWebsocket NotifyStart NotifyComplete
+                                     RegisterTask UnRegisterTask GetTotalComputeResources CheckDeviceflowDispatchFinished
+    RayClusterMgr (-> GpuClusterMgr) createRayCluster deleteRayCluster modifyRayCluster queryRayCluster
+    PerformanceMgr                   commitJob
+
+``grpc_tools`` (protoc) is not available offline, so instead of generated ``*_pb2`` classes the wire format is a JSON
+object per message (UTF-8) routed through ``grpc.method_handlers_generic_handler`` — same fully-qualified method paths
+(``/TaskMgr/submitTask`` ...), same 100 MiB message cap (ols_core/config/config.conf:2-3), insecure port like the
+reference (ols_core/simu_session.py:31-47).  ``JsonStub`` is the matching client.
+"""
+from __future__ import annotations
+
+import json
+import time
+from concurrent import futures
+from dataclasses import asdict, is_dataclass
+from typing import Any, Callable, Dict, Optional
+
+import grpc
+
+MAX_MESSAGE = 100 * 1024 * 1024
+_OPTS = [("grpc.max_send_message_length", MAX_MESSAGE), ("grpc.max_receive_message_length", MAX_MESSAGE)]
+
+
+def _ser(obj: Any) -> bytes:
+    def default(o):
+        if is_dataclass(o):
+            return asdict(o)
+        if hasattr(o, "name") and hasattr(o, "value"):
+            return o.name
+        return str(o)
+    return json.dumps(obj, default=default).encode("utf-8")
+
+
+def _de(b: bytes) -> Any:
+    return json.loads(b.decode("utf-8")) if b else {}
+
+
+def _generic(service: str, methods: Dict[str, Callable[[Dict[str, Any]], Any]]):
+    def wrap(fn):
+        def handler(request, context):
+            try:
+                return fn(request or {})
+            except Exception as e:  # noqa: BLE001
+                context.set_code(grpc.StatusCode.INTERNAL)
+                context.set_details(f"{type(e).__name__}: {e}")
+                return {"is_success": False, "error": str(e)}
+        return grpc.unary_unary_rpc_method_handler(handler, request_deserializer=_de, response_serializer=_ser)
+    return grpc.method_handlers_generic_handler(service, {m: wrap(f) for m, f in methods.items()})
+
+
+# ---- servicers ---------------------------------------------------------------------------------------------
+def task_mgr_handler(tm: Any):
+    return _generic("TaskMgr", {
+        "submitTask": lambda r: {"is_success": bool(tm.submitTask(r.get("task", r)))},
+        "stopTask": lambda r: {"is_success": bool(tm.stopTask(r["taskID"]))},
+        "getTaskStatus": lambda r: {"taskStatus": tm.getTaskStatus(r["taskID"])},
+        "getTaskQueue": lambda r: {"tasks": tm.getTaskQueue()},
+        "changeScheduler": lambda r: {"is_success": bool(tm.changeScheduler(r.get("strategy")))},
+    })
+
+
+def resource_mgr_handler(rm: Any):
+    return _generic("ResourceMgr", {
+        "getClusterAvailableResource": lambda r: rm.getClusterAvailableResource(),
+        "getClusterResourceDetail": lambda r: {"details": rm.getClusterResourceDetail()},
+        "requestClusterResource": lambda r: {"status": rm.requestClusterResource(r["task_id"], r.get("cpu", 0.0), r.get("mem", 0.0), r.get("gpu", 0.0)).name},
+        "releaseClusterResource": lambda r: {"status": rm.releaseClusterResource(r["task_id"]).name},
+        "getClusterTotalResource": lambda r: rm.getClusterTotalResource(),
+        "getResource": lambda r: rm.getResource(),
+        "requestResource": lambda r: dict(zip(("is_success", "status"), rm.requestResource(
+            r["task_id"], r.get("user_id", ""), r.get("cpu", 0.0), r.get("mem", 0.0), r.get("gpu", 0.0), r.get("phones"), r.get("type", 0)))),
+        "releaseResource": lambda r: dict(zip(("is_success", "status"), rm.releaseResource(
+            r["task_id"], r.get("user_id", ""), r.get("phones"), r.get("type", 0)))),
+        "getVMResource": lambda r: rm.getVMResource(),
+        "getPhoneResource": lambda r: rm.getPhoneResource(),
+        "getTotalResource": lambda r: rm.getTotalResource(),
+    })
+
+
+def deviceflow_handler(df: Any):
+    from ..deviceflow.service import NotifyRequest
+
+    def req(r):
+        return NotifyRequest(r["task_id"], r["routing_key"], r["compute_resource"], r.get("strategy", ""),
+                             r.get("outbound_service", {}) or {})
+    return _generic("TaskOperatorOrientedDeviceFlow", {
+        "GetDeviceflowPulsarClient": lambda r: df.GetDeviceflowPulsarClient(),
+        "GetDeviceflowWebsocket": lambda r: df.GetDeviceflowWebsocket(),
+        "NotifyStart": lambda r: {"is_success": bool(df.NotifyStart(req(r)))},
+        "NotifyComplete": lambda r: {"is_success": bool(df.NotifyComplete(req(r)))},
+        "RegisterTask": lambda r: {"is_success": bool(df.RegisterTask(r["task_id"], r.get("total_compute_resources", [])))},
+        "UnRegisterTask": lambda r: {"is_success": bool(df.UnRegisterTask(r["task_id"]))},
+        "GetTotalComputeResources": lambda r: {"total_compute_resources": df.GetTotalComputeResources(r["task_id"])},
+        "CheckDeviceflowDispatchFinished": lambda r: {"is_success": bool(df.CheckDeviceflowDispatchFinished(r["task_id"]))},
+    })
+
+
+def cluster_mgr_handler(cm: Any):
+    return _generic("RayClusterMgr", {
+        "createRayCluster": lambda r: cm.createRayCluster(r),
+        "deleteRayCluster": lambda r: cm.deleteRayCluster(r),
+        "modifyRayCluster": lambda r: cm.modifyRayCluster(r),
+        "queryRayCluster": lambda r: cm.queryRayCluster(r),
+    })
+
+
+def performance_mgr_handler(pm: Any):
+    return _generic("PerformanceMgr", {"commitJob": lambda r: pm.commitJob(r)})
+
+
+class JsonStub:
+    """Client for any of the services above:  ``JsonStub(channel, "TaskMgr").submitTask({...})``"""
+
+    def __init__(self, channel: grpc.Channel, service: str):
+        self._channel, self._service = channel, service
+
+    def __getattr__(self, method: str):
+        call = self._channel.unary_unary(f"/{self._service}/{method}", request_serializer=_ser, response_deserializer=_de)
+        return lambda request=None, timeout=30: call(request or {}, timeout=timeout)
+
+
+def connect(address: str) -> grpc.Channel:
+    return grpc.insecure_channel(address, options=_OPTS)
+
+
+class SimulatorSession:
+    """``SimulatorSession(port, services).start()`` — mounts servicers on one gRPC server.
+    ``svc``: 0 all / 1 task / 2 resource / 3 cluster / 4 performance / 5 deviceflow (simu_session.py:34-46)."""
+
+    def __init__(self, port: int = 60061, task_manager: Any = None, resource_manager: Any = None, deviceflow: Any = None,
+                 cluster_manager: Any = None, performance_manager: Any = None, svc: int = 0, max_workers: int = 10,
+                 host: str = "127.0.0.1", session_sleep_time: float = 10.0):
+        self.server = grpc.server(futures.ThreadPoolExecutor(max_workers=max_workers), options=_OPTS)
+        mounted = []
+        if task_manager is not None and svc in (0, 1):
+            self.server.add_generic_rpc_handlers((task_mgr_handler(task_manager),)); mounted.append("TaskMgr")
+        if resource_manager is not None and svc in (0, 2):
+            self.server.add_generic_rpc_handlers((resource_mgr_handler(resource_manager),)); mounted.append("ResourceMgr")
+        if cluster_manager is not None and svc in (0, 3):
+            self.server.add_generic_rpc_handlers((cluster_mgr_handler(cluster_manager),)); mounted.append("RayClusterMgr")
+        if performance_manager is not None and svc in (0, 4):
+            self.server.add_generic_rpc_handlers((performance_mgr_handler(performance_manager),)); mounted.append("PerformanceMgr")
+        if deviceflow is not None and svc in (0, 5):
+            self.server.add_generic_rpc_handlers((deviceflow_handler(deviceflow),)); mounted.append("TaskOperatorOrientedDeviceFlow")
+        self.mounted = mounted
+        self.port = self.server.add_insecure_port(f"{host}:{port}")
+        self.address = f"{host}:{self.port}"
+        self._sleep = session_sleep_time
+
+    def start(self, block: bool = False) -> "SimulatorSession":
+        self.server.start()
+        if block:
+            try:
+                while True:
+                    time.sleep(self._sleep)
+            except KeyboardInterrupt:
+                self.stop()
+        return self
+
+    def stop(self, grace: Optional[float] = 0.5) -> None:
+        self.server.stop(grace)

@@ -285,21 +285,48 @@ class FedEngine:
                 x = reference.normalize_u8(x).permute(0, 1, 4, 2, 3).contiguous()   # C,S,3,32,32
             self.x, self.y = x, self.host_y.to(self.device)
 
-    def stream_inputs(self, stream: Optional["torch.cuda.Stream"] = None) -> int:
-        """End-to-end mode: (re)upload this round's client samples and labels from pinned host memory and ingest
-        them (native: uint8 -> bf16 operand layout on the GPU).  Returns the bytes copied host->device."""
+    def _issue_h2d(self, slot: int) -> None:
+        """Enqueue the pinned-host -> device copy of one round's inputs on the copy stream (double-buffered)."""
+        st = self._copy_stream
+        # the staging slot may still be read by the ingest kernel of two rounds ago
+        st.wait_event(self._ingested[slot])
+        with torch.cuda.stream(st):
+            self._stage_x[slot].copy_(self.host_x, non_blocking=True)
+            self._stage_y[slot].copy_(self.host_y, non_blocking=True)
+            self._copied[slot].record(st)
+
+    def stream_inputs(self, prefetch_next: bool = True) -> int:
+        """End-to-end mode: this round's client samples + labels travel from pinned host memory to the GPU every round
+        and are ingested there (native: uint8 -> bf16 operand layout).  The copy runs on its own stream into one of
+        two staging buffers, so the transfer of round r+1 overlaps the compute of round r.  Returns bytes H2D."""
         nbytes = self.host_x.numel() * self.host_x.element_size() + self.host_y.numel() * self.host_y.element_size()
-        if self.backend == "native":
-            if not hasattr(self, "_stage_x"):
-                self._stage_x = torch.empty_like(self.host_x, device=self.device)
-            self._stage_x.copy_(self.host_x, non_blocking=True)
-            self.ws.labels.copy_(self.host_y, non_blocking=True)
-            self.ws.ingest_slice(self._stage_x.reshape(-1, 32, 32, 3), 0)
-        else:
+        if self.backend != "native":
             x = self.host_x.to(self.device, non_blocking=True)
             if x.dtype == torch.uint8:
                 x = reference.normalize_u8(x).permute(0, 1, 4, 2, 3).contiguous()
             self.x, self.y = x, self.host_y.to(self.device, non_blocking=True)
+            return nbytes
+        if not hasattr(self, "_stage_x"):
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+            self._stage_x = [torch.empty_like(self.host_x, device=self.device) for _ in range(2)]
+            self._stage_y = [torch.empty_like(self.host_y, device=self.device) for _ in range(2)]
+            self._copied = [torch.cuda.Event() for _ in range(2)]
+            self._ingested = [torch.cuda.Event() for _ in range(2)]
+            for e in self._ingested:
+                e.record(torch.cuda.current_stream())
+            self._slot, self._pending = 0, False
+        cur = torch.cuda.current_stream()
+        if not self._pending:
+            self._issue_h2d(self._slot)
+        slot = self._slot
+        cur.wait_event(self._copied[slot])
+        self.ws.labels.copy_(self._stage_y[slot], non_blocking=True)
+        self.ws.ingest_slice(self._stage_x[slot].reshape(-1, 32, 32, 3), 0)
+        self._ingested[slot].record(cur)
+        self._slot ^= 1
+        self._pending = prefetch_next
+        if prefetch_next:
+            self._issue_h2d(self._slot)
         return nbytes
 
     def run_round(self, round_idx: int, stream_inputs: bool = False) -> RoundResult:

@@ -90,11 +90,11 @@ constexpr int BATCH = 32;
 // kernel instances of the CNN-2 family
 //                          ROWB NKW BN  H   W   BATCH  FLIP   EPI         NSTAGE
 #define CONV1_FWD conv_taps_kernel<32, 1, 32, 32, 32, BATCH, false, EPI_POOL, 8>
-#define CONV2_FWD conv_taps_kernel<64, 5, 64, 16, 16, BATCH, false, EPI_POOL, 7>
-#define CONV2_DGRAD conv_taps_kernel<128, 5, 32, 16, 16, BATCH, true, EPI_GATE, 4>
+#define CONV2_FWD conv_fwd_fold_kernel<32, 64, 16, BATCH, 7>
+#define CONV2_DGRAD conv_dgrad_fold_kernel<32, 64, 16, BATCH, 4>
 using Conv1FwdCfg = FwdCfg<32, 1, 32, 32, 32, BATCH, false, EPI_POOL, 8>;
-using Conv2FwdCfg = FwdCfg<64, 5, 64, 16, 16, BATCH, false, EPI_POOL, 7>;
-using Conv2DgradCfg = FwdCfg<128, 5, 32, 16, 16, BATCH, true, EPI_GATE, 4>;
+using Conv2FwdCfg = FwdFoldCfg<32, 64, 16, BATCH, 7>;
+using Conv2DgradCfg = DgradFoldCfg<32, 64, 16, BATCH, 4>;
 //                              XROWB NKW YROWB H   W   BATCH NSS SYNTH_Y
 #define CONV2_WGRAD conv_wgrad_kernel<64, 5, 128, 16, 16, BATCH, 2, false>
 #define CONV1_WGRAD conv_wgrad_kernel<32, 1, 64, 32, 32, BATCH, 6, true>
@@ -172,7 +172,7 @@ int olsb_conv2_fwd(const void* p1, const void* w2_fwd, const void* master, long 
   if (int r = olsb_init()) return r;
   CUtensorMap tmA, tmW;
   if (int r = make_act_map(&tmA, p1, (uint64_t)C * BATCH, 16, 16, 32, kBoxH)) return r;
-  if (int r = make_w_map(&tmW, w2_fwd, (uint64_t)C, 64, 800, 64, 32)) return r;
+  if (int r = make_w_map(&tmW, w2_fwd, (uint64_t)C, 64, 800, 32, 32)) return r;
   FwdParams p;
   memset(&p, 0, sizeof(p));
   p.num_clients = C; p.nsplit = auto_split(C, Conv2FwdCfg::TILES_PER_CLIENT, nsplit);
@@ -194,7 +194,7 @@ int olsb_conv2_dgrad(const void* dy2, const void* w2_dgrad, void* master, const 
   if (int r = olsb_init()) return r;
   CUtensorMap tmA, tmW;
   if (int r = make_act_map(&tmA, dy2, (uint64_t)C * BATCH, 16, 16, 64, kBoxH)) return r;
-  if (int r = make_w_map(&tmW, w2_dgrad, (uint64_t)C, 25 * 32, 64, 32, 64)) return r;
+  if (int r = make_w_map(&tmW, w2_dgrad, (uint64_t)C, 25 * 32, 64, 5 * 32, 64)) return r;
   FwdParams p;
   memset(&p, 0, sizeof(p));
   p.num_clients = C; p.nsplit = auto_split(C, Conv2DgradCfg::TILES_PER_CLIENT, nsplit);

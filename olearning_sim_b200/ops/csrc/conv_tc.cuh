@@ -387,6 +387,497 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 }
 
 // ================================================================================================
+// Data-gradient kernel, horizontal taps folded into N
+// ================================================================================================
+// dX[h,w,ci] = sum_{kh,kw} dY[h-(kh-2), w-(kw-2), co] * W[kh,kw][co,ci].   A shift of the *input* column is the same
+// as a shift of the *output* column, so for every vertical tap kh ONE MMA with N = 5*CIN computes the five partial
+// products D_kw[h,w'] = sum_co dY[h-(kh-2), w', co] W[kh,kw][co,:] from the same un-shifted A tile, and the epilogue
+// sums D_kw taken from the lane of pixel w+2-kw (the 8x16 tile spans the full image width, so out-of-tile = zero
+// padding).  Versus one MMA per (kh,kw): 5x fewer TMA boxes and MMAs, 2.8x less shared-memory operand traffic —
+// the N=32 variant is capped at 40% tensor utilisation by the 128 B/clk smem read port.
+template <int CIN, int COUT, int IMG_H, int BATCH, int NSTAGE>
+struct DgradFoldCfg {
+  static constexpr int ROWB = COUT * 2;                 // bytes per A pixel row (K = COUT)
+  static constexpr int NF = 5 * CIN;                    // folded N
+  static constexpr int W_KH_BYTES = NF * ROWB;          // one vertical tap: [5*CIN rows][COUT] K-major
+  static constexpr int W_BYTES = kNKH * W_KH_BYTES;
+  static constexpr int STAGE_BYTES = kBoxH * kTileW * ROWB;
+  static constexpr int TILES_PER_CLIENT = BATCH * (IMG_H / kTileH);
+  static constexpr int TMEM_BUF_STRIDE = 256;
+  static constexpr int TMEM_COLS = 512;
+  static constexpr int SMEM_BYTES = 1024 + W_BYTES + NSTAGE * STAGE_BYTES + (int)sizeof(Barriers);
+  static_assert(ROWB == 128 && CIN == 32, "written for 64 -> 32 channels (SW128 rows, one 32-column chunk per tap)");
+  static_assert(NF % 16 == 0 && NF <= 256, "UMMA N constraint");
+};
+
+template <int CIN, int COUT, int IMG_H, int BATCH, int NSTAGE>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_dgrad_fold_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+                       const FwdParams p) {
+  using Cfg = DgradFoldCfg<CIN, COUT, IMG_H, BATCH, NSTAGE>;
+  constexpr int ROWB = Cfg::ROWB;
+  constexpr int IMG_W = kTileW;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* w_sm = smem;
+  uint8_t* a_sm = smem + Cfg::W_BYTES;
+  Barriers* bars = reinterpret_cast<Barriers*>(a_sm + NSTAGE * Cfg::STAGE_BYTES);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NSTAGE; ++i) { mbar_init(&bars->full[i], 1); mbar_init(&bars->empty[i], 1); }
+    mbar_init(&bars->wfull, 1);
+    mbar_init(&bars->wempty, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&bars->tfull[i], 1); mbar_init(&bars->tempty[i], kEpiWarps); }
+    fence_mbar_init();
+  }
+  if (warp == 5) { tmem_alloc(&bars->tmem_base, Cfg::TMEM_COLS); tmem_relinquish(); }
+  if (warp == 4 && lane == 0) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmW); }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = bars->tmem_base;
+  const int num_work = p.num_clients * p.nsplit;
+  const int tiles_per_work = (Cfg::TILES_PER_CLIENT + p.nsplit - 1) / p.nsplit;
+
+  if (warp == 4) {
+    const bool leader = elect_one();
+    int stage = 0; uint32_t phase = 0; int cur_client = -1; uint32_t wphase = 0; bool first_w = true;
+    for (int wi = blockIdx.x; wi < num_work; wi += gridDim.x) {
+      const int c = wi / p.nsplit, sp = wi % p.nsplit;
+      if (p.active && !p.active[c]) continue;
+      if (c != cur_client) {
+        if (!first_w) { mbar_wait(&bars->wempty, wphase); wphase ^= 1; }
+        first_w = false; cur_client = c;
+        if (leader) {
+          mbar_arrive_expect_tx(&bars->wfull, Cfg::W_BYTES);
+          // weights [C][25*CIN rows][COUT]: one box (COUT, 5*CIN, 1) per vertical tap
+#pragma unroll 1
+          for (int kh = 0; kh < kNKH; ++kh)
+            tma_load_3d(w_sm + kh * Cfg::W_KH_BYTES, &tmW, &bars->wfull, 0, kh * Cfg::NF, c);
+        }
+      }
+      const int t0 = sp * tiles_per_work;
+      const int t1 = min(t0 + tiles_per_work, Cfg::TILES_PER_CLIENT);
+      for (int t = t0; t < t1; ++t) {
+        const int s = t / (IMG_H / kTileH);
+        const int h0 = (t % (IMG_H / kTileH)) * kTileH;
+        mbar_wait(&bars->empty[stage], phase ^ 1);
+        if (leader) {
+          mbar_arrive_expect_tx(&bars->full[stage], Cfg::STAGE_BYTES);
+          tma_load_4d(a_sm + stage * Cfg::STAGE_BYTES, &tmA, &bars->full[stage], 0, 0, h0 - kHalo,
+                      c * p.a_n_stride + p.a_n_off + s);
+        }
+        if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 5) {
+    const bool leader = elect_one();
+    constexpr uint32_t IDESC = make_idesc_bf16(128, Cfg::NF, 0, 0);
+    const uint64_t a_desc_base = make_smem_desc(smem_u32(a_sm), 16, 8 * ROWB, LT_SW128);
+    const uint64_t b_desc_base = make_smem_desc(smem_u32(w_sm), 16, 8 * ROWB, LT_SW128);
+    int stage = 0; uint32_t phase = 0; int cur_client = -1; uint32_t wphase = 0;
+    int buf = 0; uint32_t tphase0 = 0, tphase1 = 0;
+    for (int wi = blockIdx.x; wi < num_work; wi += gridDim.x) {
+      const int c = wi / p.nsplit, sp = wi % p.nsplit;
+      if (p.active && !p.active[c]) continue;
+      bool last_of_client = true;
+      {
+        const int nwi = wi + gridDim.x;
+        if (nwi < num_work && (nwi / p.nsplit) == c) last_of_client = false;
+      }
+      if (c != cur_client) { mbar_wait(&bars->wfull, wphase); wphase ^= 1; cur_client = c; }
+      const int t0 = sp * tiles_per_work;
+      const int t1 = min(t0 + tiles_per_work, Cfg::TILES_PER_CLIENT);
+      for (int t = t0; t < t1; ++t) {
+        mbar_wait(&bars->tempty[buf], (buf ? tphase1 : tphase0) ^ 1);
+        fence_after_sync();
+        mbar_wait(&bars->full[stage], phase);
+        fence_after_sync();
+        if (leader) {
+          const uint32_t d_tmem = tmem_base + buf * Cfg::TMEM_BUF_STRIDE;
+          const uint64_t a_stage = desc_advance(a_desc_base, stage * Cfg::STAGE_BYTES);
+#pragma unroll
+          for (int kh = 0; kh < kNKH; ++kh) {
+            const uint64_t a_desc = desc_advance(a_stage, (2 * kHalo - kh) * kTileW * ROWB);
+            const uint64_t b_desc = desc_advance(b_desc_base, kh * Cfg::W_KH_BYTES);
+#pragma unroll
+            for (int ks = 0; ks < ROWB / 32; ++ks)
+              umma_bf16(d_tmem, desc_advance(a_desc, ks * 32), desc_advance(b_desc, ks * 32), IDESC,
+                        (kh | ks) ? 1u : 0u);
+          }
+          umma_commit(&bars->empty[stage]);
+          umma_commit(&bars->tfull[buf]);
+        }
+        __syncwarp();
+        if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+        if (buf) tphase1 ^= 1; else tphase0 ^= 1;
+        buf ^= 1;
+      }
+      if (last_of_client) {
+        if (leader) umma_commit(&bars->wempty);
+        __syncwarp();
+      }
+    }
+  } else {
+    int buf = 0; uint32_t tphase0 = 0, tphase1 = 0;
+    const int q = warp;
+    const int hl = 2 * q + (lane >> 4), wl = lane & 15;
+    float dbacc[CIN];
+#pragma unroll
+    for (int i = 0; i < CIN; ++i) dbacc[i] = 0.f;
+    int cur_client = -1;
+    bool had_sp0 = false;
+    __shared__ float s_db[CIN];
+    auto flush_bias = [&](int c) {
+      asm volatile("bar.sync 1, 128;");
+      if (threadIdx.x < CIN) s_db[threadIdx.x] = 0.f;
+      asm volatile("bar.sync 1, 128;");
+#pragma unroll
+      for (int i = 0; i < CIN; ++i) {
+        float v = dbacc[i];
+        v += __shfl_xor_sync(0xffffffffu, v, 16);
+        v += __shfl_xor_sync(0xffffffffu, v, 8);
+        v += __shfl_xor_sync(0xffffffffu, v, 4);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        if (lane == 0) atomicAdd(&s_db[i], v);
+        dbacc[i] = 0.f;
+      }
+      asm volatile("bar.sync 1, 128;");
+      if (threadIdx.x < CIN) {
+        const float g = s_db[threadIdx.x];
+        if (p.dbias_out) {
+          atomicAdd(&p.dbias_out[(size_t)c * CIN + threadIdx.x], g);
+        } else {
+          float* bp = &p.bias_master[(size_t)c * p.bias_stride + threadIdx.x];
+          float upd = -p.lr * g;
+          if (had_sp0 && p.bias_global) upd -= p.lr * p.mu * (*bp - p.bias_global[threadIdx.x]);
+          atomicAdd(bp, upd);
+        }
+      }
+      asm volatile("bar.sync 1, 128;");
+    };
+    for (int wi = blockIdx.x; wi < num_work; wi += gridDim.x) {
+      const int c = wi / p.nsplit, sp = wi % p.nsplit;
+      if (p.active && !p.active[c]) continue;
+      if (c != cur_client) {
+        if (cur_client >= 0) flush_bias(cur_client);
+        cur_client = c;
+        had_sp0 = false;
+      }
+      if (sp == 0) had_sp0 = true;
+      const int t0 = sp * tiles_per_work;
+      const int t1 = min(t0 + tiles_per_work, Cfg::TILES_PER_CLIENT);
+      for (int t = t0; t < t1; ++t) {
+        const int s = t / (IMG_H / kTileH);
+        const int h0 = (t % (IMG_H / kTileH)) * kTileH;
+        const size_t n_out = (size_t)c * BATCH + s;
+        const size_t pbase = ((n_out * IMG_H + (h0 + hl)) * IMG_W + wl) * CIN;
+        // forward activation of this pixel (ReLU gate) — issued before the TMEM wait to overlap its latency
+        uint4 pq[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) pq[k] = __ldg(reinterpret_cast<const uint4*>(p.pooled + pbase + k * 8));
+        mbar_wait(&bars->tfull[buf], buf ? tphase1 : tphase0);
+        fence_after_sync();
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(32 * q) << 16) + buf * Cfg::TMEM_BUF_STRIDE;
+        float acc[CIN];
+        {
+          uint32_t v[32];
+          tmem_ld32(taddr + 2 * CIN, v);                      // kw = 2: no column shift
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < CIN; ++i) acc[i] = __uint_as_float(v[i]);
+        }
+#pragma unroll
+        for (int kw = 0; kw < 5; ++kw) {
+          if (kw == 2) continue;
+          uint32_t v[32];
+          tmem_ld32(taddr + kw * CIN, v);
+          tmem_ld_wait();
+          const int src_w = wl + 2 - kw;                      // D_kw is taken from the pixel 2-kw columns to the right
+          const bool inb = (src_w >= 0) && (src_w < IMG_W);
+          const int src_lane = (lane & 16) | (src_w & 15);
+#pragma unroll
+          for (int i = 0; i < CIN; ++i) {
+            const float o = __uint_as_float(__shfl_sync(0xffffffffu, v[i], src_lane));
+            acc[i] += inb ? o : 0.f;
+          }
+        }
+        // TMEM buffer drained: release it before the (long-latency) global stores
+        fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars->tempty[buf]);
+        const uint32_t* pw32 = reinterpret_cast<const uint32_t*>(pq);
+        uint4 o[4];
+        uint32_t* ow = reinterpret_cast<uint32_t*>(o);
+#pragma unroll
+        for (int i = 0; i < CIN / 2; ++i) {
+          const uint32_t pr = pw32[i];
+          const float g0 = bf16lo(pr) > 0.f ? acc[2 * i] : 0.f;
+          const float g1 = bf16hi(pr) > 0.f ? acc[2 * i + 1] : 0.f;
+          dbacc[2 * i] += g0; dbacc[2 * i + 1] += g1;
+          ow[i] = pack_bf16x2(g0, g1);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(p.dpool + pbase + k * 8) = o[k];
+        if (buf) tphase1 ^= 1; else tphase0 ^= 1;
+        buf ^= 1;
+      }
+    }
+    if (cur_client >= 0) flush_bias(cur_client);
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 5) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+// ================================================================================================
+// Forward kernel, horizontal taps folded into N (same column-shift identity as the folded data gradient)
+// ================================================================================================
+// out[h,w,co] = sum_{kh,kw} X[h+kh-2, w+kw-2, ci] W[co][kh,kw][ci]  =  sum_kw D_kw[h, w+kw-2, co],
+// D_kw[h,w',co] = sum_kh X[h+kh-2, w', ci] W[co][kh,kw][ci].  The B rows are ordered (co-chunk j, kw, co%32) so one
+// accumulator group of N = 5*32 = 160 columns holds everything a 32-channel output chunk needs; the two groups
+// (j = 0,1) ping-pong inside a tile: the epilogue pools group 0 while the tensor core fills group 1.
+template <int CIN, int COUT, int IMG_H, int BATCH, int NSTAGE>
+struct FwdFoldCfg {
+  static constexpr int ROWB = CIN * 2;
+  static constexpr int NG = COUT / 32;                  // accumulator groups (32 output channels each)
+  static constexpr int NF = 5 * 32;                     // folded N per group
+  static constexpr int W_BOX_BYTES = 32 * ROWB;         // one (kh, j, kw) block: 32 rows x CIN
+  static constexpr int W_KH_BYTES = NG * 5 * W_BOX_BYTES;
+  static constexpr int W_BYTES = kNKH * W_KH_BYTES;
+  static constexpr int STAGE_BYTES = kBoxH * kTileW * ROWB;
+  static constexpr int TILES_PER_CLIENT = BATCH * (IMG_H / kTileH);
+  static constexpr int TMEM_BUF_STRIDE = 256;
+  static constexpr int TMEM_COLS = 512;
+  static constexpr int SMEM_BYTES = 1024 + W_BYTES + NSTAGE * STAGE_BYTES + (int)sizeof(Barriers);
+  static_assert(ROWB == 64 && NG == 2, "written for 32 -> 64 channels (SW64 rows, two accumulator groups)");
+};
+
+template <int CIN, int COUT, int IMG_H, int BATCH, int NSTAGE>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_fwd_fold_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+                     const FwdParams p) {
+  using Cfg = FwdFoldCfg<CIN, COUT, IMG_H, BATCH, NSTAGE>;
+  constexpr int ROWB = Cfg::ROWB;
+  constexpr int IMG_W = kTileW;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* w_sm = smem;
+  uint8_t* a_sm = smem + Cfg::W_BYTES;
+  Barriers* bars = reinterpret_cast<Barriers*>(a_sm + NSTAGE * Cfg::STAGE_BYTES);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NSTAGE; ++i) { mbar_init(&bars->full[i], 1); mbar_init(&bars->empty[i], 1); }
+    mbar_init(&bars->wfull, 1);
+    mbar_init(&bars->wempty, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&bars->tfull[i], 1); mbar_init(&bars->tempty[i], kEpiWarps); }
+    fence_mbar_init();
+  }
+  if (warp == 5) { tmem_alloc(&bars->tmem_base, Cfg::TMEM_COLS); tmem_relinquish(); }
+  if (warp == 4 && lane == 0) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmW); }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = bars->tmem_base;
+  const int num_work = p.num_clients * p.nsplit;
+  const int tiles_per_work = (Cfg::TILES_PER_CLIENT + p.nsplit - 1) / p.nsplit;
+
+  if (warp == 4) {
+    const bool leader = elect_one();
+    int stage = 0; uint32_t phase = 0; int cur_client = -1; uint32_t wphase = 0; bool first_w = true;
+    for (int wi = blockIdx.x; wi < num_work; wi += gridDim.x) {
+      const int c = wi / p.nsplit, sp = wi % p.nsplit;
+      if (p.active && !p.active[c]) continue;
+      if (c != cur_client) {
+        if (!first_w) { mbar_wait(&bars->wempty, wphase); wphase ^= 1; }
+        first_w = false; cur_client = c;
+        if (leader) {
+          mbar_arrive_expect_tx(&bars->wfull, Cfg::W_BYTES);
+          // forward weight copy [C][COUT][25*CIN]: box (CIN, 32 rows, 1) at ((kh*5+kw)*CIN, j*32, c)
+#pragma unroll 1
+          for (int b = 0; b < kNKH * Cfg::NG * 5; ++b) {
+            const int kh = b / (Cfg::NG * 5), r = b % (Cfg::NG * 5), j = r / 5, kw = r % 5;
+            tma_load_3d(w_sm + b * Cfg::W_BOX_BYTES, &tmW, &bars->wfull, (kh * 5 + kw) * CIN, j * 32, c);
+          }
+        }
+      }
+      const int t0 = sp * tiles_per_work;
+      const int t1 = min(t0 + tiles_per_work, Cfg::TILES_PER_CLIENT);
+      for (int t = t0; t < t1; ++t) {
+        const int s = t / (IMG_H / kTileH);
+        const int h0 = (t % (IMG_H / kTileH)) * kTileH;
+        mbar_wait(&bars->empty[stage], phase ^ 1);
+        if (leader) {
+          mbar_arrive_expect_tx(&bars->full[stage], Cfg::STAGE_BYTES);
+          tma_load_4d(a_sm + stage * Cfg::STAGE_BYTES, &tmA, &bars->full[stage], 0, 0, h0 - kHalo,
+                      c * p.a_n_stride + p.a_n_off + s);
+        }
+        if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 5) {
+    const bool leader = elect_one();
+    constexpr uint32_t IDESC = make_idesc_bf16(128, Cfg::NF, 0, 0);
+    const uint64_t a_desc_base = make_smem_desc(smem_u32(a_sm), 16, 8 * ROWB, LT_SW64);
+    const uint64_t b_desc_base = make_smem_desc(smem_u32(w_sm), 16, 8 * ROWB, LT_SW64);
+    int stage = 0; uint32_t phase = 0; int cur_client = -1; uint32_t wphase = 0;
+    uint32_t tphase = 0;
+    for (int wi = blockIdx.x; wi < num_work; wi += gridDim.x) {
+      const int c = wi / p.nsplit, sp = wi % p.nsplit;
+      if (p.active && !p.active[c]) continue;
+      bool last_of_client = true;
+      {
+        const int nwi = wi + gridDim.x;
+        if (nwi < num_work && (nwi / p.nsplit) == c) last_of_client = false;
+      }
+      if (c != cur_client) { mbar_wait(&bars->wfull, wphase); wphase ^= 1; cur_client = c; }
+      const int t0 = sp * tiles_per_work;
+      const int t1 = min(t0 + tiles_per_work, Cfg::TILES_PER_CLIENT);
+      for (int t = t0; t < t1; ++t) {
+        mbar_wait(&bars->full[stage], phase);
+        fence_after_sync();
+        const uint64_t a_stage = desc_advance(a_desc_base, stage * Cfg::STAGE_BYTES);
+#pragma unroll
+        for (int j = 0; j < Cfg::NG; ++j) {
+          mbar_wait(&bars->tempty[j], tphase ^ 1);
+          fence_after_sync();
+          if (leader) {
+            const uint32_t d_tmem = tmem_base + j * Cfg::TMEM_BUF_STRIDE;
+#pragma unroll
+            for (int kh = 0; kh < kNKH; ++kh) {
+              const uint64_t a_desc = desc_advance(a_stage, kh * kTileW * ROWB);
+              const uint64_t b_desc = desc_advance(b_desc_base, kh * Cfg::W_KH_BYTES + j * 5 * Cfg::W_BOX_BYTES);
+#pragma unroll
+              for (int ks = 0; ks < ROWB / 32; ++ks)
+                umma_bf16(d_tmem, desc_advance(a_desc, ks * 32), desc_advance(b_desc, ks * 32), IDESC,
+                          (kh | ks) ? 1u : 0u);
+            }
+            if (j == Cfg::NG - 1) umma_commit(&bars->empty[stage]);
+            umma_commit(&bars->tfull[j]);
+          }
+          __syncwarp();
+        }
+        if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+        tphase ^= 1;
+      }
+      if (last_of_client) {
+        if (leader) umma_commit(&bars->wempty);
+        __syncwarp();
+      }
+    }
+  } else {
+    uint32_t tphase = 0;
+    const int q = warp;
+    const int wl = lane & 15;
+    const int b0 = lane & 1, b4 = (lane >> 4) & 1;
+    const int sl = b0 * 2 + b4;
+    const int pos = (b4 << 1) | b0;
+    float bias_r[Cfg::NG * 8];
+    int cur_client = -1;
+    for (int wi = blockIdx.x; wi < num_work; wi += gridDim.x) {
+      const int c = wi / p.nsplit, sp = wi % p.nsplit;
+      if (p.active && !p.active[c]) continue;
+      if (c != cur_client) {
+        cur_client = c;
+        const float* bias = p.bias + (size_t)c * p.bias_stride;
+#pragma unroll
+        for (int j = 0; j < Cfg::NG; ++j)
+#pragma unroll
+          for (int k = 0; k < 8; ++k) bias_r[j * 8 + k] = __ldg(&bias[j * 32 + sl * 8 + k]);
+      }
+      const int t0 = sp * tiles_per_work;
+      const int t1 = min(t0 + tiles_per_work, Cfg::TILES_PER_CLIENT);
+      for (int t = t0; t < t1; ++t) {
+        const int s = t / (IMG_H / kTileH);
+        const int h0 = (t % (IMG_H / kTileH)) * kTileH;
+        const size_t n_out = (size_t)c * BATCH + s;
+        const int ph = (h0 >> 1) + q, pw = wl >> 1;
+        const size_t obase = ((n_out * (IMG_H / 2) + ph) * (IMG_W / 2) + pw) * COUT;
+#pragma unroll
+        for (int j = 0; j < Cfg::NG; ++j) {
+          mbar_wait(&bars->tfull[j], tphase);
+          fence_after_sync();
+          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(32 * q) << 16) + j * Cfg::TMEM_BUF_STRIDE;
+          float acc[32];
+          {
+            uint32_t v[32];
+            tmem_ld32(taddr + 2 * 32, v);                       // kw = 2: no column shift
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) acc[i] = __uint_as_float(v[i]);
+          }
+#pragma unroll
+          for (int kw = 0; kw < 5; ++kw) {
+            if (kw == 2) continue;
+            uint32_t v[32];
+            tmem_ld32(taddr + kw * 32, v);
+            tmem_ld_wait();
+            const int src_w = wl + kw - 2;
+            const bool inb = (src_w >= 0) && (src_w < IMG_W);
+            const int src_lane = (lane & 16) | (src_w & 15);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const float o = __uint_as_float(__shfl_sync(0xffffffffu, v[i], src_lane));
+              acc[i] += inb ? o : 0.f;
+            }
+          }
+          fence_before_sync();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bars->tempty[j]);          // group drained: the tensor core may refill it
+          uint32_t v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const uint32_t bits = __float_as_uint(acc[i]);
+            const uint32_t key = bits ^ (static_cast<uint32_t>(static_cast<int32_t>(bits) >> 31) | 0x80000000u);
+            v[i] = (key & ~3u) | static_cast<uint32_t>(3 - pos);
+          }
+          uint32_t m16[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const uint32_t give = b0 ? v[i] : v[16 + i];
+            const uint32_t keep = b0 ? v[16 + i] : v[i];
+            m16[i] = max(keep, __shfl_xor_sync(0xffffffffu, give, 1));
+          }
+          uint32_t m8[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const uint32_t give = b4 ? m16[i] : m16[8 + i];
+            const uint32_t keep = b4 ? m16[8 + i] : m16[i];
+            m8[i] = max(keep, __shfl_xor_sync(0xffffffffu, give, 16));
+          }
+          float f[8];
+          uint32_t cd[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const uint32_t key = m8[i];
+            cd[i] = 3u - (key & 3u);
+            const uint32_t kk = key & ~3u;
+            const uint32_t bits = (kk & 0x80000000u) ? (kk ^ 0x80000000u) : ~kk;
+            f[i] = fmaxf(__uint_as_float(bits) + bias_r[j * 8 + i], 0.f);
+          }
+          uint4 pv;
+          pv.x = pack_bf16x2(f[0], f[1]); pv.y = pack_bf16x2(f[2], f[3]);
+          pv.z = pack_bf16x2(f[4], f[5]); pv.w = pack_bf16x2(f[6], f[7]);
+          uint2 cv;
+          cv.x = cd[0] | (cd[1] << 8) | (cd[2] << 16) | (cd[3] << 24);
+          cv.y = cd[4] | (cd[5] << 8) | (cd[6] << 16) | (cd[7] << 24);
+          const size_t off = obase + j * 32 + sl * 8;
+          *reinterpret_cast<uint4*>(p.out + off) = pv;
+          *reinterpret_cast<uint2*>(p.code + off) = cv;
+        }
+        tphase ^= 1;
+      }
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 5) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+// ================================================================================================
 // Weight-gradient kernel (+ fused SGD / FedProx update of master and operand copies)
 // ================================================================================================
 struct WgradParams {
