@@ -315,6 +315,8 @@ class RoundRunner:
         finally:
             for e in {id(e): e for e in self.engines.values()}.values():
                 try:
+                    if getattr(e, "ckpt", None) is not None:
+                        e.ckpt.wait()                      # the last round's checkpoint must be on disk before we return
                     e.close()
                 except Exception:  # noqa: BLE001
                     pass

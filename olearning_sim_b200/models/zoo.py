@@ -61,8 +61,7 @@ class ModelSpec:
                 parts.append(torch.randn(s, generator=g) * 0.02)
             else:
                 fan_in = math.prod(s[1:]) if len(s) > 1 else s[0]
-                bound = math.sqrt(6.0 / fan_in) / math.sqrt(3.0) * math.sqrt(3.0) / math.sqrt(2.0)  # kaiming_uniform(a=sqrt(5))~1/sqrt(fan_in)*sqrt(3)
-                bound = 1.0 / math.sqrt(fan_in) * math.sqrt(3.0)
+                bound = 1.0 / math.sqrt(fan_in)          # torch.nn default (kaiming_uniform with a=sqrt(5))
                 parts.append((torch.rand(s, generator=g) * 2 - 1) * bound)
         return self.flatten({n: p for (n, _), p in zip(self.shapes, parts)})
 

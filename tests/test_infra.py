@@ -1,0 +1,254 @@
+"""gRPC session, cluster manager, blob stores, config layering, queue / fragment repos, logger, checkpoints, gates."""
+import json
+import os
+import threading
+import time
+
+import pytest
+import torch
+
+from olearning_sim_b200.api.grpc_service import JsonStub, SimulatorSession, connect
+from olearning_sim_b200.api.schema import TaskStatus
+from olearning_sim_b200.cluster.manager import ClusterBuilder, ClusterUtils, Director, GpuClusterManager, LocalClusterApi
+from olearning_sim_b200.control.jobs import InProcessJobExecutor
+from olearning_sim_b200.control.operatorflow import OperatorFlow, WaitingForGlobalAggregation
+from olearning_sim_b200.control.repo import FlowTableRepo, LogTableRepo, ResTableRepo, SqlDataBase, TaskTableRepo
+from olearning_sim_b200.control.resource_manager import FakePhoneMgr, ResourceManager
+from olearning_sim_b200.control.task_manager import TaskManager
+from olearning_sim_b200.deviceflow.bus import FakeClock, InMemoryBus
+from olearning_sim_b200.deviceflow.service import DeviceFlowService
+from olearning_sim_b200.engine.checkpoint import CheckpointManager
+from olearning_sim_b200.utils.config import load_config
+from olearning_sim_b200.utils.file_repo import LocalFileRepo, get_file_repo
+from olearning_sim_b200.utils.logger import Logger
+from olearning_sim_b200.utils.misc_repos import (Fragment, JsonFragmentRepo, PerformanceManager, ProtoFragmentRepo,
+                                                 QueueRepo)
+from tests.helpers import make_task_json
+from tests.test_control_plane import StubRunner
+
+
+# ---- gRPC façade ---------------------------------------------------------------------------------------------
+def test_grpc_session_serves_all_services_with_reference_method_names():
+    StubRunner.gate = None
+    repo = TaskTableRepo()
+    rm = ResourceManager(ResTableRepo(), totals={"cpu": 4, "mem": 8, "gpu": 0}, phone_mgr=FakePhoneMgr({"u1": {"High": 2}}))
+    df = DeviceFlowService(bus=InMemoryBus(virtual_time=True), repo=FlowTableRepo(), clock=FakeClock())
+    tm = TaskManager(repo=repo, resource_manager=rm, deviceflow=df, executor=InProcessJobExecutor(runner_factory=StubRunner))
+    sess = SimulatorSession(port=0, task_manager=tm, resource_manager=rm, deviceflow=df,
+                            cluster_manager=GpuClusterManager(LocalClusterApi(gpu_count=8)),
+                            performance_manager=PerformanceManager()).start()
+    try:
+        assert sess.mounted == ["TaskMgr", "ResourceMgr", "RayClusterMgr", "PerformanceMgr", "TaskOperatorOrientedDeviceFlow"]
+        ch = connect(sess.address)
+        t, r, d = JsonStub(ch, "TaskMgr"), JsonStub(ch, "ResourceMgr"), JsonStub(ch, "TaskOperatorOrientedDeviceFlow")
+        assert t.submitTask({"task": make_task_json(task_id="g1")}) == {"is_success": True}
+        assert t.getTaskQueue() == {"tasks": ["g1"]} and t.getTaskStatus({"taskID": "g1"}) == {"taskStatus": "QUEUED"}
+        assert t.getTaskStatus({"taskID": "zz"})["taskStatus"] == "MISSING"
+        assert r.getResource()["cluster"]["cpu"] == 4 and r.getPhoneResource() == {"u1": {"High": 2}}
+        assert r.requestClusterResource({"task_id": "x", "cpu": 9})["status"] == "NOT_ENOUGH_RES"
+        assert r.requestResource({"task_id": "x", "user_id": "u1", "cpu": 1, "mem": 1, "phones": {"High": 1}, "type": 0}) == {"is_success": True, "status": "SUCCESS"}
+        assert r.getClusterResourceDetail()["details"][0]["task_id"] == "x"
+        assert r.releaseResource({"task_id": "x", "user_id": "u1", "type": 0})["is_success"]
+        assert d.RegisterTask({"task_id": "g1", "total_compute_resources": ["logical_simulation"]}) == {"is_success": True}
+        assert d.GetTotalComputeResources({"task_id": "g1"}) == {"total_compute_resources": ["logical_simulation"]}
+        assert "topic" in d.GetDeviceflowPulsarClient()
+        tm.schedule_once(inline=True)
+        deadline = time.time() + 10
+        while time.time() < deadline and t.getTaskStatus({"taskID": "g1"})["taskStatus"] != "SUCCEEDED":
+            time.sleep(0.05)
+        assert t.getTaskStatus({"taskID": "g1"})["taskStatus"] == "SUCCEEDED"
+        assert t.stopTask({"taskID": "g1"})["is_success"] and t.changeScheduler({"strategy": "default"})["is_success"]
+        c = JsonStub(ch, "RayClusterMgr")
+        assert c.createRayCluster() == {"ok": True}
+        q = json.loads(c.queryRayCluster({"k8s_namespace": "default", "ray_label": "demo1-cluster"})["json_data"])
+        assert q["items"][0]["spec"]["workerGroupSpecs"][0]["replicas"] == 4
+        assert JsonStub(ch, "PerformanceMgr").commitJob({"task_id": "g1", "t_round_ms": 10.0, "client_steps": 40})["is_success"]
+    finally:
+        sess.stop()
+
+
+# ---- cluster manager ----------------------------------------------------------------------------------------------
+def test_cluster_builder_utils_and_manager_lifecycle():
+    b = ClusterBuilder()
+    doc = b.build_meta("c1", "ns", {"lab": "yes"}).build_head().build_worker("workers", replicas=2, min_replicas=1, max_replicas=4, gpus=1).get_cluster()
+    assert b.succeeded and doc["spec"]["workerGroupSpecs"][0]["template"]["resources"]["requests"]["nvidia.com/gpu"] == 1
+    assert not ClusterBuilder().build_meta("c2").build_worker("w", replicas=9, max_replicas=4).succeeded
+    u = ClusterUtils()
+    d2, ok = u.update_worker_group_replicas(doc, "workers", 8, 2, 6)
+    assert ok and d2["spec"]["workerGroupSpecs"][0]["replicas"] == 6 and doc["spec"]["workerGroupSpecs"][0]["replicas"] == 2
+    assert not u.update_worker_group_replicas(doc, "workers", 2, 1, 5)[1]
+    assert u.duplicate_worker_group(doc, "workers", "w2")[1] and u.delete_worker_group(doc, "workers")[1]
+    assert u.is_valid_name("ray-demo1") and not u.is_valid_name("Bad_Name")
+    assert Director().build_large_cluster("big")["spec"]["workerGroupSpecs"][0]["replicas"] == 8
+    api = LocalClusterApi(gpu_count=4)
+    m = GpuClusterManager(api)
+    assert m.createRayCluster() == {"ok": True} and m.createRayCluster() == {"ok": False}        # duplicate
+    assert m.modifyRayCluster({"k8s_namespace": "default", "ray_name": "olsb-demo1", "ray_label": "demo1-cluster",
+                               "worker_min_replicas": 1, "worker_replicas": 8, "worker_max_replicas": 8}) == {"ok": True}
+    st = api.get_ray_cluster("olsb-demo1")["status"]
+    assert st == {"state": "pending", "desiredGpus": 8, "availableGpus": 4}                        # more GPUs than the box has
+    assert m.modifyRayCluster({"k8s_namespace": "", "ray_name": "x", "ray_label": "y", "worker_min_replicas": 0,
+                               "worker_replicas": 0, "worker_max_replicas": 0}) == {"ok": False}
+    assert m.deleteRayCluster({"k8s_namespace": "default", "ray_label": "demo1-cluster"}) == {"ok": True}
+    assert json.loads(m.queryRayCluster({"k8s_namespace": "default"})["json_data"]) == {"items": []}
+
+
+# ---- blob stores / config / repos -----------------------------------------------------------------------------------
+def test_local_file_repo_and_skip_if_exists(tmp_path):
+    repo = LocalFileRepo(str(tmp_path / "store"), "bkt")
+    src = tmp_path / "m.bin"
+    src.write_bytes(b"model-v1")
+    assert repo.upload_file(str(src), "t1/model_0.bin")
+    assert repo.listdir_object_name("t1/") == ["t1/model_0.bin"]
+    assert repo.download_payload("t1/model_0.bin") == b"model-v1"
+    dst = tmp_path / "dl" / "m.bin"
+    assert repo.download_if_missing("t1/model_0.bin", str(dst)) and dst.read_bytes() == b"model-v1"
+    dst.write_bytes(b"local-edit")
+    assert repo.download_if_missing("t1/model_0.bin", str(dst)) and dst.read_bytes() == b"local-edit"   # not re-downloaded
+    assert repo.delete_file("t1/model_0.bin") and not repo.download_file("t1/model_0.bin", str(dst))
+    with pytest.raises(ValueError):
+        repo.upload_file(str(src), "../../escape")
+    assert isinstance(get_file_repo("FILE", {"root": str(tmp_path)}), LocalFileRepo)
+    with pytest.raises(RuntimeError):
+        get_file_repo("S3", {"endpoint_url": "x", "access_key": "a", "secret_key": "b", "bucket": "c"})   # boto3 absent
+
+
+def test_config_layering_and_reference_ini_compat(tmp_path, monkeypatch):
+    ini = tmp_path / "config.conf"
+    ini.write_text("[grpc]\nresmgr = '10.0.0.1:60062'\n[taskMgr]\nscheduler_sleep_time = 1\ninterrupt_queue_time = 60\n"
+                   "[ray_cluster]\nworker_replicas = 2\n")
+    y = tmp_path / "deviceflow_config.yaml"
+    y.write_text("grpc_service_address: ${DF_HOST:-127.0.0.9}\nsource_topic: topic_x\n")
+    monkeypatch.setenv("OLSB_TASKMGR__RELEASE_SLEEP_TIME", "3")
+    cfg = load_config([str(ini), str(y)], overrides=["storage.task_table=/tmp/t.sqlite", "taskMgr.scheduler_sleep_time=0.5"])
+    assert cfg.grpc.resmgr == "10.0.0.1:60062"                       # quotes stripped
+    assert cfg.taskMgr.scheduler_sleep_time == 0.5 and cfg.taskMgr.interrupt_queue_time == 60.0
+    assert cfg.taskMgr.release_sleep_time == 3.0                     # environment layer
+    assert cfg.cluster.worker_replicas == 2                          # [ray_cluster] section accepted
+    assert cfg.deviceflow.grpc_service_address == "127.0.0.9" and cfg.deviceflow.source_topic == "topic_x"
+    assert cfg.storage.task_table == "/tmp/t.sqlite" and cfg.hybrid.alpha == 3.5
+
+
+def test_sql_database_generic_api(tmp_path):
+    db = SqlDataBase(str(tmp_path / "x.sqlite"), "deviceflow_table", ["task_id", "flow_id", "flow"])
+    assert db.add_item({"task_id": ["t"], "flow_id": ["f1"]}) and db.add_item({"task_id": "t", "flow_id": "f2", "flow": "{}"})
+    assert db.get_values_by_conditions("flow_id", task_id="t") == ["f1", "f2"]
+    assert db.set_item_value("flow_id", "f1", "flow", '{"a":1}') and db.get_item_value("flow_id", "f1", "flow") == '{"a":1}'
+    assert [r["flow_id"] for r in db.get_all_items_not_None("flow")] == ["f1", "f2"]
+    assert db.delete_item("flow_id", "f1") and not db.check_item_in_database("flow_id", "f1")
+    with pytest.raises(KeyError):
+        db.get_item_value("flow_id", "f2", "no_such_column")
+    with pytest.raises(KeyError):
+        db.get_values_by_conditions("flow_id", **{"task_id; DROP TABLE x": 1})      # column names are whitelisted
+
+
+def test_queue_and_fragment_repos(tmp_path):
+    q = QueueRepo(str(tmp_path / "q.sqlite"))
+    assert q.rpush("tasks", "a") == 1 and q.rpush("tasks", "b") == 2
+    q2 = QueueRepo(str(tmp_path / "q.sqlite"))                                       # durable across instances
+    assert q2.lpop("tasks") == "a" and q2.lpop("tasks") == "b" and q2.lpop("tasks") is None
+    bus = InMemoryBus(virtual_time=True)
+    for cls in (JsonFragmentRepo, ProtoFragmentRepo):
+        repo = cls(bus, f"frag_{cls.__name__}")
+        prod = bus.create_producer(f"frag_{cls.__name__}")
+        for i in range(3):
+            prod.send(repo.encode(Fragment("t", f"c{i}", 2, 10 + i, bytes([i, 255]), {"k": i})))
+        got = repo.consume(10)
+        assert [(f.client_id, f.round, f.num_samples, f.payload, f.meta) for f in got] == \
+            [(f"c{i}", 2, 10 + i, bytes([i, 255]), {"k": i}) for i in range(3)]
+
+
+def test_logger_four_field_signature_and_sinks(tmp_path):
+    lg = Logger()
+    repo = LogTableRepo()
+    lg.set_logger(jsonl_path=str(tmp_path / "log.jsonl"), repo=repo, stderr_level="ERROR")
+    lg.info(task_id="t1", system_name="TaskMgr", module_name="test", message="hello")
+    lg.error("t1", "Deviceflow", "test", "boom")
+    lg.flush()
+    time.sleep(0.1)
+    lines = [json.loads(l) for l in open(tmp_path / "log.jsonl")]
+    assert [(l["log_type"], l["system_name"], l["message"]) for l in lines[-2:]] == [("INFO", "TaskMgr", "hello"), ("ERROR", "Deviceflow", "boom")]
+    assert {r["message"] for r in repo.all_rows()} >= {"hello", "boom"}
+    lg.set_logger(jsonl_path="", repo=None)
+    lg.jsonl_path, lg.repo = None, None
+
+
+def test_performance_manager_summary():
+    pm = PerformanceManager({"hbm_gbs": 1000.0})
+    for r in range(4):
+        pm.commitJob({"task_id": "t", "round": r, "t_round_ms": 20.0, "client_steps": 100, "hbm_bytes": 5e9})
+    s = pm.summary("t")
+    assert s["rounds"] == 4 and s["rounds_per_s"] == pytest.approx(50.0) and s["client_steps_per_s"] == pytest.approx(5000.0)
+    assert s["hbm_fraction_of_measured"] == pytest.approx(0.25)
+    assert not pm.commitJob({})["is_success"]
+
+
+# ---- checkpoints ----------------------------------------------------------------------------------------------------------
+def test_checkpoint_atomic_keep_and_resume(tmp_path):
+    cm = CheckpointManager(str(tmp_path), "taskA", rank=0, keep=2, asynchronous=True)
+    for r in range(5):
+        cm.save(r, {"round": r, "engine": {"global": torch.full((4,), float(r))}})
+    cm.wait()
+    names = sorted(os.listdir(tmp_path))
+    assert names == ["taskA_3_rank0.ckpt", "taskA_4_rank0.ckpt"]          # {task_id}_{current_round} template, newest 2 kept
+    st = cm.load_latest()
+    assert st["round"] == 4 and torch.equal(st["engine"]["global"], torch.full((4,), 4.0))
+    open(tmp_path / "taskA_5_rank0.ckpt", "wb").write(b"torn write")      # crash mid-save of round 5
+    assert CheckpointManager(str(tmp_path), "taskA").load_latest()["round"] == 4
+    assert CheckpointManager(str(tmp_path), "other").load_latest() is None
+
+
+def test_engine_resume_continues_from_checkpoint(tmp_path):
+    from olearning_sim_b200.control.run_task import RoundRunner
+    tj = make_task_json(task_id="ck", rounds=4, operator_params={"model": "mlp2", "local_steps": 1, "batch": 8, "shard": 8,
+                                                                 "lr": 0.1, "device": "cpu", "backend": "torch"})
+    full = RoundRunner(make_task_json(task_id="ck_full", rounds=4, operator_params=json.loads(
+        tj["operatorflow"]["operators"][0]["logical_simulation"]["operator_params"])))
+    assert full.run()
+    # interrupted after 2 rounds, then restarted with the same checkpoint dir
+    ev = threading.Event()
+    r1 = RoundRunner({**tj, "operatorflow": {**tj["operatorflow"], "flow_setting": {**tj["operatorflow"]["flow_setting"], "round": 2}}},
+                     checkpoint_dir=str(tmp_path))
+    assert r1.run()
+    r2 = RoundRunner(tj, checkpoint_dir=str(tmp_path))
+    assert r2.run()
+    assert [h["round"] for h in r2.history] == [2, 3]                     # rounds 0-1 were not recomputed
+    assert abs(r2.history[-1]["loss"] - full.history[-1]["loss"]) < 1e-5  # same trajectory as the uninterrupted run
+
+
+# ---- operatorflow gates ---------------------------------------------------------------------------------------------------
+def test_gate_waiting_for_global_aggregation_with_fake_clock():
+    clock = {"t": 0, "round": 7}
+    def sleep(s):
+        clock["t"] += s
+        if clock["t"] >= 6:
+            clock["round"] = 8                                            # the aggregator advances after 6 s
+    WaitingForGlobalAggregation.services["tg"] = lambda: clock["round"]
+    p = {"strategy": "waiting_for_global_aggregation", "wait_interval": 2, "total_timeout": 10}
+    of = OperatorFlow("tg", 1, p, p, sleep=sleep)
+    assert of.start(0) and of.stop(0) and clock["t"] == 6
+    clock.update(t=0, round=8)
+    of2 = OperatorFlow("tg", 1, p, {**p, "total_timeout": 4}, sleep=lambda s: clock.update(t=clock["t"] + s))
+    assert of2.start(0) and not of2.stop(0)                               # aggregator never advances -> timeout
+
+
+def test_gate_sample_and_aggregation_markers(tmp_path):
+    src = tmp_path / "all_clients"
+    src.mkdir()
+    for i in range(30):
+        (src / f"client_{i:03d}.bin").write_bytes(b"x")
+    done = []
+    def aggregator(round_idx, folder):
+        done.append((round_idx, len([f for f in os.listdir(folder) if f.startswith("client_")])))
+        open(os.path.join(folder, "aggregation_finished.txt"), "w").write("ok")
+    p = {"strategy": "sample_and_aggregation", "wait_interval": 1, "total_timeout": 3}
+    of = OperatorFlow("ts", 2, p, p, gate_params={"root": str(tmp_path), "sample_num": 10, "aggregator": aggregator},
+                      sleep=lambda s: None)
+    assert of.start(0) and of.stop(0) and done == [(0, 10)]
+    assert os.path.exists(tmp_path / "round_0" / "simulation_finished.txt")
+    p2 = {"strategy": "sample_dc_and_aggregation", "wait_interval": 1, "total_timeout": 1}
+    of2 = OperatorFlow("ts", 1, p2, p2, gate_params={"root": str(tmp_path), "bundle_num": 3, "files_per_bundle": 4}, sleep=lambda s: None)
+    assert of2.start(1) and sorted(os.listdir(tmp_path / "round_1")) == ["bundle_0", "bundle_1", "bundle_2"]
+    assert not of2.stop(1)                                                # nobody wrote aggregation_finished.txt
+    with pytest.raises(ValueError):
+        OperatorFlow("t", 1, {"strategy": "nope"}, {"strategy": ""})
