@@ -54,6 +54,11 @@ class FedConfig:
     device: str = "auto"
     use_cuda_graph: bool = True
     dynamic_nums: int = 0            # tolerated failed clients per round (reference: dynamic_nums)
+    # DeviceFlow integration: the operator's strategy JSON (real_time_dispatch / flow_dispatch) drives
+    # which client updates reach the aggregator each round; `online_trace` is a safe expression in t = round index
+    # (e.g. "0.6+0.4*math.sin(t/4)") scaling p_online — the diurnal online/offline + access-spike trace.
+    deviceflow_strategy: Optional[str] = None
+    online_trace: Optional[str] = None
 
     def __post_init__(self):
         if self.algorithm == "fedprox" and self.mu <= 0:
@@ -115,10 +120,11 @@ class FedEngine:
             dev = f"cuda:{torch.cuda.current_device()}" if torch.cuda.is_available() else "cpu"
         self.device = torch.device(dev)
         backend = cfg.backend
+        native_ok = self.device.type == "cuda" and cfg.model in ("cnn2", "mlp2") and cfg.batch == 32
         if backend == "auto":
-            backend = "native" if (self.device.type == "cuda" and cfg.model == "cnn2") else "torch"
-        if backend == "native" and (self.device.type != "cuda" or cfg.model != "cnn2"):
-            raise RuntimeError("the native backend needs CUDA and the cnn2 family")
+            backend = "native" if native_ok else "torch"
+        if backend == "native" and not native_ok:
+            raise RuntimeError("the native backend needs CUDA, batch 32 and the cnn2 / mlp2 families")
         self.backend = backend
         self.spec = get_model(cfg.model, **cfg.model_kwargs)
         self.c0, self.c1 = shard_range(cfg.num_clients, world, rank)
@@ -139,17 +145,62 @@ class FedEngine:
             self._init_torch()
 
     # ==================================================================================================
+    # DeviceFlow -> per-round masks
+    # ==================================================================================================
+    def _round_flow(self, round_idx: int):
+        """(p_online_scale, drop_probability, arrive_tick[C_local] | None, max_tick) for this round.
+        Flow strategies: the k-th *finishing* participant (order = Philox stream 2) is message k on the shelf; the
+        schedule's slots / drop lists / discarded leftovers then decide whether its update reaches the aggregator."""
+        cfg = self.cfg
+        scale = 1.0
+        if cfg.online_trace:
+            from ..deviceflow import safe_expr
+            scale = float(min(max(safe_expr.evaluate(cfg.online_trace, float(round_idx)), 0.0), 1.0))
+        drop_p, ticks, max_tick = cfg.drop_probability, None, 0
+        if cfg.deviceflow_strategy:
+            import json as _json
+            import random as _random
+            from ..deviceflow.strategy import Strategy, schedule_to_ticks
+            st = cfg.deviceflow_strategy
+            if Strategy.check_real_time_dispatch(st):
+                _, drop_p = Strategy.real_time_strategy_analysis(st)
+            else:
+                flow_id = f"engine_train_{round_idx}"
+                _, amount, drops = Strategy.flow_strategy_analysis(st, flow_id, rng=_random.Random(f"{cfg.seed}:{round_idx}"))
+                n = cfg.num_clients
+                u = philox.round_uniforms(n, 0, cfg.seed, round_idx)
+                pon = np.full(n, cfg.p_online * scale, np.float32)
+                part = u[0] < pon
+                order = np.argsort(np.where(part, u[2], 2.0), kind="stable")        # finishing order of participants
+                slot_of_msg = schedule_to_ticks(amount, drops, int(part.sum()))
+                t_all = np.full(n, -1, np.int32)
+                t_all[order[: int(part.sum())]] = slot_of_msg
+                ticks = t_all[self.c0:self.c1]
+                max_tick = max(len(amount) - 1, 0)
+        return scale, float(drop_p), ticks, max_tick
+
+    # ==================================================================================================
     # native backend
     # ==================================================================================================
     def _init_native(self) -> None:
         from ..parallel.comm import SymmetricHeap
-        from .cnn2_native import Cnn2Workspace
-        assert self.cfg.batch == CNN2.BATCH, f"native cnn2 kernels are compiled for batch {CNN2.BATCH}"
         heap = SymmetricHeap(group=self.group, device=self.device)
-        self.ws = Cnn2Workspace(self.C, self.cfg.shard, device=self.device, heap=heap)
+        if self.cfg.model == "cnn2":
+            from .cnn2_native import Cnn2Workspace
+            self.ws = Cnn2Workspace(self.C, self.cfg.shard, device=self.device, heap=heap)
+            self._g0 = CNN2.init(self.cfg.seed)
+        else:
+            from .mlp_native import MlpLayout, MlpWorkspace
+            sh = dict(self.spec.shapes)
+            lay = MlpLayout(sh["fc1.weight"][1], sh["fc1.weight"][0], sh["fc2.weight"][0])
+            self.ws = MlpWorkspace(self.C, self.cfg.shard, lay, device=self.device, heap=heap)
+            self._g0 = lay.pack(self.spec.init(self.cfg.seed))
         d = self.device
         S = self.cfg.local_steps
         self.p_online_t = torch.full((self.C,), float(self.cfg.p_online), device=d)
+        self.p_online_round = self.p_online_t.clone()
+        self.tick_host = torch.zeros(self.C, dtype=torch.int32).pin_memory()
+        self.tick_dev = torch.zeros(self.C, dtype=torch.int32, device=d)
         self.local_steps_t = torch.from_numpy(self.local_steps_np).to(d)
         self.participate = torch.ones(self.C, dtype=torch.uint8, device=d)
         self.step_active = torch.ones(S, self.C, dtype=torch.uint8, device=d)
@@ -157,20 +208,29 @@ class FedEngine:
         self.counters = torch.zeros(4, dtype=torch.int32, device=d)
         self.result_dev = torch.zeros(8, device=d)
         self.result_host = torch.zeros(8).pin_memory()
-        self.ws.set_global(CNN2.init(self.cfg.seed))
-        self.P = CNN2.P
+        self.ws.set_global(self._g0)
+        self.P = self.ws.P
 
     def _native_round_body(self, round_idx: int) -> None:
         """All device work of one round on the current stream; no host synchronisation."""
         from ..ops import native
         cfg, ws = self.cfg, self.ws
         ws.reset_round_stats()
-        native.deviceflow_mask(self.C, self.c0, cfg.seed, round_idx, self.p_online_t if cfg.p_online < 1.0 else None,
-                               cfg.drop_probability, None, 0, ws.n_samples, self.local_steps_t if cfg.hetero_steps else None,
+        scale, drop_p, ticks, max_tick = self._round_flow(round_idx)
+        sampled = cfg.p_online * scale < 1.0
+        if sampled:
+            self.p_online_round.copy_(self.p_online_t).mul_(scale)
+        tick_t = None
+        if ticks is not None:
+            self.tick_host.copy_(torch.from_numpy(ticks))
+            self.tick_dev.copy_(self.tick_host, non_blocking=True)
+            tick_t = self.tick_dev
+        native.deviceflow_mask(self.C, self.c0, cfg.seed, round_idx, self.p_online_round if sampled else None,
+                               drop_p, tick_t, max_tick, ws.n_samples, self.local_steps_t if cfg.hetero_steps else None,
                                cfg.local_steps, self.participate, self.step_active, self.agg_weight, self.counters)
         ws.kernel_launches += 1
-        need_mask = cfg.p_online < 1.0 or cfg.hetero_steps
-        ws.broadcast(self.participate if cfg.p_online < 1.0 else None)
+        need_mask = sampled or cfg.hetero_steps
+        ws.broadcast(self.participate if sampled else None)
         for s in range(cfg.local_steps):
             ws.local_step(s, lr=cfg.lr, mu=cfg.mu, active=self.step_active[s] if need_mask else None)
         ws.reduce_and_update(self.agg_weight, opt=cfg.server_opt, server_lr=cfg.server_lr)
@@ -222,9 +282,11 @@ class FedEngine:
 
     def _torch_round(self, round_idx: int) -> RoundResult:
         cfg = self.cfg
+        scale, drop_p, ticks, max_tick = self._round_flow(round_idx)
+        sampled = cfg.p_online * scale < 1.0
         m = philox.round_mask(self.C, self.c0, cfg.seed, round_idx,
-                              np.full(self.C, cfg.p_online, np.float32) if cfg.p_online < 1.0 else None,
-                              cfg.drop_probability, None, 0, self.n_samples_np,
+                              np.full(self.C, cfg.p_online * scale, np.float32) if sampled else None,
+                              drop_p, ticks, max_tick, self.n_samples_np,
                               self.local_steps_np if cfg.hetero_steps else None, cfg.local_steps)
         d = self.device
         part = torch.from_numpy(m["participate"].astype(bool)).to(d)
@@ -279,6 +341,8 @@ class FedEngine:
             self.host_y = self.host_y.pin_memory()
         if self.backend == "native":
             self.ws.load_data(self.host_x.to(self.device, non_blocking=True), self.host_y.to(self.device))
+        elif False:
+            pass
         else:
             x = self.host_x.to(self.device)
             if x.dtype == torch.uint8:
@@ -305,6 +369,10 @@ class FedEngine:
             if x.dtype == torch.uint8:
                 x = reference.normalize_u8(x).permute(0, 1, 4, 2, 3).contiguous()
             self.x, self.y = x, self.host_y.to(self.device, non_blocking=True)
+            return nbytes
+        if self.cfg.model != "cnn2":
+            self.ws.x.copy_(self.host_x.to(self.device, non_blocking=True).reshape(self.ws.x.shape))
+            self.ws.labels.copy_(self.host_y.to(self.device, non_blocking=True))
             return nbytes
         if not hasattr(self, "_stage_x"):
             self._copy_stream = torch.cuda.Stream(device=self.device)
@@ -353,6 +421,15 @@ class FedEngine:
     def global_model(self) -> torch.Tensor:
         return self.ws.get_global() if self.backend == "native" else self.global_w
 
+    def spec_flat_global(self) -> torch.Tensor:
+        """The global model in the zoo's flat (torch state_dict order) format, whatever the backend's packing."""
+        g = self.global_model()
+        if self.backend != "native":
+            return g
+        if self.cfg.model == "cnn2":
+            return self.spec.flatten(CNN2.unpack(g))
+        return self.spec.flatten(self.spec.unflatten(self.ws.L.unpack(g.cpu())))
+
     def set_global_model(self, flat: torch.Tensor) -> None:
         if self.backend == "native":
             self.ws.set_global(flat)
@@ -361,17 +438,18 @@ class FedEngine:
 
     def evaluate(self) -> Dict[str, float]:
         """Mean loss / accuracy of the current global model over every local client's shard."""
-        g = self.global_model()
-        if self.backend == "native":
-            x = reference.normalize_u8(self.host_x.to(self.device)[:, :CNN2.BATCH])
-            losses, logits = reference.cnn2_loss(g[None, :].repeat(self.C, 1), x, self.host_y.to(self.device)[:, :CNN2.BATCH])
-            acc = (logits.argmax(-1) == self.host_y.to(self.device)[:, :CNN2.BATCH]).float().mean()
-            out = torch.tensor([losses.mean().item(), acc.item(), 1.0], dtype=torch.float64)
-        else:
-            B = self.cfg.batch
-            w = g[None, :].expand(self.C, -1)
-            l = self._loss_fn(w, self.x[:, :B], self.y[:, :B]).mean()
-            out = torch.tensor([l.item(), float("nan"), 1.0], dtype=torch.float64)
+        g = self.spec_flat_global()
+        B = self.cfg.batch
+        x = self.host_x.to(self.device)[:, :B]
+        y = self.host_y.to(self.device)[:, :B]
+        if x.dtype == torch.uint8:
+            x = reference.normalize_u8(x).permute(0, 1, 4, 2, 3)
+        from torch.func import vmap
+        w = g.to(self.device)[None, :].expand(self.C, -1)
+        logits = vmap(lambda f, xx: self.spec.apply(self.spec.unflatten(f), xx))(w, x.contiguous())
+        loss = torch.nn.functional.cross_entropy(logits.reshape(-1, logits.shape[-1]), y.reshape(-1).long())
+        acc = (logits.argmax(-1) == y).float().mean()
+        out = torch.tensor([loss.item(), acc.item(), 1.0], dtype=torch.float64)
         if self.world > 1:
             t = out.to(self.device) if self.device.type == "cuda" else out
             dist.all_reduce(t, group=self.group)

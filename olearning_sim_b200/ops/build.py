@@ -17,7 +17,7 @@ CSRC = HERE / "csrc"
 LIB = HERE / "_olsb200_kernels.so"
 STAMP = HERE / "_olsb200_kernels.stamp"
 SOURCES = ["api.cu"]
-HEADERS = ["tc05.cuh", "conv_tc.cuh", "fl_kernels.cuh"]
+HEADERS = ["tc05.cuh", "conv_tc.cuh", "fl_kernels.cuh", "linear_tc.cuh"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

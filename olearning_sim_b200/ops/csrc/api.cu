@@ -9,6 +9,7 @@
 
 #include "conv_tc.cuh"
 #include "fl_kernels.cuh"
+#include "linear_tc.cuh"
 
 using namespace convtc;
 using flk::Cnn2Layout;
@@ -89,17 +90,17 @@ int make_w_map(CUtensorMap* tm, const void* base, uint64_t C, int rows, int k, i
 constexpr int BATCH = 32;
 // kernel instances of the CNN-2 family
 //                          ROWB NKW BN  H   W   BATCH  FLIP   EPI         NSTAGE
-#define CONV1_FWD conv_taps_kernel<32, 1, 32, 32, 32, BATCH, false, EPI_POOL, 8>
+#define CONV1_FWD conv_taps_kernel<32, 1, 32, 32, 32, BATCH, false, EPI_POOL, 12, 2>
 #define CONV2_FWD conv_fwd_fold_kernel<32, 64, 16, BATCH, 7>
 #define CONV2_DGRAD conv_dgrad_fold_kernel<32, 64, 16, BATCH, 4>
-using Conv1FwdCfg = FwdCfg<32, 1, 32, 32, 32, BATCH, false, EPI_POOL, 8>;
+using Conv1FwdCfg = FwdCfg<32, 1, 32, 32, 32, BATCH, false, EPI_POOL, 12, 2>;
 using Conv2FwdCfg = FwdFoldCfg<32, 64, 16, BATCH, 7>;
 using Conv2DgradCfg = DgradFoldCfg<32, 64, 16, BATCH, 4>;
 //                              XROWB NKW YROWB H   W   BATCH NSS SYNTH_Y
 #define CONV2_WGRAD conv_wgrad_kernel<64, 5, 128, 16, 16, BATCH, 2, false>
-#define CONV1_WGRAD conv_wgrad_kernel<32, 1, 64, 32, 32, BATCH, 6, true>
+#define CONV1_WGRAD conv_wgrad_kernel<32, 1, 64, 32, 32, BATCH, 8, true, 2>
 using Conv2WgradCfg = WgradCfg<64, 5, 128, 2>;
-using Conv1WgradCfg = WgradCfg<32, 1, 64, 6>;
+using Conv1WgradCfg = WgradCfg<32, 1, 64, 8>;
 
 bool g_attr_set = false;
 int set_attrs() {
@@ -161,7 +162,7 @@ int olsb_conv1_fwd(const void* x5, long long x_total, int x_n_stride, int x_n_of
   p.out = (__nv_bfloat16*)p1; p.code = (uint8_t*)code1;
   const int work = C * p.nsplit;
   const int grid = work < g_sms ? work : g_sms;
-  CONV1_FWD<<<grid, kThreads, Conv1FwdCfg::SMEM_BYTES, (cudaStream_t)stream>>>(tmA, tmW, p);
+  CONV1_FWD<<<grid, Conv1FwdCfg::THREADS, Conv1FwdCfg::SMEM_BYTES, (cudaStream_t)stream>>>(tmA, tmW, p);
   CK(cudaGetLastError());
   return 0;
 }
@@ -244,7 +245,7 @@ int olsb_conv1_wgrad(const void* x5, long long x_total, int x_n_stride, int x_n_
   p.lr = lr; p.mu = mu; p.grad_out = (float*)grad_out;
   p.dpool = (const __nv_bfloat16*)dp1; p.pcode = (const uint8_t*)code1;
   const int grid = C < g_sms ? C : g_sms;
-  CONV1_WGRAD<<<grid, kThreads, Conv1WgradCfg::SMEM_BYTES, (cudaStream_t)stream>>>(tmX, tmX, p);
+  CONV1_WGRAD<<<grid, 320, Conv1WgradCfg::SMEM_BYTES, (cudaStream_t)stream>>>(tmX, tmX, p);
   CK(cudaGetLastError());
   return 0;
 }
@@ -442,4 +443,100 @@ int olsb_memcpy_h2d_async(void* dst, const void* src, unsigned long long bytes, 
   return 0;
 }
 
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// Generic per-client GEMM family (fully-connected layers).  See linear_tc.cuh.
+struct OlsbOperand {            // bf16 tensor [C][rows][inner] with arbitrary strides (elements)
+  const void* base; long long client_stride; long long row_stride; int rows; int inner;
+};
+struct OlsbGemm {
+  int variant;                  // 0 forward (bias+act, transposed store), 1 dgrad (ReLU gate + bias SGD), 2 wgrad (+SGD)
+  int C, M, N, K;
+  OlsbOperand a, b;
+  const void* active; float lr, mu;
+  void* out_t; long long out_stride; int out_ld; const void* bias; long long bias_stride; int relu;
+  const void* mask_t; void* b_master; long long b_stride; const void* b_global; void* db_out;
+  void* w_master; long long w_stride; int w_ld; const void* w_global; void* w_bf16; long long wb_stride;
+  void* grad_out; long long g_stride;
+};
+
+namespace {
+int make_operand_map(CUtensorMap* tm, const OlsbOperand& o, int C, int box_rows) {
+  const uint64_t dims[3] = {(uint64_t)o.inner, (uint64_t)o.rows, (uint64_t)C};
+  const uint64_t str[2] = {(uint64_t)o.row_stride, (uint64_t)o.client_stride};
+  const uint32_t box[3] = {64u, (uint32_t)box_rows, 1u};
+  return make_map(tm, o.base, 3, dims, str, box, 128);
+}
+template <bool A_MN, bool B_MN, int N_TILE, int KC, int EPI, int NSTAGE>
+int launch_gemm(const OlsbGemm* g, cudaStream_t stream) {
+  using Cfg = lintc::GemmCfg<A_MN, B_MN, N_TILE, KC, NSTAGE>;
+  auto kern = lintc::client_gemm_kernel<A_MN, B_MN, N_TILE, KC, EPI, NSTAGE>;
+  static bool attr = false;
+  if (!attr) { CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES)); attr = true; }
+  CUtensorMap tmA, tmB;
+  if (int r = make_operand_map(&tmA, g->a, g->C, A_MN ? KC : 128)) return r;
+  if (int r = make_operand_map(&tmB, g->b, g->C, B_MN ? KC : N_TILE)) return r;
+  lintc::GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.num_clients = g->C; p.M = g->M; p.N = g->N; p.K = g->K;
+  p.m_tiles = (g->M + 127) / 128; p.n_tiles = (g->N + N_TILE - 1) / N_TILE; p.k_chunks = (g->K + KC - 1) / KC;
+  p.active = (const uint8_t*)g->active; p.lr = g->lr; p.mu = g->mu;
+  p.out_t = (__nv_bfloat16*)g->out_t; p.out_stride = g->out_stride; p.out_ld = g->out_ld;
+  p.bias = (const float*)g->bias; p.bias_stride = g->bias_stride; p.relu = g->relu;
+  p.mask_t = (const __nv_bfloat16*)g->mask_t; p.b_master = (float*)g->b_master; p.b_stride = g->b_stride;
+  p.b_global = (const float*)g->b_global; p.db_out = (float*)g->db_out;
+  p.w_master = (float*)g->w_master; p.w_stride = g->w_stride; p.w_ld = g->w_ld; p.w_global = (const float*)g->w_global;
+  p.w_bf16 = (__nv_bfloat16*)g->w_bf16; p.wb_stride = g->wb_stride; p.grad_out = (float*)g->grad_out; p.g_stride = g->g_stride;
+  if (EPI == lintc::EPI_MASK_T && p.n_tiles != 1) { snprintf(g_err, sizeof(g_err), "dgrad epilogue needs the batch in one N tile"); return -4; }
+  const int work = g->C * p.m_tiles * p.n_tiles;
+  const int grid = work < g_sms ? work : g_sms;
+  kern<<<grid, lintc::kThreads, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  CK(cudaGetLastError());
+  return 0;
+}
+}  // namespace
+
+extern "C" {
+int olsb_client_gemm(const OlsbGemm* g, void* stream) {
+  if (int r = olsb_init()) return r;
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (g->variant) {
+    case 0: return launch_gemm<false, false, 32, 64, lintc::EPI_BIAS_ACT_T, 6>(g, st);
+    case 1: return launch_gemm<true, false, 32, 64, lintc::EPI_MASK_T, 6>(g, st);
+    case 2: return launch_gemm<true, true, 256, 32, lintc::EPI_SGD, 6>(g, st);
+    default: snprintf(g_err, sizeof(g_err), "unknown gemm variant %d", g->variant); return -5;
+  }
+}
+
+int olsb_client_xent(int C, int batch, int classes, int ld, const void* active, const void* logits, const void* labels,
+                     int label_stride, int label_off, void* dlogits, void* loss_sum, void* nonfinite, void* b_master,
+                     long long b_stride, const void* b_global, float lr, float mu, void* db_out, void* stream) {
+  lintc::XentParams p;
+  p.num_clients = C; p.batch = batch; p.classes = classes; p.ld = ld; p.active = (const uint8_t*)active;
+  p.logits = (const __nv_bfloat16*)logits; p.labels = (const int32_t*)labels; p.label_stride = label_stride;
+  p.label_off = label_off; p.dlogits = (__nv_bfloat16*)dlogits; p.loss_sum = (float*)loss_sum;
+  p.nonfinite = (int32_t*)nonfinite; p.b_master = (float*)b_master; p.b_stride = b_stride;
+  p.b_global = (const float*)b_global; p.lr = lr; p.mu = mu; p.db_out = (float*)db_out;
+  if (batch > 32 || classes > 16) { snprintf(g_err, sizeof(g_err), "xent kernel supports batch<=32, classes<=16"); return -6; }
+  const int wpb = 4;
+  lintc::client_xent_kernel<<<(C + wpb - 1) / wpb, wpb * 32, 0, (cudaStream_t)stream>>>(p);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int olsb_bcast_scatter_generic(const void* const* global_peers, int nranks, int shard_len, int P, void* global_local,
+                               void* master, void* master_bf16, int C, const void* participate, void* stream) {
+  if (int r = olsb_init()) return r;
+  lintc::BcastGenericParams p;
+  memset(&p, 0, sizeof(p));
+  for (int i = 0; i < nranks && i < 8; ++i) p.global_peers[i] = const_cast<void*>(global_peers[i]);
+  p.nranks = nranks; p.shard_len = shard_len; p.P = P; p.global_local = (float*)global_local; p.master = (float*)master;
+  p.master_bf16 = (__nv_bfloat16*)master_bf16; p.num_clients = C; p.participate = (const uint8_t*)participate;
+  const int th = 256, gx = (P / 4 + th - 1) / th;
+  int gy = (4 * g_sms + gx - 1) / gx; if (gy > C) gy = C; if (gy < 1) gy = 1;
+  lintc::bcast_scatter_generic_kernel<<<dim3(gx, gy), th, 0, (cudaStream_t)stream>>>(p);
+  CK(cudaGetLastError());
+  return 0;
+}
 }  // extern "C"

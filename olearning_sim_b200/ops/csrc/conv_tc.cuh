@@ -36,12 +36,12 @@ constexpr int kTileH = 8, kTileW = 16, kHalo = 2, kBoxH = kTileH + 2 * kHalo;  /
 constexpr int kNKH = 5;
 
 struct Barriers {
-  uint64_t full[8];
-  uint64_t empty[8];
+  uint64_t full[32];
+  uint64_t empty[32];
   uint64_t wfull;
   uint64_t wempty;
-  uint64_t tfull[2];
-  uint64_t tempty[2];
+  uint64_t tfull[4];
+  uint64_t tempty[4];
   uint32_t tmem_base;
   uint32_t pad;
 };
@@ -71,8 +71,10 @@ struct FwdParams {
   float* dbias_out;             // optional [C][BN]: raw bias grad (tests); when set the bias is NOT updated
 };
 
-template <int ROWB, int NKW, int BN, int IMG_H, int IMG_W, int BATCH, bool FLIP, int EPI, int NSTAGE>
+template <int ROWB, int NKW, int BN, int IMG_H, int IMG_W, int BATCH, bool FLIP, int EPI, int NSTAGE, int NEPG = 1>
 struct FwdCfg {
+  static constexpr int NBUF = 2 * NEPG;                  // TMEM accumulator buffers (two per epilogue group)
+  static constexpr int THREADS = (4 * NEPG + 2) * 32;
   static constexpr int KT = ROWB / 2;
   static constexpr int NTAPS = NKW * kNKH;
   static constexpr int W_TAP_BYTES = BN * ROWB;
@@ -80,17 +82,19 @@ struct FwdCfg {
   static constexpr int STAGE_BYTES = kBoxH * kTileW * ROWB;
   static constexpr int TILES_X = IMG_W / kTileW, TILES_Y = IMG_H / kTileH;
   static constexpr int TILES_PER_CLIENT = BATCH * TILES_X * TILES_Y;
-  static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : 256));
+  static constexpr int TMEM_COLS = (NBUF * BN <= 32) ? 32 : (NBUF * BN <= 64 ? 64 : (NBUF * BN <= 128 ? 128 : 256));
   static constexpr int SMEM_BYTES = 1024 + W_BYTES + NSTAGE * STAGE_BYTES + (int)sizeof(Barriers);
+  static_assert(EPI == EPI_POOL || NEPG == 1, "the gate epilogue reduces over one epilogue group");
   static_assert(W_TAP_BYTES % 1024 == 0 || ROWB < 128, "weight tap chunk must keep swizzle alignment");
   static_assert(BN % 32 == 0, "epilogue works on 32-column chunks");
 };
 
-template <int ROWB, int NKW, int BN, int IMG_H, int IMG_W, int BATCH, bool FLIP, int EPI, int NSTAGE>
-__global__ void __launch_bounds__(kThreads, 1)
+template <int ROWB, int NKW, int BN, int IMG_H, int IMG_W, int BATCH, bool FLIP, int EPI, int NSTAGE, int NEPG = 1>
+__global__ void __launch_bounds__((4 * NEPG + 2) * 32, 1)
 conv_taps_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                  const FwdParams p) {
-  using Cfg = FwdCfg<ROWB, NKW, BN, IMG_H, IMG_W, BATCH, FLIP, EPI, NSTAGE>;
+  using Cfg = FwdCfg<ROWB, NKW, BN, IMG_H, IMG_W, BATCH, FLIP, EPI, NSTAGE, NEPG>;
+  constexpr int kProdWarp = 4 * NEPG, kMmaWarp = 4 * NEPG + 1, NBUF = Cfg::NBUF;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* w_sm = smem;
@@ -104,11 +108,11 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     for (int i = 0; i < NSTAGE; ++i) { mbar_init(&bars->full[i], 1); mbar_init(&bars->empty[i], 1); }
     mbar_init(&bars->wfull, 1);
     mbar_init(&bars->wempty, 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(&bars->tfull[i], 1); mbar_init(&bars->tempty[i], kEpiWarps); }
+    for (int i = 0; i < NBUF; ++i) { mbar_init(&bars->tfull[i], 1); mbar_init(&bars->tempty[i], kEpiWarps); }
     fence_mbar_init();
   }
-  if (warp == 5) { tmem_alloc(&bars->tmem_base, Cfg::TMEM_COLS); tmem_relinquish(); }
-  if (warp == 4 && lane == 0) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmW); }
+  if (warp == kMmaWarp) { tmem_alloc(&bars->tmem_base, Cfg::TMEM_COLS); tmem_relinquish(); }
+  if (warp == kProdWarp && lane == 0) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmW); }
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
@@ -117,7 +121,7 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int num_work = p.num_clients * p.nsplit;
   const int tiles_per_work = (Cfg::TILES_PER_CLIENT + p.nsplit - 1) / p.nsplit;
 
-  if (warp == 4) {
+  if (warp == kProdWarp) {
     // ------------------------------------------------------------------ TMA producer (warp-converged)
     const bool leader = elect_one();
     int stage = 0; uint32_t phase = 0; int cur_client = -1; uint32_t wphase = 0; bool first_w = true;
@@ -156,7 +160,7 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == kMmaWarp) {
     // ------------------------------------------------------------------ MMA issuer (warp-converged)
     const bool leader = elect_one();
     constexpr uint32_t LT = layout_type_for_row_bytes(ROWB);
@@ -164,7 +168,7 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const uint64_t a_desc_base = make_smem_desc(smem_u32(a_sm), 16, 8 * ROWB, LT);
     const uint64_t b_desc_base = make_smem_desc(smem_u32(w_sm), 16, 8 * ROWB, LT);
     int stage = 0; uint32_t phase = 0; int cur_client = -1; uint32_t wphase = 0;
-    int buf = 0; uint32_t tphase0 = 0, tphase1 = 0;
+    uint32_t seq = 0;                                    // tiles issued by this CTA: buffer = seq % NBUF
     for (int wi = blockIdx.x; wi < num_work; wi += gridDim.x) {
       const int c = wi / p.nsplit, sp = wi % p.nsplit;
       if (p.active && !p.active[c]) continue;
@@ -177,7 +181,8 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int t0 = sp * tiles_per_work;
       const int t1 = min(t0 + tiles_per_work, Cfg::TILES_PER_CLIENT);
       for (int t = t0; t < t1; ++t) {
-        mbar_wait(&bars->tempty[buf], (buf ? tphase1 : tphase0) ^ 1);
+        const int buf = seq % NBUF;
+        mbar_wait(&bars->tempty[buf], ((seq / NBUF) & 1) ^ 1);
         fence_after_sync();
         const uint32_t d_tmem = tmem_base + buf * BN;
         uint32_t acc = 0;
@@ -207,8 +212,7 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         if (leader) umma_commit(&bars->tfull[buf]);
         __syncwarp();
-        if (buf) tphase1 ^= 1; else tphase0 ^= 1;
-        buf ^= 1;
+        ++seq;
       }
       if (last_of_client) {
         if (leader) umma_commit(&bars->wempty);
@@ -217,8 +221,9 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else {
     // ------------------------------------------------------------------ epilogue warps (TMEM lanes 32*warp ..)
-    int buf = 0; uint32_t tphase0 = 0, tphase1 = 0;
-    const int q = warp;  // 0..3
+    uint32_t seq = 0;
+    const int q = warp & 3;            // TMEM lane quarter
+    const int grp = warp >> 2;         // epilogue group: handles tiles with seq % NEPG == grp
     const int hl = 2 * q + (lane >> 4), wl = lane & 15;
     constexpr int NDB = (EPI == EPI_GATE) ? BN : 1;
     float dbacc[NDB];
@@ -289,7 +294,10 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int r = t % (Cfg::TILES_X * Cfg::TILES_Y);
         const int h0 = (r / Cfg::TILES_X) * kTileH, w0 = (r % Cfg::TILES_X) * kTileW;
         const size_t n_out = (size_t)c * BATCH + s;
-        mbar_wait(&bars->tfull[buf], buf ? tphase1 : tphase0);
+        const uint32_t myseq = seq++;
+        if ((int)(myseq % NEPG) != grp) continue;
+        const int buf = myseq % NBUF;
+        mbar_wait(&bars->tfull[buf], (myseq / NBUF) & 1);
         fence_after_sync();
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(32 * q) << 16) + buf * BN;
 
@@ -374,8 +382,6 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         fence_before_sync();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars->tempty[buf]);
-        if (buf) tphase1 ^= 1; else tphase0 ^= 1;
-        buf ^= 1;
       }
     }
     if (cur_client >= 0) flush_bias(cur_client);
@@ -383,7 +389,7 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   fence_before_sync();
   __syncthreads();
-  if (warp == 5) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  if (warp == kMmaWarp) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
 // ================================================================================================
@@ -912,8 +918,8 @@ struct WgradCfg {
   static_assert(SS_BYTES % 1024 == 0, "superstage must keep 1024B alignment");
 };
 
-template <int XROWB, int NKW, int YROWB, int IMG_H, int IMG_W, int BATCH, int NSS, bool SYNTH_Y>
-__global__ void __launch_bounds__(kThreads, 1)
+template <int XROWB, int NKW, int YROWB, int IMG_H, int IMG_W, int BATCH, int NSS, bool SYNTH_Y, int NEPG = 1>
+__global__ void __launch_bounds__((4 * NEPG + 2) * 32, 1)
 conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
                   const WgradParams p) {
   using Cfg = WgradCfg<XROWB, NKW, YROWB, NSS>;
@@ -921,6 +927,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   constexpr int TILES_X = IMG_W / kTileW, TILES_Y = IMG_H / kTileH;
   constexpr int CHUNKS = BATCH * TILES_X * TILES_Y;   // pixel chunks (K dimension, 128 pixels each)
   static_assert(!SYNTH_Y || YROWB == 64, "operand synthesis is written for 32 output channels (SW64 rows)");
+  static_assert(SYNTH_Y || NEPG == 1, "extra epilogue groups only help the operand-synthesis variant");
+  constexpr int kProdWarp = 4 * NEPG, kMmaWarp = 4 * NEPG + 1;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   Barriers* bars = reinterpret_cast<Barriers*>(smem + NSS * Cfg::SS_BYTES);
@@ -933,14 +941,14 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     mbar_init(&bars->tempty[0], kEpiWarps);
     fence_mbar_init();
   }
-  if (warp == 5) { tmem_alloc(&bars->tmem_base, Cfg::TMEM_COLS); tmem_relinquish(); }
-  if (warp == 4 && lane == 0) { tma_prefetch_desc(&tmX); if (!SYNTH_Y) tma_prefetch_desc(&tmY); }
+  if (warp == kMmaWarp) { tmem_alloc(&bars->tmem_base, Cfg::TMEM_COLS); tmem_relinquish(); }
+  if (warp == kProdWarp && lane == 0) { tma_prefetch_desc(&tmX); if (!SYNTH_Y) tma_prefetch_desc(&tmY); }
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem_base = bars->tmem_base;
 
-  if (warp == 4) {
+  if (warp == kProdWarp) {
     const bool leader = elect_one();
     int ss = 0; uint32_t phase = 0;
     for (int c = blockIdx.x; c < p.num_clients; c += gridDim.x) {
@@ -972,7 +980,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         if (++ss == NSS) { ss = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == kMmaWarp) {
     const bool leader = elect_one();
     constexpr uint32_t LTX = layout_type_for_row_bytes(XROWB);
     constexpr uint32_t LTY = layout_type_for_row_bytes(YROWB);
@@ -1016,10 +1024,11 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     }
   } else {
     uint32_t tphase = 0;
-    const int q = warp;
+    const int q = warp & 3;
+    const int grp = warp >> 2;              // synthesis group: owns chunks with (running chunk index) % NEPG == grp
     const int L = 32 * q + lane;            // accumulator row / (SYNTH_Y) pixel of the chunk
+    uint32_t cseq = 0;                      // running chunk index of this CTA: stage = cseq % NSS
     const int ci = L / KT, cin = L % KT;    // chunk index inside the M tile, input channel
-    int ss = 0; uint32_t phase = 0;
     for (int c = blockIdx.x; c < p.num_clients; c += gridDim.x) {
       if (p.active && !p.active[c]) continue;
       if (SYNTH_Y) {
@@ -1036,9 +1045,12 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         // register ring, kDepth chunks of global loads in flight per thread (hides ~kDepth x the per-chunk work)
         constexpr int kDepth = 4;
         uint4 gq[kDepth][4], cq[kDepth][2];
-        auto issue = [&](int t, int slot) {
-          if (t < CHUNKS) {
-            const size_t pb = src_off(t);
+        // this group's chunks of the client: t = first + NEPG*i
+        const int first = (int)((grp + NEPG - (cseq % NEPG)) % NEPG);
+        const int mine = (CHUNKS - first + NEPG - 1) / NEPG;
+        auto issue = [&](int i, int slot) {
+          if (i < mine) {
+            const size_t pb = src_off(first + NEPG * i);
 #pragma unroll
             for (int k = 0; k < 4; ++k) gq[slot][k] = __ldg(reinterpret_cast<const uint4*>(p.dpool + pb + k * 8));
 #pragma unroll
@@ -1048,25 +1060,27 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
 #pragma unroll
         for (int d = 0; d < kDepth - 1; ++d) issue(d, d);
 #pragma unroll 1
-        for (int tb = 0; tb < CHUNKS; tb += kDepth) {
+        for (int ib = 0; ib < mine; ib += kDepth) {
 #pragma unroll
           for (int u = 0; u < kDepth; ++u) {
-            const int t = tb + u;
-            if (t >= CHUNKS) break;
-            issue(t + kDepth - 1, (u + kDepth - 1) % kDepth);
+            const int i = ib + u;
+            if (i >= mine) break;
+            issue(i + kDepth - 1, (u + kDepth - 1) % kDepth);
             const uint32_t* gw = reinterpret_cast<const uint32_t*>(gq[u]);
             const uint32_t* cw = reinterpret_cast<const uint32_t*>(cq[u]);
             uint4 o[4];
             uint32_t* ow = reinterpret_cast<uint32_t*>(o);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {                         // channel pair (2i, 2i+1)
-              const uint32_t c2 = (cw[i >> 1] >> ((i & 1) * 16)) & 0xFFFFu;
-              uint32_t val = gw[i];
+            for (int e = 0; e < 16; ++e) {                         // channel pair (2e, 2e+1)
+              const uint32_t c2 = (cw[e >> 1] >> ((e & 1) * 16)) & 0xFFFFu;
+              uint32_t val = gw[e];
               if ((c2 & 0xFFu) != (uint32_t)posy) val &= 0xFFFF0000u;
               if ((c2 >> 8) != (uint32_t)posy) val &= 0x0000FFFFu;
-              ow[i] = val;
+              ow[e] = val;
             }
-            mbar_wait(&bars->empty[ss], phase ^ 1);
+            const uint32_t gs = cseq + first + NEPG * i;           // global chunk sequence number
+            const int ss = gs % NSS;
+            mbar_wait(&bars->empty[ss], ((gs / NSS) & 1) ^ 1);
             uint8_t* ybase = smem + ss * Cfg::SS_BYTES + NKW * Cfg::XSTAGE + L * YROWB;
             const int sw = (L >> 1) & 3;                           // SW64: 16B-chunk index ^= bits[7:8] of the byte address
 #pragma unroll
@@ -1074,10 +1088,11 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(&bars->full[ss]);
-            if (++ss == NSS) { ss = 0; phase ^= 1; }
           }
         }
+        cseq += CHUNKS;
       }
+      if (grp != 0) continue;                                       // group 0 drains TMEM / applies the update
       mbar_wait(&bars->tfull[0], tphase);
       fence_after_sync();
       float* wm = p.w_master + (size_t)c * p.p_stride + p.w_off;
@@ -1148,7 +1163,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   }
   fence_before_sync();
   __syncthreads();
-  if (warp == 5) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  if (warp == kMmaWarp) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
 }  // namespace convtc

@@ -158,40 +158,67 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_fc_xent_kernel(const Hea
   for (int c = blockIdx.x; c < p.num_clients; c += gridDim.x) {
     if (p.active && !p.active[c]) continue;
     float* wm = p.master + (size_t)c * p.P;
-    for (int i = tid * 4; i < L::WFC_N; i += kHeadThreads * 4)
-      *reinterpret_cast<float4*>(Ws + i) = *reinterpret_cast<const float4*>(wm + L::WFC + i);
+    // 40 float4 per thread, 8 loads in flight per thread before the first shared-memory store
+#pragma unroll 1
+    for (int i0 = tid * 4; i0 < L::WFC_N; i0 += kHeadThreads * 4 * 8) {
+      float4 t8[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) t8[u] = __ldg(reinterpret_cast<const float4*>(wm + L::WFC + i0 + u * kHeadThreads * 4));
+#pragma unroll
+      for (int u = 0; u < 8; ++u) *reinterpret_cast<float4*>(Ws + i0 + u * kHeadThreads * 4) = t8[u];
+    }
     if (tid < 64) db2[tid] = 0.f;
     __syncthreads();
 
-    // ---- logits
+    // ---- logits: a warp owns 4 samples; per k-chunk the 10 weight rows are read from smem once and reused for
+    // the 4 samples, and the activations of the next chunk are already in flight (register double buffer)
     const __nv_bfloat16* x = p.p2 + (size_t)c * 32 * 4096;
-    for (int si = 0; si < 4; ++si) {
-      const int s = warp * 4 + si;
-      float acc[10];
+    {
+      float acc[4][10];
 #pragma unroll
-      for (int j = 0; j < 10; ++j) acc[j] = 0.f;
+      for (int si = 0; si < 4; ++si)
+#pragma unroll
+        for (int j = 0; j < 10; ++j) acc[si][j] = 0.f;
+      const __nv_bfloat16* xw = x + (size_t)(warp * 4) * 4096 + lane * 8;
+      uint4 nxt[4];
+#pragma unroll
+      for (int si = 0; si < 4; ++si) nxt[si] = __ldg(reinterpret_cast<const uint4*>(xw + (size_t)si * 4096));
+#pragma unroll 1
       for (int k = lane * 8; k < 4096; k += 256) {
-        const uint4 xv = *reinterpret_cast<const uint4*>(x + (size_t)s * 4096 + k);
-        const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w};
-        float xf[8];
+        uint4 cur[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) { xf[2 * e] = __uint_as_float(xw[e] << 16); xf[2 * e + 1] = __uint_as_float(xw[e] & 0xFFFF0000u); }
+        for (int si = 0; si < 4; ++si) cur[si] = nxt[si];
+        if (k + 256 < 4096) {
+#pragma unroll
+          for (int si = 0; si < 4; ++si) nxt[si] = __ldg(reinterpret_cast<const uint4*>(xw + (size_t)si * 4096 + (k - lane * 8) + 256));
+        }
+        float xf[4][8];
+#pragma unroll
+        for (int si = 0; si < 4; ++si) {
+          const uint32_t xw4[4] = {cur[si].x, cur[si].y, cur[si].z, cur[si].w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) { xf[si][2 * e] = __uint_as_float(xw4[e] << 16); xf[si][2 * e + 1] = __uint_as_float(xw4[e] & 0xFFFF0000u); }
+        }
 #pragma unroll
         for (int j = 0; j < 10; ++j) {
           const float4 w0 = *reinterpret_cast<const float4*>(Ws + j * 4096 + k);
           const float4 w1 = *reinterpret_cast<const float4*>(Ws + j * 4096 + k + 4);
-          acc[j] += xf[0] * w0.x + xf[1] * w0.y + xf[2] * w0.z + xf[3] * w0.w + xf[4] * w1.x + xf[5] * w1.y +
-                    xf[6] * w1.z + xf[7] * w1.w;
+#pragma unroll
+          for (int si = 0; si < 4; ++si)
+            acc[si][j] += xf[si][0] * w0.x + xf[si][1] * w0.y + xf[si][2] * w0.z + xf[si][3] * w0.w +
+                          xf[si][4] * w1.x + xf[si][5] * w1.y + xf[si][6] * w1.z + xf[si][7] * w1.w;
         }
       }
 #pragma unroll
-      for (int j = 0; j < 10; ++j) {
-        float v = acc[j];
-        v += __shfl_xor_sync(0xffffffffu, v, 16); v += __shfl_xor_sync(0xffffffffu, v, 8);
-        v += __shfl_xor_sync(0xffffffffu, v, 4);  v += __shfl_xor_sync(0xffffffffu, v, 2);
-        v += __shfl_xor_sync(0xffffffffu, v, 1);
-        if (lane == 0) logit[s * 10 + j] = v + wm[L::BFC + j];
-      }
+      for (int si = 0; si < 4; ++si)
+#pragma unroll
+        for (int j = 0; j < 10; ++j) {
+          float v = acc[si][j];
+          v += __shfl_xor_sync(0xffffffffu, v, 16); v += __shfl_xor_sync(0xffffffffu, v, 8);
+          v += __shfl_xor_sync(0xffffffffu, v, 4);  v += __shfl_xor_sync(0xffffffffu, v, 2);
+          v += __shfl_xor_sync(0xffffffffu, v, 1);
+          if (lane == 0) logit[(warp * 4 + si) * 10 + j] = v + wm[L::BFC + j];
+        }
     }
     __syncthreads();
 
@@ -242,14 +269,25 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_fc_xent_kernel(const Hea
       float dbl0 = 0.f, dbl1 = 0.f;
       // 8 samples per batch: all global loads of a batch are issued before the first dependent store, so the
       // L2/HBM latency is paid once per batch instead of once per sample
+      uint32_t xn8[8];
+      uint16_t cn8[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        xn8[u] = __ldg(reinterpret_cast<const uint32_t*>(x + (size_t)u * 4096 + k));
+        cn8[u] = __ldg(reinterpret_cast<const uint16_t*>(code + (size_t)u * 4096 + k));
+      }
 #pragma unroll 1
       for (int s0 = 0; s0 < 32; s0 += 8) {
         uint32_t xr8[8];
         uint16_t cr8[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          xr8[u] = __ldg(reinterpret_cast<const uint32_t*>(x + (size_t)(s0 + u) * 4096 + k));
-          cr8[u] = __ldg(reinterpret_cast<const uint16_t*>(code + (size_t)(s0 + u) * 4096 + k));
+        for (int u = 0; u < 8; ++u) { xr8[u] = xn8[u]; cr8[u] = cn8[u]; }
+        if (s0 + 8 < 32) {
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            xn8[u] = __ldg(reinterpret_cast<const uint32_t*>(x + (size_t)(s0 + 8 + u) * 4096 + k));
+            cn8[u] = __ldg(reinterpret_cast<const uint16_t*>(code + (size_t)(s0 + 8 + u) * 4096 + k));
+          }
         }
 #pragma unroll
         for (int u = 0; u < 8; ++u) {

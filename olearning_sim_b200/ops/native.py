@@ -194,4 +194,61 @@ def philox_host(c0, c1, c2, c3, k0, k1):
     return tuple(int(v) for v in out)
 
 
+# --------------------------------------------------------------------------------------------------
+# generic per-client GEMM family (fully-connected layers) — csrc/linear_tc.cuh
+class Operand(C.Structure):
+    _fields_ = [("base", C.c_void_p), ("client_stride", C.c_longlong), ("row_stride", C.c_longlong),
+                ("rows", C.c_int), ("inner", C.c_int)]
+
+
+class GemmArgs(C.Structure):
+    _fields_ = [("variant", C.c_int), ("C", C.c_int), ("M", C.c_int), ("N", C.c_int), ("K", C.c_int),
+                ("a", Operand), ("b", Operand), ("active", C.c_void_p), ("lr", C.c_float), ("mu", C.c_float),
+                ("out_t", C.c_void_p), ("out_stride", C.c_longlong), ("out_ld", C.c_int),
+                ("bias", C.c_void_p), ("bias_stride", C.c_longlong), ("relu", C.c_int),
+                ("mask_t", C.c_void_p), ("b_master", C.c_void_p), ("b_stride", C.c_longlong), ("b_global", C.c_void_p),
+                ("db_out", C.c_void_p),
+                ("w_master", C.c_void_p), ("w_stride", C.c_longlong), ("w_ld", C.c_int), ("w_global", C.c_void_p),
+                ("w_bf16", C.c_void_p), ("wb_stride", C.c_longlong), ("grad_out", C.c_void_p), ("g_stride", C.c_longlong)]
+
+
+GEMM_FWD, GEMM_DGRAD, GEMM_WGRAD = 0, 1, 2
+
+
+def operand(t: torch.Tensor, elem_offset: int, client_stride: int, row_stride: int, rows: int, inner: int) -> Operand:
+    """bf16 operand view [C][rows][inner] inside tensor `t` (strides in elements).  TMA needs 16-byte aligned bases
+    and strides."""
+    assert t.dtype == torch.bfloat16 and t.is_cuda
+    base = t.data_ptr() + 2 * elem_offset
+    assert base % 16 == 0 and (client_stride * 2) % 16 == 0 and (row_stride * 2) % 16 == 0, "TMA alignment"
+    return Operand(C.c_void_p(base), client_stride, row_stride, rows, inner)
+
+
+def _vp(t: Optional[torch.Tensor], elem_offset: int = 0):
+    if t is None:
+        return None
+    return C.c_void_p(t.data_ptr() + t.element_size() * elem_offset)
+
+
+def client_gemm(args: GemmArgs) -> None:
+    _ck(require().olsb_client_gemm(C.byref(args), _stream()))
+
+
+def client_xent(num_clients, batch, classes, ld, active, logits, labels, label_off, dlogits, loss_sum, nonfinite,
+                b_master=None, b_offset=0, b_stride=0, b_global=None, lr=0.0, mu=0.0, db_out=None) -> None:
+    _ck(require().olsb_client_xent(C.c_int(num_clients), C.c_int(batch), C.c_int(classes), C.c_int(ld), _p(active),
+                                   _p(logits), _p(labels), C.c_int(labels.shape[1]), C.c_int(label_off), _p(dlogits),
+                                   _p(loss_sum), _p(nonfinite), _vp(b_master, b_offset), C.c_longlong(b_stride),
+                                   _vp(b_global, b_offset) if b_global is not None else None, C.c_float(lr),
+                                   C.c_float(mu), _p(db_out), _stream()))
+
+
+def bcast_scatter_generic(global_peer_ptrs: Sequence[int], shard_len: int, P: int, global_local, master, master_bf16,
+                          participate) -> None:
+    n = len(global_peer_ptrs)
+    _ck(require().olsb_bcast_scatter_generic(_ptr_array(global_peer_ptrs), C.c_int(n), C.c_int(shard_len), C.c_int(P),
+                                             _p(global_local), _p(master), _p(master_bf16), C.c_int(master.shape[0]),
+                                             _p(participate), _stream()))
+
+
 assert CNN2.P % 4 == 0

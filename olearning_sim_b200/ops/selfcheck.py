@@ -324,10 +324,116 @@ def check_mask(c: int) -> Dict:
     return {"err": 0.0 if ok else 1.0, "tol": 0.5, "counters": cnt.cpu().tolist()}
 
 
+# ---- generic per-client GEMM family (linear_tc.cuh) ------------------------------------------------------------
+def _mlp_ws(c: int, shard: int = 64):
+    from ..engine.mlp_native import MlpLayout, MlpWorkspace
+    from ..models.zoo import get_model
+    ws = MlpWorkspace(c, shard, MlpLayout(), device="cuda")
+    spec = get_model("mlp2")
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(c, shard, 784, generator=g)
+    y = torch.randint(0, 10, (c, shard), generator=g, dtype=torch.int32)
+    ws.load_data(x, y)
+    rows = torch.stack([ws.L.pack(spec.init(100 + i)) for i in range(c)]).cuda()
+    ws.master.copy_(rows)
+    ws.master_bf16.copy_(rows.to(torch.bfloat16))
+    ws.global_local.copy_(rows[0])
+    return ws, spec
+
+
+def check_gemm(c: int) -> Dict:
+    """the three GEMM variants against torch on the MLP-2 shapes (K tails, M=10 row tile, N=784 with a partial tile)"""
+    ws, _ = _mlp_ws(c)
+    L, P = ws.L, ws.P
+    op, vp = native.operand, native._vp
+    off = B
+    Xf = ws.x[:, off:off + B].float()
+    W1 = ws.master_bf16[:, L.W1:L.W1 + 200 * 784].float().reshape(c, 200, 784)
+    W2 = ws.master_bf16[:, L.W2:L.W2 + 2000].float().reshape(c, 10, 200)
+    b1 = ws.master[:, L.B1:L.B1 + 200]
+    res = {}
+    # forward (K-major x K-major, bias + ReLU, transposed store), K = 784 = 12*64 + 16
+    a = native.GemmArgs(variant=native.GEMM_FWD, C=c, M=200, N=B, K=784, a=op(ws.master_bf16, L.W1, P, 784, 200, 784),
+                        b=op(ws.x, off * 784, ws.shard * 784, 784, B, 784), out_t=vp(ws.h), out_stride=B * 200, out_ld=200,
+                        bias=vp(ws.master, L.B1), bias_stride=P, relu=1)
+    native.client_gemm(a)
+    href = torch.relu(torch.bmm(Xf, W1.transpose(1, 2)) + b1[:, None, :])
+    res["fwd"] = rel_err(ws.h.float(), href)
+    # dgrad (A MN-major, K = 10), ReLU gate + raw bias gradient
+    dl = (torch.randn(c, B, 16, device="cuda") * 0.1)
+    dl[..., 10:] = 0
+    ws.dlogits.copy_(dl.to(torch.bfloat16))
+    dbo = torch.zeros(c, 200, device="cuda")
+    a = native.GemmArgs(variant=native.GEMM_DGRAD, C=c, M=200, N=B, K=10, a=op(ws.master_bf16, L.W2, P, 200, 10, 200),
+                        b=op(ws.dlogits, 0, B * 16, 16, B, 16), out_t=vp(ws.dh), out_stride=B * 200, out_ld=200,
+                        mask_t=vp(ws.h), db_out=vp(dbo))
+    native.client_gemm(a)
+    dlf = ws.dlogits.float()[..., :10]
+    dh_ref = torch.bmm(dlf, W2) * (ws.h.float() > 0)
+    res["dgrad"] = rel_err(ws.dh.float(), dh_ref)
+    res["db"] = rel_err(dbo, dh_ref.sum(1))
+    # wgrad (both MN-major, K = batch), N = 784 -> 4 N tiles, the last one 16 wide
+    gout = torch.zeros(c, 200 * 784, device="cuda")
+    a = native.GemmArgs(variant=native.GEMM_WGRAD, C=c, M=200, N=784, K=B, a=op(ws.dh, 0, B * 200, 200, B, 200),
+                        b=op(ws.x, off * 784, ws.shard * 784, 784, B, 784), w_ld=784, grad_out=vp(gout), g_stride=200 * 784)
+    native.client_gemm(a)
+    gref = torch.bmm(ws.dh.float().transpose(1, 2), Xf).reshape(c, -1)
+    res["wgrad"] = rel_err(gout, gref)
+    # wgrad with fused SGD on the small layer (M = 10)
+    m0 = ws.master.clone()
+    a = native.GemmArgs(variant=native.GEMM_WGRAD, C=c, M=10, N=200, K=B, a=op(ws.dlogits, 0, B * 16, 16, B, 16),
+                        b=op(ws.h, 0, B * 200, 200, B, 200), lr=0.5, w_master=vp(ws.master, L.W2), w_stride=P, w_ld=200,
+                        w_bf16=vp(ws.master_bf16, L.W2), wb_stride=P)
+    native.client_gemm(a)
+    torch.cuda.synchronize()
+    exp = m0[:, L.W2:L.W2 + 2000] - 0.5 * torch.bmm(dlf.transpose(1, 2), ws.h.float()).reshape(c, -1)
+    res["sgd"] = rel_err(ws.master[:, L.W2:L.W2 + 2000], exp)
+    res["sgd_bf16"] = rel_err(ws.master_bf16[:, L.W2:L.W2 + 2000].float(), exp.to(torch.bfloat16).float())
+    untouched = torch.cat([ws.master[:, :L.W2], ws.master[:, L.W2 + 2000:]], 1) - torch.cat([m0[:, :L.W2], m0[:, L.W2 + 2000:]], 1)
+    res["untouched"] = float(untouched.abs().max())
+    res["err"] = max(res["fwd"], res["dgrad"], res["db"], res["wgrad"], res["sgd"], res["sgd_bf16"], res["untouched"])
+    res["tol"] = 1e-2
+    ws.close()
+    return res
+
+
+def check_mlp_step(c: int) -> Dict:
+    """six-launch MLP local step vs autograd SGD on the same bf16-rounded operands"""
+    ws, spec = _mlp_ws(c)
+    L = ws.L
+    g0 = ws.L.pack(spec.init(7)).cuda()
+    ws.set_global(g0)
+    ws.broadcast()
+    lr = 0.1
+    ws.local_step(0, lr=lr)
+    torch.cuda.synchronize()
+    x = ws.x[:, :B].float()
+    y = ws.labels[:, :B].long()
+    w = g0[None, :].repeat(c, 1).clone().requires_grad_(True)
+    wq = w.detach().to(torch.bfloat16).float() + (w - w.detach())   # bf16-rounded operand values, identity gradient
+    W1 = wq[:, L.W1:L.W1 + 200 * 784].reshape(c, 200, 784)
+    W2 = wq[:, L.W2:L.W2 + 2000].reshape(c, 10, 200)
+    h = torch.relu(torch.bmm(x, W1.transpose(1, 2)) + w[:, None, L.B1:L.B1 + 200])
+    hq = h.detach().to(torch.bfloat16).float() + (h - h.detach())
+    lg = torch.bmm(hq, W2.transpose(1, 2)) + w[:, None, L.B2:L.B2 + 10]
+    loss = F.cross_entropy(lg.reshape(c * B, 10), y.reshape(-1), reduction="none").reshape(c, B).mean(1)
+    (g,) = torch.autograd.grad(loss.sum(), w)
+    new = g0[None, :] - lr * g
+    d_k, d_r = ws.master - g0[None, :], new - g0[None, :]
+    res = {"loss": rel_err(ws.loss_sum, loss.detach()), "delta": rel_err(d_k, d_r), "tol": 5e-2}
+    for name, o, n in (("W1", L.W1, 200 * 784), ("b1", L.B1, 200), ("W2", L.W2, 2000), ("b2", L.B2, 10)):
+        res[f"d_{name}"] = rel_err(d_k[:, o:o + n], d_r[:, o:o + n])
+        res[f"n_{name}"] = float(d_r[:, o:o + n].norm())
+    res["err"] = max(res["loss"], res["delta"])
+    ws.close()
+    return res
+
+
 CHECKS: Dict[str, Callable[[int], Dict]] = {
     "ingest": check_ingest, "conv1_fwd": check_conv1_fwd, "conv2_fwd": check_conv2_fwd, "head": check_head,
     "conv2_dgrad": check_conv2_dgrad, "conv2_wgrad": check_conv2_wgrad, "conv1_wgrad": check_conv1_wgrad,
     "bcast": check_bcast, "reduce": check_reduce, "mask": check_mask, "local_step": check_local_step,
+    "gemm": check_gemm, "mlp_step": check_mlp_step,
 }
 
 

@@ -13,7 +13,7 @@ def sc():
 
 
 @pytest.mark.parametrize("name", ["ingest", "bcast", "reduce", "mask", "conv1_fwd", "conv2_fwd", "head",
-                                  "conv2_dgrad", "conv2_wgrad", "conv1_wgrad", "local_step"])
+                                  "conv2_dgrad", "conv2_wgrad", "conv1_wgrad", "local_step", "gemm", "mlp_step"])
 @pytest.mark.parametrize("clients", [3, 150])
 def test_kernel_matches_oracle(sc, name, clients):
     torch.manual_seed(1234 + clients)
@@ -50,4 +50,23 @@ def test_engine_round_native_vs_torch_backend():
         db = gb[k].cpu() - CNN2.unpack(g0)[k]
         rel = (da - db).norm() / (db.norm() + 1e-12)
         assert rel < 8e-2, (k, float(rel))
+    a.close()
+
+
+def test_engine_mlp_native_vs_torch_backend():
+    """MLP-2 through the generic tcgen05 GEMM family vs the torch.func backend (same seeds / data / masks)."""
+    from olearning_sim_b200.engine.fed_engine import FedConfig, FedEngine
+    kw = dict(model="mlp2", num_clients=10, local_steps=2, shard=64, lr=0.1, p_online=0.8, drop_probability=0.2,
+              hetero_steps=True, seed=5)
+    a = FedEngine(FedConfig(backend="native", **kw)); a.load_synthetic()
+    b = FedEngine(FedConfig(backend="torch", **kw)); b.load_synthetic()
+    assert a.backend == "native" and a.kernel_launches() == 0
+    ra, rb = a.run_round(0), b.run_round(0)
+    assert a.kernel_launches() == 1 + 1 + 2 * 6 + 2
+    assert (ra.participants, ra.dropped, ra.arrived, ra.client_steps) == (rb.participants, rb.dropped, rb.arrived, rb.client_steps)
+    assert abs(ra.loss - rb.loss) < 3e-2 * max(1.0, abs(rb.loss)), (ra, rb)
+    ga, gb = a.spec_flat_global().cpu(), b.spec_flat_global().cpu()
+    g0 = a.spec.init(5)
+    rel = ((ga - g0) - (gb - g0)).norm() / (gb - g0).norm()
+    assert rel < 8e-2, float(rel)
     a.close()

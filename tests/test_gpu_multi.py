@@ -1,0 +1,24 @@
+"""Multi-GPU: the fused P2P broadcast / reduce kernels over N ranks must reproduce the single-rank model."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
+@pytest.mark.parametrize("opt", ["avg", "adam"])
+def test_two_ranks_match_single_rank(opt):
+    env = dict(os.environ, OPT=opt, CLIENTS="40")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29533" if opt == "avg" else "29534", os.path.join(ROOT, "tools", "mgpu_check.py")]
+    out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert lines, out.stderr[-2000:]
+    res = json.loads(lines[-1])
+    assert res["world"] == 2 and res["ok"], res
