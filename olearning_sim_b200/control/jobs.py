@@ -113,31 +113,43 @@ class SubprocessJobExecutor(JobExecutor):
     olearning_sim_b200.control.run_task --task-file f.json`` (N = GPUs granted by the ResourceManager)."""
 
     def __init__(self, nproc_per_node: int = 1, workdir: Optional[str] = None, repo_path: Optional[str] = None,
-                 master_port_base: int = 29600):
+                 master_port_base: int = 29600, max_restarts: int = 0, shrink_on_restart: bool = False,
+                 env: Optional[Dict[str, str]] = None):
+        """``max_restarts`` > 0 turns the executor into an elastic supervisor: a job whose process group dies (rank
+        loss) is relaunched from its last round checkpoint, on one rank fewer when ``shrink_on_restart`` — clients are
+        re-sharded by world size, so the survivors simply take over the lost rank's clients."""
         self.nproc, self.workdir, self.repo_path = nproc_per_node, workdir or "/tmp/olsb_jobs", repo_path
+        self.max_restarts, self.shrink, self.env = max_restarts, shrink_on_restart, env
         self._port = master_port_base
         self._jobs: Dict[str, Dict[str, Any]] = {}
         self._lock = threading.Lock()
         os.makedirs(self.workdir, exist_ok=True)
+
+    def _launch(self, job_id: str, path: str, nproc: int, attempt: int):
+        with self._lock:
+            port = self._port
+            self._port += 1
+        if nproc > 1:
+            cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}",
+                   "--master-addr", "127.0.0.1", "--master-port", str(port), "-m",
+                   "olearning_sim_b200.control.run_task", "--task-file", path]
+        else:
+            cmd = [sys.executable, "-m", "olearning_sim_b200.control.run_task", "--task-file", path]
+        log = open(os.path.join(self.workdir, f"{job_id}.log"), "a")
+        log.write(f"--- attempt {attempt}, {nproc} rank(s)\n")
+        log.flush()
+        env = dict(os.environ, **(self.env or {}))
+        return subprocess.Popen(cmd, stdout=log, stderr=subprocess.STDOUT, start_new_session=True, env=env), log.name
 
     def submit_job(self, task_json, context=None) -> str:
         job_id = f"job_{uuid.uuid4().hex[:12]}"
         path = os.path.join(self.workdir, f"{job_id}.json")
         with open(path, "w") as f:
             json.dump({"task": task_json, "context": {**(context or {}), "repo_path": self.repo_path}}, f)
+        proc, logname = self._launch(job_id, path, self.nproc, 0)
         with self._lock:
-            port = self._port
-            self._port += 1
-        if self.nproc > 1:
-            cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={self.nproc}",
-                   "--master-addr", "127.0.0.1", "--master-port", str(port), "-m",
-                   "olearning_sim_b200.control.run_task", "--task-file", path]
-        else:
-            cmd = [sys.executable, "-m", "olearning_sim_b200.control.run_task", "--task-file", path]
-        log = open(os.path.join(self.workdir, f"{job_id}.log"), "w")
-        proc = subprocess.Popen(cmd, stdout=log, stderr=subprocess.STDOUT, start_new_session=True)
-        with self._lock:
-            self._jobs[job_id] = {"proc": proc, "stopped": False, "log": log.name}
+            self._jobs[job_id] = {"proc": proc, "stopped": False, "log": logname, "path": path, "nproc": self.nproc,
+                                  "restarts": 0}
         return job_id
 
     def get_job_status(self, job_id: str) -> str:
@@ -150,6 +162,13 @@ class SubprocessJobExecutor(JobExecutor):
             return JobStatus.RUNNING
         if rec["stopped"]:
             return JobStatus.STOPPED
+        if rc != 0 and rec["restarts"] < self.max_restarts:
+            # elastic recovery: relaunch from the last checkpoint, optionally without the lost rank
+            rec["restarts"] += 1
+            if self.shrink and rec["nproc"] > 1:
+                rec["nproc"] -= 1
+            rec["proc"], _ = self._launch(job_id, rec["path"], rec["nproc"], rec["restarts"])
+            return JobStatus.RUNNING
         return JobStatus.SUCCEEDED if rc == 0 else JobStatus.FAILED
 
     def get_job_error(self, job_id: str) -> str:

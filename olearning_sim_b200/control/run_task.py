@@ -129,7 +129,8 @@ class ScriptActor:
 class RoundRunner:
     def __init__(self, task_json: Dict[str, Any], stop_event: Optional[threading.Event] = None, repo: Any = None,
                  deviceflow: Any = None, working_dir: Optional[str] = None, gate_params: Optional[Dict[str, Any]] = None,
-                 rank: int = 0, world: int = 1, checkpoint_dir: Optional[str] = None, **_: Any):
+                 rank: int = 0, world: int = 1, checkpoint_dir: Optional[str] = None, trace_path: Optional[str] = None,
+                 performance_mgr: Any = None, **_: Any):
         self.params = Params(task_json)
         self.stop_event = stop_event or threading.Event()
         self.repo, self.deviceflow, self.working_dir = repo, deviceflow, working_dir or tempfile.mkdtemp(prefix="olsb_job_")
@@ -138,6 +139,12 @@ class RoundRunner:
         self.checkpoint_dir = checkpoint_dir or self.params.engine.get("checkpoint_dir")
         self.engines: Dict[str, Any] = {}
         self.history: List[Dict[str, Any]] = []
+        trace_path = trace_path or self.params.engine.get("trace_path")
+        self.trace = None
+        if trace_path:
+            from ..utils.tracing import TraceWriter
+            self.trace = TraceWriter(trace_path)
+        self.performance_mgr = performance_mgr
 
     # ---- deviceflow wiring (utils_run_task.py:53-144) ----------------------------------------------------
     def _df_start(self, operator: Dict[str, Any], round_idx: int) -> Dict[str, Any]:
@@ -234,9 +241,18 @@ class RoundRunner:
             res_failed = 0
         else:
             res = eng.run_round(round_idx)
-            self.history.append({"round": round_idx, "operator": operator.get("name"), "loss": res.loss,
-                                 "participants": res.participants, "dropped": res.dropped, "arrived": res.arrived,
-                                 "failed": res.failed, "client_steps": res.client_steps, "wall_s": res.wall_s})
+            rec = {"round": round_idx, "operator": operator.get("name"), "loss": res.loss,
+                   "participants": res.participants, "dropped": res.dropped, "arrived": res.arrived,
+                   "failed": res.failed, "client_steps": res.client_steps, "wall_s": res.wall_s,
+                   **({"phases_ms": res.extras["phases_ms"]} if "phases_ms" in res.extras else {})}
+            self.history.append(rec)
+            if self.rank == 0:
+                if self.trace is not None:
+                    self.trace.write({"task_id": self.params.task_id, **rec})
+                if self.performance_mgr is not None:
+                    self.performance_mgr.commitJob({"task_id": self.params.task_id, "round": round_idx,
+                                                    "t_round_ms": res.wall_s * 1e3, "client_steps": res.client_steps,
+                                                    "phases_ms": res.extras.get("phases_ms", {})})
             res_failed = res.failed
             if getattr(eng, "ckpt", None) is not None:
                 eng.ckpt.save(round_idx, {"engine": eng.state_dict(), "round": round_idx})
@@ -326,6 +342,7 @@ def main(argv: Optional[List[str]] = None) -> int:
     ap = argparse.ArgumentParser()
     ap.add_argument("--task", type=str, default=None, help="task json string")
     ap.add_argument("--task-file", type=str, default=None, help="file with {'task': ..., 'context': ...}")
+    ap.add_argument("--profile", type=str, default=None, help="write one JSON record per round (phase timings) to this file")
     a = ap.parse_args(argv)
     ctx: Dict[str, Any] = {}
     if a.task_file:
@@ -342,8 +359,10 @@ def main(argv: Optional[List[str]] = None) -> int:
     if ctx.get("repo_path"):
         from .repo import TaskTableRepo
         repo = TaskTableRepo(ctx["repo_path"])
+    if a.profile:
+        task.setdefault("engine", {})["profile"] = True
     runner = RoundRunner(task, repo=repo, working_dir=ctx.get("working_dir"), rank=rank, world=world,
-                         checkpoint_dir=ctx.get("checkpoint_dir"))
+                         checkpoint_dir=ctx.get("checkpoint_dir"), trace_path=a.profile or ctx.get("trace_path"))
     ok = runner.run()
     if rank == 0:
         print(json.dumps({"task_id": runner.params.task_id, "ok": ok, "history": runner.history[-3:]}))

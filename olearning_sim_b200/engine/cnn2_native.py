@@ -27,7 +27,12 @@ OPT_CODES = {"avg": 0, "sgd": 0, "fedavg": 0, "momentum": 1, "fedavgm": 1, "adam
 
 class Cnn2Workspace:
     def __init__(self, num_clients: int, shard: int, device="cuda", heap: Optional[SymmetricHeap] = None,
-                 reduce_groups: int = 0):
+                 reduce_groups: int = 0, wave: Optional[int] = None, hbm_budget_bytes: Optional[int] = None):
+        """``wave``: number of clients whose activations are resident at once.  Weights, optimiser-free masters and data
+        shards of *all* clients stay in HBM (1.1 MB + data per client); the 4.6 MB of per-step activations are
+        time-multiplexed over waves when the population does not fit (the reference scales clients by adding Ray
+        actors; here the "long axis" is clients x parameters).  Default: everything resident if it fits
+        in ``hbm_budget_bytes`` (80 % of free memory), otherwise the largest wave that does."""
         assert shard % B == 0, f"client shard size must be a multiple of the local batch ({B})"
         native.require()
         self.C, self.shard, self.dev = num_clients, shard, torch.device(device)
@@ -44,19 +49,30 @@ class Cnn2Workspace:
         C = num_clients
         d = self.dev
         bf, u8, f32, i32 = torch.bfloat16, torch.uint8, torch.float32, torch.int32
+        act_bytes = B * (16 * 16 * 32 * 3 + 8 * 8 * 64 * 3 + 16 * 16 * 64 * 2 + 16 * 16 * 32 * 2)      # per client
+        fixed_bytes = P * 4 + (CNN2.W1_N + CNN2.W2_N) * 2 + shard * (32 * 32 * 16 * 2 + 4)
+        if wave is None:
+            if hbm_budget_bytes is None:
+                free, _ = torch.cuda.mem_get_info(d)
+                hbm_budget_bytes = int(free * 0.8)
+            room = hbm_budget_bytes - C * fixed_bytes
+            wave = C if room >= C * act_bytes else max(sms, (room // act_bytes) // sms * sms)
+            if wave <= 0:
+                raise MemoryError(f"{C} CNN-2 clients need {C * fixed_bytes / 2**30:.1f} GiB of weights+data alone")
+        self.wave = W = max(1, min(int(wave), C))
         self.x5 = torch.empty(C * shard, 32, 32, 16, dtype=bf, device=d)
         self.labels = torch.zeros(C, shard, dtype=i32, device=d)
         self.master = torch.zeros(C, P, dtype=f32, device=d)
         self.global_local = torch.zeros(P, dtype=f32, device=d)
         self.w1_fwd = torch.zeros(C, CNN2.W1_N, dtype=bf, device=d)
         self.w2_fwd = torch.zeros(C, CNN2.W2_N, dtype=bf, device=d)
-        self.w2_dgrad = torch.zeros(C, CNN2.W2_N, dtype=bf, device=d)
-        self.p1 = torch.empty(C * B, 16, 16, 32, dtype=bf, device=d)
-        self.code1 = torch.empty(C * B, 16, 16, 32, dtype=u8, device=d)
-        self.p2 = torch.empty(C * B, 8, 8, 64, dtype=bf, device=d)
-        self.code2 = torch.empty(C * B, 8, 8, 64, dtype=u8, device=d)
-        self.dy2 = torch.empty(C * B, 16, 16, 64, dtype=bf, device=d)
-        self.dp1 = torch.empty(C * B, 16, 16, 32, dtype=bf, device=d)
+        self.w2_dgrad = None      # not needed: the data-gradient kernel reads w2_fwd as an MN-major operand
+        self.p1 = torch.empty(W * B, 16, 16, 32, dtype=bf, device=d)
+        self.code1 = torch.empty(W * B, 16, 16, 32, dtype=u8, device=d)
+        self.p2 = torch.empty(W * B, 8, 8, 64, dtype=bf, device=d)
+        self.code2 = torch.empty(W * B, 8, 8, 64, dtype=u8, device=d)
+        self.dy2 = torch.empty(W * B, 16, 16, 64, dtype=bf, device=d)
+        self.dp1 = torch.empty(W * B, 16, 16, 32, dtype=bf, device=d)
         self.loss_sum = torch.zeros(C, dtype=f32, device=d)
         self.nonfinite = torch.zeros(C, dtype=i32, device=d)
         self.n_samples = torch.full((C,), shard, dtype=i32, device=d)
@@ -117,18 +133,21 @@ class Cnn2Workspace:
     def local_step(self, step_idx: int, lr: float, mu: float = 0.0, active: Optional[torch.Tensor] = None,
                    nsplit: int = 0) -> None:
         off = (step_idx * B) % self.shard
-        a = native.Cnn2StepArgs()
-        a.x5 = self.x5.data_ptr(); a.x_total = self.x5.shape[0]; a.x_n_stride = self.shard; a.x_n_off = off
-        a.labels = self.labels.data_ptr(); a.label_stride = self.shard; a.label_off = off
-        a.master = self.master.data_ptr(); a.global_w = self.global_local.data_ptr(); a.P = self.P; a.C = self.C
-        a.active = active.data_ptr() if active is not None else None
-        a.w1_fwd = self.w1_fwd.data_ptr(); a.w2_fwd = self.w2_fwd.data_ptr(); a.w2_dgrad = self.w2_dgrad.data_ptr()
-        a.p1 = self.p1.data_ptr(); a.code1 = self.code1.data_ptr(); a.p2 = self.p2.data_ptr()
-        a.code2 = self.code2.data_ptr(); a.dy2 = self.dy2.data_ptr(); a.dp1 = self.dp1.data_ptr()
-        a.loss_sum = self.loss_sum.data_ptr(); a.nonfinite = self.nonfinite.data_ptr()
-        a.lr = lr; a.mu = mu; a.use_prox = 1 if mu > 0 else 0; a.nsplit = nsplit
-        native.cnn2_local_step(a)
-        self.kernel_launches += native.KERNELS_PER_LOCAL_STEP
+        for w0 in range(0, self.C, self.wave):                       # waves share the activation buffers
+            w1 = min(w0 + self.wave, self.C)
+            a = native.Cnn2StepArgs()
+            x5 = self.x5[w0 * self.shard:w1 * self.shard]
+            a.x5 = x5.data_ptr(); a.x_total = x5.shape[0]; a.x_n_stride = self.shard; a.x_n_off = off
+            a.labels = self.labels[w0:w1].data_ptr(); a.label_stride = self.shard; a.label_off = off
+            a.master = self.master[w0:w1].data_ptr(); a.global_w = self.global_local.data_ptr(); a.P = self.P; a.C = w1 - w0
+            a.active = active[w0:w1].data_ptr() if active is not None else None
+            a.w1_fwd = self.w1_fwd[w0:w1].data_ptr(); a.w2_fwd = self.w2_fwd[w0:w1].data_ptr(); a.w2_dgrad = None
+            a.p1 = self.p1.data_ptr(); a.code1 = self.code1.data_ptr(); a.p2 = self.p2.data_ptr()
+            a.code2 = self.code2.data_ptr(); a.dy2 = self.dy2.data_ptr(); a.dp1 = self.dp1.data_ptr()
+            a.loss_sum = self.loss_sum[w0:w1].data_ptr(); a.nonfinite = self.nonfinite[w0:w1].data_ptr()
+            a.lr = lr; a.mu = mu; a.use_prox = 1 if mu > 0 else 0; a.nsplit = nsplit
+            native.cnn2_local_step(a)
+            self.kernel_launches += native.KERNELS_PER_LOCAL_STEP
 
     def reduce_and_update(self, weight: torch.Tensor, opt: str = "avg", server_lr: float = 1.0, beta1: float = 0.9,
                           beta2: float = 0.99, eps: float = 1e-3) -> None:

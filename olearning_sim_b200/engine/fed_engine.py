@@ -59,6 +59,8 @@ class FedConfig:
     # (e.g. "0.6+0.4*math.sin(t/4)") scaling p_online — the diurnal online/offline + access-spike trace.
     deviceflow_strategy: Optional[str] = None
     online_trace: Optional[str] = None
+    wave: Optional[int] = None       # clients with resident activations at once (None = auto from free HBM)
+    profile: bool = False            # CUDA-event phase timing (mask / broadcast / local / reduce), max over ranks
 
     def __post_init__(self):
         if self.algorithm == "fedprox" and self.mu <= 0:
@@ -131,6 +133,10 @@ class FedEngine:
         self.C = self.c1 - self.c0
         self.client_ids = np.arange(self.c0, self.c1)
         self.round_log: List[RoundResult] = []
+        from ..utils.faults import FaultInjector
+        from ..utils.tracing import PhaseTimer
+        self.faults = FaultInjector.from_env()
+        self.timer = PhaseTimer(enabled=cfg.profile, device=self.device)
         self._graph = None
         self._graph_key = None
         # per-client static attributes
@@ -187,7 +193,7 @@ class FedEngine:
         heap = SymmetricHeap(group=self.group, device=self.device)
         if self.cfg.model == "cnn2":
             from .cnn2_native import Cnn2Workspace
-            self.ws = Cnn2Workspace(self.C, self.cfg.shard, device=self.device, heap=heap)
+            self.ws = Cnn2Workspace(self.C, self.cfg.shard, device=self.device, heap=heap, wave=self.cfg.wave)
             self._g0 = CNN2.init(self.cfg.seed)
         else:
             from .mlp_native import MlpLayout, MlpWorkspace
@@ -230,18 +236,29 @@ class FedEngine:
                                cfg.local_steps, self.participate, self.step_active, self.agg_weight, self.counters)
         ws.kernel_launches += 1
         need_mask = sampled or cfg.hetero_steps
-        ws.broadcast(self.participate if sampled else None)
-        for s in range(cfg.local_steps):
-            ws.local_step(s, lr=cfg.lr, mu=cfg.mu, active=self.step_active[s] if need_mask else None)
-        ws.reduce_and_update(self.agg_weight, opt=cfg.server_opt, server_lr=cfg.server_lr)
+        with self.timer.phase("broadcast"):
+            ws.broadcast(self.participate if sampled else None)
+        for cid in self.faults.corrupted_clients(round_idx) if self.faults else []:
+            if self.c0 <= cid < self.c1:
+                ws.master[cid - self.c0].fill_(float("nan"))             # poisoned replica: must be masked by the reduce
+                if hasattr(ws, "master_bf16"):
+                    ws.master_bf16[cid - self.c0].fill_(float("nan"))
+                else:
+                    ws.w1_fwd[cid - self.c0].fill_(float("nan"))
+        with self.timer.phase("local_steps"):
+            for s in range(cfg.local_steps):
+                ws.local_step(s, lr=cfg.lr, mu=cfg.mu, active=self.step_active[s] if need_mask else None)
+        with self.timer.phase("reduce_update"):
+            ws.reduce_and_update(self.agg_weight, opt=cfg.server_opt, server_lr=cfg.server_lr)
 
     def _native_finish(self, round_idx: int) -> RoundResult:
         ws = self.ws
         # tiny result vector assembled on device, one D2H copy per round (the "loss or metric" read-back)
         part = self.participate.float().sum()
-        loss = (ws.loss_sum * self.participate.float()).sum() / self.cfg.local_steps
+        ok = (ws.nonfinite == 0) & (self.participate > 0)
+        loss = torch.where(ok, ws.loss_sum, torch.zeros_like(ws.loss_sum)).sum() / self.cfg.local_steps
         self.result_dev[0] = loss
-        self.result_dev[1] = part
+        self.result_dev[1] = ok.float().sum()
         self.result_dev[2:6] = self.counters.float()
         self.result_dev[6] = ws.nonfinite.float().sum()
         self.result_dev[7] = self.step_active.float().sum()
@@ -293,8 +310,12 @@ class FedEngine:
         step_active = torch.from_numpy(m["step_active"].astype(bool)).to(d)
         weight = torch.from_numpy(m["agg_weight"]).to(d)
         # broadcast: refresh replicas of sampled clients
-        self.master = torch.where(part[:, None], self.global_w[None, :].expand_as(self.master), self.master)
+        with self.timer.phase("broadcast"):
+            self.master = torch.where(part[:, None], self.global_w[None, :].expand_as(self.master), self.master)
         self.loss_sum.zero_()
+        for cid in self.faults.corrupted_clients(round_idx) if self.faults else []:
+            if self.c0 <= cid < self.c1:
+                self.master[cid - self.c0] = float("nan")
         B = cfg.batch
         for s in range(cfg.local_steps):
             off = (s * B) % cfg.shard
@@ -310,7 +331,8 @@ class FedEngine:
         weight = torch.where(finite, weight, torch.zeros_like(weight))
         delta, wsum = reference.fedavg_delta(self.master, self.global_w, weight)
         pack = torch.cat([delta, torch.tensor([wsum], device=d, dtype=delta.dtype)])
-        stats = torch.tensor([float((self.loss_sum * part).sum() / cfg.local_steps), float(part.sum()),
+        okm = finite & part
+        stats = torch.tensor([float(torch.where(okm, self.loss_sum, torch.zeros_like(self.loss_sum)).sum() / cfg.local_steps), float(okm.sum()),
                               *[float(v) for v in m["counters"]], float((~finite).sum()), float(step_active.sum())],
                              dtype=torch.float64)
         if self.world > 1:
@@ -399,6 +421,8 @@ class FedEngine:
 
     def run_round(self, round_idx: int, stream_inputs: bool = False) -> RoundResult:
         t0 = time.perf_counter()
+        if self.faults:
+            self.faults.at_round_start(round_idx, self.rank)
         if stream_inputs:
             h2d = self.stream_inputs()
         if self.backend == "native":
@@ -407,6 +431,8 @@ class FedEngine:
         else:
             res = self._torch_round(round_idx)
         res.wall_s = time.perf_counter() - t0
+        if self.cfg.profile:
+            res.extras["phases_ms"] = self.timer.collect(self.group, self.world)
         if stream_inputs:
             res.extras["h2d_bytes"] = h2d
             res.extras["d2h_bytes"] = 32 if self.backend == "native" else 64

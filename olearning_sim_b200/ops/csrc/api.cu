@@ -116,10 +116,18 @@ int set_attrs() {
 }
 
 int auto_split(int C, int tiles_per_client, int nsplit) {
+  // Work items per client.  Cost model: waves(s)/s client-times, where waves = ceil(C*s / #SMs); every extra split
+  // re-loads the client's weights (~100 KB), so ties (and near-ties within 6 %) go to the smaller split.
   if (nsplit > 0) return nsplit;
-  int s = 1;
-  while (C * s < 2 * g_sms && s < 8 && (tiles_per_client % (s * 2) == 0)) s *= 2;
-  return s;
+  int best = 1;
+  double best_cost = 1e30;
+  for (int s = 1; s <= 8; s *= 2) {
+    if (tiles_per_client % s) break;
+    const int waves = (C * s + g_sms - 1) / g_sms;
+    const double cost = (double)waves / s * (1.0 + 0.06 * (s > 1) + 0.02 * (s > 2) + 0.02 * (s > 4));
+    if (cost < best_cost - 1e-9) { best_cost = cost; best = s; }
+  }
+  return best;
 }
 }  // namespace
 
@@ -195,7 +203,7 @@ int olsb_conv2_dgrad(const void* dy2, const void* w2_dgrad, void* master, const 
   if (int r = olsb_init()) return r;
   CUtensorMap tmA, tmW;
   if (int r = make_act_map(&tmA, dy2, (uint64_t)C * BATCH, 16, 16, 64, kBoxH)) return r;
-  if (int r = make_w_map(&tmW, w2_dgrad, (uint64_t)C, 25 * 32, 64, 5 * 32, 64)) return r;
+  if (int r = make_w_map(&tmW, w2_dgrad /* = forward copy w2_fwd */, (uint64_t)C, 64, 800, 64, 32)) return r;
   FwdParams p;
   memset(&p, 0, sizeof(p));
   p.num_clients = C; p.nsplit = auto_split(C, Conv2DgradCfg::TILES_PER_CLIENT, nsplit);
@@ -292,7 +300,7 @@ int olsb_cnn2_local_step(const OlsbCnn2Step* s, void* stream) {
   if ((r = olsb_head(s->C, s->active, s->p2, s->code2, s->labels, s->label_stride, s->label_off, s->master, gw, s->P,
                      s->lr, s->mu, s->dy2, s->loss_sum, s->nonfinite, nullptr, 1, nullptr, nullptr, stream)))
     return r;
-  if ((r = olsb_conv2_dgrad(s->dy2, s->w2_dgrad, s->master, gw, s->P, s->C, s->active, s->p1, s->dp1, s->lr, s->mu,
+  if ((r = olsb_conv2_dgrad(s->dy2, s->w2_fwd, s->master, gw, s->P, s->C, s->active, s->p1, s->dp1, s->lr, s->mu,
                             nullptr, s->nsplit, stream))) return r;
   if ((r = olsb_conv2_wgrad(s->p1, s->dy2, s->master, gw, s->P, s->C, s->active, s->w2_fwd, s->w2_dgrad, s->lr, s->mu,
                             nullptr, stream))) return r;

@@ -405,7 +405,8 @@ template <int CIN, int COUT, int IMG_H, int BATCH, int NSTAGE>
 struct DgradFoldCfg {
   static constexpr int ROWB = COUT * 2;                 // bytes per A pixel row (K = COUT)
   static constexpr int NF = 5 * CIN;                    // folded N
-  static constexpr int W_KH_BYTES = NF * ROWB;          // one vertical tap: [5*CIN rows][COUT] K-major
+  static constexpr int W_BOX_BYTES = COUT * CIN * 2;    // one (kh,kw) tap as loaded from the forward copy: [COUT rows][CIN]
+  static constexpr int W_KH_BYTES = 5 * W_BOX_BYTES;   // one vertical tap = 5 MN-major chunks (kw) of the B operand
   static constexpr int W_BYTES = kNKH * W_KH_BYTES;
   static constexpr int STAGE_BYTES = kBoxH * kTileW * ROWB;
   static constexpr int TILES_PER_CLIENT = BATCH * (IMG_H / kTileH);
@@ -457,10 +458,11 @@ conv_dgrad_fold_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         first_w = false; cur_client = c;
         if (leader) {
           mbar_arrive_expect_tx(&bars->wfull, Cfg::W_BYTES);
-          // weights [C][25*CIN rows][COUT]: one box (COUT, 5*CIN, 1) per vertical tap
+          // B operand straight from the *forward* weight copy [C][COUT][25*CIN]: box (CIN, COUT, 1) at (tap*CIN, 0, c)
+          // lands as [COUT k-rows][CIN n-elements] = one MN-major SW64 chunk per tap -> no transposed weight copy
 #pragma unroll 1
-          for (int kh = 0; kh < kNKH; ++kh)
-            tma_load_3d(w_sm + kh * Cfg::W_KH_BYTES, &tmW, &bars->wfull, 0, kh * Cfg::NF, c);
+          for (int t = 0; t < 5 * kNKH; ++t)
+            tma_load_3d(w_sm + t * Cfg::W_BOX_BYTES, &tmW, &bars->wfull, t * CIN, 0, c);
         }
       }
       const int t0 = sp * tiles_per_work;
@@ -479,9 +481,10 @@ conv_dgrad_fold_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     }
   } else if (warp == 5) {
     const bool leader = elect_one();
-    constexpr uint32_t IDESC = make_idesc_bf16(128, Cfg::NF, 0, 0);
+    constexpr uint32_t IDESC = make_idesc_bf16(128, Cfg::NF, 0, 1);           // B is MN-major
     const uint64_t a_desc_base = make_smem_desc(smem_u32(a_sm), 16, 8 * ROWB, LT_SW128);
-    const uint64_t b_desc_base = make_smem_desc(smem_u32(w_sm), 16, 8 * ROWB, LT_SW128);
+    // B: 5 chunks (kw) of [COUT k-rows][CIN] with 64-byte rows: LBO = chunk stride, SBO = 8 k-rows
+    const uint64_t b_desc_base = make_smem_desc(smem_u32(w_sm), Cfg::W_BOX_BYTES, 8 * CIN * 2, LT_SW64);
     int stage = 0; uint32_t phase = 0; int cur_client = -1; uint32_t wphase = 0;
     int buf = 0; uint32_t tphase0 = 0, tphase1 = 0;
     for (int wi = blockIdx.x; wi < num_work; wi += gridDim.x) {
@@ -509,7 +512,7 @@ conv_dgrad_fold_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             const uint64_t b_desc = desc_advance(b_desc_base, kh * Cfg::W_KH_BYTES);
 #pragma unroll
             for (int ks = 0; ks < ROWB / 32; ++ks)
-              umma_bf16(d_tmem, desc_advance(a_desc, ks * 32), desc_advance(b_desc, ks * 32), IDESC,
+              umma_bf16(d_tmem, desc_advance(a_desc, ks * 32), desc_advance(b_desc, ks * 16 * CIN * 2), IDESC,
                         (kh | ks) ? 1u : 0u);
           }
           umma_commit(&bars->empty[stage]);

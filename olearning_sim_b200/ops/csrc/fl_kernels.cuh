@@ -110,11 +110,12 @@ __global__ void bcast_scatter_cnn2_kernel(const BcastParams p) {
       __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
       o.x = *reinterpret_cast<uint32_t*>(&a); o.y = *reinterpret_cast<uint32_t*>(&b);
       *reinterpret_cast<uint2*>(p.w2_fwd + (size_t)c * L::W2_N + j) = o;
-      // dgrad copy [tap][cin][cout]
-      const int cout = j / 800, rem = j % 800;   // rem = tap*32 + cin (4 consecutive cin)
+      if (p.w2_dgrad) {   // optional transposed copy [tap][cin][cout] (the data-gradient kernel reads the forward copy MN-major)
+        const int cout = j / 800, rem = j % 800;   // rem = tap*32 + cin (4 consecutive cin)
 #pragma unroll
-      for (int e = 0; e < 4; ++e)
-        p.w2_dgrad[(size_t)c * L::W2_N + (size_t)(rem + e) * 64 + cout] = __float2bfloat16_rn(vv[e]);
+        for (int e = 0; e < 4; ++e)
+          p.w2_dgrad[(size_t)c * L::W2_N + (size_t)(rem + e) * 64 + cout] = __float2bfloat16_rn(vv[e]);
+      }
     }
   }
 }

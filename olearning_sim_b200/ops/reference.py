@@ -98,7 +98,9 @@ def cnn2_local_step(flat: torch.Tensor, x_nhwc: torch.Tensor, labels: torch.Tens
 # --------------------------------------------------------------------------------------------------
 def fedavg_delta(master: torch.Tensor, global_w: torch.Tensor, weight: torch.Tensor) -> Tuple[torch.Tensor, float]:
     """sum_c a_c (w_c - w_g), sum_c a_c"""
-    d = (weight[:, None] * (master - global_w[None, :])).sum(dim=0)
+    # rows with zero weight are skipped outright (a poisoned replica is NaN, and 0 * NaN would poison the sum)
+    delta = torch.where(weight[:, None] > 0, master - global_w[None, :], torch.zeros_like(master))
+    d = (weight[:, None] * delta).sum(dim=0)
     return d, float(weight.sum())
 
 

@@ -168,12 +168,12 @@ def check_head(c: int) -> Dict:
 
 def check_conv2_dgrad(c: int) -> Dict:
     master = _rand_master(c)
-    _, _, w2d = _operand_copies(master)
+    _, w2f, _ = _operand_copies(master)
     dy2 = (torch.randn(c * B, 16, 16, 64, device="cuda") * 0.1).to(torch.bfloat16)
     p1 = torch.randn(c * B, 16, 16, 32, device="cuda").clamp_min(0).to(torch.bfloat16)
     dp1 = torch.zeros(c * B, 16, 16, 32, dtype=torch.bfloat16, device="cuda")
     db1 = torch.zeros(c, 32, device="cuda")
-    native.conv2_dgrad(dy2, w2d, master, None, c, None, p1, dp1, 0.1, 0.0, db1)
+    native.conv2_dgrad(dy2, w2f, master, None, c, None, p1, dp1, 0.1, 0.0, db1)      # B operand = forward weight copy
     torch.cuda.synchronize()
     v = reference.cnn2_views(master)
     x = p1.float().reshape(c, B, 16, 16, 32).clone().requires_grad_(True)

@@ -126,3 +126,35 @@ def test_script_operator_reference_contract(tmp_path):
     assert tm.submitTask(tj2)
     tm.schedule_once(inline=True)
     assert tm.wait_for("script2", 120) == TaskStatus.FAILED
+
+
+def test_poisoned_client_is_masked_and_counted(monkeypatch):
+    """fault injection: a client whose replica turns NaN must not poison the aggregate and counts as failed"""
+    monkeypatch.setenv("OLSB_FAULTS", "corrupt:client=3,round=1")
+    e = FedEngine(FedConfig(model="mlp2", num_clients=6, local_steps=1, batch=8, shard=8, lr=0.1, device="cpu", backend="torch"))
+    e.load_synthetic()
+    res = [e.run_round(r) for r in range(3)]
+    assert [r.failed for r in res] == [0, 1, 0]
+    assert all(r.loss == r.loss for r in res) and bool(torch.isfinite(e.global_model()).all())
+
+
+def test_elastic_restart_after_rank_loss(tmp_path):
+    """kill rank 1 in round 1 of a 2-rank job: the supervisor relaunches on 1 rank from the round-0 checkpoint and the
+    task still SUCCEEDS with every client accounted for (clients are re-sharded by world size)."""
+    db = str(tmp_path / "tasks.sqlite")
+    repo = TaskTableRepo(db)
+    rm = ResourceManager(ResTableRepo(), totals={"cpu": 8, "mem": 32, "gpu": 0}, phone_mgr=FakePhoneMgr())
+    ex = SubprocessJobExecutor(nproc_per_node=2, workdir=str(tmp_path / "jobs"), repo_path=db, master_port_base=29781,
+                               max_restarts=1, shrink_on_restart=True,
+                               env={"OLSB_FAULTS": "kill:rank=1,round=1", "OLSB_FAULT_MARKER": str(tmp_path / "killed")})
+    tm = TaskManager(repo=repo, resource_manager=rm, executor=ex, job_context={"checkpoint_dir": str(tmp_path / "ckpt")})
+    tm._job_context.pop("repo", None); tm._job_context.pop("deviceflow", None)
+    assert tm.submitTask(make_task_json(task_id="elastic", rounds=3, nums=(8,), operator_params=MLP, num_request=(2,)))
+    tm.schedule_once(inline=True)
+    st = tm.wait_for("elastic", 300, poll=0.5)
+    job_id = repo.get_task_value("elastic", "job_id")
+    log = ex.get_job_error(job_id)
+    assert st == TaskStatus.SUCCEEDED, log
+    assert os.path.exists(tmp_path / "killed") and "attempt 1, 1 rank(s)" in log
+    assert repo.get_task_value("elastic", "logical_round") == 3
+    assert sorted(os.listdir(tmp_path / "ckpt"))[-1].startswith("elastic_2_")

@@ -70,3 +70,26 @@ def test_engine_mlp_native_vs_torch_backend():
     rel = ((ga - g0) - (gb - g0)).norm() / (gb - g0).norm()
     assert rel < 8e-2, float(rel)
     a.close()
+
+
+def test_wave_scheduling_matches_all_resident():
+    """activations time-multiplexed over waves of 4 clients == everything resident"""
+    from olearning_sim_b200.engine.fed_engine import FedConfig, FedEngine
+    kw = dict(model="cnn2", num_clients=10, local_steps=2, shard=64, lr=0.05, seed=9, backend="native", hetero_steps=True)
+    a = FedEngine(FedConfig(**kw)); a.load_synthetic()
+    b = FedEngine(FedConfig(wave=4, **kw)); b.load_synthetic()
+    assert a.ws.wave == 10 and b.ws.wave == 4
+    ra, rb = a.run_round(0), b.run_round(0)
+    assert abs(ra.loss - rb.loss) < 1e-6 and torch.equal(a.global_model(), b.global_model())
+    assert b.kernel_launches() == 1 + 1 + 2 * 3 * 6 + 2          # 3 waves per local step
+    a.close()
+
+
+def test_poisoned_client_masked_on_gpu(monkeypatch):
+    monkeypatch.setenv("OLSB_FAULTS", "corrupt:client=2,round=0")
+    from olearning_sim_b200.engine.fed_engine import FedConfig, FedEngine
+    e = FedEngine(FedConfig(model="cnn2", num_clients=6, local_steps=1, shard=64, backend="native", profile=True)); e.load_synthetic()
+    r = e.run_round(0)
+    assert r.failed == 1 and r.loss == r.loss and bool(torch.isfinite(e.global_model()).all())
+    assert set(r.extras["phases_ms"]) == {"broadcast", "local_steps", "reduce_update"}
+    e.close()
