@@ -39,6 +39,14 @@ class ResourceDetail:
     gpu: float = 0.0
 
 
+@dataclass
+class Resource:
+    """ols_core/resourceMgr/res_param.py:12-14 (+ gpu: the unit the B200 executor schedules)"""
+    cpu: float = 0.0
+    mem: float = 0.0
+    gpu: float = 0.0
+
+
 def detect_cluster_totals() -> Dict[str, float]:
     cpu = float(os.cpu_count() or 1)
     mem_gb = 0.0

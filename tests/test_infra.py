@@ -252,3 +252,27 @@ def test_gate_sample_and_aggregation_markers(tmp_path):
     assert not of2.stop(1)                                                # nobody wrote aggregation_finished.txt
     with pytest.raises(ValueError):
         OperatorFlow("t", 1, {"strategy": "nope"}, {"strategy": ""})
+
+
+def test_oflserver_helpers_on_local_store(tmp_path):
+    """utils_oflserver-style flat helpers over the local store: upload / list selection files / cached download / delete"""
+    from olearning_sim_b200.utils import oflserver as o
+    cfg = {"file": {"root": str(tmp_path / "store")}, "bus": {"topic": "gh", "url": "mem://x"}}
+    for i in range(3):
+        f = tmp_path / f"c{i}.json"
+        f.write_text("{}")
+        assert o.uploadS3File(cfg, str(f), f"sel/round0/c{i}.json")
+    (tmp_path / "m.bin").write_bytes(b"abc")
+    assert o.uploadS3File(cfg, str(tmp_path / "m.bin"), "sel/round0/model.bin")
+    assert o.getS3SelectionFiles(cfg, "sel/round0") == [f"sel/round0/c{i}.json" for i in range(3)]
+    dst = tmp_path / "dl" / "model.bin"
+    assert o.downloadS3File(cfg, str(dst), "sel/round0/model.bin") and dst.read_bytes() == b"abc"
+    assert o.deleteS3File(cfg, "sel/round0/model.bin")
+    assert o.downloadS3File(cfg, str(dst), "sel/round0/model.bin")          # local copy exists -> no transfer needed
+    assert o.uploadMinioFile(cfg, str(tmp_path / "m.bin"), "models/a.bin") and o.listdirMinioFile(cfg, "models") == ["models/a.bin"]
+    assert o.get_gradient_house_pulsar(cfg) == {"url": "mem://x", "topic": "gh"}
+    bus, prod = o.getPulsarObjects(cfg)
+    c = bus.subscribe("gh", "t")
+    prod.send(b"hello")
+    assert c.receive(100).data() == b"hello"
+    assert o.getSqlTaskRepo().check_task_in_database("nope") is False
