@@ -249,28 +249,16 @@ class FedEngine:
             for s in range(cfg.local_steps):
                 ws.local_step(s, lr=cfg.lr, mu=cfg.mu, active=self.step_active[s] if need_mask else None)
         with self.timer.phase("reduce_update"):
-            ws.reduce_and_update(self.agg_weight, opt=cfg.server_opt, server_lr=cfg.server_lr)
+            ws.reduce_and_update(self.agg_weight, opt=cfg.server_opt, server_lr=cfg.server_lr,
+                                 accounting=(self.participate, self.step_active, self.counters, cfg.local_steps))
 
     def _native_finish(self, round_idx: int) -> RoundResult:
-        ws = self.ws
-        # tiny result vector assembled on device, one D2H copy per round (the "loss or metric" read-back)
-        part = self.participate.float().sum()
-        ok = (ws.nonfinite == 0) & (self.participate > 0)
-        loss = torch.where(ok, ws.loss_sum, torch.zeros_like(ws.loss_sum)).sum() / self.cfg.local_steps
-        self.result_dev[0] = loss
-        self.result_dev[1] = ok.float().sum()
-        self.result_dev[2:6] = self.counters.float()
-        self.result_dev[6] = ws.nonfinite.float().sum()
-        self.result_dev[7] = self.step_active.float().sum()
-        self.result_host.copy_(self.result_dev, non_blocking=True)
+        # the job-wide 8-float record was assembled on the device (round_stats_kernel per rank, summed over ranks
+        # inside fedavg_finish_kernel): one 32-byte D2H copy per round is the "loss or metric" read-back
+        self.result_host.copy_(self.ws.round_out, non_blocking=True)
         torch.cuda.current_stream().synchronize()
-        r = self.result_host
-        vals = torch.tensor([r[0], r[1], r[2], r[3], r[4], r[5], r[6], r[7]], dtype=torch.float64)
-        if self.world > 1:
-            t = vals.to(self.device)
-            dist.all_reduce(t, group=self.group)
-            vals = t.cpu()
-        part_n = int(vals[1].item())
+        vals = self.result_host.tolist()
+        part_n = int(vals[1])
         return RoundResult(round=round_idx, participants=int(vals[2]), dropped=int(vals[3]), late=int(vals[4]),
                            arrived=int(vals[5]), failed=int(vals[6]),
                            loss=float(vals[0] / max(part_n, 1)), client_steps=int(vals[7]))

@@ -78,6 +78,10 @@ class MlpWorkspace:
         self.groups = max(1, min(16, max(1, C // 8)))
         hp = self.heap
         hp.alloc("global", P * 4); hp.alloc("partial", self.groups * P * 4); hp.alloc("wsum", 64 * 4); hp.alloc("flags", 256)
+        hp.alloc("round", 256)
+        self.round_rec = hp.tensor("round", f32, (8,))
+        self.round_rec.zero_()
+        self.round_out = torch.zeros(8, dtype=f32, device=d)
         self.global_w = hp.tensor("global", f32, (P,))
         self.partial = hp.tensor("partial", f32, (self.groups, P))
         self.wsum = hp.tensor("wsum", f32, (self.groups,))
@@ -155,7 +159,12 @@ class MlpWorkspace:
                    w_bf16=vp(mb, L.W1), wb_stride=P)
 
     def reduce_and_update(self, weight: torch.Tensor, opt: str = "avg", server_lr: float = 1.0, beta1: float = 0.9,
-                          beta2: float = 0.99, eps: float = 1e-3) -> None:
+                          beta2: float = 0.99, eps: float = 1e-3, accounting=None) -> None:
+        if accounting is not None:
+            # (participate, step_active, counters, local_steps): 8-float record, summed over ranks by the finish kernel
+            part, step_active, counters, nsteps = accounting
+            native.round_stats(self.loss_sum, self.nonfinite, part, step_active, counters, self.C, step_active.shape[0],
+                               1.0 / nsteps, self.round_rec)
         native.fedavg_partial(self.master, self.global_local, weight, self.nonfinite, self.groups, self.partial, self.wsum)
         self.epoch += 1
         self.server_step += 1
@@ -163,8 +172,8 @@ class MlpWorkspace:
         native.fedavg_finish(hb["partial"].peer_ptrs, hb["wsum"].peer_ptrs, hb["flags"].peer_ptrs if self.world > 1 else None,
                              self.rank, self.groups, self.P, self.shard_len, self.epoch, self.global_w, self.opt_m,
                              self.opt_v, OPT_CODES[opt], server_lr, beta1, beta2, eps, self.server_step, self.stats,
-                             self.arrive_ctr)
-        self.kernel_launches += 2
+                             self.arrive_ctr, hb["round"].peer_ptrs if accounting is not None else None, self.round_out)
+        self.kernel_launches += 2 + (accounting is not None)
 
     def reset_round_stats(self) -> None:
         self.loss_sum.zero_()

@@ -190,7 +190,7 @@ int olsb_conv2_fwd(const void* p1, const void* w2_fwd, const void* master, long 
   p.out = (__nv_bfloat16*)p2; p.code = (uint8_t*)code2;
   const int work = C * p.nsplit;
   const int grid = work < g_sms ? work : g_sms;
-  CONV2_FWD<<<grid, kThreads, Conv2FwdCfg::SMEM_BYTES, (cudaStream_t)stream>>>(tmA, tmW, p);
+  CONV2_FWD<<<grid, kFoldThreads, Conv2FwdCfg::SMEM_BYTES, (cudaStream_t)stream>>>(tmA, tmW, p);
   CK(cudaGetLastError());
   return 0;
 }
@@ -214,7 +214,7 @@ int olsb_conv2_dgrad(const void* dy2, const void* w2_dgrad, void* master, const 
   p.lr = lr; p.mu = mu; p.dbias_out = (float*)dbias_out;
   const int work = C * p.nsplit;
   const int grid = work < g_sms ? work : g_sms;
-  CONV2_DGRAD<<<grid, kThreads, Conv2DgradCfg::SMEM_BYTES, (cudaStream_t)stream>>>(tmA, tmW, p);
+  CONV2_DGRAD<<<grid, kFoldThreads, Conv2DgradCfg::SMEM_BYTES, (cudaStream_t)stream>>>(tmA, tmW, p);
   CK(cudaGetLastError());
   return 0;
 }
@@ -348,7 +348,7 @@ int olsb_fedavg_partial(const void* master, const void* global_w, const void* we
 int olsb_fedavg_finish(const void* const* partial_peers, const void* const* wsum_peers, const void* const* flag_peers,
                        int nranks, int rank, int groups, int P, int shard_len, unsigned epoch, void* global_w,
                        void* opt_m, void* opt_v, int opt, float server_lr, float beta1, float beta2, float eps, int step,
-                       void* stats, void* arrive_ctr, void* stream) {
+                       void* stats, void* arrive_ctr, const void* const* round_peers, void* round_out, void* stream) {
   if (int r = olsb_init()) return r;
   flk::FinishParams p;
   memset(&p, 0, sizeof(p));
@@ -361,6 +361,10 @@ int olsb_fedavg_finish(const void* const* partial_peers, const void* const* wsum
   p.global_w = (float*)global_w; p.opt_m = (float*)opt_m; p.opt_v = (float*)opt_v; p.opt = opt;
   p.server_lr = server_lr; p.beta1 = beta1; p.beta2 = beta2; p.eps = eps; p.step = step;
   p.stats = (float*)stats; p.arrive_ctr = (uint32_t*)arrive_ctr;
+  if (round_peers && round_out) {
+    for (int i = 0; i < nranks && i < flk::kMaxPeers; ++i) p.round_peers.p[i] = const_cast<void*>(round_peers[i]);
+    p.round_out = (float*)round_out;
+  }
   CK(cudaMemsetAsync(arrive_ctr, 0, 2 * sizeof(uint32_t), (cudaStream_t)stream));
   CK(cudaMemsetAsync(stats, 0, 4 * sizeof(float), (cudaStream_t)stream));
   const int th = 256;
@@ -368,6 +372,15 @@ int olsb_fedavg_finish(const void* const* partial_peers, const void* const* wsum
   if (grid > g_sms) grid = g_sms;   // all CTAs must be co-resident for the in-kernel gates
   if (grid < 1) grid = 1;
   flk::fedavg_finish_kernel<<<grid, th, 0, (cudaStream_t)stream>>>(p);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int olsb_round_stats(const void* loss_sum, const void* nonfinite, const void* participate, const void* step_active,
+                     const void* counters, int C, int S, float inv_steps, void* out, void* stream) {
+  flk::round_stats_kernel<<<1, 512, 0, (cudaStream_t)stream>>>((const float*)loss_sum, (const int*)nonfinite,
+                                                               (const uint8_t*)participate, (const uint8_t*)step_active,
+                                                               (const int*)counters, C, S, inv_steps, (float*)out);
   CK(cudaGetLastError());
   return 0;
 }

@@ -32,6 +32,8 @@ using namespace tc05;
 
 constexpr int kEpiWarps = 4;
 constexpr int kThreads = 192;  // warps 0-3 epilogue, warp 4 TMA producer, warp 5 MMA issuer
+// folded conv2 kernels: two epilogue warp sets (warps 0-7), warp 8 TMA producer, warp 9 MMA issuer
+constexpr int kFoldTmaWarp = 8, kFoldMmaWarp = 9, kFoldThreads = 320;
 constexpr int kTileH = 8, kTileW = 16, kHalo = 2, kBoxH = kTileH + 2 * kHalo;  // 12
 constexpr int kNKH = 5;
 
@@ -418,7 +420,7 @@ struct DgradFoldCfg {
 };
 
 template <int CIN, int COUT, int IMG_H, int BATCH, int NSTAGE>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kFoldThreads, 1)
 conv_dgrad_fold_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                        const FwdParams p) {
   using Cfg = DgradFoldCfg<CIN, COUT, IMG_H, BATCH, NSTAGE>;
@@ -438,8 +440,8 @@ conv_dgrad_fold_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     for (int i = 0; i < 2; ++i) { mbar_init(&bars->tfull[i], 1); mbar_init(&bars->tempty[i], kEpiWarps); }
     fence_mbar_init();
   }
-  if (warp == 5) { tmem_alloc(&bars->tmem_base, Cfg::TMEM_COLS); tmem_relinquish(); }
-  if (warp == 4 && lane == 0) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmW); }
+  if (warp == kFoldMmaWarp) { tmem_alloc(&bars->tmem_base, Cfg::TMEM_COLS); tmem_relinquish(); }
+  if (warp == kFoldTmaWarp && lane == 0) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmW); }
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
@@ -447,7 +449,7 @@ conv_dgrad_fold_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   const int num_work = p.num_clients * p.nsplit;
   const int tiles_per_work = (Cfg::TILES_PER_CLIENT + p.nsplit - 1) / p.nsplit;
 
-  if (warp == 4) {
+  if (warp == kFoldTmaWarp) {
     const bool leader = elect_one();
     int stage = 0; uint32_t phase = 0; int cur_client = -1; uint32_t wphase = 0; bool first_w = true;
     for (int wi = blockIdx.x; wi < num_work; wi += gridDim.x) {
@@ -479,7 +481,7 @@ conv_dgrad_fold_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == kFoldMmaWarp) {
     const bool leader = elect_one();
     constexpr uint32_t IDESC = make_idesc_bf16(128, Cfg::NF, 0, 1);           // B is MN-major
     const uint64_t a_desc_base = make_smem_desc(smem_u32(a_sm), 16, 8 * ROWB, LT_SW128);
@@ -529,19 +531,25 @@ conv_dgrad_fold_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       }
     }
   } else {
-    int buf = 0; uint32_t tphase0 = 0, tphase1 = 0;
-    const int q = warp;
+    // two epilogue groups: group g drains TMEM buffer g (= every other tile), so one group's TMEM-load / shuffle
+    // latency is covered by the other group's arithmetic on the same scheduler
+    const int grp = warp >> 2;
+    int buf = 0; uint32_t tph = 0;
+    const int q = warp & 3;
+    const int tid_g = threadIdx.x & 127;
     const int hl = 2 * q + (lane >> 4), wl = lane & 15;
     float dbacc[CIN];
 #pragma unroll
     for (int i = 0; i < CIN; ++i) dbacc[i] = 0.f;
     int cur_client = -1;
     bool had_sp0 = false;
-    __shared__ float s_db[CIN];
+    __shared__ float s_db_all[2][CIN];
+    float* s_db = s_db_all[grp];
+    auto gsync = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(1 + grp)); };
     auto flush_bias = [&](int c) {
-      asm volatile("bar.sync 1, 128;");
-      if (threadIdx.x < CIN) s_db[threadIdx.x] = 0.f;
-      asm volatile("bar.sync 1, 128;");
+      gsync();
+      if (tid_g < CIN) s_db[tid_g] = 0.f;
+      gsync();
 #pragma unroll
       for (int i = 0; i < CIN; ++i) {
         float v = dbacc[i];
@@ -553,19 +561,19 @@ conv_dgrad_fold_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         if (lane == 0) atomicAdd(&s_db[i], v);
         dbacc[i] = 0.f;
       }
-      asm volatile("bar.sync 1, 128;");
-      if (threadIdx.x < CIN) {
-        const float g = s_db[threadIdx.x];
+      gsync();
+      if (tid_g < CIN) {
+        const float g = s_db[tid_g];
         if (p.dbias_out) {
-          atomicAdd(&p.dbias_out[(size_t)c * CIN + threadIdx.x], g);
+          atomicAdd(&p.dbias_out[(size_t)c * CIN + tid_g], g);
         } else {
-          float* bp = &p.bias_master[(size_t)c * p.bias_stride + threadIdx.x];
+          float* bp = &p.bias_master[(size_t)c * p.bias_stride + tid_g];
           float upd = -p.lr * g;
-          if (had_sp0 && p.bias_global) upd -= p.lr * p.mu * (*bp - p.bias_global[threadIdx.x]);
+          if (grp == 0 && had_sp0 && p.bias_global) upd -= p.lr * p.mu * (*bp - p.bias_global[tid_g]);
           atomicAdd(bp, upd);
         }
       }
-      asm volatile("bar.sync 1, 128;");
+      gsync();
     };
     for (int wi = blockIdx.x; wi < num_work; wi += gridDim.x) {
       const int c = wi / p.nsplit, sp = wi % p.nsplit;
@@ -578,7 +586,8 @@ conv_dgrad_fold_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       if (sp == 0) had_sp0 = true;
       const int t0 = sp * tiles_per_work;
       const int t1 = min(t0 + tiles_per_work, Cfg::TILES_PER_CLIENT);
-      for (int t = t0; t < t1; ++t) {
+      for (int t = t0; t < t1; ++t, buf ^= 1) {
+        if (buf != grp) continue;
         const int s = t / (IMG_H / kTileH);
         const int h0 = (t % (IMG_H / kTileH)) * kTileH;
         const size_t n_out = (size_t)c * BATCH + s;
@@ -587,7 +596,7 @@ conv_dgrad_fold_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         uint4 pq[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) pq[k] = __ldg(reinterpret_cast<const uint4*>(p.pooled + pbase + k * 8));
-        mbar_wait(&bars->tfull[buf], buf ? tphase1 : tphase0);
+        mbar_wait(&bars->tfull[buf], tph);
         fence_after_sync();
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(32 * q) << 16) + buf * Cfg::TMEM_BUF_STRIDE;
         float acc[CIN];
@@ -605,13 +614,11 @@ conv_dgrad_fold_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           tmem_ld32(taddr + kw * CIN, v);
           tmem_ld_wait();
           const int src_w = wl + 2 - kw;                      // D_kw is taken from the pixel 2-kw columns to the right
-          const bool inb = (src_w >= 0) && (src_w < IMG_W);
+          const float inb = ((src_w >= 0) && (src_w < IMG_W)) ? 1.f : 0.f;     // outside the image = zero padding
           const int src_lane = (lane & 16) | (src_w & 15);
 #pragma unroll
-          for (int i = 0; i < CIN; ++i) {
-            const float o = __uint_as_float(__shfl_sync(0xffffffffu, v[i], src_lane));
-            acc[i] += inb ? o : 0.f;
-          }
+          for (int i = 0; i < CIN; ++i)
+            acc[i] = fmaf(__uint_as_float(__shfl_sync(0xffffffffu, v[i], src_lane)), inb, acc[i]);
         }
         // TMEM buffer drained: release it before the (long-latency) global stores
         fence_before_sync();
@@ -630,15 +637,14 @@ conv_dgrad_fold_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         }
 #pragma unroll
         for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(p.dpool + pbase + k * 8) = o[k];
-        if (buf) tphase1 ^= 1; else tphase0 ^= 1;
-        buf ^= 1;
+        tph ^= 1;
       }
     }
     if (cur_client >= 0) flush_bias(cur_client);
   }
   fence_before_sync();
   __syncthreads();
-  if (warp == 5) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  if (warp == kFoldMmaWarp) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
 // ================================================================================================
@@ -665,7 +671,7 @@ struct FwdFoldCfg {
 };
 
 template <int CIN, int COUT, int IMG_H, int BATCH, int NSTAGE>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kFoldThreads, 1)
 conv_fwd_fold_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                      const FwdParams p) {
   using Cfg = FwdFoldCfg<CIN, COUT, IMG_H, BATCH, NSTAGE>;
@@ -685,8 +691,8 @@ conv_fwd_fold_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     for (int i = 0; i < 2; ++i) { mbar_init(&bars->tfull[i], 1); mbar_init(&bars->tempty[i], kEpiWarps); }
     fence_mbar_init();
   }
-  if (warp == 5) { tmem_alloc(&bars->tmem_base, Cfg::TMEM_COLS); tmem_relinquish(); }
-  if (warp == 4 && lane == 0) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmW); }
+  if (warp == kFoldMmaWarp) { tmem_alloc(&bars->tmem_base, Cfg::TMEM_COLS); tmem_relinquish(); }
+  if (warp == kFoldTmaWarp && lane == 0) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmW); }
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
@@ -694,7 +700,7 @@ conv_fwd_fold_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   const int num_work = p.num_clients * p.nsplit;
   const int tiles_per_work = (Cfg::TILES_PER_CLIENT + p.nsplit - 1) / p.nsplit;
 
-  if (warp == 4) {
+  if (warp == kFoldTmaWarp) {
     const bool leader = elect_one();
     int stage = 0; uint32_t phase = 0; int cur_client = -1; uint32_t wphase = 0; bool first_w = true;
     for (int wi = blockIdx.x; wi < num_work; wi += gridDim.x) {
@@ -727,7 +733,7 @@ conv_fwd_fold_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == kFoldMmaWarp) {
     const bool leader = elect_one();
     constexpr uint32_t IDESC = make_idesc_bf16(128, Cfg::NF, 0, 0);
     const uint64_t a_desc_base = make_smem_desc(smem_u32(a_sm), 16, 8 * ROWB, LT_SW64);
@@ -778,13 +784,15 @@ conv_fwd_fold_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       }
     }
   } else {
+    // epilogue warp set j (warps 4j .. 4j+3) owns accumulator group j: two warps per scheduler, one per group
     uint32_t tphase = 0;
-    const int q = warp;
+    const int q = warp & 3;
+    const int jg = warp >> 2;
     const int wl = lane & 15;
     const int b0 = lane & 1, b4 = (lane >> 4) & 1;
     const int sl = b0 * 2 + b4;
     const int pos = (b4 << 1) | b0;
-    float bias_r[Cfg::NG * 8];
+    float bias_r[8];
     int cur_client = -1;
     for (int wi = blockIdx.x; wi < num_work; wi += gridDim.x) {
       const int c = wi / p.nsplit, sp = wi % p.nsplit;
@@ -793,9 +801,7 @@ conv_fwd_fold_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         cur_client = c;
         const float* bias = p.bias + (size_t)c * p.bias_stride;
 #pragma unroll
-        for (int j = 0; j < Cfg::NG; ++j)
-#pragma unroll
-          for (int k = 0; k < 8; ++k) bias_r[j * 8 + k] = __ldg(&bias[j * 32 + sl * 8 + k]);
+        for (int k = 0; k < 8; ++k) bias_r[k] = __ldg(&bias[jg * 32 + sl * 8 + k]);
       }
       const int t0 = sp * tiles_per_work;
       const int t1 = min(t0 + tiles_per_work, Cfg::TILES_PER_CLIENT);
@@ -805,8 +811,8 @@ conv_fwd_fold_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         const size_t n_out = (size_t)c * BATCH + s;
         const int ph = (h0 >> 1) + q, pw = wl >> 1;
         const size_t obase = ((n_out * (IMG_H / 2) + ph) * (IMG_W / 2) + pw) * COUT;
-#pragma unroll
-        for (int j = 0; j < Cfg::NG; ++j) {
+        {
+          const int j = jg;
           mbar_wait(&bars->tfull[j], tphase);
           fence_after_sync();
           const uint32_t taddr = tmem_base + (static_cast<uint32_t>(32 * q) << 16) + j * Cfg::TMEM_BUF_STRIDE;
@@ -825,13 +831,11 @@ conv_fwd_fold_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             tmem_ld32(taddr + kw * 32, v);
             tmem_ld_wait();
             const int src_w = wl + kw - 2;
-            const bool inb = (src_w >= 0) && (src_w < IMG_W);
+            const float inb = ((src_w >= 0) && (src_w < IMG_W)) ? 1.f : 0.f;   // outside the image = zero padding
             const int src_lane = (lane & 16) | (src_w & 15);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const float o = __uint_as_float(__shfl_sync(0xffffffffu, v[i], src_lane));
-              acc[i] += inb ? o : 0.f;
-            }
+            for (int i = 0; i < 32; ++i)
+              acc[i] = fmaf(__uint_as_float(__shfl_sync(0xffffffffu, v[i], src_lane)), inb, acc[i]);
           }
           fence_before_sync();
           __syncwarp();
@@ -865,7 +869,7 @@ conv_fwd_fold_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             cd[i] = 3u - (key & 3u);
             const uint32_t kk = key & ~3u;
             const uint32_t bits = (kk & 0x80000000u) ? (kk ^ 0x80000000u) : ~kk;
-            f[i] = fmaxf(__uint_as_float(bits) + bias_r[j * 8 + i], 0.f);
+            f[i] = fmaxf(__uint_as_float(bits) + bias_r[i], 0.f);
           }
           uint4 pv;
           pv.x = pack_bf16x2(f[0], f[1]); pv.y = pack_bf16x2(f[2], f[3]);
@@ -883,7 +887,7 @@ conv_fwd_fold_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   }
   fence_before_sync();
   __syncthreads();
-  if (warp == 5) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  if (warp == kFoldMmaWarp) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
 // ================================================================================================

@@ -445,6 +445,8 @@ struct FinishParams {
   int step;                 // Adam step (1-based)
   float* stats;             // [4]: total weight, |delta|^2 of owned shard, participants(unused), spare
   uint32_t* arrive_ctr;     // [2] zero-initialised scratch for the intra-grid barriers
+  PeerPtrs round_peers;     // float* [8] per rank: this round's local accounting (round_stats_kernel) or null
+  float* round_out;         // [8] sum over ranks of round_peers (every rank gets the job-wide numbers)
 };
 
 __device__ __forceinline__ void grid_gate(uint32_t* ctr, uint32_t nblocks) {
@@ -517,11 +519,54 @@ __global__ void fedavg_finish_kernel(const FinishParams p) {
   dn += __shfl_xor_sync(0xffffffffu, dn, 1);
   if ((threadIdx.x & 31) == 0 && dn != 0.f) atomicAdd(&p.stats[1], dn);
   if (blockIdx.x == 0 && threadIdx.x == 0) p.stats[0] = wtot;
+  // job-wide round accounting: sum the 8-float records of all ranks (they were complete before the entry barrier)
+  if (blockIdx.x == 0 && threadIdx.x < 8 && p.round_out) {
+    float a = 0.f;
+    for (int r = 0; r < p.nranks; ++r) a += static_cast<const float*>(p.round_peers.p[r])[threadIdx.x];
+    p.round_out[threadIdx.x] = a;
+  }
   // exit barrier: new shard visible to every peer before anyone starts the next broadcast pull
   if (p.nranks > 1) {
     grid_gate(p.arrive_ctr + 1, gridDim.x);
     if (blockIdx.x == 0) peer_barrier(p.flags, p.nranks, p.rank, p.epoch * 2 + 2);
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Per-round result accounting (reference: analyze_results, ols_core/taskMgr/run_task.py:149-210, sums success /
+// failed per device class on the host).  One CTA folds the per-client loss / non-finite flags / masks into an
+// 8-float record: [masked loss sum / local_steps, finite participants, counters[0..3], non-finite clients,
+// client-steps executed].  fedavg_finish_kernel then adds the records of all ranks.
+// ---------------------------------------------------------------------------------------------
+__global__ void round_stats_kernel(const float* __restrict__ loss_sum, const int* __restrict__ nonfinite,
+                                   const uint8_t* __restrict__ participate, const uint8_t* __restrict__ step_active,
+                                   const int* __restrict__ counters, int C, int S, float inv_steps,
+                                   float* __restrict__ out) {
+  float loss = 0.f, ok = 0.f, bad = 0.f, steps = 0.f;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const bool nf = nonfinite[c] != 0;
+    const bool part = participate[c] != 0;
+    if (part && !nf) { loss += loss_sum[c]; ok += 1.f; }
+    if (nf) bad += 1.f;
+  }
+  for (int i = threadIdx.x; i < C * S; i += blockDim.x) steps += step_active[i] ? 1.f : 0.f;
+  __shared__ float red[4][32];
+  float v[4] = {loss, ok, bad, steps};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    float x = v[k];
+    for (int o = 16; o; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    if ((threadIdx.x & 31) == 0) red[k][threadIdx.x >> 5] = x;
+  }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    float x = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) x += red[threadIdx.x][w];
+    v[0] = x;
+    const int slot = threadIdx.x == 0 ? 0 : threadIdx.x == 1 ? 1 : threadIdx.x == 2 ? 6 : 7;
+    out[slot] = threadIdx.x == 0 ? x * inv_steps : x;
+  }
+  if (threadIdx.x >= 4 && threadIdx.x < 8) out[threadIdx.x - 2] = (float)counters[threadIdx.x - 4];
 }
 
 // ---------------------------------------------------------------------------------------------

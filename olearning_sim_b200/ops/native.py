@@ -158,14 +158,23 @@ def fedavg_partial(master, global_w, weight, nonfinite, groups: int, partial, ws
 
 def fedavg_finish(partial_peer_ptrs, wsum_peer_ptrs, flag_peer_ptrs, rank: int, groups: int, P: int, shard_len: int,
                   epoch: int, global_w, opt_m, opt_v, opt: int, server_lr: float, beta1: float, beta2: float,
-                  eps: float, step: int, stats, arrive_ctr) -> None:
+                  eps: float, step: int, stats, arrive_ctr, round_peer_ptrs=None, round_out=None) -> None:
     n = len(partial_peer_ptrs)
     flags = _ptr_array(flag_peer_ptrs) if flag_peer_ptrs is not None else None
+    rnd = _ptr_array(round_peer_ptrs) if round_peer_ptrs is not None else None
     _ck(require().olsb_fedavg_finish(_ptr_array(partial_peer_ptrs), _ptr_array(wsum_peer_ptrs), flags, C.c_int(n),
                                      C.c_int(rank), C.c_int(groups), C.c_int(P), C.c_int(shard_len),
                                      C.c_uint(epoch), _p(global_w), _p(opt_m), _p(opt_v), C.c_int(opt),
                                      C.c_float(server_lr), C.c_float(beta1), C.c_float(beta2), C.c_float(eps),
-                                     C.c_int(step), _p(stats), _p(arrive_ctr), _stream()))
+                                     C.c_int(step), _p(stats), _p(arrive_ctr), rnd,
+                                     _p(round_out) if rnd is not None else None, _stream()))
+
+
+def round_stats(loss_sum, nonfinite, participate, step_active, counters, num_clients: int, steps: int, inv_steps: float,
+                out) -> None:
+    """8-float per-rank round record: [loss, finite participants, counters[0..3], non-finite clients, client-steps]"""
+    _ck(require().olsb_round_stats(_p(loss_sum), _p(nonfinite), _p(participate), _p(step_active), _p(counters),
+                                   C.c_int(num_clients), C.c_int(steps), C.c_float(inv_steps), _p(out), _stream()))
 
 
 def deviceflow_mask(num_clients, client_base, seed, round_idx, p_online, drop_probability, arrive_tick, max_tick,

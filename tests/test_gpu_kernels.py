@@ -80,8 +80,10 @@ def test_wave_scheduling_matches_all_resident():
     b = FedEngine(FedConfig(wave=4, **kw)); b.load_synthetic()
     assert a.ws.wave == 10 and b.ws.wave == 4
     ra, rb = a.run_round(0), b.run_round(0)
-    assert abs(ra.loss - rb.loss) < 1e-6 and torch.equal(a.global_model(), b.global_model())
-    assert b.kernel_launches() == 1 + 1 + 2 * 3 * 6 + 2          # 3 waves per local step
+    # bias gradients are accumulated with float atomics, so the two runs agree to rounding, not bit for bit
+    assert abs(ra.loss - rb.loss) < 1e-5 and (ra.participants, ra.client_steps) == (rb.participants, rb.client_steps)
+    assert torch.allclose(a.global_model(), b.global_model(), rtol=0, atol=2e-6)
+    assert b.kernel_launches() - a.kernel_launches() == 2 * 2 * 6        # 3 waves instead of 1, 2 local steps, 6 kernels
     a.close()
 
 
