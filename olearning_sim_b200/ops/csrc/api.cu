@@ -73,10 +73,10 @@ int make_map(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, 
 }
 
 // activation tensor [N][H][W][Cel] -> 4-D map, box (Cel, 16, box_h, 1)
-int make_act_map(CUtensorMap* tm, const void* base, uint64_t n, int H, int W, int cel, int box_h) {
+int make_act_map(CUtensorMap* tm, const void* base, uint64_t n, int H, int W, int cel, int box_h, int box_w = 16) {
   const uint64_t dims[4] = {(uint64_t)cel, (uint64_t)W, (uint64_t)H, n};
   const uint64_t str[3] = {(uint64_t)cel, (uint64_t)W * cel, (uint64_t)H * W * cel};
-  const uint32_t box[4] = {(uint32_t)cel, 16u, (uint32_t)box_h, 1u};
+  const uint32_t box[4] = {(uint32_t)cel, (uint32_t)box_w, (uint32_t)box_h, 1u};
   return make_map(tm, base, 4, dims, str, box, cel * 2);
 }
 // weight tensor [C][rows][k] -> 3-D map, box (box_k, box_rows, 1)
@@ -99,9 +99,13 @@ using Conv2DgradCfg = DgradFoldCfg<32, 64, 16, BATCH, 4>;
 //                              XROWB NKW YROWB H   W   BATCH NSS SYNTH_Y
 #define CONV2_WGRAD conv_wgrad_kernel<64, 5, 128, 16, 16, BATCH, 2, false>
 #define CONV1_WGRAD conv_wgrad_kernel<32, 1, 64, 32, 32, BATCH, 8, true, 2>
+// conv2 weight gradient with ONE 12x20 halo box per chunk (horizontal taps = 1-pixel operand shifts)
+#define CONV2_WGRAD_WIDE conv_wgrad_kernel<64, 5, 128, 16, 16, BATCH, 6, false, 1, 20>
+using Conv2WgradWideCfg = WgradCfg<64, 5, 128, 6, 20>;
 using Conv2WgradCfg = WgradCfg<64, 5, 128, 2>;
 using Conv1WgradCfg = WgradCfg<32, 1, 64, 8>;
 
+int g_wgrad2_mode = 0;   // 0: five 12x16 boxes per chunk, 1: one 12x20 box, 2: one box + swizzle base offset
 bool g_attr_set = false;
 int set_attrs() {
   if (g_attr_set) return 0;
@@ -110,6 +114,7 @@ int set_attrs() {
   CK(cudaFuncSetAttribute(CONV2_DGRAD, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv2DgradCfg::SMEM_BYTES));
   CK(cudaFuncSetAttribute(CONV2_WGRAD, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv2WgradCfg::SMEM_BYTES));
   CK(cudaFuncSetAttribute(CONV1_WGRAD, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv1WgradCfg::SMEM_BYTES));
+  CK(cudaFuncSetAttribute(CONV2_WGRAD_WIDE, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv2WgradWideCfg::SMEM_BYTES));
   CK(cudaFuncSetAttribute(flk::head_fc_xent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, flk::kHeadSmem));
   g_attr_set = true;
   return 0;
@@ -224,7 +229,8 @@ int olsb_conv2_wgrad(const void* p1, const void* dy2, void* master, const void* 
                      void* stream) {
   if (int r = olsb_init()) return r;
   CUtensorMap tmX, tmY;
-  if (int r = make_act_map(&tmX, p1, (uint64_t)C * BATCH, 16, 16, 32, kBoxH)) return r;
+  const bool wide = g_wgrad2_mode != 0;
+  if (int r = make_act_map(&tmX, p1, (uint64_t)C * BATCH, 16, 16, 32, kBoxH, wide ? 20 : 16)) return r;
   if (int r = make_act_map(&tmY, dy2, (uint64_t)C * BATCH, 16, 16, 64, kTileH)) return r;
   WgradParams p;
   memset(&p, 0, sizeof(p));
@@ -233,7 +239,11 @@ int olsb_conv2_wgrad(const void* p1, const void* dy2, void* master, const void* 
   p.w_off = Cnn2Layout::W2; p.w_fwd = (__nv_bfloat16*)w2_fwd; p.w_dgrad = (__nv_bfloat16*)w2_dgrad;
   p.lr = lr; p.mu = mu; p.grad_out = (float*)grad_out;
   const int grid = C < g_sms ? C : g_sms;
-  CONV2_WGRAD<<<grid, kThreads, Conv2WgradCfg::SMEM_BYTES, (cudaStream_t)stream>>>(tmX, tmY, p);
+  p.desc_mode = g_wgrad2_mode == 2 ? 1 : 0;
+  if (wide)
+    CONV2_WGRAD_WIDE<<<grid, kThreads, Conv2WgradWideCfg::SMEM_BYTES, (cudaStream_t)stream>>>(tmX, tmY, p);
+  else
+    CONV2_WGRAD<<<grid, kThreads, Conv2WgradCfg::SMEM_BYTES, (cudaStream_t)stream>>>(tmX, tmY, p);
   CK(cudaGetLastError());
   return 0;
 }
@@ -374,6 +384,12 @@ int olsb_fedavg_finish(const void* const* partial_peers, const void* const* wsum
   flk::fedavg_finish_kernel<<<grid, th, 0, (cudaStream_t)stream>>>(p);
   CK(cudaGetLastError());
   return 0;
+}
+
+// runtime switches (kernel variants under evaluation); returns the previous value, -1 for an unknown name
+int olsb_set_option(const char* name, int value) {
+  if (!strcmp(name, "wgrad2_mode")) { const int o = g_wgrad2_mode; g_wgrad2_mode = value; return o; }
+  return -1;
 }
 
 int olsb_round_stats(const void* loss_sum, const void* nonfinite, const void* participate, const void* step_active,

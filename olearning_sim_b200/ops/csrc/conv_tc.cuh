@@ -906,30 +906,41 @@ struct WgradParams {
   float lr, mu;
   float* grad_out;               // optional [C][BN*NTAPS*KT] raw gradient (tests); when set no update is applied
   // SYNTH_Y: the dY operand is synthesised from the pooled gradient instead of being loaded by TMA
+  int desc_mode;                 // wide-box variant: 1 = encode the swizzle base offset of unaligned operand starts
   const __nv_bfloat16* dpool;    // [C*BATCH][H/2][W/2][BN]
   const uint8_t* pcode;          // same shape, argmax position 0..3
 };
 
-template <int XROWB, int NKW, int YROWB, int NSS>
+// XBW = width (pixels) of the X halo box.  kTileW: one box per horizontal tap (the tap is the TMA x-coordinate).
+// kTileW + 2*kHalo: ONE box with both halos per chunk; the horizontal tap becomes a 1-pixel (= one smem row) shift of
+// the MN-major A operand's start address, which cuts the L2->smem traffic of the layer input 4x (12x20 pixels once
+// instead of 5 boxes of 12x16).
+template <int XROWB, int NKW, int YROWB, int NSS, int XBW = kTileW>
 struct WgradCfg {
   static constexpr int KT = XROWB / 2;          // input channels per tap chunk
   static constexpr int BN = YROWB / 2;          // output channels
   static constexpr int NTAPS = NKW * kNKH;
   static constexpr int MTILES = (NKW == 5) ? 7 : 1;
-  static constexpr int XSTAGE = kBoxH * kTileW * XROWB;
+  static constexpr bool WIDE = XBW != kTileW;
+  static constexpr int NXB = WIDE ? 1 : NKW;    // X boxes per stage
+  static constexpr int XPITCH = XBW * XROWB;    // bytes per box row
+  static constexpr int XBOX_BYTES = kBoxH * XPITCH;
+  static constexpr int XSTAGE = (XBOX_BYTES + 1023) / 1024 * 1024;
   static constexpr int YSTAGE = kTileH * kTileW * YROWB;
-  static constexpr int SS_BYTES = NKW * XSTAGE + YSTAGE;
+  static constexpr int SS_BYTES = NXB * XSTAGE + YSTAGE;
   static constexpr int TMEM_NEED = MTILES * BN;
   static constexpr int TMEM_COLS = TMEM_NEED <= 32 ? 32 : (TMEM_NEED <= 64 ? 64 : (TMEM_NEED <= 128 ? 128 : (TMEM_NEED <= 256 ? 256 : 512)));
   static constexpr int SMEM_BYTES = 1024 + NSS * SS_BYTES + (int)sizeof(Barriers);
   static_assert(SS_BYTES % 1024 == 0, "superstage must keep 1024B alignment");
 };
 
-template <int XROWB, int NKW, int YROWB, int IMG_H, int IMG_W, int BATCH, int NSS, bool SYNTH_Y, int NEPG = 1>
+template <int XROWB, int NKW, int YROWB, int IMG_H, int IMG_W, int BATCH, int NSS, bool SYNTH_Y, int NEPG = 1,
+          int XBW = kTileW>
 __global__ void __launch_bounds__((4 * NEPG + 2) * 32, 1)
 conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
                   const WgradParams p) {
-  using Cfg = WgradCfg<XROWB, NKW, YROWB, NSS>;
+  using Cfg = WgradCfg<XROWB, NKW, YROWB, NSS, XBW>;
+  static_assert(!Cfg::WIDE || (NKW == 5 && IMG_W == kTileW && !SYNTH_Y), "wide box: conv2 geometry only");
   constexpr int KT = Cfg::KT, BN = Cfg::BN;
   constexpr int TILES_X = IMG_W / kTileW, TILES_Y = IMG_H / kTileH;
   constexpr int CHUNKS = BATCH * TILES_X * TILES_Y;   // pixel chunks (K dimension, 128 pixels each)
@@ -974,15 +985,19 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
           for (uint32_t o = 0; o < WB; o += 16384) prefetch_l2_bulk(wmb + o, min(16384u, WB - o));
         }
         if (leader) {
-          mbar_arrive_expect_tx(&bars->full[ss], SYNTH_Y ? NKW * Cfg::XSTAGE : Cfg::SS_BYTES);
+          mbar_arrive_expect_tx(&bars->full[ss], Cfg::NXB * Cfg::XBOX_BYTES + (SYNTH_Y ? 0 : Cfg::YSTAGE));
           uint8_t* base = smem + ss * Cfg::SS_BYTES;
           const int nx = c * p.x_n_stride + p.x_n_off + s;
+          if (Cfg::WIDE) {
+            tma_load_4d(base, &tmX, &bars->full[ss], 0, w0 - kHalo, h0 - kHalo, nx);
+          } else {
 #pragma unroll 1
-          for (int kw = 0; kw < NKW; ++kw) {
-            const int dw = (NKW == 1) ? 0 : (kw - kHalo);
-            tma_load_4d(base + kw * Cfg::XSTAGE, &tmX, &bars->full[ss], 0, w0 + dw, h0 - kHalo, nx);
+            for (int kw = 0; kw < NKW; ++kw) {
+              const int dw = (NKW == 1) ? 0 : (kw - kHalo);
+              tma_load_4d(base + kw * Cfg::XSTAGE, &tmX, &bars->full[ss], 0, w0 + dw, h0 - kHalo, nx);
+            }
           }
-          if (!SYNTH_Y) tma_load_4d(base + NKW * Cfg::XSTAGE, &tmY, &bars->full[ss], 0, w0, h0, c * BATCH + s);
+          if (!SYNTH_Y) tma_load_4d(base + Cfg::NXB * Cfg::XSTAGE, &tmY, &bars->full[ss], 0, w0, h0, c * BATCH + s);
         }
         if (++ss == NSS) { ss = 0; phase ^= 1; }
       }
@@ -994,10 +1009,13 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     constexpr uint32_t IDESC = make_idesc_bf16(128, BN, 1, 1);
     const uint32_t sbase = smem_u32(smem);
     // A-operand descriptor templates (stage 0): M tile = 4 taps stacked along MN via the leading-dim offset
-    const uint64_t a_kw = make_smem_desc(sbase, kTileW * XROWB, 8 * XROWB, LTX);                       // kh 0..3 of one kw box
-    const uint64_t a_r = make_smem_desc(sbase + 4 * kTileW * XROWB, Cfg::XSTAGE, 8 * XROWB, LTX);     // kh 4 of kw 0..3
-    const uint64_t a_l = make_smem_desc(sbase + 4 * Cfg::XSTAGE + 4 * kTileW * XROWB, kTileW * XROWB, 8 * XROWB, LTX);
-    const uint64_t b_y = make_smem_desc(sbase + NKW * Cfg::XSTAGE, 16, 8 * YROWB, LTY);
+    constexpr uint32_t XP = Cfg::XPITCH;
+    // per-tap strides: next vertical tap = one box row, next horizontal tap = next box (narrow) / next pixel (wide)
+    constexpr uint32_t KW_STEP = Cfg::WIDE ? XROWB : Cfg::XSTAGE;
+    const uint64_t a_kw = make_smem_desc(sbase, XP, 8 * XROWB, LTX);                                   // kh 0..3 of one kw
+    const uint64_t a_r = make_smem_desc(sbase + 4 * XP, KW_STEP, 8 * XROWB, LTX);                      // kh 4 of kw 0..3
+    const uint64_t a_l = make_smem_desc(sbase + 4 * KW_STEP + 4 * XP, XP, 8 * XROWB, LTX);
+    const uint64_t b_y = make_smem_desc(sbase + Cfg::NXB * Cfg::XSTAGE, 16, 8 * YROWB, LTY);
     int ss = 0; uint32_t phase = 0; uint32_t tphase = 0;
     for (int c = blockIdx.x; c < p.num_clients; c += gridDim.x) {
       if (p.active && !p.active[c]) continue;
@@ -1012,12 +1030,13 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
           const uint32_t accum = t > 0 ? 1u : 0u;
 #pragma unroll
           for (int mt = 0; mt < Cfg::MTILES; ++mt) {
-            const uint64_t a0 = (mt < NKW) ? desc_advance(a_kw, soff + mt * Cfg::XSTAGE)
+            const uint64_t a0 = (mt < NKW) ? desc_advance(a_kw, soff + mt * KW_STEP)
                                            : (mt == NKW ? desc_advance(a_r, soff) : desc_advance(a_l, soff));
 #pragma unroll
             for (int ks = 0; ks < (kTileH * kTileW) / 16; ++ks) {
-              umma_bf16(tmem_base + mt * BN, desc_advance(a0, ks * 16 * XROWB), desc_advance(b0, ks * 16 * YROWB), IDESC,
-                        ks > 0 ? 1u : accum);
+              uint64_t ad = desc_advance(a0, ks * XP);            // k-step = one tile row = one box row
+              if (Cfg::WIDE && p.desc_mode) ad = desc_set_base_offset(ad);
+              umma_bf16(tmem_base + mt * BN, ad, desc_advance(b0, ks * 16 * YROWB), IDESC, ks > 0 ? 1u : accum);
             }
           }
           umma_commit(&bars->empty[ss]);
@@ -1088,7 +1107,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             const uint32_t gs = cseq + first + NEPG * i;           // global chunk sequence number
             const int ss = gs % NSS;
             mbar_wait(&bars->empty[ss], ((gs / NSS) & 1) ^ 1);
-            uint8_t* ybase = smem + ss * Cfg::SS_BYTES + NKW * Cfg::XSTAGE + L * YROWB;
+            uint8_t* ybase = smem + ss * Cfg::SS_BYTES + Cfg::NXB * Cfg::XSTAGE + L * YROWB;
             const int sw = (L >> 1) & 3;                           // SW64: 16B-chunk index ^= bits[7:8] of the byte address
 #pragma unroll
             for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(ybase + ((k ^ sw) << 4)) = o[k];

@@ -203,6 +203,13 @@ __device__ __forceinline__ uint64_t desc_advance(uint64_t d, uint32_t bytes) {
   return d + static_cast<uint64_t>(bytes >> 4);
 }
 
+// Matrix base offset (bits [49,52)): phase of the swizzle pattern when the operand does not start on a pattern
+// boundary, = (start address >> 7) & 7.
+__device__ __forceinline__ uint64_t desc_set_base_offset(uint64_t d) {
+  const uint64_t bo = (d >> 3) & 7u;                 // address field holds addr >> 4
+  return (d & ~(uint64_t(7) << 49)) | (bo << 49);
+}
+
 // 32-bit instruction descriptor for kind::f16 with bf16 A/B and fp32 accumulator.
 //   [4,6) D fmt (1=f32)  [7,10) A fmt (1=bf16)  [10,13) B fmt (1=bf16)  15: A MN-major  16: B MN-major
 //   [17,23) N>>3         [24,29) M>>4

@@ -170,6 +170,14 @@ def fedavg_finish(partial_peer_ptrs, wsum_peer_ptrs, flag_peer_ptrs, rank: int, 
                                      _p(round_out) if rnd is not None else None, _stream()))
 
 
+def set_option(name: str, value: int) -> int:
+    """Runtime kernel-variant switch (``wgrad2_mode``: 0 five-box, 1 one wide box, 2 wide box + swizzle base offset)."""
+    old = require().olsb_set_option(name.encode(), C.c_int(value))
+    if old < 0:
+        raise KeyError(name)
+    return int(old)
+
+
 def round_stats(loss_sum, nonfinite, participate, step_active, counters, num_clients: int, steps: int, inv_steps: float,
                 out) -> None:
     """8-float per-rank round record: [loss, finite participants, counters[0..3], non-finite clients, client-steps]"""

@@ -209,6 +209,44 @@ def check_conv2_wgrad(c: int) -> Dict:
     return res
 
 
+def check_conv2_wgrad_wide(c: int) -> Dict:
+    """conv2 weight gradient with one 12x20 halo box per chunk (modes 1/2 of the ``wgrad2_mode`` switch): error per
+    horizontal tap (the taps are 64-byte operand shifts inside a swizzle pattern) and time against the 5-box kernel"""
+    master = _rand_master(c)
+    _, w2f, w2d = _operand_copies(master)
+    dy2 = (torch.randn(c * B, 16, 16, 64, device="cuda") * 0.1).to(torch.bfloat16)
+    p1 = torch.randn(c * B, 16, 16, 32, device="cuda").clamp_min(0).to(torch.bfloat16)
+    w = reference.cnn2_views(master)["w2"].clone().requires_grad_(True)
+    y = _conv_ref(p1.float().reshape(c, B, 16, 16, 32), w, None)
+    y.backward(dy2.float().reshape(c, B, 16, 16, 64))
+    gref = w.grad.permute(0, 1, 3, 4, 2).reshape(c, 64, 5, 5, 32)       # cout, kh, kw, cin
+    res: Dict = {"tol": 1e-2, "err": 0.0}
+    try:
+        for mode in (0, 1, 2):
+            native.set_option("wgrad2_mode", mode)
+            gout = torch.zeros(c, CNN2.W2_N, device="cuda")
+            native.conv2_wgrad(p1, dy2, master, None, c, None, w2f, w2d, 0.1, 0.0, gout)
+            torch.cuda.synchronize()
+            g = gout.reshape(c, 64, 5, 5, 32)
+            res[f"mode{mode}_kw"] = [round(rel_err(g[:, :, :, k], gref[:, :, :, k]), 5) for k in range(5)]
+            res[f"mode{mode}_kh"] = [round(rel_err(g[:, :, k], gref[:, :, k]), 5) for k in range(5)]
+            res[f"mode{mode}_us"] = round(_time_us(lambda: native.conv2_wgrad(p1, dy2, master, None, c, None, w2f, w2d,
+                                                                              0.1, 0.0, gout)), 1)
+    finally:
+        native.set_option("wgrad2_mode", 0)
+    return res
+
+
+def _time_us(fn, iters: int = 5) -> float:
+    fn(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) * 1000.0 / iters
+
+
 def check_conv1_wgrad(c: int) -> Dict:
     shard, off = 2 * B, B
     xu8, x5 = _make_x5(c, shard, seed=5)
@@ -437,10 +475,14 @@ CHECKS: Dict[str, Callable[[int], Dict]] = {
 }
 
 
+# kernel variants under evaluation: run only when named explicitly with --only
+EXPERIMENTAL: Dict[str, Callable[[int], Dict]] = {"conv2_wgrad_wide": check_conv2_wgrad_wide}
+
+
 def run_all(clients: List[int], only: List[str] | None = None) -> List[Dict]:
     out = []
-    for name, fn in CHECKS.items():
-        if only and name not in only:
+    for name, fn in {**CHECKS, **EXPERIMENTAL}.items():
+        if (only and name not in only) or (not only and name in EXPERIMENTAL):
             continue
         for c in clients:
             rec: Dict = {"check": name, "clients": c}
