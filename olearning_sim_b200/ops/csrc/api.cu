@@ -87,6 +87,26 @@ int make_w_map(CUtensorMap* tm, const void* base, uint64_t C, int rows, int k, i
   return make_map(tm, base, 3, dims, str, box, box_k * 2);
 }
 
+// conv1 input X5 [N][32][32][16] stored pre-swizzled by the ingest kernel: 4-D map {256 el = 16 px, 2 halves, 32 rows, N}
+// without TMA swizzling -> a 12-row halo box is 12 box rows of 512 B instead of 192 rows of 32 B
+int make_x5_row_map(CUtensorMap* tm, const void* base, uint64_t n, int box_h) {
+  const uint64_t dims[4] = {256, 2, 32, n};
+  const uint64_t str[3] = {256, 512, 32 * 512};
+  const uint32_t box[4] = {256, 1, (uint32_t)box_h, 1};
+  cuuint64_t gd[4], gs[3];
+  cuuint32_t bx[4], es[4];
+  for (int i = 0; i < 4; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+  for (int i = 0; i < 3; ++i) gs[i] = str[i] * 2;
+  CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gd, gs, bx, es,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    snprintf(g_err, sizeof(g_err), "cuTensorMapEncodeTiled (x5 row map) failed with CUresult %d", (int)r);
+    return -3;
+  }
+  return 0;
+}
+
 constexpr int BATCH = 32;
 // kernel instances of the CNN-2 family
 //                          ROWB NKW BN  H   W   BATCH  FLIP   EPI         NSTAGE
@@ -105,6 +125,7 @@ using Conv2WgradWideCfg = WgradCfg<64, 5, 128, 6, 20>;
 using Conv2WgradCfg = WgradCfg<64, 5, 128, 2>;
 using Conv1WgradCfg = WgradCfg<32, 1, 64, 8>;
 
+int g_x5_rows = 1;       // 1: X5 is stored pre-swizzled and fetched with 512-byte box rows, 0: 32-byte swizzled rows
 int g_wgrad2_mode = 0;   // 0: five 12x16 boxes per chunk, 1: one 12x20 box, 2: one box + swizzle base offset
 bool g_attr_set = false;
 int set_attrs() {
@@ -154,7 +175,7 @@ int olsb_ingest_u8(const void* src_u8, void* dst_x5, long long nsamples, void* s
   const size_t npix = (size_t)nsamples * 32 * 32;
   const int th = 256;
   flk::ingest_u8_kernel<<<(unsigned)((npix + th - 1) / th), th, 0, (cudaStream_t)stream>>>(
-      (const uint8_t*)src_u8, (__nv_bfloat16*)dst_x5, npix);
+      (const uint8_t*)src_u8, (__nv_bfloat16*)dst_x5, npix, g_x5_rows);
   CK(cudaGetLastError());
   return 0;
 }
@@ -165,10 +186,12 @@ int olsb_conv1_fwd(const void* x5, long long x_total, int x_n_stride, int x_n_of
                    void* stream) {
   if (int r = olsb_init()) return r;
   CUtensorMap tmA, tmW;
-  if (int r = make_act_map(&tmA, x5, (uint64_t)x_total, 32, 32, 16, kBoxH)) return r;
+  if (int r = g_x5_rows ? make_x5_row_map(&tmA, x5, (uint64_t)x_total, kBoxH)
+                        : make_act_map(&tmA, x5, (uint64_t)x_total, 32, 32, 16, kBoxH)) return r;
   if (int r = make_w_map(&tmW, w1_fwd, (uint64_t)C, 32, 80, 32, 16)) return r;
   FwdParams p;
   memset(&p, 0, sizeof(p));
+  p.a_rowmap = g_x5_rows;
   p.num_clients = C; p.nsplit = auto_split(C, Conv1FwdCfg::TILES_PER_CLIENT, nsplit);
   p.a_n_stride = x_n_stride; p.a_n_off = x_n_off; p.active = (const uint8_t*)active;
   p.bias = (const float*)master + Cnn2Layout::B1; p.bias_stride = (int)P;
@@ -254,9 +277,11 @@ int olsb_conv1_wgrad(const void* x5, long long x_total, int x_n_stride, int x_n_
                      void* w1_fwd, float lr, float mu, void* grad_out, void* stream) {
   if (int r = olsb_init()) return r;
   CUtensorMap tmX;
-  if (int r = make_act_map(&tmX, x5, (uint64_t)x_total, 32, 32, 16, kBoxH)) return r;
+  if (int r = g_x5_rows ? make_x5_row_map(&tmX, x5, (uint64_t)x_total, kBoxH)
+                        : make_act_map(&tmX, x5, (uint64_t)x_total, 32, 32, 16, kBoxH)) return r;
   WgradParams p;
   memset(&p, 0, sizeof(p));
+  p.x_rowmap = g_x5_rows;
   p.num_clients = C; p.x_n_stride = x_n_stride; p.x_n_off = x_n_off; p.active = (const uint8_t*)active;
   p.w_master = (float*)master; p.w_global = (const float*)global_w; p.p_stride = (size_t)P;
   p.w_off = Cnn2Layout::W1; p.w_fwd = (__nv_bfloat16*)w1_fwd; p.w_dgrad = nullptr;
@@ -388,6 +413,7 @@ int olsb_fedavg_finish(const void* const* partial_peers, const void* const* wsum
 
 // runtime switches (kernel variants under evaluation); returns the previous value, -1 for an unknown name
 int olsb_set_option(const char* name, int value) {
+  if (!strcmp(name, "x5_rows")) { const int o = g_x5_rows; g_x5_rows = value; return o; }
   if (!strcmp(name, "wgrad2_mode")) { const int o = g_wgrad2_mode; g_wgrad2_mode = value; return o; }
   return -1;
 }

@@ -59,6 +59,7 @@ struct FwdParams {
   int a_n_stride;        // samples per client in the A tensor
   int a_n_off;           // first sample of this step's batch inside the client's block
   const uint8_t* active; // [C] or nullptr: 0 => client skipped this step (straggler / not sampled)
+  int a_rowmap;          // A tensor map is the no-swizzle "row" map (see make_x5_row_map): x coordinate = w0 / 16
   // EPI_POOL
   const float* bias;     // [C][bias_stride] fp32
   int bias_stride;
@@ -156,7 +157,8 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (leader) {
             mbar_arrive_expect_tx(&bars->full[stage], Cfg::STAGE_BYTES);
             const int dw = (NKW == 1) ? 0 : (FLIP ? (kHalo - kw) : (kw - kHalo));
-            tma_load_4d(a_sm + stage * Cfg::STAGE_BYTES, &tmA, &bars->full[stage], 0, w0 + dw, h0 - kHalo, n);
+            tma_load_4d(a_sm + stage * Cfg::STAGE_BYTES, &tmA, &bars->full[stage], 0,
+                        p.a_rowmap ? (w0 / kTileW) : (w0 + dw), h0 - kHalo, n);
           }
           if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
         }
@@ -906,6 +908,7 @@ struct WgradParams {
   float lr, mu;
   float* grad_out;               // optional [C][BN*NTAPS*KT] raw gradient (tests); when set no update is applied
   // SYNTH_Y: the dY operand is synthesised from the pooled gradient instead of being loaded by TMA
+  int x_rowmap;                  // X tensor map is the no-swizzle row map: x coordinate = w0 / 16
   int desc_mode;                 // wide-box variant: 1 = encode the swizzle base offset of unaligned operand starts
   const __nv_bfloat16* dpool;    // [C*BATCH][H/2][W/2][BN]
   const uint8_t* pcode;          // same shape, argmax position 0..3
@@ -994,7 +997,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
 #pragma unroll 1
             for (int kw = 0; kw < NKW; ++kw) {
               const int dw = (NKW == 1) ? 0 : (kw - kHalo);
-              tma_load_4d(base + kw * Cfg::XSTAGE, &tmX, &bars->full[ss], 0, w0 + dw, h0 - kHalo, nx);
+              tma_load_4d(base + kw * Cfg::XSTAGE, &tmX, &bars->full[ss], 0, p.x_rowmap ? (w0 / kTileW) : (w0 + dw),
+                          h0 - kHalo, nx);
             }
           }
           if (!SYNTH_Y) tma_load_4d(base + Cfg::NXB * Cfg::XSTAGE, &tmY, &bars->full[ss], 0, w0, h0, c * BATCH + s);

@@ -45,7 +45,11 @@ __device__ __forceinline__ float bf2f(__nv_bfloat16 v) { return __bfloat162float
 // uint8 [N][32][32][3]  ->  bf16 [N][32][32][16] with channel = kw*3+c holding x[h][w+kw-2][c] (zero outside).
 // The 5 horizontal taps of conv1 are unrolled into the channel dim once at upload time, so conv1 runs as a
 // 5-tap (vertical) implicit GEMM with K=16 per tap instead of wasting 13/16 of a K=16 MMA on 3 channels.
-__global__ void ingest_u8_kernel(const uint8_t* __restrict__ src, __nv_bfloat16* __restrict__ dst, size_t npix) {
+// preswizzle: store the pixel's two 16-byte halves swapped when (w & 4).  That is exactly the 32-byte swizzle the
+// tensor core applies to a tile of 32-byte pixel rows (address bit 4 ^= bit 7), done once in HBM, so TMA can fetch a
+// whole 16-pixel image row as ONE 512-byte unswizzled box row instead of sixteen 32-byte rows (TMA cost is per row).
+__global__ void ingest_u8_kernel(const uint8_t* __restrict__ src, __nv_bfloat16* __restrict__ dst, size_t npix,
+                                 int preswizzle) {
   const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (i >= npix) return;
   const int w = i & 31;
@@ -63,8 +67,9 @@ __global__ void ingest_u8_kernel(const uint8_t* __restrict__ src, __nv_bfloat16*
   }
   v[15] = __float2bfloat16_rn(0.f);
   uint4* o = reinterpret_cast<uint4*>(dst + i * 16);
-  o[0] = reinterpret_cast<uint4*>(v)[0];
-  o[1] = reinterpret_cast<uint4*>(v)[1];
+  const int sw = (preswizzle && (w & 4)) ? 1 : 0;
+  o[sw] = reinterpret_cast<uint4*>(v)[0];
+  o[sw ^ 1] = reinterpret_cast<uint4*>(v)[1];
 }
 
 // ---------------------------------------------------------------------------------------------

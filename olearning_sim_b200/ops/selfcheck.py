@@ -73,7 +73,7 @@ def check_ingest(c: int) -> Dict:
     x = torch.randint(0, 256, (n, 32, 32, 3), dtype=torch.uint8, device="cuda")
     out = torch.empty(n, 32, 32, 16, dtype=torch.bfloat16, device="cuda")
     native.ingest_u8(x, out)
-    ref = reference.ingest_ref(x).to(torch.bfloat16)
+    ref = reference.ingest_ref(x, preswizzle=True).to(torch.bfloat16)
     return {"err": rel_err(out.float(), ref.float()), "tol": 1e-4}
 
 

@@ -62,7 +62,7 @@ def test_engine_mlp_native_vs_torch_backend():
     b = FedEngine(FedConfig(backend="torch", **kw)); b.load_synthetic()
     assert a.backend == "native" and a.kernel_launches() == 0
     ra, rb = a.run_round(0), b.run_round(0)
-    assert a.kernel_launches() == 1 + 1 + 2 * 6 + 2
+    assert a.kernel_launches() == 1 + 1 + 2 * 6 + 3          # mask, broadcast, 2 steps x 6, accounting + reduce + finish
     assert (ra.participants, ra.dropped, ra.arrived, ra.client_steps) == (rb.participants, rb.dropped, rb.arrived, rb.client_steps)
     assert abs(ra.loss - rb.loss) < 3e-2 * max(1.0, abs(rb.loss)), (ra, rb)
     ga, gb = a.spec_flat_global().cpu(), b.spec_flat_global().cpu()

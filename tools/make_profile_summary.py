@@ -22,6 +22,10 @@ hdr = rows[0]; idx = {h: i for i, h in enumerate(hdr)}
 def g(r, k):
     try: return float(r[idx[k]].replace(",", ""))
     except Exception: return float("nan")
+def gbytes(r, k):
+    """DRAM byte counters come with a per-column unit (byte / Kbyte / Mbyte / Gbyte): normalise to GB"""
+    u = rows[1][idx[k]].lower()
+    return g(r, k) * {"byte": 1e-9, "kbyte": 1e-6, "mbyte": 1e-3, "gbyte": 1.0}.get(u, float("nan"))
 seen = {}
 for r in rows[2:]:
     name = r[idx["Kernel Name"]]
@@ -53,7 +57,7 @@ for key, (role, gf, mb) in work.items():
     floor = max(gf * C / (peaks["bf16_tflops"] * 1e3), mb * MB * C / (peaks["hbm_gbs"] * 1e9)) * 1e6
     tot_t += t_us; tot_floor += floor
     out.append(f"| `{key}…` | {role} | {t_us:.0f} | {g(r,'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active'):.1f} | "
-               f"{g(r,'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed'):.1f} | {r[idx['dram__bytes_read.sum']]}/{r[idx['dram__bytes_write.sum']]} {rows[1][idx['dram__bytes_read.sum']]} | "
+               f"{g(r,'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed'):.1f} | {gbytes(r,'dram__bytes_read.sum'):.2f} / {gbytes(r,'dram__bytes_write.sum'):.2f} | "
                f"{r[idx['launch__registers_per_thread']]} | {gf*C:.0f} | {tf:.0f} ({100*tf/peaks['bf16_tflops']:.0f}%) | {mb*C:.0f} | {gbs:.0f} ({100*gbs*1e9/(peaks['hbm_gbs']*1e9):.0f}%) | {floor:.0f} | {floor/t_us:.2f} |")
 out += ["", f"Local step total: {tot_t:.0f} us measured vs {tot_floor:.0f} us roofline-limited "
         f"(slower of FLOPs at measured cuBLAS peak and algorithmic bytes at measured copy bandwidth, per kernel) → "
