@@ -117,10 +117,10 @@ using Conv1FwdCfg = FwdCfg<32, 1, 32, 32, 32, BATCH, false, EPI_POOL, 12, 2>;
 using Conv2FwdCfg = FwdFoldCfg<32, 64, 16, BATCH, 7>;
 using Conv2DgradCfg = DgradFoldCfg<32, 64, 16, BATCH, 4>;
 //                              XROWB NKW YROWB H   W   BATCH NSS SYNTH_Y
-#define CONV2_WGRAD conv_wgrad_kernel<64, 5, 128, 16, 16, BATCH, 2, false>
+#define CONV2_WGRAD conv_wgrad_kernel<64, 5, 128, 16, 16, BATCH, 2, false, 2>
 #define CONV1_WGRAD conv_wgrad_kernel<32, 1, 64, 32, 32, BATCH, 8, true, 2>
 // conv2 weight gradient with ONE 12x20 halo box per chunk (horizontal taps = 1-pixel operand shifts)
-#define CONV2_WGRAD_WIDE conv_wgrad_kernel<64, 5, 128, 16, 16, BATCH, 6, false, 1, 20>
+#define CONV2_WGRAD_WIDE conv_wgrad_kernel<64, 5, 128, 16, 16, BATCH, 6, false, 2, 20>
 using Conv2WgradWideCfg = WgradCfg<64, 5, 128, 6, 20>;
 using Conv2WgradCfg = WgradCfg<64, 5, 128, 2>;
 using Conv1WgradCfg = WgradCfg<32, 1, 64, 8>;
@@ -264,9 +264,9 @@ int olsb_conv2_wgrad(const void* p1, const void* dy2, void* master, const void* 
   const int grid = C < g_sms ? C : g_sms;
   p.desc_mode = g_wgrad2_mode == 2 ? 1 : 0;
   if (wide)
-    CONV2_WGRAD_WIDE<<<grid, kThreads, Conv2WgradWideCfg::SMEM_BYTES, (cudaStream_t)stream>>>(tmX, tmY, p);
+    CONV2_WGRAD_WIDE<<<grid, 320, Conv2WgradWideCfg::SMEM_BYTES, (cudaStream_t)stream>>>(tmX, tmY, p);
   else
-    CONV2_WGRAD<<<grid, kThreads, Conv2WgradCfg::SMEM_BYTES, (cudaStream_t)stream>>>(tmX, tmY, p);
+    CONV2_WGRAD<<<grid, 320, Conv2WgradCfg::SMEM_BYTES, (cudaStream_t)stream>>>(tmX, tmY, p);
   CK(cudaGetLastError());
   return 0;
 }

@@ -53,6 +53,45 @@ struct Barriers {
 // ================================================================================================
 enum { EPI_POOL = 0, EPI_GATE = 1 };
 
+// 2x2 max-pool + ReLU of 32 channels held by the four lanes l, l^1, l^16, l^17 of a warp (one window = 2 rows x 2
+// columns of the 8x16 tile).  x = accumulator + bias.  Keys are the raw fp32 bits with (3 - window position) in the two
+// LSBs, compared as SIGNED integers: exact among non-negative values, and every negative value sorts below every
+// positive one — which is all ReLU needs (an all-negative window yields 0 whoever wins, and its gradient is gated
+// off downstream).  One integer max therefore carries value and argmax (ties -> smallest position) at one ALU op
+// per element; the sign-fixing key transform this replaces made the conv1 forward kernel ALU-bound (80% pipe).
+// Lane (b0 = lane&1, b4 = lane>>4&1) ends with channels [8*(2*b0+b4), +8): pv = bf16 values, cv = argmax codes.
+__device__ __forceinline__ void pool2x2_relu(const float (&x)[32], int b0, int b4, uint4& pv, uint2& cv) {
+  const int tag = 3 - ((b4 << 1) | b0);
+  int v[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = (__float_as_int(x[i]) & ~3) | tag;
+  int m16[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {                       // partner lane^1: b0=0 keeps channels [0,16), b0=1 [16,32)
+    const int give = b0 ? v[i] : v[16 + i];
+    const int keep = b0 ? v[16 + i] : v[i];
+    m16[i] = max(keep, __shfl_xor_sync(0xffffffffu, give, 1));
+  }
+  int m8[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {                        // partner lane^16: b4=0 keeps the low 8, b4=1 the high 8
+    const int give = b4 ? m16[i] : m16[8 + i];
+    const int keep = b4 ? m16[8 + i] : m16[i];
+    m8[i] = max(keep, __shfl_xor_sync(0xffffffffu, give, 16));
+  }
+  float f[8];
+  uint32_t cd[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    cd[i] = 3u - (static_cast<uint32_t>(m8[i]) & 3u);
+    f[i] = fmaxf(__int_as_float(m8[i] & ~3), 0.f);
+  }
+  pv.x = pack_bf16x2(f[0], f[1]); pv.y = pack_bf16x2(f[2], f[3]);
+  pv.z = pack_bf16x2(f[4], f[5]); pv.w = pack_bf16x2(f[6], f[7]);
+  cv.x = cd[0] | (cd[1] << 8) | (cd[2] << 16) | (cd[3] << 24);
+  cv.y = cd[4] | (cd[5] << 8) | (cd[6] << 16) | (cd[7] << 24);
+}
+
 struct FwdParams {
   int num_clients;
   int nsplit;            // work items per client
@@ -239,8 +278,7 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // this lane's output slice after the pooling butterfly: channels [j*32 + sl*8, +8)
     const int b0 = lane & 1, b4 = (lane >> 4) & 1;
     const int sl = b0 * 2 + b4;
-    const int pos = (b4 << 1) | b0;                      // position inside the 2x2 window (row-major)
-    float bias_r[(EPI == EPI_POOL) ? BN / 4 : 1];
+    float bias_r[(EPI == EPI_POOL) ? BN : 1];
 
     auto flush_bias = [&](int c) {
       if (EPI != EPI_GATE) return;
@@ -285,9 +323,7 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (EPI == EPI_POOL) {
           const float* bias = p.bias + (size_t)c * p.bias_stride;
 #pragma unroll
-          for (int j = 0; j < BN / 32; ++j)
-#pragma unroll
-            for (int k = 0; k < 8; ++k) bias_r[j * 8 + k] = __ldg(&bias[j * 32 + sl * 8 + k]);
+          for (int k = 0; k < BN; ++k) bias_r[k] = __ldg(&bias[k]);
         }
       }
       if (sp == 0) had_sp0 = true;
@@ -306,9 +342,8 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(32 * q) << 16) + buf * BN;
 
         if (EPI == EPI_POOL) {
-          // max-pool commutes with the (per-channel) bias add and with ReLU:  relu(max(acc) + b).
-          // Keys: order-preserving uint image of the fp32 accumulator with (3-pos) stashed in the two LSBs, so a
-          // single unsigned max carries value and argmax together (ties -> smallest position).
+          // relu(max_i(acc_i) + b) == relu(max_i(acc_i + b)): the bias goes in first (FMA pipe) so the pooling keys
+          // can be compared as signed integers (pool2x2_relu)
           const int ph = (h0 >> 1) + q, pw = (w0 >> 1) + (wl >> 1);
           const size_t obase = ((n_out * (IMG_H / 2) + ph) * (IMG_W / 2) + pw) * BN;
 #pragma unroll
@@ -316,44 +351,12 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             uint32_t v[32];
             tmem_ld32(taddr + j * 32, v);
             tmem_ld_wait();
+            float x[32];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const uint32_t bits = v[i];
-              const uint32_t key = bits ^ (static_cast<uint32_t>(static_cast<int32_t>(bits) >> 31) | 0x80000000u);
-              v[i] = (key & ~3u) | static_cast<uint32_t>(3 - pos);
-            }
-            // butterfly 1 (partner = lane^1): b0=0 keeps channels [0,16), b0=1 keeps [16,32)
-            uint32_t m16[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const uint32_t give = b0 ? v[i] : v[16 + i];
-              const uint32_t keep = b0 ? v[16 + i] : v[i];
-              m16[i] = max(keep, __shfl_xor_sync(0xffffffffu, give, 1));
-            }
-            // butterfly 2 (partner = lane^16): b4=0 keeps the low 8, b4=1 the high 8
-            uint32_t m8[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const uint32_t give = b4 ? m16[i] : m16[8 + i];
-              const uint32_t keep = b4 ? m16[8 + i] : m16[i];
-              m8[i] = max(keep, __shfl_xor_sync(0xffffffffu, give, 16));
-            }
-            float f[8];
-            uint32_t cd[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const uint32_t key = m8[i];
-              cd[i] = 3u - (key & 3u);
-              const uint32_t kk = key & ~3u;
-              const uint32_t bits = (kk & 0x80000000u) ? (kk ^ 0x80000000u) : ~kk;
-              f[i] = fmaxf(__uint_as_float(bits) + bias_r[j * 8 + i], 0.f);
-            }
+            for (int i = 0; i < 32; ++i) x[i] = __uint_as_float(v[i]) + bias_r[j * 32 + i];
             uint4 pv;
-            pv.x = pack_bf16x2(f[0], f[1]); pv.y = pack_bf16x2(f[2], f[3]);
-            pv.z = pack_bf16x2(f[4], f[5]); pv.w = pack_bf16x2(f[6], f[7]);
             uint2 cv;
-            cv.x = cd[0] | (cd[1] << 8) | (cd[2] << 16) | (cd[3] << 24);
-            cv.y = cd[4] | (cd[5] << 8) | (cd[6] << 16) | (cd[7] << 24);
+            pool2x2_relu(x, b0, b4, pv, cv);
             const size_t off = obase + j * 32 + sl * 8;
             *reinterpret_cast<uint4*>(p.out + off) = pv;
             *reinterpret_cast<uint2*>(p.code + off) = cv;
@@ -793,8 +796,7 @@ conv_fwd_fold_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     const int wl = lane & 15;
     const int b0 = lane & 1, b4 = (lane >> 4) & 1;
     const int sl = b0 * 2 + b4;
-    const int pos = (b4 << 1) | b0;
-    float bias_r[8];
+    float bias_r[32];
     int cur_client = -1;
     for (int wi = blockIdx.x; wi < num_work; wi += gridDim.x) {
       const int c = wi / p.nsplit, sp = wi % p.nsplit;
@@ -803,7 +805,7 @@ conv_fwd_fold_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         cur_client = c;
         const float* bias = p.bias + (size_t)c * p.bias_stride;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) bias_r[k] = __ldg(&bias[jg * 32 + sl * 8 + k]);
+        for (int k = 0; k < 32; ++k) bias_r[k] = __ldg(&bias[jg * 32 + k]);
       }
       const int t0 = sp * tiles_per_work;
       const int t1 = min(t0 + tiles_per_work, Cfg::TILES_PER_CLIENT);
@@ -824,7 +826,7 @@ conv_fwd_fold_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             tmem_ld32(taddr + 2 * 32, v);                       // kw = 2: no column shift
             tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) acc[i] = __uint_as_float(v[i]);
+            for (int i = 0; i < 32; ++i) acc[i] = __uint_as_float(v[i]) + bias_r[i];
           }
 #pragma unroll
           for (int kw = 0; kw < 5; ++kw) {
@@ -842,43 +844,9 @@ conv_fwd_fold_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           fence_before_sync();
           __syncwarp();
           if (lane == 0) mbar_arrive(&bars->tempty[j]);          // group drained: the tensor core may refill it
-          uint32_t v[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const uint32_t bits = __float_as_uint(acc[i]);
-            const uint32_t key = bits ^ (static_cast<uint32_t>(static_cast<int32_t>(bits) >> 31) | 0x80000000u);
-            v[i] = (key & ~3u) | static_cast<uint32_t>(3 - pos);
-          }
-          uint32_t m16[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const uint32_t give = b0 ? v[i] : v[16 + i];
-            const uint32_t keep = b0 ? v[16 + i] : v[i];
-            m16[i] = max(keep, __shfl_xor_sync(0xffffffffu, give, 1));
-          }
-          uint32_t m8[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const uint32_t give = b4 ? m16[i] : m16[8 + i];
-            const uint32_t keep = b4 ? m16[8 + i] : m16[i];
-            m8[i] = max(keep, __shfl_xor_sync(0xffffffffu, give, 16));
-          }
-          float f[8];
-          uint32_t cd[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const uint32_t key = m8[i];
-            cd[i] = 3u - (key & 3u);
-            const uint32_t kk = key & ~3u;
-            const uint32_t bits = (kk & 0x80000000u) ? (kk ^ 0x80000000u) : ~kk;
-            f[i] = fmaxf(__uint_as_float(bits) + bias_r[i], 0.f);
-          }
           uint4 pv;
-          pv.x = pack_bf16x2(f[0], f[1]); pv.y = pack_bf16x2(f[2], f[3]);
-          pv.z = pack_bf16x2(f[4], f[5]); pv.w = pack_bf16x2(f[6], f[7]);
           uint2 cv;
-          cv.x = cd[0] | (cd[1] << 8) | (cd[2] << 16) | (cd[3] << 24);
-          cv.y = cd[4] | (cd[5] << 8) | (cd[6] << 16) | (cd[7] << 24);
+          pool2x2_relu(acc, b0, b4, pv, cv);
           const size_t off = obase + j * 32 + sl * 8;
           *reinterpret_cast<uint4*>(p.out + off) = pv;
           *reinterpret_cast<uint2*>(p.code + off) = cv;
@@ -948,7 +916,6 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   constexpr int TILES_X = IMG_W / kTileW, TILES_Y = IMG_H / kTileH;
   constexpr int CHUNKS = BATCH * TILES_X * TILES_Y;   // pixel chunks (K dimension, 128 pixels each)
   static_assert(!SYNTH_Y || YROWB == 64, "operand synthesis is written for 32 output channels (SW64 rows)");
-  static_assert(SYNTH_Y || NEPG == 1, "extra epilogue groups only help the operand-synthesis variant");
   constexpr int kProdWarp = 4 * NEPG, kMmaWarp = 4 * NEPG + 1;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -959,7 +926,9 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   if (threadIdx.x == 0) {
     for (int i = 0; i < NSS; ++i) { mbar_init(&bars->full[i], SYNTH_Y ? 1 + kEpiWarps : 1); mbar_init(&bars->empty[i], 1); }
     mbar_init(&bars->tfull[0], 1);
-    mbar_init(&bars->tempty[0], kEpiWarps);
+    // SYNTH_Y: only group 0 drains TMEM (one M tile).  Otherwise the groups drain alternate M tiles: the fused
+    // update is latency-bound (batches of 32 dependent-free loads), so twice the warps halve the tensor-idle time.
+    mbar_init(&bars->tempty[0], (SYNTH_Y || Cfg::MTILES == 1) ? kEpiWarps : kEpiWarps * NEPG);
     fence_mbar_init();
   }
   if (warp == kMmaWarp) { tmem_alloc(&bars->tmem_base, Cfg::TMEM_COLS); tmem_relinquish(); }
@@ -1122,7 +1091,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         }
         cseq += CHUNKS;
       }
-      if (grp != 0) continue;                                       // group 0 drains TMEM / applies the update
+      constexpr bool kSplitDrain = !SYNTH_Y && Cfg::MTILES > 1;
+      if (!kSplitDrain && grp != 0) continue;                       // group 0 drains TMEM / applies the update
       mbar_wait(&bars->tfull[0], tphase);
       fence_after_sync();
       float* wm = p.w_master + (size_t)c * p.p_stride + p.w_off;
@@ -1131,7 +1101,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       __nv_bfloat16* wd = p.w_dgrad ? p.w_dgrad + (size_t)c * BN * Cfg::NTAPS * KT : nullptr;
       float* go = p.grad_out ? p.grad_out + (size_t)c * BN * Cfg::NTAPS * KT : nullptr;
 #pragma unroll 1
-      for (int mt = 0; mt < Cfg::MTILES; ++mt) {
+      for (int mt = kSplitDrain ? grp : 0; mt < Cfg::MTILES; mt += kSplitDrain ? NEPG : 1) {
         int kh, kw; bool valid;
         if (mt < NKW) { kh = ci; kw = mt; valid = kh < kNKH; }
         else if (mt == NKW) { kh = 4; kw = ci; valid = kw < 4; }
