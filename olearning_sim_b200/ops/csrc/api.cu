@@ -126,6 +126,7 @@ using Conv2WgradCfg = WgradCfg<64, 5, 128, 2>;
 using Conv1WgradCfg = WgradCfg<32, 1, 64, 8>;
 
 int g_x5_rows = 1;       // 1: X5 is stored pre-swizzled and fetched with 512-byte box rows, 0: 32-byte swizzled rows
+int g_wgrad2_ws = 0;     // 1: weight-stationary (B-collector) MMAs in the conv2 weight gradient
 int g_wgrad2_mode = 0;   // 0: five 12x16 boxes per chunk, 1: one 12x20 box, 2: one box + swizzle base offset
 bool g_attr_set = false;
 int set_attrs() {
@@ -263,6 +264,7 @@ int olsb_conv2_wgrad(const void* p1, const void* dy2, void* master, const void* 
   p.lr = lr; p.mu = mu; p.grad_out = (float*)grad_out;
   const int grid = C < g_sms ? C : g_sms;
   p.desc_mode = g_wgrad2_mode == 2 ? 1 : 0;
+  p.mma_ws = g_wgrad2_ws;
   if (wide)
     CONV2_WGRAD_WIDE<<<grid, 320, Conv2WgradWideCfg::SMEM_BYTES, (cudaStream_t)stream>>>(tmX, tmY, p);
   else
@@ -414,6 +416,7 @@ int olsb_fedavg_finish(const void* const* partial_peers, const void* const* wsum
 // runtime switches (kernel variants under evaluation); returns the previous value, -1 for an unknown name
 int olsb_set_option(const char* name, int value) {
   if (!strcmp(name, "x5_rows")) { const int o = g_x5_rows; g_x5_rows = value; return o; }
+  if (!strcmp(name, "wgrad2_ws")) { const int o = g_wgrad2_ws; g_wgrad2_ws = value; return o; }
   if (!strcmp(name, "wgrad2_mode")) { const int o = g_wgrad2_mode; g_wgrad2_mode = value; return o; }
   return -1;
 }

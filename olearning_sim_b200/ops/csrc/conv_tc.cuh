@@ -877,6 +877,7 @@ struct WgradParams {
   float* grad_out;               // optional [C][BN*NTAPS*KT] raw gradient (tests); when set no update is applied
   // SYNTH_Y: the dY operand is synthesised from the pooled gradient instead of being loaded by TMA
   int x_rowmap;                  // X tensor map is the no-swizzle row map: x coordinate = w0 / 16
+  int mma_ws;                    // 1: weight-stationary MMAs (dY slice latched in the B collector across the M tiles)
   int desc_mode;                 // wide-box variant: 1 = encode the swizzle base offset of unaligned operand starts
   const __nv_bfloat16* dpool;    // [C*BATCH][H/2][W/2][BN]
   const uint8_t* pcode;          // same shape, argmax position 0..3
@@ -1001,15 +1002,34 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
           const uint32_t soff = ss * Cfg::SS_BYTES;
           const uint64_t b0 = desc_advance(b_y, soff);
           const uint32_t accum = t > 0 ? 1u : 0u;
-#pragma unroll
-          for (int mt = 0; mt < Cfg::MTILES; ++mt) {
-            const uint64_t a0 = (mt < NKW) ? desc_advance(a_kw, soff + mt * KW_STEP)
-                                           : (mt == NKW ? desc_advance(a_r, soff) : desc_advance(a_l, soff));
+          auto a_tile = [&](int mt) -> uint64_t {
+            return (mt < NKW) ? desc_advance(a_kw, soff + mt * KW_STEP)
+                              : (mt == NKW ? desc_advance(a_r, soff) : desc_advance(a_l, soff));
+          };
+          if (Cfg::MTILES > 1 && p.mma_ws) {
+            // k-step outermost: the 7 M tiles of a k-step share the dY slice, latched once in the B collector
 #pragma unroll
             for (int ks = 0; ks < (kTileH * kTileW) / 16; ++ks) {
-              uint64_t ad = desc_advance(a0, ks * XP);            // k-step = one tile row = one box row
-              if (Cfg::WIDE && p.desc_mode) ad = desc_set_base_offset(ad);
-              umma_bf16(tmem_base + mt * BN, ad, desc_advance(b0, ks * 16 * YROWB), IDESC, ks > 0 ? 1u : accum);
+              const uint64_t bd = desc_advance(b0, ks * 16 * YROWB);
+              const uint32_t acc = ks > 0 ? 1u : accum;
+#pragma unroll
+              for (int mt = 0; mt < Cfg::MTILES; ++mt) {
+                const uint64_t ad = desc_advance(a_tile(mt), ks * XP);
+                if (mt == 0) umma_bf16_ws<WS_FILL>(tmem_base + mt * BN, ad, bd, IDESC, acc);
+                else if (mt == Cfg::MTILES - 1) umma_bf16_ws<WS_LAST>(tmem_base + mt * BN, ad, bd, IDESC, acc);
+                else umma_bf16_ws<WS_USE>(tmem_base + mt * BN, ad, bd, IDESC, acc);
+              }
+            }
+          } else {
+#pragma unroll
+            for (int mt = 0; mt < Cfg::MTILES; ++mt) {
+              const uint64_t a0 = a_tile(mt);
+#pragma unroll
+              for (int ks = 0; ks < (kTileH * kTileW) / 16; ++ks) {
+                uint64_t ad = desc_advance(a0, ks * XP);            // k-step = one tile row = one box row
+                if (Cfg::WIDE && p.desc_mode) ad = desc_set_base_offset(ad);
+                umma_bf16(tmem_base + mt * BN, ad, desc_advance(b0, ks * 16 * YROWB), IDESC, ks > 0 ? 1u : accum);
+              }
             }
           }
           umma_commit(&bars->empty[ss]);

@@ -18,6 +18,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "tc05.cuh"
+
 namespace flk {
 
 // ---------------------------------------------------------------------------------------------
@@ -149,7 +151,10 @@ struct HeadParams {
 };
 
 constexpr int kHeadThreads = 256;
-constexpr int kHeadSmem = (10 * 4096 + 32 * 10 + 32 * 10 + 64 + 16) * 4;
+// backward-phase staging ring: a slice = 8 samples x 512 features of the pooled activation (bf16) and its argmax code,
+// fetched by 1-D bulk copies four slices ahead of their use
+constexpr int kHeadSlots = 4, kHeadSliceX = 8 * 512 * 2, kHeadSliceC = 8 * 512, kHeadSlice = kHeadSliceX + kHeadSliceC;
+constexpr int kHeadSmem = (10 * 4096 + 32 * 10 + 32 * 10 + 64 + 16) * 4 + kHeadSlots * kHeadSlice + 64;
 
 __global__ void __launch_bounds__(kHeadThreads, 1) head_fc_xent_kernel(const HeadParams p) {
   using L = Cnn2Layout;
@@ -159,11 +164,37 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_fc_xent_kernel(const Hea
   float* dlog = logit + 320;         // [32][10]
   float* db2 = dlog + 320;           // [64]
   float* misc = db2 + 64;            // [16]
+  uint8_t* ring = reinterpret_cast<uint8_t*>(misc + 16);
+  uint64_t* rfull = reinterpret_cast<uint64_t*>(ring + kHeadSlots * kHeadSlice);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int i = 0; i < kHeadSlots; ++i) tc05::mbar_init(&rfull[i], 1);
+    tc05::fence_mbar_init();
+  }
+  __syncthreads();
+  uint32_t nslice = 0;               // slices consumed so far by this CTA (slot = nslice % 4, parity = nslice / 4 & 1)
 
   for (int c = blockIdx.x; c < p.num_clients; c += gridDim.x) {
     if (p.active && !p.active[c]) continue;
     float* wm = p.master + (size_t)c * p.P;
+    // slice n of a client = (feature block it = n / 4, sample batch b = n % 4); issued by one thread
+    auto issue_slice = [&](int n, uint32_t seq) {
+      const int it = n >> 2, s0 = (n & 3) * 8, slot = seq % kHeadSlots;
+      uint8_t* dst = ring + slot * kHeadSlice;
+      const __nv_bfloat16* xs = p.p2 + ((size_t)c * 32 + s0) * 4096 + it * 512;
+      const uint8_t* cs = p.code2 + ((size_t)c * 32 + s0) * 4096 + it * 512;
+      tc05::mbar_arrive_expect_tx(&rfull[slot], kHeadSlice);
+#pragma unroll 1
+      for (int u = 0; u < 8; ++u) {
+        tc05::bulk_copy_g2s(dst + u * 1024, xs + (size_t)u * 4096, 1024, &rfull[slot]);
+        tc05::bulk_copy_g2s(dst + kHeadSliceX + u * 512, cs + (size_t)u * 4096, 512, &rfull[slot]);
+      }
+    };
+    // the first four slices of the backward phase travel while the weights load and the logits are computed
+    if (tid == 0) {
+      tc05::fence_proxy_async_smem();
+      for (int n = 0; n < kHeadSlots; ++n) issue_slice(n, nslice + n);
+    }
     // 40 float4 per thread, 8 loads in flight per thread before the first shared-memory store
 #pragma unroll 1
     for (int i0 = tid * 4; i0 < L::WFC_N; i0 += kHeadThreads * 4 * 8) {
@@ -273,27 +304,25 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_fc_xent_kernel(const Hea
       for (int j = 0; j < 10; ++j) { w0[j] = Ws[j * 4096 + k]; w1[j] = Ws[j * 4096 + k + 1]; g0[j] = 0.f; g1[j] = 0.f; }
       const int pix = k >> 6, ch = k & 63, ph = pix >> 3, pw = pix & 7;
       float dbl0 = 0.f, dbl1 = 0.f;
-      // 8 samples per batch: all global loads of a batch are issued before the first dependent store, so the
-      // L2/HBM latency is paid once per batch instead of once per sample
-      uint32_t xn8[8];
-      uint16_t cn8[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        xn8[u] = __ldg(reinterpret_cast<const uint32_t*>(x + (size_t)u * 4096 + k));
-        cn8[u] = __ldg(reinterpret_cast<const uint16_t*>(code + (size_t)u * 4096 + k));
-      }
+      // 8 samples per batch, staged in shared memory by bulk copies issued four slices (~2 us of work) ahead
 #pragma unroll 1
       for (int s0 = 0; s0 < 32; s0 += 8) {
+        const uint32_t seq = nslice++;
+        const int slot = seq % kHeadSlots;
+        tc05::mbar_wait(&rfull[slot], (seq / kHeadSlots) & 1);
+        const uint8_t* sl = ring + slot * kHeadSlice;
         uint32_t xr8[8];
         uint16_t cr8[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) { xr8[u] = xn8[u]; cr8[u] = cn8[u]; }
-        if (s0 + 8 < 32) {
-#pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            xn8[u] = __ldg(reinterpret_cast<const uint32_t*>(x + (size_t)(s0 + 8 + u) * 4096 + k));
-            cn8[u] = __ldg(reinterpret_cast<const uint16_t*>(code + (size_t)(s0 + 8 + u) * 4096 + k));
-          }
+        for (int u = 0; u < 8; ++u) {
+          xr8[u] = *reinterpret_cast<const uint32_t*>(sl + u * 1024 + tid * 4);
+          cr8[u] = *reinterpret_cast<const uint16_t*>(sl + kHeadSliceX + u * 512 + tid * 2);
+        }
+        // everyone has read the slot: refill it with the slice four ahead (same client only)
+        __syncthreads();
+        if (tid == 0 && it * 4 + (s0 >> 3) + kHeadSlots < 32) {
+          tc05::fence_proxy_async_smem();
+          issue_slice(it * 4 + (s0 >> 3) + kHeadSlots, seq + kHeadSlots);
         }
 #pragma unroll
         for (int u = 0; u < 8; ++u) {

@@ -102,6 +102,15 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* tm, ui
       : "memory");
 }
 
+// 1-D bulk copy global -> shared (bytes multiple of 16, both addresses 16-byte aligned); completion is counted in
+// bytes on `bar` (pair with mbar_arrive_expect_tx).
+__device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gptr, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gptr), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
 // L2 prefetch of a contiguous global range (bytes multiple of 16): warms L2 for data an epilogue will read later.
 __device__ __forceinline__ void prefetch_l2_bulk(const void* gptr, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
@@ -140,6 +149,28 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint
       "}\n" ::"r"(d_tmem),
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
+}
+// Weight-stationary form: the B operand is latched in collector buffer b0 and reused by the following MMAs that name
+// the same B (FILL: read B from shared memory and keep it; USE: reuse and keep; LAST: reuse and release).  Consecutive
+// MMAs that differ only in A / D then fetch B once instead of once per MMA — the shared-memory operand pipe is what
+// bounds small-N SS-mode MMAs.
+enum { WS_FILL = 0, WS_USE = 1, WS_LAST = 2 };
+template <int MODE>
+__device__ __forceinline__ void umma_bf16_ws(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  if (MODE == WS_FILL) {
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+                 "tcgen05.mma.ws.cta_group::1.kind::f16.collector::b0::fill [%0], %1, %2, %3, p;\n}\n" ::"r"(d_tmem),
+                 "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+  } else if (MODE == WS_USE) {
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+                 "tcgen05.mma.ws.cta_group::1.kind::f16.collector::b0::use [%0], %1, %2, %3, p;\n}\n" ::"r"(d_tmem),
+                 "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+  } else {
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+                 "tcgen05.mma.ws.cta_group::1.kind::f16.collector::b0::lastuse [%0], %1, %2, %3, p;\n}\n" ::"r"(d_tmem),
+                 "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+  }
 }
 // Arrives (count 1) on `bar` once every previously issued MMA of this thread has completed.
 // Implies tcgen05.fence::before_thread_sync.

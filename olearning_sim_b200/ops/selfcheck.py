@@ -222,18 +222,21 @@ def check_conv2_wgrad_wide(c: int) -> Dict:
     gref = w.grad.permute(0, 1, 3, 4, 2).reshape(c, 64, 5, 5, 32)       # cout, kh, kw, cin
     res: Dict = {"tol": 1e-2, "err": 0.0}
     try:
-        for mode in (0, 1, 2):
+        for mode, ws in ((0, 0), (0, 1), (1, 0), (1, 1)):
             native.set_option("wgrad2_mode", mode)
+            native.set_option("wgrad2_ws", ws)
             gout = torch.zeros(c, CNN2.W2_N, device="cuda")
             native.conv2_wgrad(p1, dy2, master, None, c, None, w2f, w2d, 0.1, 0.0, gout)
             torch.cuda.synchronize()
             g = gout.reshape(c, 64, 5, 5, 32)
-            res[f"mode{mode}_kw"] = [round(rel_err(g[:, :, :, k], gref[:, :, :, k]), 5) for k in range(5)]
-            res[f"mode{mode}_kh"] = [round(rel_err(g[:, :, k], gref[:, :, k]), 5) for k in range(5)]
-            res[f"mode{mode}_us"] = round(_time_us(lambda: native.conv2_wgrad(p1, dy2, master, None, c, None, w2f, w2d,
-                                                                              0.1, 0.0, gout)), 1)
+            tag = f"box{mode}_ws{ws}"
+            res[f"{tag}_kw"] = [round(rel_err(g[:, :, :, k], gref[:, :, :, k]), 5) for k in range(5)]
+            res[f"{tag}_kh"] = [round(rel_err(g[:, :, k], gref[:, :, k]), 5) for k in range(5)]
+            res[f"{tag}_us"] = round(_time_us(lambda: native.conv2_wgrad(p1, dy2, master, None, c, None, w2f, w2d,
+                                                                         0.1, 0.0, gout)), 1)
     finally:
         native.set_option("wgrad2_mode", 0)
+        native.set_option("wgrad2_ws", 0)
     return res
 
 
