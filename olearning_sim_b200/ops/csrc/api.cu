@@ -126,7 +126,6 @@ using Conv2WgradCfg = WgradCfg<64, 5, 128, 2>;
 using Conv1WgradCfg = WgradCfg<32, 1, 64, 8>;
 
 int g_x5_rows = 1;       // 1: X5 is stored pre-swizzled and fetched with 512-byte box rows, 0: 32-byte swizzled rows
-int g_dgrad_ws = 0;      // 1: conv2 data gradient issues tile pairs with weight-stationary MMAs
 int g_wgrad2_ws = 1;     // 1: weight-stationary (B-collector) MMAs in the conv2 weight gradient
 int g_wgrad2_mode = 1;   // 0: five 12x16 boxes per chunk, 1: one 12x20 box, 2: one box + swizzle base offset
 bool g_attr_set = false;
@@ -242,7 +241,6 @@ int olsb_conv2_dgrad(const void* dy2, const void* w2_dgrad, void* master, const 
   p.bias_master = (float*)master + Cnn2Layout::B1; p.bias_stride = (int)P;
   p.bias_global = global_w ? (const float*)global_w + Cnn2Layout::B1 : nullptr;
   p.lr = lr; p.mu = mu; p.dbias_out = (float*)dbias_out;
-  p.mma_ws = g_dgrad_ws;
   const int work = C * p.nsplit;
   const int grid = work < g_sms ? work : g_sms;
   CONV2_DGRAD<<<grid, kFoldThreads, Conv2DgradCfg::SMEM_BYTES, (cudaStream_t)stream>>>(tmA, tmW, p);
@@ -418,7 +416,6 @@ int olsb_fedavg_finish(const void* const* partial_peers, const void* const* wsum
 // runtime switches (kernel variants under evaluation); returns the previous value, -1 for an unknown name
 int olsb_set_option(const char* name, int value) {
   if (!strcmp(name, "x5_rows")) { const int o = g_x5_rows; g_x5_rows = value; return o; }
-  if (!strcmp(name, "dgrad_ws")) { const int o = g_dgrad_ws; g_dgrad_ws = value; return o; }
   if (!strcmp(name, "wgrad2_ws")) { const int o = g_wgrad2_ws; g_wgrad2_ws = value; return o; }
   if (!strcmp(name, "wgrad2_mode")) { const int o = g_wgrad2_mode; g_wgrad2_mode = value; return o; }
   return -1;

@@ -98,7 +98,6 @@ struct FwdParams {
   int a_n_stride;        // samples per client in the A tensor
   int a_n_off;           // first sample of this step's batch inside the client's block
   const uint8_t* active; // [C] or nullptr: 0 => client skipped this step (straggler / not sampled)
-  int mma_ws;            // folded dgrad: issue tiles in pairs with weight-stationary MMAs (B collector reuse)
   int a_rowmap;          // A tensor map is the no-swizzle "row" map (see make_x5_row_map): x coordinate = w0 / 16
   // EPI_POOL
   const float* bias;     // [C][bias_stride] fp32
@@ -506,46 +505,7 @@ conv_dgrad_fold_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       if (c != cur_client) { mbar_wait(&bars->wfull, wphase); wphase ^= 1; cur_client = c; }
       const int t0 = sp * tiles_per_work;
       const int t1 = min(t0 + tiles_per_work, Cfg::TILES_PER_CLIENT);
-      for (int t = t0; t < t1;) {
-        if (p.mma_ws && t + 1 < t1) {
-          // two tiles at once: the weight slice of every (kh, k-step) is latched in the B collector by the first
-          // tile's MMA and reused by the second, halving the weight traffic on the shared-memory operand pipe
-          const int stage2 = (stage + 1 == NSTAGE) ? 0 : stage + 1;
-          const uint32_t phase2 = (stage + 1 == NSTAGE) ? (phase ^ 1) : phase;
-          mbar_wait(&bars->tempty[0], tphase0 ^ 1);
-          mbar_wait(&bars->tempty[1], tphase1 ^ 1);
-          fence_after_sync();
-          mbar_wait(&bars->full[stage], phase);
-          mbar_wait(&bars->full[stage2], phase2);
-          fence_after_sync();
-          if (leader) {
-            const uint32_t d_a = tmem_base + buf * Cfg::TMEM_BUF_STRIDE;
-            const uint32_t d_b = tmem_base + (buf ^ 1) * Cfg::TMEM_BUF_STRIDE;
-            const uint64_t a_sa = desc_advance(a_desc_base, stage * Cfg::STAGE_BYTES);
-            const uint64_t a_sb = desc_advance(a_desc_base, stage2 * Cfg::STAGE_BYTES);
-#pragma unroll
-            for (int kh = 0; kh < kNKH; ++kh) {
-              const uint32_t aoff = (2 * kHalo - kh) * kTileW * ROWB;
-              const uint64_t b_desc = desc_advance(b_desc_base, kh * Cfg::W_KH_BYTES);
-#pragma unroll
-              for (int ks = 0; ks < ROWB / 32; ++ks) {
-                const uint64_t bd = desc_advance(b_desc, ks * 16 * CIN * 2);
-                umma_bf16_ws<WS_FILL>(d_a, desc_advance(a_sa, aoff + ks * 32), bd, IDESC, (kh | ks) ? 1u : 0u);
-                umma_bf16_ws<WS_LAST>(d_b, desc_advance(a_sb, aoff + ks * 32), bd, IDESC, (kh | ks) ? 1u : 0u);
-              }
-            }
-            umma_commit(&bars->empty[stage]);
-            umma_commit(&bars->empty[stage2]);
-            umma_commit(&bars->tfull[buf]);
-            umma_commit(&bars->tfull[buf ^ 1]);
-          }
-          __syncwarp();
-          stage = (stage2 + 1 == NSTAGE) ? 0 : stage2 + 1;
-          phase = (stage2 + 1 == NSTAGE) ? (phase2 ^ 1) : phase2;
-          tphase0 ^= 1; tphase1 ^= 1;
-          t += 2;
-          continue;
-        }
+      for (int t = t0; t < t1; ++t) {
         mbar_wait(&bars->tempty[buf], (buf ? tphase1 : tphase0) ^ 1);
         fence_after_sync();
         mbar_wait(&bars->full[stage], phase);
@@ -569,7 +529,6 @@ conv_dgrad_fold_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
         if (buf) tphase1 ^= 1; else tphase0 ^= 1;
         buf ^= 1;
-        ++t;
       }
       if (last_of_client) {
         if (leader) umma_commit(&bars->wempty);
