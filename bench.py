@@ -38,7 +38,22 @@ def parse_args():
     ap.add_argument("--local-steps", type=int, default=5)
     ap.add_argument("--shard", type=int, default=64)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5],
+                    help="BASELINE.json config: 2 FedAvg CNN-2 x1024 (flagship, default), 3 FedAvg ResNet-18 x512 with "
+                         "online/offline + spike trace, 4 FedProx CNN-2 x4096 heterogeneous steps, 5 FedAvg BERT-mini x256")
     return ap.parse_args()
+
+
+# BASELINE.json configs other than the flagship; --clients / --local-steps override the preset when given explicitly
+PRESETS = {
+    2: dict(model="cnn2", clients=1024, local_steps=5, shard=64, algorithm="fedavg"),
+    3: dict(model="resnet18", clients=512, local_steps=5, shard=64, algorithm="fedavg", p_online=0.8,
+            online_trace="0.6+0.4*math.sin(t/4)", drop_probability=0.05),
+    4: dict(model="cnn2", clients=4096, local_steps=5, shard=64, algorithm="fedprox", mu=0.01, hetero_steps=True),
+    5: dict(model="bert_mini", clients=256, local_steps=2, shard=64, algorithm="fedavg"),
+}
+MODEL_DESC = {"cnn2": "cnn2 (conv5x5x32-pool-conv5x5x64-pool-fc10, 94666 params)", "resnet18": "resnet18 (GroupNorm, CIFAR stem)",
+              "bert_mini": "bert_mini (4 layers, hidden 256, seq 128)"}
 
 
 class ClockSampler:
@@ -107,9 +122,16 @@ def main() -> int:
             print(json.dumps({"metric": METRIC, "value": None, "error": "no CUDA device"}))
         return 1
     dev = torch.device("cuda", local)
-    backend = "native" if args.impl == "ours" else "torch"
-    cfg = FedConfig(model="cnn2", num_clients=args.clients, local_steps=args.local_steps, batch=32, shard=args.shard,
-                    lr=0.05, algorithm="fedavg", backend=backend, device=str(dev), seed=0)
+    pre = dict(PRESETS[args.config])
+    if args.config != 2:
+        # presets carry their own sizes unless the flags were given explicitly
+        if "--clients" not in sys.argv: args.clients = pre["clients"]
+        if "--local-steps" not in sys.argv: args.local_steps = pre["local_steps"]
+    model = pre.pop("model"); pre.pop("clients"); pre.pop("local_steps"); pre.pop("shard")
+    native_ok = model in ("cnn2", "mlp2")
+    backend = "native" if (args.impl == "ours" and native_ok) else "torch"
+    cfg = FedConfig(model=model, num_clients=args.clients, local_steps=args.local_steps, batch=32, shard=args.shard,
+                    lr=0.05, backend=backend, device=str(dev), seed=0, **pre)
     eng = FedEngine(cfg, rank, world)
     eng.load_synthetic()
 
@@ -175,9 +197,10 @@ def main() -> int:
             "ms_per_step": ms_per_round, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "bf16" if backend == "native" else "fp32", "data": "synthetic",
             "impl": args.impl, "rounds_per_sec": 1e3 / ms_per_round,
-            "config": {"model": "cnn2 (conv5x5x32-pool-conv5x5x64-pool-fc10, 94666 params)", "algorithm": "fedavg",
+            "config": {"id": args.config, "model": MODEL_DESC[model], "algorithm": cfg.algorithm, "backend": backend,
                        "clients": args.clients, "local_steps": args.local_steps, "local_batch": 32,
-                       "samples_per_client": args.shard, "global_batch": args.clients * 32, "seq_len": None,
+                       "samples_per_client": args.shard, "global_batch": args.clients * 32,
+                       "seq_len": 128 if model == "bert_mini" else None,
                        "parallelism": f"clients sharded dp{world}",
                        "l2": "inputs larger than L2 (per-round working set of GBs streams through HBM)"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches,

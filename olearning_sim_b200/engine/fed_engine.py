@@ -60,6 +60,7 @@ class FedConfig:
     deviceflow_strategy: Optional[str] = None
     online_trace: Optional[str] = None
     wave: Optional[int] = None       # clients with resident activations at once (None = auto from free HBM)
+    torch_chunk: Optional[int] = None  # torch backend: clients per vmap chunk (None = sized from the parameter count)
     profile: bool = False            # CUDA-event phase timing (mask / broadcast / local / reduce), max over ranks
 
     def __post_init__(self):
@@ -282,8 +283,12 @@ class FedEngine:
         def loss_fn(flat, x, y):
             return spec.loss(flat, x, y)
 
-        self._grad_fn = vmap(grad(loss_fn, has_aux=False), in_dims=(0, 0, 0), randomness="different")
-        self._loss_fn = vmap(loss_fn, in_dims=(0, 0, 0))
+        from torch.func import grad_and_value
+        # one pass yields gradient and loss; clients are processed in chunks so activations of big models fit in HBM
+        chunk = self.cfg.torch_chunk or max(1, min(self.C, int(20e9 / (max(self.P, 1) * 48))))
+        self._chunk = chunk if chunk < self.C else None
+        self._grad_loss_fn = vmap(grad_and_value(loss_fn), in_dims=(0, 0, 0), randomness="different",
+                                  chunk_size=self._chunk)
 
     def _torch_round(self, round_idx: int) -> RoundResult:
         cfg = self.cfg
@@ -309,9 +314,8 @@ class FedEngine:
             off = (s * B) % cfg.shard
             xb, yb = self.x[:, off:off + B], self.y[:, off:off + B]
             w = self.master
-            g = self._grad_fn(w, xb, yb)
-            with torch.no_grad():
-                self.loss_sum += self._loss_fn(w, xb, yb) * step_active[s]
+            g, loss = self._grad_loss_fn(w, xb, yb)
+            self.loss_sum += loss.detach() * step_active[s]
             if cfg.mu > 0:
                 g = g + cfg.mu * (w - self.global_w[None, :])
             self.master = torch.where(step_active[s][:, None], w - cfg.lr * g, w)
