@@ -38,6 +38,9 @@ def parse_args():
     ap.add_argument("--local-steps", type=int, default=5)
     ap.add_argument("--shard", type=int, default=64)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--phases", action="store_true",
+                    help="after the timed regions, run 3 extra rounds with CUDA-event phase timers and report "
+                         "broadcast / local / reduce times and the peer-memory bus bandwidth they imply")
     ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5],
                     help="BASELINE.json config: 2 FedAvg CNN-2 x1024 (flagship, default), 3 FedAvg ResNet-18 x512 with "
                          "online/offline + spike trace, 4 FedProx CNN-2 x4096 heterogeneous steps, 5 FedAvg BERT-mini x256")
@@ -191,6 +194,23 @@ def main() -> int:
                "d2h_bytes_per_step": int(d2h), "ms_per_step": wall / K * 1e3, "timing": "host wall clock, max over ranks",
                "last_loss": res.loss}
 
+    phases = None
+    if args.phases and backend == "native":
+        eng.cfg.profile = True
+        eng.timer.enabled = True
+        acc = {}
+        for r in range(3):
+            res = eng.run_round(W + 2 * K + 4 + r)
+            for k, v in res.extras["phases_ms"].items():
+                acc[k] = acc.get(k, 0.0) + v / 3
+        P4 = eng.P * 4
+        far = (world - 1) / world
+        # per rank: broadcast pulls the (world-1)/world remote shards of the model; reduce pulls `groups` partial
+        # shards from every peer.  Bus bandwidth = bytes crossing NVLink into this GPU / phase time.
+        groups = getattr(eng.ws, "groups", 1)
+        phases = {"ms": acc, "bcast_remote_bytes": int(P4 * far), "reduce_remote_bytes": int(groups * P4 / world * (world - 1)),
+                  "bcast_bus_GBps": P4 * far / max(acc.get("broadcast", 0), 1e-9) / 1e6,
+                  "reduce_bus_GBps": groups * P4 / world * (world - 1) / max(acc.get("reduce_update", 0), 1e-9) / 1e6}
     if rank == 0:
         out = {
             "metric": METRIC, "value": value, "unit": "client_steps/s", "n_gpus": world, "steps": K, "warmup": W,
@@ -205,6 +225,8 @@ def main() -> int:
                        "l2": "inputs larger than L2 (per-round working set of GBs streams through HBM)"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
         }
+        if phases:
+            out["phases"] = phases
         print(json.dumps(out))
     sync()
     eng.close()

@@ -217,6 +217,8 @@ class FedEngine:
         self.result_host = torch.zeros(8).pin_memory()
         self.ws.set_global(self._g0)
         self.P = self.ws.P
+        self._graphs: Dict[bool, Any] = {}
+        self._graph_ok, self._graph_warm, self.graph_error = True, False, None
 
     def _native_round_body(self, round_idx: int) -> None:
         """All device work of one round on the current stream; no host synchronisation."""
@@ -247,11 +249,43 @@ class FedEngine:
                 else:
                     ws.w1_fwd[cid - self.c0].fill_(float("nan"))
         with self.timer.phase("local_steps"):
-            for s in range(cfg.local_steps):
-                ws.local_step(s, lr=cfg.lr, mu=cfg.mu, active=self.step_active[s] if need_mask else None)
+            self._local_steps(need_mask)
         with self.timer.phase("reduce_update"):
             ws.reduce_and_update(self.agg_weight, opt=cfg.server_opt, server_lr=cfg.server_lr,
                                  accounting=(self.participate, self.step_active, self.counters, cfg.local_steps))
+
+    def _local_steps(self, need_mask: bool) -> None:
+        """The S x (6 kernels x waves) local-step block.  Every kernel argument of the block is round-invariant (buffer
+        addresses, step offsets, lr / mu; the masks live in fixed buffers), so after a warm-up round it is captured once
+        into a CUDA graph per mask variant and replayed: one launch per round instead of 30+ host-side launches."""
+        cfg, ws = self.cfg, self.ws
+
+        def eager():
+            for s in range(cfg.local_steps):
+                ws.local_step(s, lr=cfg.lr, mu=cfg.mu, active=self.step_active[s] if need_mask else None)
+
+        if not (cfg.use_cuda_graph and self._graph_ok):
+            return eager()
+        entry = self._graphs.get(need_mask)
+        if entry is None:
+            if not self._graph_warm:
+                self._graph_warm = True          # first round runs eagerly (lazy attribute setup, first-use checks)
+                return eager()
+            try:
+                before = ws.kernel_launches
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                    eager()
+                entry = (g, ws.kernel_launches - before)
+                ws.kernel_launches = before       # capture records launches, it does not execute them
+                self._graphs[need_mask] = entry
+            except Exception as e:  # noqa: BLE001 - a failed capture must not take the job down
+                self._graph_ok = False
+                self.graph_error = f"{type(e).__name__}: {e}"
+                torch.cuda.synchronize(self.device)
+                return eager()
+        entry[0].replay()
+        ws.kernel_launches += entry[1]
 
     def _native_finish(self, round_idx: int) -> RoundResult:
         # the job-wide 8-float record was assembled on the device (round_stats_kernel per rank, summed over ranks
@@ -495,4 +529,5 @@ class FedEngine:
 
     def close(self) -> None:
         if self.backend == "native":
+            self._graphs.clear()          # graphs reference workspace memory: drop them before the slabs are freed
             self.ws.close()

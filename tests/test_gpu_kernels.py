@@ -87,6 +87,23 @@ def test_wave_scheduling_matches_all_resident():
     a.close()
 
 
+def test_cuda_graph_replay_matches_eager_launches():
+    """rounds 2+ replay the captured local-step block: same model as the eager engine, same launch accounting"""
+    from olearning_sim_b200.engine.fed_engine import FedConfig, FedEngine
+    kw = dict(model="cnn2", num_clients=8, local_steps=2, shard=64, lr=0.05, seed=3, backend="native", p_online=0.7,
+              hetero_steps=True)
+    a = FedEngine(FedConfig(use_cuda_graph=True, **kw)); a.load_synthetic()
+    b = FedEngine(FedConfig(use_cuda_graph=False, **kw)); b.load_synthetic()
+    for r in range(4):
+        ra, rb = a.run_round(r), b.run_round(r)
+        assert (ra.participants, ra.client_steps, ra.failed) == (rb.participants, rb.client_steps, rb.failed)
+        assert abs(ra.loss - rb.loss) < 1e-5
+    assert a.graph_error is None and len(a._graphs) == 1 and not b._graphs
+    assert a.kernel_launches() == b.kernel_launches()
+    assert torch.allclose(a.global_model(), b.global_model(), rtol=0, atol=5e-6)
+    a.close(); b.close()
+
+
 def test_poisoned_client_masked_on_gpu(monkeypatch):
     monkeypatch.setenv("OLSB_FAULTS", "corrupt:client=2,round=0")
     from olearning_sim_b200.engine.fed_engine import FedConfig, FedEngine

@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Attribute ncu warp-stall samples to CUDA source lines.
 
-usage: ncu_source_lines.py <report.ncu-rep> <kernel-regex> [top_n]
+usage: ncu_source_lines.py <report.ncu-rep> <kernel-regex> [top_n] [name-substring]
+(the regex matches the base name; the optional substring picks one template instance, e.g. "<32, 1, 64")
 
 ncu's CSV source page is SASS-only, so the per-instruction samples are joined with `nvdisasm --print-line-info` of the
 in-tree library by instruction offset inside the kernel (the library must be the build that was profiled)."""
@@ -13,10 +14,15 @@ lib = os.path.join(root, "olearning_sim_b200/ops/_olsb200_kernels.so")
 raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", f"regex:{kre}"],
                      capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
-kname = rows[0][1]
-hdr = rows[1]; idx = {h: i for i, h in enumerate(hdr)}
+want = sys.argv[4] if len(sys.argv) > 4 else ""
+starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name" and want in r[1]]
+if not starts:
+    sys.exit(f"no captured kernel matches regex {kre!r} / substring {want!r}")
+s0 = starts[0]
+kname = rows[s0][1]
+hdr = rows[s0 + 1]; idx = {h: i for i, h in enumerate(hdr)}
 inst = []
-for r in rows[2:]:
+for r in rows[s0 + 2:]:
     if len(r) != len(hdr) or not r[0].startswith("0x"):
         if r and r[0] == "Kernel Name": break        # next kernel instance
         continue
@@ -43,7 +49,13 @@ for l in dis.splitlines():
         off2line.setdefault((cur_fn, int(m.group(1), 16)), line)
 # choose the function instance whose size matches best (template instances share the short name)
 fns = collections.Counter(fn for fn, _ in off2line)
-best = max(fns, key=lambda fn: sum(1 for a, *_ in inst if (fn, a - base) in off2line))
+def _targs(name):          # template arguments as a normalised tuple of ints/bools
+    return tuple(int(x) if x.lstrip("-").isdigit() else (1 if x == "true" else 0)
+                 for x in re.findall(r"-?\d+|true|false", re.sub(r"\(int\)|\(bool\)", "", name.split("(CU")[0].split("<", 1)[-1])))
+def _margs(fn):            # same from the mangled name: Li<digits>E / Lb<0|1>E
+    return tuple(int(x) for x in re.findall(r"L[ib](\d+)E", fn))
+cands = [fn for fn in fns if _margs(fn) == _targs(kname)] or list(fns)
+best = max(cands, key=lambda fn: sum(1 for a, *_ in inst if (fn, a - base) in off2line))
 agg, why = collections.Counter(), collections.defaultdict(collections.Counter)
 tot = sum(s for _, _, s, _ in inst)
 for a, src, s, r in inst:
