@@ -116,6 +116,8 @@ constexpr int BATCH = 32;
 using Conv1FwdCfg = FwdCfg<32, 1, 32, 32, 32, BATCH, false, EPI_POOL, 12, 2>;
 using Conv2FwdCfg = FwdFoldCfg<32, 64, 16, BATCH, 7>;
 using Conv2DgradCfg = DgradFoldCfg<32, 64, 16, BATCH, 4>;
+#define CONV2_DGRAD_PAIR conv_dgrad_pair_kernel<32, 64, 16, BATCH, 6>
+using Conv2DgradPairCfg = DgradPairCfg<32, 64, 16, BATCH, 6>;
 //                              XROWB NKW YROWB H   W   BATCH NSS SYNTH_Y
 #define CONV2_WGRAD conv_wgrad_kernel<64, 5, 128, 16, 16, BATCH, 2, false, 2>
 #define CONV1_WGRAD conv_wgrad_kernel<32, 1, 64, 32, 32, BATCH, 8, true, 2>
@@ -126,6 +128,7 @@ using Conv2WgradCfg = WgradCfg<64, 5, 128, 2>;
 using Conv1WgradCfg = WgradCfg<32, 1, 64, 8>;
 
 int g_x5_rows = 1;       // 1: X5 is stored pre-swizzled and fetched with 512-byte box rows, 0: 32-byte swizzled rows
+int g_dgrad_pair = 0;    // 1: conv2 data gradient on CTA pairs (cta_group::2, weight operand split across the pair)
 int g_wgrad2_ws = 1;     // 1: weight-stationary (B-collector) MMAs in the conv2 weight gradient
 int g_wgrad2_mode = 1;   // 0: five 12x16 boxes per chunk, 1: one 12x20 box, 2: one box + swizzle base offset
 bool g_attr_set = false;
@@ -134,6 +137,7 @@ int set_attrs() {
   CK(cudaFuncSetAttribute(CONV1_FWD, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv1FwdCfg::SMEM_BYTES));
   CK(cudaFuncSetAttribute(CONV2_FWD, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv2FwdCfg::SMEM_BYTES));
   CK(cudaFuncSetAttribute(CONV2_DGRAD, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv2DgradCfg::SMEM_BYTES));
+  CK(cudaFuncSetAttribute(CONV2_DGRAD_PAIR, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv2DgradPairCfg::SMEM_BYTES));
   CK(cudaFuncSetAttribute(CONV2_WGRAD, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv2WgradCfg::SMEM_BYTES));
   CK(cudaFuncSetAttribute(CONV1_WGRAD, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv1WgradCfg::SMEM_BYTES));
   CK(cudaFuncSetAttribute(CONV2_WGRAD_WIDE, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv2WgradWideCfg::SMEM_BYTES));
@@ -142,7 +146,7 @@ int set_attrs() {
   return 0;
 }
 
-int auto_split(int C, int tiles_per_client, int nsplit) {
+int auto_split(int C, int tiles_per_client, int nsplit, int units = 0) {
   // Work items per client.  Cost model: waves(s)/s client-times, where waves = ceil(C*s / #SMs); every extra split
   // re-loads the client's weights (~100 KB), so ties (and near-ties within 6 %) go to the smaller split.
   if (nsplit > 0) return nsplit;
@@ -150,7 +154,8 @@ int auto_split(int C, int tiles_per_client, int nsplit) {
   double best_cost = 1e30;
   for (int s = 1; s <= 8; s *= 2) {
     if (tiles_per_client % s) break;
-    const int waves = (C * s + g_sms - 1) / g_sms;
+    const int nu = units > 0 ? units : g_sms;      // schedulable units: SMs, or CTA pairs for cta_group::2 kernels
+    const int waves = (C * s + nu - 1) / nu;
     const double cost = (double)waves / s * (1.0 + 0.06 * (s > 1) + 0.02 * (s > 2) + 0.02 * (s > 4));
     if (cost < best_cost - 1e-9) { best_cost = cost; best = s; }
   }
@@ -231,17 +236,30 @@ int olsb_conv2_dgrad(const void* dy2, const void* w2_dgrad, void* master, const 
                      void* stream) {
   if (int r = olsb_init()) return r;
   CUtensorMap tmA, tmW;
+  const bool pair = g_dgrad_pair != 0;
   if (int r = make_act_map(&tmA, dy2, (uint64_t)C * BATCH, 16, 16, 64, kBoxH)) return r;
-  if (int r = make_w_map(&tmW, w2_dgrad /* = forward copy w2_fwd */, (uint64_t)C, 64, 800, 64, 32)) return r;
+  // B operand = forward weight copy [C][64][800]: 32-channel (pair kernel: 16-channel) MN-major chunks per tap
+  if (int r = make_w_map(&tmW, w2_dgrad /* = forward copy w2_fwd */, (uint64_t)C, 64, 800, 64, pair ? 16 : 32)) return r;
   FwdParams p;
   memset(&p, 0, sizeof(p));
-  p.num_clients = C; p.nsplit = auto_split(C, Conv2DgradCfg::TILES_PER_CLIENT, nsplit);
+  p.num_clients = C;
+  p.nsplit = auto_split(C, Conv2DgradCfg::TILES_PER_CLIENT, nsplit, pair ? g_sms / 2 : 0);
   p.a_n_stride = BATCH; p.a_n_off = 0; p.active = (const uint8_t*)active;
   p.pooled = (const __nv_bfloat16*)p1; p.dpool = (__nv_bfloat16*)dp1;
   p.bias_master = (float*)master + Cnn2Layout::B1; p.bias_stride = (int)P;
   p.bias_global = global_w ? (const float*)global_w + Cnn2Layout::B1 : nullptr;
   p.lr = lr; p.mu = mu; p.dbias_out = (float*)dbias_out;
   const int work = C * p.nsplit;
+  if (pair) {
+    if (p.nsplit > 32 || (Conv2DgradPairCfg::TILES_PER_CLIENT % (2 * p.nsplit))) {
+      snprintf(g_err, sizeof(g_err), "dgrad pair kernel needs an even number of tiles per work item (nsplit %d)", p.nsplit);
+      return -4;
+    }
+    const int npairs = work < g_sms / 2 ? work : g_sms / 2;
+    CONV2_DGRAD_PAIR<<<2 * npairs, kFoldThreads, Conv2DgradPairCfg::SMEM_BYTES, (cudaStream_t)stream>>>(tmA, tmW, p);
+    CK(cudaGetLastError());
+    return 0;
+  }
   const int grid = work < g_sms ? work : g_sms;
   CONV2_DGRAD<<<grid, kFoldThreads, Conv2DgradCfg::SMEM_BYTES, (cudaStream_t)stream>>>(tmA, tmW, p);
   CK(cudaGetLastError());
@@ -416,6 +434,7 @@ int olsb_fedavg_finish(const void* const* partial_peers, const void* const* wsum
 // runtime switches (kernel variants under evaluation); returns the previous value, -1 for an unknown name
 int olsb_set_option(const char* name, int value) {
   if (!strcmp(name, "x5_rows")) { const int o = g_x5_rows; g_x5_rows = value; return o; }
+  if (!strcmp(name, "dgrad_pair")) { const int o = g_dgrad_pair; g_dgrad_pair = value; return o; }
   if (!strcmp(name, "wgrad2_ws")) { const int o = g_wgrad2_ws; g_wgrad2_ws = value; return o; }
   if (!strcmp(name, "wgrad2_mode")) { const int o = g_wgrad2_mode; g_wgrad2_mode = value; return o; }
   return -1;

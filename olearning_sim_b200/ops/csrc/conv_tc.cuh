@@ -351,6 +351,13 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             uint32_t v[32];
             tmem_ld32(taddr + j * 32, v);
             tmem_ld_wait();
+            if (j == BN / 32 - 1) {
+              // accumulator is in registers: hand the TMEM buffer back before the pooling arithmetic and the stores
+              // (released at the end of the tile, the MMA warp waited ~1/4 of its time for a free buffer)
+              fence_before_sync();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&bars->tempty[buf]);
+            }
             float x[32];
 #pragma unroll
             for (int i = 0; i < 32; ++i) x[i] = __uint_as_float(v[i]) + bias_r[j * 32 + i];
@@ -385,10 +392,10 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
 #pragma unroll
           for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(p.dpool + pbase + k * 8) = o[k];
+          fence_before_sync();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bars->tempty[buf]);
         }
-        fence_before_sync();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&bars->tempty[buf]);
       }
     }
     if (cur_client >= 0) flush_bias(cur_client);
@@ -650,6 +657,294 @@ conv_dgrad_fold_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   fence_before_sync();
   __syncthreads();
   if (warp == kFoldMmaWarp) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+// ================================================================================================
+// Data-gradient kernel, CTA-pair version (cta_group::2)
+// ================================================================================================
+// Same math and epilogue as conv_dgrad_fold_kernel; two CTAs on the SMs of one TPC work on two tiles of the same
+// client at a time as ONE M=256 MMA.  The folded weight operand (N = 160) is split between the two CTAs (each holds
+// 80 columns = five 16-channel MN-major chunks per vertical tap), so per tile the tensor core fetches 4 KB of A and
+// 2.5 KB of B from its SM's shared memory instead of 4 + 5 KB — the folded kernels are bound by exactly that pipe.
+//   warps 0-7  epilogue (two sets, alternate steps)      warp 8  TMA producer (own tile + own half of the weights)
+//   warp 9     leader: MMA issuer for the pair           peer: relay that tells the leader "my operands have landed"
+struct PairBarriers {
+  uint64_t full[8];      // A stage landed in THIS CTA (tx count)
+  uint64_t pfull[8];     // leader only: the peer's A stage landed (remote arrive by the peer's relay warp)
+  uint64_t empty[8];     // stage consumed (multicast commit)
+  uint64_t wfull, pwfull, wempty;
+  uint64_t tfull[2];     // accumulator ready (multicast commit)
+  uint64_t tempty[2];    // leader only: accumulator drained by both CTAs (4 local + 4 remote warps)
+  uint32_t tmem_base;
+  uint32_t pad;
+};
+
+template <int CIN, int COUT, int IMG_H, int BATCH, int NSTAGE>
+struct DgradPairCfg {
+  static constexpr int ROWB = COUT * 2;                 // bytes per A pixel row (K = COUT)
+  static constexpr int NF = 5 * CIN;                    // folded N of the pair's MMA
+  static constexpr int CHUNK_BYTES = COUT * 16 * 2;     // one MN-major SW32 chunk: [COUT k-rows][16 input channels]
+  static constexpr int CHUNKS_PER_CTA = NF / 16 / 2;    // 5 chunks of 16 columns per vertical tap and CTA
+  static constexpr int W_KH_BYTES = CHUNKS_PER_CTA * CHUNK_BYTES;
+  static constexpr int W_BYTES = kNKH * W_KH_BYTES;
+  static constexpr int STAGE_BYTES = kBoxH * kTileW * ROWB;
+  static constexpr int TILES_PER_CLIENT = BATCH * (IMG_H / kTileH);
+  static constexpr int TMEM_BUF_STRIDE = 256;
+  static constexpr int TMEM_COLS = 512;
+  static constexpr int SMEM_BYTES = 1024 + W_BYTES + NSTAGE * STAGE_BYTES + (int)sizeof(PairBarriers);
+  static_assert(ROWB == 128 && CIN == 32 && NSTAGE <= 8, "written for 64 -> 32 channels");
+};
+
+template <int CIN, int COUT, int IMG_H, int BATCH, int NSTAGE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFoldThreads, 1)
+conv_dgrad_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+                       const FwdParams p) {
+  using Cfg = DgradPairCfg<CIN, COUT, IMG_H, BATCH, NSTAGE>;
+  constexpr int ROWB = Cfg::ROWB;
+  constexpr int IMG_W = kTileW;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* w_sm = smem;
+  uint8_t* a_sm = smem + Cfg::W_BYTES;
+  PairBarriers* bars = reinterpret_cast<PairBarriers*>(a_sm + NSTAGE * Cfg::STAGE_BYTES);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool is_leader = rank == 0;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NSTAGE; ++i) { mbar_init(&bars->full[i], 1); mbar_init(&bars->pfull[i], 1); mbar_init(&bars->empty[i], 1); }
+    mbar_init(&bars->wfull, 1); mbar_init(&bars->pwfull, 1); mbar_init(&bars->wempty, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&bars->tfull[i], 1); mbar_init(&bars->tempty[i], 2 * kEpiWarps); }
+    fence_mbar_init();
+  }
+  if (warp == kFoldMmaWarp) { tmem_alloc2(&bars->tmem_base, Cfg::TMEM_COLS); tmem_relinquish2(); }
+  if (warp == kFoldTmaWarp && lane == 0) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmW); }
+  fence_before_sync();
+  cluster_sync();                       // barriers of both CTAs initialised before any remote arrive / multicast commit
+  fence_after_sync();
+  const uint32_t tmem_base = bars->tmem_base;
+  const int num_work = p.num_clients * p.nsplit;
+  const int tiles_per_work = Cfg::TILES_PER_CLIENT / p.nsplit;     // even by construction (host picks nsplit)
+  const int steps_per_work = tiles_per_work / 2;
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+
+  if (warp == kFoldTmaWarp) {
+    const bool leader = elect_one();
+    int stage = 0; uint32_t phase = 0; int cur_client = -1; uint32_t wphase = 0; bool first_w = true;
+    for (int wi = pair; wi < num_work; wi += npairs) {
+      const int c = wi / p.nsplit, sp = wi % p.nsplit;
+      if (p.active && !p.active[c]) continue;
+      if (c != cur_client) {
+        if (!first_w) { mbar_wait(&bars->wempty, wphase); wphase ^= 1; }
+        first_w = false; cur_client = c;
+        if (leader) {
+          mbar_arrive_expect_tx(&bars->wfull, Cfg::W_BYTES);
+          // this CTA's half of the folded weight operand: global 16-column chunk g = 5*rank + j -> (kw = g/2, half)
+#pragma unroll 1
+          for (int kh = 0; kh < kNKH; ++kh)
+#pragma unroll 1
+            for (int j = 0; j < Cfg::CHUNKS_PER_CTA; ++j) {
+              const int g = Cfg::CHUNKS_PER_CTA * (int)rank + j;
+              tma_load_3d(w_sm + kh * Cfg::W_KH_BYTES + j * Cfg::CHUNK_BYTES, &tmW, &bars->wfull,
+                          (kh * 5 + (g >> 1)) * CIN + (g & 1) * 16, 0, c);
+            }
+        }
+      }
+      const int t0 = sp * tiles_per_work;
+      for (int k = 0; k < steps_per_work; ++k) {
+        const int t = t0 + 2 * k + (int)rank;
+        const int s = t / (IMG_H / kTileH);
+        const int h0 = (t % (IMG_H / kTileH)) * kTileH;
+        mbar_wait(&bars->empty[stage], phase ^ 1);
+        if (leader) {
+          mbar_arrive_expect_tx(&bars->full[stage], Cfg::STAGE_BYTES);
+          tma_load_4d(a_sm + stage * Cfg::STAGE_BYTES, &tmA, &bars->full[stage], 0, 0, h0 - kHalo,
+                      c * p.a_n_stride + p.a_n_off + s);
+        }
+        if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == kFoldMmaWarp && !is_leader) {
+    // relay: forward "landed" events of this CTA's operands to the leader's pfull / pwfull barriers
+    int stage = 0; uint32_t phase = 0; int cur_client = -1; uint32_t wphase = 0;
+    for (int wi = pair; wi < num_work; wi += npairs) {
+      const int c = wi / p.nsplit;
+      if (p.active && !p.active[c]) continue;
+      if (c != cur_client) {
+        mbar_wait(&bars->wfull, wphase); wphase ^= 1; cur_client = c;
+        if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&bars->pwfull), 0));
+        __syncwarp();
+      }
+      for (int k = 0; k < steps_per_work; ++k) {
+        mbar_wait(&bars->full[stage], phase);
+        if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&bars->pfull[stage]), 0));
+        __syncwarp();
+        if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == kFoldMmaWarp) {
+    const bool leader = elect_one();
+    constexpr uint32_t IDESC = make_idesc_bf16(256, Cfg::NF, 0, 1);           // pair MMA, B is MN-major
+    const uint64_t a_desc_base = make_smem_desc(smem_u32(a_sm), 16, 8 * ROWB, LT_SW128);
+    // B: chunks of [COUT k-rows][16 channels] with 32-byte rows: LBO = chunk stride, SBO = 8 k-rows
+    const uint64_t b_desc_base = make_smem_desc(smem_u32(w_sm), Cfg::CHUNK_BYTES, 8 * 32, LT_SW32);
+    int stage = 0; uint32_t phase = 0; int cur_client = -1; uint32_t wphase = 0;
+    int buf = 0; uint32_t tphase0 = 0, tphase1 = 0;
+    for (int wi = pair; wi < num_work; wi += npairs) {
+      const int c = wi / p.nsplit;
+      if (p.active && !p.active[c]) continue;
+      bool last_of_client = true;
+      {
+        const int nwi = wi + npairs;
+        if (nwi < num_work && (nwi / p.nsplit) == c) last_of_client = false;
+      }
+      if (c != cur_client) {
+        mbar_wait(&bars->wfull, wphase); mbar_wait(&bars->pwfull, wphase); wphase ^= 1; cur_client = c;
+      }
+      for (int k = 0; k < steps_per_work; ++k) {
+        mbar_wait(&bars->tempty[buf], (buf ? tphase1 : tphase0) ^ 1);
+        fence_after_sync();
+        mbar_wait(&bars->full[stage], phase);
+        mbar_wait(&bars->pfull[stage], phase);
+        fence_after_sync();
+        if (leader) {
+          const uint32_t d_tmem = tmem_base + buf * Cfg::TMEM_BUF_STRIDE;
+          const uint64_t a_stage = desc_advance(a_desc_base, stage * Cfg::STAGE_BYTES);
+#pragma unroll
+          for (int kh = 0; kh < kNKH; ++kh) {
+            const uint64_t a_desc = desc_advance(a_stage, (2 * kHalo - kh) * kTileW * ROWB);
+            const uint64_t b_desc = desc_advance(b_desc_base, kh * Cfg::W_KH_BYTES);
+#pragma unroll
+            for (int ks = 0; ks < ROWB / 32; ++ks)
+              umma_bf16_2cta(d_tmem, desc_advance(a_desc, ks * 32), desc_advance(b_desc, ks * 16 * 32), IDESC,
+                             (kh | ks) ? 1u : 0u);
+          }
+          umma_commit_2cta(&bars->empty[stage], 3);
+          umma_commit_2cta(&bars->tfull[buf], 3);
+        }
+        __syncwarp();
+        if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+        if (buf) tphase1 ^= 1; else tphase0 ^= 1;
+        buf ^= 1;
+      }
+      if (last_of_client) {
+        if (leader) umma_commit_2cta(&bars->wempty, 3);
+        __syncwarp();
+      }
+    }
+  } else {
+    const int grp = warp >> 2;
+    int buf = 0; uint32_t tph = 0;
+    const int q = warp & 3;
+    const int tid_g = threadIdx.x & 127;
+    const int hl = 2 * q + (lane >> 4), wl = lane & 15;
+    const uint32_t tempty_leader[2] = {mapa_u32(smem_u32(&bars->tempty[0]), 0), mapa_u32(smem_u32(&bars->tempty[1]), 0)};
+    float dbacc[CIN];
+#pragma unroll
+    for (int i = 0; i < CIN; ++i) dbacc[i] = 0.f;
+    int cur_client = -1;
+    bool had_sp0 = false;
+    __shared__ float s_db_all[2][CIN];
+    float* s_db = s_db_all[grp];
+    auto gsync = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(1 + grp)); };
+    auto flush_bias = [&](int c) {
+      gsync();
+      if (tid_g < CIN) s_db[tid_g] = 0.f;
+      gsync();
+#pragma unroll
+      for (int i = 0; i < CIN; ++i) {
+        float v = dbacc[i];
+        v += __shfl_xor_sync(0xffffffffu, v, 16);
+        v += __shfl_xor_sync(0xffffffffu, v, 8);
+        v += __shfl_xor_sync(0xffffffffu, v, 4);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        if (lane == 0) atomicAdd(&s_db[i], v);
+        dbacc[i] = 0.f;
+      }
+      gsync();
+      if (tid_g < CIN) {
+        const float g = s_db[tid_g];
+        if (p.dbias_out) {
+          atomicAdd(&p.dbias_out[(size_t)c * CIN + tid_g], g);
+        } else {
+          float* bp = &p.bias_master[(size_t)c * p.bias_stride + tid_g];
+          float upd = -p.lr * g;
+          // the FedProx pull is applied once per client: leader CTA, warp set 0, the work item that owns split 0
+          if (is_leader && grp == 0 && had_sp0 && p.bias_global) upd -= p.lr * p.mu * (*bp - p.bias_global[tid_g]);
+          atomicAdd(bp, upd);
+        }
+      }
+      gsync();
+    };
+    for (int wi = pair; wi < num_work; wi += npairs) {
+      const int c = wi / p.nsplit, sp = wi % p.nsplit;
+      if (p.active && !p.active[c]) continue;
+      if (c != cur_client) {
+        if (cur_client >= 0) flush_bias(cur_client);
+        cur_client = c;
+        had_sp0 = false;
+      }
+      if (sp == 0) had_sp0 = true;
+      const int t0 = sp * tiles_per_work;
+      for (int k = 0; k < steps_per_work; ++k, buf ^= 1) {
+        if (buf != grp) continue;
+        const int t = t0 + 2 * k + (int)rank;
+        const int s = t / (IMG_H / kTileH);
+        const int h0 = (t % (IMG_H / kTileH)) * kTileH;
+        const size_t n_out = (size_t)c * BATCH + s;
+        const size_t pbase = ((n_out * IMG_H + (h0 + hl)) * IMG_W + wl) * CIN;
+        uint4 pq[4];
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) pq[kk] = __ldg(reinterpret_cast<const uint4*>(p.pooled + pbase + kk * 8));
+        mbar_wait(&bars->tfull[buf], tph);
+        fence_after_sync();
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(32 * q) << 16) + buf * Cfg::TMEM_BUF_STRIDE;
+        float acc[CIN];
+        {
+          uint32_t v[32];
+          tmem_ld32(taddr + 2 * CIN, v);                      // kw = 2: no column shift
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < CIN; ++i) acc[i] = __uint_as_float(v[i]);
+        }
+#pragma unroll
+        for (int kw = 0; kw < 5; ++kw) {
+          if (kw == 2) continue;
+          uint32_t v[32];
+          tmem_ld32(taddr + kw * CIN, v);
+          tmem_ld_wait();
+          const int src_w = wl + 2 - kw;
+          const float inb = ((src_w >= 0) && (src_w < IMG_W)) ? 1.f : 0.f;
+          const int src_lane = (lane & 16) | (src_w & 15);
+#pragma unroll
+          for (int i = 0; i < CIN; ++i)
+            acc[i] = fmaf(__uint_as_float(__shfl_sync(0xffffffffu, v[i], src_lane)), inb, acc[i]);
+        }
+        fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(tempty_leader[buf]);     // the leader's barrier counts both CTAs' warps
+        const uint32_t* pw32 = reinterpret_cast<const uint32_t*>(pq);
+        uint4 o[4];
+        uint32_t* ow = reinterpret_cast<uint32_t*>(o);
+#pragma unroll
+        for (int i = 0; i < CIN / 2; ++i) {
+          const uint32_t pr = pw32[i];
+          const float g0 = bf16lo(pr) > 0.f ? acc[2 * i] : 0.f;
+          const float g1 = bf16hi(pr) > 0.f ? acc[2 * i + 1] : 0.f;
+          dbacc[2 * i] += g0; dbacc[2 * i + 1] += g1;
+          ow[i] = pack_bf16x2(g0, g1);
+        }
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) *reinterpret_cast<uint4*>(p.dpool + pbase + kk * 8) = o[kk];
+        tph ^= 1;
+      }
+    }
+    if (cur_client >= 0) flush_bias(cur_client);
+  }
+  fence_before_sync();
+  cluster_sync();                       // no CTA may exit (or free TMEM) while its peer can still signal it
+  if (warp == kFoldMmaWarp) tmem_dealloc2(tmem_base, Cfg::TMEM_COLS);
 }
 
 // ================================================================================================

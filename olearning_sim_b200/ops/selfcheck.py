@@ -184,6 +184,35 @@ def check_conv2_dgrad(c: int) -> Dict:
             "dp1": rel_err(dp1.float(), ref), "db1": rel_err(db1, ref.reshape(c, -1, 32).sum(1))}
 
 
+def check_conv2_dgrad_pair(c: int) -> Dict:
+    """conv2 data gradient on CTA pairs (cta_group::2, ``dgrad_pair`` switch) vs the single-CTA kernel: numerics, time"""
+    master = _rand_master(c)
+    _, w2f, _ = _operand_copies(master)
+    dy2 = (torch.randn(c * B, 16, 16, 64, device="cuda") * 0.1).to(torch.bfloat16)
+    p1 = torch.randn(c * B, 16, 16, 32, device="cuda").clamp_min(0).to(torch.bfloat16)
+    v = reference.cnn2_views(master)
+    x = p1.float().reshape(c, B, 16, 16, 32).clone().requires_grad_(True)
+    y = _conv_ref(x, v["w2"].to(torch.bfloat16).float(), None)
+    y.backward(dy2.float().reshape(c, B, 16, 16, 64))
+    ref = torch.where(x > 0, x.grad, torch.zeros_like(x.grad)).reshape(c * B, 16, 16, 32)
+    res: Dict = {"tol": 1.5e-2, "err": 0.0}
+    try:
+        for mode in (0, 1):
+            native.set_option("dgrad_pair", mode)
+            dp1 = torch.zeros(c * B, 16, 16, 32, dtype=torch.bfloat16, device="cuda")
+            db1 = torch.zeros(c, 32, device="cuda")
+            native.conv2_dgrad(dy2, w2f, master, None, c, None, p1, dp1, 0.1, 0.0, db1)
+            torch.cuda.synchronize()
+            res[f"pair{mode}_dp1"] = rel_err(dp1.float(), ref)
+            res[f"pair{mode}_db1"] = rel_err(db1, ref.reshape(c, -1, 32).sum(1))
+            res[f"pair{mode}_us"] = round(_time_us(lambda: native.conv2_dgrad(dy2, w2f, master, None, c, None, p1, dp1,
+                                                                           0.1, 0.0, db1)), 1)
+            res["err"] = max(res["err"], res[f"pair{mode}_dp1"], res[f"pair{mode}_db1"])
+    finally:
+        native.set_option("dgrad_pair", 0)
+    return res
+
+
 def check_conv2_wgrad(c: int) -> Dict:
     master = _rand_master(c)
     w1f, w2f, w2d = _operand_copies(master)
@@ -479,7 +508,8 @@ CHECKS: Dict[str, Callable[[int], Dict]] = {
 
 
 # kernel variants under evaluation: run only when named explicitly with --only
-EXPERIMENTAL: Dict[str, Callable[[int], Dict]] = {"conv2_wgrad_wide": check_conv2_wgrad_wide}
+EXPERIMENTAL: Dict[str, Callable[[int], Dict]] = {"conv2_wgrad_wide": check_conv2_wgrad_wide,
+                                                    "conv2_dgrad_pair": check_conv2_dgrad_pair}
 
 
 def run_all(clients: List[int], only: List[str] | None = None) -> List[Dict]:

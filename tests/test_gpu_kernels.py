@@ -100,7 +100,8 @@ def test_cuda_graph_replay_matches_eager_launches():
         assert abs(ra.loss - rb.loss) < 1e-5
     assert a.graph_error is None and len(a._graphs) == 1 and not b._graphs
     assert a.kernel_launches() == b.kernel_launches()
-    assert torch.allclose(a.global_model(), b.global_model(), rtol=0, atol=5e-6)
+    ga, gb = a.global_model(), b.global_model()          # bias gradients use float atomics: equal to rounding only
+    assert float((ga - gb).norm() / gb.norm()) < 1e-4
     a.close(); b.close()
 
 
