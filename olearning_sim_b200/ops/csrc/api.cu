@@ -110,10 +110,10 @@ int make_x5_row_map(CUtensorMap* tm, const void* base, uint64_t n, int box_h) {
 constexpr int BATCH = 32;
 // kernel instances of the CNN-2 family
 //                          ROWB NKW BN  H   W   BATCH  FLIP   EPI         NSTAGE
-#define CONV1_FWD conv_taps_kernel<32, 1, 32, 32, 32, BATCH, false, EPI_POOL, 12, 2>
+#define CONV1_FWD conv_taps_kernel<32, 1, 32, 32, 32, BATCH, false, EPI_POOL, 12, 2, 2>
 #define CONV2_FWD conv_fwd_fold_kernel<32, 64, 16, BATCH, 7>
 #define CONV2_DGRAD conv_dgrad_fold_kernel<32, 64, 16, BATCH, 4>
-using Conv1FwdCfg = FwdCfg<32, 1, 32, 32, 32, BATCH, false, EPI_POOL, 12, 2>;
+using Conv1FwdCfg = FwdCfg<32, 1, 32, 32, 32, BATCH, false, EPI_POOL, 12, 2, 2>;
 using Conv2FwdCfg = FwdFoldCfg<32, 64, 16, BATCH, 7>;
 using Conv2DgradCfg = DgradFoldCfg<32, 64, 16, BATCH, 4>;
 #define CONV2_DGRAD_PAIR conv_dgrad_pair_kernel<32, 64, 16, BATCH, 6>

@@ -92,6 +92,34 @@ __device__ __forceinline__ void pool2x2_relu(const float (&x)[32], int b0, int b
   cv.y = cd[4] | (cd[5] << 8) | (cd[6] << 16) | (cd[7] << 24);
 }
 
+// Sum of the five folded accumulator chunks of a pixel, each taken from the lane that holds the horizontally shifted
+// pixel:  acc[i] = init[i] + sum_kw D_kw[lane + dir*(kw-2)][i]   (dir = +1 forward, -1 data gradient).
+// The TMEM load of chunk n+1 is in flight while chunk n goes through its 32 shuffle+FMA pairs, so only the first
+// tcgen05.ld latency is exposed instead of all five.
+template <int DIR>
+__device__ __forceinline__ void fold_kw_sum(uint32_t taddr, int lane, int wl, const float* init, float (&acc)[32]) {
+  constexpr int ORDER[5] = {2, 0, 1, 3, 4};            // centre tap first: it needs no shuffle
+  uint32_t va[32], vb[32];
+  tmem_ld32(taddr + ORDER[0] * 32, va);
+  tmem_ld_wait();
+  tmem_ld32(taddr + ORDER[1] * 32, vb);
+#pragma unroll
+  for (int i = 0; i < 32; ++i) acc[i] = __uint_as_float(va[i]) + (init ? init[i] : 0.f);
+#pragma unroll
+  for (int n = 1; n < 5; ++n) {
+    uint32_t (&cur)[32] = (n & 1) ? vb : va;
+    uint32_t (&nxt)[32] = (n & 1) ? va : vb;
+    tmem_ld_wait();
+    if (n + 1 < 5) tmem_ld32(taddr + ORDER[n + 1] * 32, nxt);
+    const int src_w = wl + DIR * (ORDER[n] - 2);
+    const float inb = ((src_w >= 0) && (src_w < kTileW)) ? 1.f : 0.f;        // outside the image = zero padding
+    const int src_lane = (lane & 16) | (src_w & 15);
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      acc[i] = fmaf(__uint_as_float(__shfl_sync(0xffffffffu, cur[i], src_lane)), inb, acc[i]);
+  }
+}
+
 struct FwdParams {
   int num_clients;
   int nsplit;            // work items per client
@@ -113,10 +141,14 @@ struct FwdParams {
   float* dbias_out;             // optional [C][BN]: raw bias grad (tests); when set the bias is NOT updated
 };
 
-template <int ROWB, int NKW, int BN, int IMG_H, int IMG_W, int BATCH, bool FLIP, int EPI, int NSTAGE, int NEPG = 1>
+// NMMA: MMA-issuing warps.  With few, small MMAs per tile (conv1: five N=32 MMAs) the serial per-tile work of ONE
+// issuing warp (two barrier waits, fences, descriptor setup, two commits, ~700 cycles) is the bottleneck of the whole
+// pipeline; NMMA = 2 gives even and odd tiles their own issuer.
+template <int ROWB, int NKW, int BN, int IMG_H, int IMG_W, int BATCH, bool FLIP, int EPI, int NSTAGE, int NEPG = 1,
+          int NMMA = 1>
 struct FwdCfg {
   static constexpr int NBUF = 2 * NEPG;                  // TMEM accumulator buffers (two per epilogue group)
-  static constexpr int THREADS = (4 * NEPG + 2) * 32;
+  static constexpr int THREADS = (4 * NEPG + 1 + NMMA) * 32;
   static constexpr int KT = ROWB / 2;
   static constexpr int NTAPS = NKW * kNKH;
   static constexpr int W_TAP_BYTES = BN * ROWB;
@@ -131,11 +163,12 @@ struct FwdCfg {
   static_assert(BN % 32 == 0, "epilogue works on 32-column chunks");
 };
 
-template <int ROWB, int NKW, int BN, int IMG_H, int IMG_W, int BATCH, bool FLIP, int EPI, int NSTAGE, int NEPG = 1>
-__global__ void __launch_bounds__((4 * NEPG + 2) * 32, 1)
+template <int ROWB, int NKW, int BN, int IMG_H, int IMG_W, int BATCH, bool FLIP, int EPI, int NSTAGE, int NEPG = 1,
+          int NMMA = 1>
+__global__ void __launch_bounds__((4 * NEPG + 1 + NMMA) * 32, 1)
 conv_taps_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                  const FwdParams p) {
-  using Cfg = FwdCfg<ROWB, NKW, BN, IMG_H, IMG_W, BATCH, FLIP, EPI, NSTAGE, NEPG>;
+  using Cfg = FwdCfg<ROWB, NKW, BN, IMG_H, IMG_W, BATCH, FLIP, EPI, NSTAGE, NEPG, NMMA>;
   constexpr int kProdWarp = 4 * NEPG, kMmaWarp = 4 * NEPG + 1, NBUF = Cfg::NBUF;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -149,7 +182,7 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (threadIdx.x == 0) {
     for (int i = 0; i < NSTAGE; ++i) { mbar_init(&bars->full[i], 1); mbar_init(&bars->empty[i], 1); }
     mbar_init(&bars->wfull, 1);
-    mbar_init(&bars->wempty, 1);
+    mbar_init(&bars->wempty, NMMA);
     for (int i = 0; i < NBUF; ++i) { mbar_init(&bars->tfull[i], 1); mbar_init(&bars->tempty[i], kEpiWarps); }
     fence_mbar_init();
   }
@@ -203,8 +236,10 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
       }
     }
-  } else if (warp == kMmaWarp) {
-    // ------------------------------------------------------------------ MMA issuer (warp-converged)
+  } else if (warp >= kMmaWarp && warp < kMmaWarp + NMMA) {
+    // ------------------------------------------------------------------ MMA issuer(s) (warp-converged); issuer m
+    // owns the tiles with seq % NMMA == m and walks the stage / buffer rings in lock step with the others
+    const int mpar = warp - kMmaWarp;
     const bool leader = elect_one();
     constexpr uint32_t LT = layout_type_for_row_bytes(ROWB);
     constexpr uint32_t IDESC = make_idesc_bf16(128, BN, 0, 0);
@@ -224,6 +259,12 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int t0 = sp * tiles_per_work;
       const int t1 = min(t0 + tiles_per_work, Cfg::TILES_PER_CLIENT);
       for (int t = t0; t < t1; ++t) {
+        if (NMMA > 1 && (int)(seq % NMMA) != mpar) {            // another issuer's tile: just advance the rings
+#pragma unroll 1
+          for (int kw = 0; kw < NKW; ++kw) { if (++stage == NSTAGE) { stage = 0; phase ^= 1; } }
+          ++seq;
+          continue;
+        }
         const int buf = seq % NBUF;
         mbar_wait(&bars->tempty[buf], ((seq / NBUF) & 1) ^ 1);
         fence_after_sync();
@@ -612,26 +653,7 @@ conv_dgrad_fold_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         fence_after_sync();
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(32 * q) << 16) + buf * Cfg::TMEM_BUF_STRIDE;
         float acc[CIN];
-        {
-          uint32_t v[32];
-          tmem_ld32(taddr + 2 * CIN, v);                      // kw = 2: no column shift
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < CIN; ++i) acc[i] = __uint_as_float(v[i]);
-        }
-#pragma unroll
-        for (int kw = 0; kw < 5; ++kw) {
-          if (kw == 2) continue;
-          uint32_t v[32];
-          tmem_ld32(taddr + kw * CIN, v);
-          tmem_ld_wait();
-          const int src_w = wl + 2 - kw;                      // D_kw is taken from the pixel 2-kw columns to the right
-          const float inb = ((src_w >= 0) && (src_w < IMG_W)) ? 1.f : 0.f;     // outside the image = zero padding
-          const int src_lane = (lane & 16) | (src_w & 15);
-#pragma unroll
-          for (int i = 0; i < CIN; ++i)
-            acc[i] = fmaf(__uint_as_float(__shfl_sync(0xffffffffu, v[i], src_lane)), inb, acc[i]);
-        }
+        fold_kw_sum<-1>(taddr, lane, wl, nullptr, acc);       // D_kw is taken from the pixel 2-kw columns to the right
         // TMEM buffer drained: release it before the (long-latency) global stores
         fence_before_sync();
         __syncwarp();
@@ -901,29 +923,10 @@ conv_dgrad_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         fence_after_sync();
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(32 * q) << 16) + buf * Cfg::TMEM_BUF_STRIDE;
         float acc[CIN];
-        {
-          uint32_t v[32];
-          tmem_ld32(taddr + 2 * CIN, v);                      // kw = 2: no column shift
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < CIN; ++i) acc[i] = __uint_as_float(v[i]);
-        }
-#pragma unroll
-        for (int kw = 0; kw < 5; ++kw) {
-          if (kw == 2) continue;
-          uint32_t v[32];
-          tmem_ld32(taddr + kw * CIN, v);
-          tmem_ld_wait();
-          const int src_w = wl + 2 - kw;
-          const float inb = ((src_w >= 0) && (src_w < IMG_W)) ? 1.f : 0.f;
-          const int src_lane = (lane & 16) | (src_w & 15);
-#pragma unroll
-          for (int i = 0; i < CIN; ++i)
-            acc[i] = fmaf(__uint_as_float(__shfl_sync(0xffffffffu, v[i], src_lane)), inb, acc[i]);
-        }
+        fold_kw_sum<-1>(taddr, lane, wl, nullptr, acc);       // D_kw is taken from the pixel 2-kw columns to the right
         fence_before_sync();
         __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(tempty_leader[buf]);     // the leader's barrier counts both CTAs' warps
+        if (lane == 0) mbar_arrive_cluster_relaxed(tempty_leader[buf]);   // the leader's barrier counts both CTAs' warps
         const uint32_t* pw32 = reinterpret_cast<const uint32_t*>(pq);
         uint4 o[4];
         uint32_t* ow = reinterpret_cast<uint32_t*>(o);
@@ -1116,26 +1119,7 @@ conv_fwd_fold_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           fence_after_sync();
           const uint32_t taddr = tmem_base + (static_cast<uint32_t>(32 * q) << 16) + j * Cfg::TMEM_BUF_STRIDE;
           float acc[32];
-          {
-            uint32_t v[32];
-            tmem_ld32(taddr + 2 * 32, v);                       // kw = 2: no column shift
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) acc[i] = __uint_as_float(v[i]) + bias_r[i];
-          }
-#pragma unroll
-          for (int kw = 0; kw < 5; ++kw) {
-            if (kw == 2) continue;
-            uint32_t v[32];
-            tmem_ld32(taddr + kw * 32, v);
-            tmem_ld_wait();
-            const int src_w = wl + kw - 2;
-            const float inb = ((src_w >= 0) && (src_w < IMG_W)) ? 1.f : 0.f;   // outside the image = zero padding
-            const int src_lane = (lane & 16) | (src_w & 15);
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              acc[i] = fmaf(__uint_as_float(__shfl_sync(0xffffffffu, v[i], src_lane)), inb, acc[i]);
-          }
+          fold_kw_sum<+1>(taddr, lane, wl, bias_r, acc);
           fence_before_sync();
           __syncwarp();
           if (lane == 0) mbar_arrive(&bars->tempty[j]);          // group drained: the tensor core may refill it

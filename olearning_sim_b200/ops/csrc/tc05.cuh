@@ -195,6 +195,12 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t local, uint32_t rank) {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// Same without release semantics: for signals whose ordering is established otherwise (tcgen05.wait::ld + tcgen05 fence
+// before "accumulator drained").  The releasing form is a cluster-scope memory barrier: it waited for the epilogue's
+// outstanding global stores and cost 21 % of all warp samples in the first version of the pair kernel.
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
 __device__ __forceinline__ void tmem_alloc2(uint32_t* smem_dst, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)),
                "r"(ncols)
