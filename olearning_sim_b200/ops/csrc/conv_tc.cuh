@@ -695,8 +695,8 @@ struct PairBarriers {
   uint64_t pfull[8];     // leader only: the peer's A stage landed (remote arrive by the peer's relay warp)
   uint64_t empty[8];     // stage consumed (multicast commit)
   uint64_t wfull, pwfull, wempty;
-  uint64_t tfull[2];     // accumulator ready (multicast commit)
-  uint64_t tempty[2];    // leader only: accumulator drained by both CTAs (4 local + 4 remote warps)
+  uint64_t tfull[3];     // accumulator ready (multicast commit)
+  uint64_t tempty[3];    // leader only: accumulator drained by both CTAs (4 local + 4 remote warps)
   uint32_t tmem_base;
   uint32_t pad;
 };
@@ -711,7 +711,10 @@ struct DgradPairCfg {
   static constexpr int W_BYTES = kNKH * W_KH_BYTES;
   static constexpr int STAGE_BYTES = kBoxH * kTileW * ROWB;
   static constexpr int TILES_PER_CLIENT = BATCH * (IMG_H / kTileH);
-  static constexpr int TMEM_BUF_STRIDE = 256;
+  // three accumulator buffers: draining one tile (five TMEM loads, 128 shuffles through the shared-memory pipe) takes
+  // about two MMA steps, so with two buffers the tensor core idled a third of the time waiting for a free one
+  static constexpr int NBUF = 3;
+  static constexpr int TMEM_BUF_STRIDE = 160;
   static constexpr int TMEM_COLS = 512;
   static constexpr int SMEM_BYTES = 1024 + W_BYTES + NSTAGE * STAGE_BYTES + (int)sizeof(PairBarriers);
   static_assert(ROWB == 128 && CIN == 32 && NSTAGE <= 8, "written for 64 -> 32 channels");
@@ -736,7 +739,7 @@ conv_dgrad_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   if (threadIdx.x == 0) {
     for (int i = 0; i < NSTAGE; ++i) { mbar_init(&bars->full[i], 1); mbar_init(&bars->pfull[i], 1); mbar_init(&bars->empty[i], 1); }
     mbar_init(&bars->wfull, 1); mbar_init(&bars->pwfull, 1); mbar_init(&bars->wempty, 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(&bars->tfull[i], 1); mbar_init(&bars->tempty[i], 2 * kEpiWarps); }
+    for (int i = 0; i < Cfg::NBUF; ++i) { mbar_init(&bars->tfull[i], 1); mbar_init(&bars->tempty[i], 2 * kEpiWarps); }
     fence_mbar_init();
   }
   if (warp == kFoldMmaWarp) { tmem_alloc2(&bars->tmem_base, Cfg::TMEM_COLS); tmem_relinquish2(); }
@@ -811,7 +814,7 @@ conv_dgrad_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     // B: chunks of [COUT k-rows][16 channels] with 32-byte rows: LBO = chunk stride, SBO = 8 k-rows
     const uint64_t b_desc_base = make_smem_desc(smem_u32(w_sm), Cfg::CHUNK_BYTES, 8 * 32, LT_SW32);
     int stage = 0; uint32_t phase = 0; int cur_client = -1; uint32_t wphase = 0;
-    int buf = 0; uint32_t tphase0 = 0, tphase1 = 0;
+    uint32_t seq = 0;                                   // steps issued: buffer = seq % NBUF
     for (int wi = pair; wi < num_work; wi += npairs) {
       const int c = wi / p.nsplit;
       if (p.active && !p.active[c]) continue;
@@ -823,8 +826,9 @@ conv_dgrad_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       if (c != cur_client) {
         mbar_wait(&bars->wfull, wphase); mbar_wait(&bars->pwfull, wphase); wphase ^= 1; cur_client = c;
       }
-      for (int k = 0; k < steps_per_work; ++k) {
-        mbar_wait(&bars->tempty[buf], (buf ? tphase1 : tphase0) ^ 1);
+      for (int k = 0; k < steps_per_work; ++k, ++seq) {
+        const int buf = seq % Cfg::NBUF;
+        mbar_wait(&bars->tempty[buf], ((seq / Cfg::NBUF) & 1) ^ 1);
         fence_after_sync();
         mbar_wait(&bars->full[stage], phase);
         mbar_wait(&bars->pfull[stage], phase);
@@ -846,8 +850,6 @@ conv_dgrad_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         }
         __syncwarp();
         if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
-        if (buf) tphase1 ^= 1; else tphase0 ^= 1;
-        buf ^= 1;
       }
       if (last_of_client) {
         if (leader) umma_commit_2cta(&bars->wempty, 3);
@@ -856,11 +858,11 @@ conv_dgrad_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     }
   } else {
     const int grp = warp >> 2;
-    int buf = 0; uint32_t tph = 0;
+    uint32_t seq = 0;
     const int q = warp & 3;
     const int tid_g = threadIdx.x & 127;
     const int hl = 2 * q + (lane >> 4), wl = lane & 15;
-    const uint32_t tempty_leader[2] = {mapa_u32(smem_u32(&bars->tempty[0]), 0), mapa_u32(smem_u32(&bars->tempty[1]), 0)};
+    const uint32_t tempty_leader0 = mapa_u32(smem_u32(&bars->tempty[0]), 0);
     float dbacc[CIN];
 #pragma unroll
     for (int i = 0; i < CIN; ++i) dbacc[i] = 0.f;
@@ -909,8 +911,9 @@ conv_dgrad_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       }
       if (sp == 0) had_sp0 = true;
       const int t0 = sp * tiles_per_work;
-      for (int k = 0; k < steps_per_work; ++k, buf ^= 1) {
-        if (buf != grp) continue;
+      for (int k = 0; k < steps_per_work; ++k, ++seq) {
+        if ((int)(seq & 1) != grp) continue;
+        const int buf = seq % Cfg::NBUF;
         const int t = t0 + 2 * k + (int)rank;
         const int s = t / (IMG_H / kTileH);
         const int h0 = (t % (IMG_H / kTileH)) * kTileH;
@@ -919,14 +922,14 @@ conv_dgrad_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         uint4 pq[4];
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) pq[kk] = __ldg(reinterpret_cast<const uint4*>(p.pooled + pbase + kk * 8));
-        mbar_wait(&bars->tfull[buf], tph);
+        mbar_wait(&bars->tfull[buf], (seq / Cfg::NBUF) & 1);
         fence_after_sync();
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(32 * q) << 16) + buf * Cfg::TMEM_BUF_STRIDE;
         float acc[CIN];
         fold_kw_sum<-1>(taddr, lane, wl, nullptr, acc);       // D_kw is taken from the pixel 2-kw columns to the right
         fence_before_sync();
         __syncwarp();
-        if (lane == 0) mbar_arrive_cluster_relaxed(tempty_leader[buf]);   // the leader's barrier counts both CTAs' warps
+        if (lane == 0) mbar_arrive_cluster_relaxed(tempty_leader0 + buf * 8);   // the leader's barrier counts both CTAs' warps
         const uint32_t* pw32 = reinterpret_cast<const uint32_t*>(pq);
         uint4 o[4];
         uint32_t* ow = reinterpret_cast<uint32_t*>(o);
@@ -940,7 +943,6 @@ conv_dgrad_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         }
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) *reinterpret_cast<uint4*>(p.dpool + pbase + kk * 8) = o[kk];
-        tph ^= 1;
       }
     }
     if (cur_client >= 0) flush_bias(cur_client);

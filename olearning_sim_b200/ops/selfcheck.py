@@ -209,7 +209,7 @@ def check_conv2_dgrad_pair(c: int) -> Dict:
                                                                            0.1, 0.0, db1)), 1)
             res["err"] = max(res["err"], res[f"pair{mode}_dp1"], res[f"pair{mode}_db1"])
     finally:
-        native.set_option("dgrad_pair", 0)
+        native.set_option("dgrad_pair", -1)       # default: automatic by client count
     return res
 
 
