@@ -166,9 +166,10 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_fc_xent_kernel(const Hea
   float* misc = db2 + 64;            // [16]
   uint8_t* ring = reinterpret_cast<uint8_t*>(misc + 16);
   uint64_t* rfull = reinterpret_cast<uint64_t*>(ring + kHeadSlots * kHeadSlice);
+  uint64_t* rempty = rfull + kHeadSlots;      // slot consumed: one arrival per warp
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
-    for (int i = 0; i < kHeadSlots; ++i) tc05::mbar_init(&rfull[i], 1);
+    for (int i = 0; i < kHeadSlots; ++i) { tc05::mbar_init(&rfull[i], 1); tc05::mbar_init(&rempty[i], kHeadThreads / 32); }
     tc05::fence_mbar_init();
   }
   __syncthreads();
@@ -178,20 +179,23 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_fc_xent_kernel(const Hea
     if (p.active && !p.active[c]) continue;
     float* wm = p.master + (size_t)c * p.P;
     // slice n of a client = (feature block it = n / 4, sample batch b = n % 4); issued by one thread
+    // issued by the 16 low lanes of warp 0 together: lane l copies sample l/2's activation (even l) or code (odd l) row
     auto issue_slice = [&](int n, uint32_t seq) {
       const int it = n >> 2, s0 = (n & 3) * 8, slot = seq % kHeadSlots;
       uint8_t* dst = ring + slot * kHeadSlice;
-      const __nv_bfloat16* xs = p.p2 + ((size_t)c * 32 + s0) * 4096 + it * 512;
-      const uint8_t* cs = p.code2 + ((size_t)c * 32 + s0) * 4096 + it * 512;
-      tc05::mbar_arrive_expect_tx(&rfull[slot], kHeadSlice);
-#pragma unroll 1
-      for (int u = 0; u < 8; ++u) {
-        tc05::bulk_copy_g2s(dst + u * 1024, xs + (size_t)u * 4096, 1024, &rfull[slot]);
-        tc05::bulk_copy_g2s(dst + kHeadSliceX + u * 512, cs + (size_t)u * 4096, 512, &rfull[slot]);
+      if (lane == 0) tc05::mbar_arrive_expect_tx(&rfull[slot], kHeadSlice);
+      __syncwarp();
+      if (lane < 16) {
+        const int u = lane >> 1;
+        if (lane & 1)
+          tc05::bulk_copy_g2s(dst + kHeadSliceX + u * 512, p.code2 + ((size_t)c * 32 + s0 + u) * 4096 + it * 512, 512,
+                              &rfull[slot]);
+        else
+          tc05::bulk_copy_g2s(dst + u * 1024, p.p2 + ((size_t)c * 32 + s0 + u) * 4096 + it * 512, 1024, &rfull[slot]);
       }
     };
     // the first four slices of the backward phase travel while the weights load and the logits are computed
-    if (tid == 0) {
+    if (warp == 0) {
       tc05::fence_proxy_async_smem();
       for (int n = 0; n < kHeadSlots; ++n) issue_slice(n, nslice + n);
     }
@@ -293,6 +297,17 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_fc_xent_kernel(const Hea
     }
     __syncthreads();
 
+    // warm L2 with the next client's FC weights and pooled activations while this client's backward phase runs: the
+    // weight stage-in and the first logits loads of the next client then hit L2 instead of HBM
+    if (tid == 0) {
+      const int cn = c + gridDim.x;
+      if (cn < p.num_clients && (!p.active || p.active[cn])) {
+        const char* wn = reinterpret_cast<const char*>(p.master + (size_t)cn * p.P + L::WFC);
+        for (int o = 0; o < L::WFC_N * 4; o += 16384) tc05::prefetch_l2_bulk(wn + o, 16384);
+        const char* xn = reinterpret_cast<const char*>(p.p2 + (size_t)cn * 32 * 4096);
+        for (int o = 0; o < 32 * 4096 * 2; o += 16384) tc05::prefetch_l2_bulk(xn + o, 16384);
+      }
+    }
     // ---- backward: dW_fc, dP2 -> un-pool -> dY2_pre, db2, db_fc ; SGD on W_fc
     const uint8_t* code = p.code2 + (size_t)c * 32 * 4096;
     __nv_bfloat16* dy = p.dy2 + (size_t)c * 32 * 16 * 16 * 64;
@@ -318,9 +333,13 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_fc_xent_kernel(const Hea
           xr8[u] = *reinterpret_cast<const uint32_t*>(sl + u * 1024 + tid * 4);
           cr8[u] = *reinterpret_cast<const uint16_t*>(sl + kHeadSliceX + u * 512 + tid * 2);
         }
-        // everyone has read the slot: refill it with the slice four ahead (same client only)
-        __syncthreads();
-        if (tid == 0 && it * 4 + (s0 >> 3) + kHeadSlots < 32) {
+        // refill the slot with the slice four ahead once every warp has read it.  Only warp 0 (the issuer) waits for
+        // that; the other warps signal "consumed" on the slot's mbarrier and run on (a full __syncthreads here cost
+        // 16 % of all warp samples).  The 8 values read above are in registers, so the slot may be overwritten.
+        __syncwarp();
+        if (lane == 0) tc05::mbar_arrive(&rempty[slot]);
+        if (warp == 0 && it * 4 + (s0 >> 3) + kHeadSlots < 32) {
+          tc05::mbar_wait(&rempty[slot], (seq / kHeadSlots) & 1);
           tc05::fence_proxy_async_smem();
           issue_slice(it * 4 + (s0 >> 3) + kHeadSlots, seq + kHeadSlots);
         }
