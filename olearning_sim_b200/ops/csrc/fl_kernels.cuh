@@ -297,17 +297,6 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_fc_xent_kernel(const Hea
     }
     __syncthreads();
 
-    // warm L2 with the next client's FC weights and pooled activations while this client's backward phase runs: the
-    // weight stage-in and the first logits loads of the next client then hit L2 instead of HBM
-    if (tid == 0) {
-      const int cn = c + gridDim.x;
-      if (cn < p.num_clients && (!p.active || p.active[cn])) {
-        const char* wn = reinterpret_cast<const char*>(p.master + (size_t)cn * p.P + L::WFC);
-        for (int o = 0; o < L::WFC_N * 4; o += 16384) tc05::prefetch_l2_bulk(wn + o, 16384);
-        const char* xn = reinterpret_cast<const char*>(p.p2 + (size_t)cn * 32 * 4096);
-        for (int o = 0; o < 32 * 4096 * 2; o += 16384) tc05::prefetch_l2_bulk(xn + o, 16384);
-      }
-    }
     // ---- backward: dW_fc, dP2 -> un-pool -> dY2_pre, db2, db_fc ; SGD on W_fc
     const uint8_t* code = p.code2 + (size_t)c * 32 * 4096;
     __nv_bfloat16* dy = p.dy2 + (size_t)c * 32 * 16 * 16 * 64;
