@@ -276,3 +276,13 @@ def test_oflserver_helpers_on_local_store(tmp_path):
     prod.send(b"hello")
     assert c.receive(100).data() == b"hello"
     assert o.getSqlTaskRepo().check_task_in_database("nope") is False
+
+
+def test_deviceflow_config_getters(tmp_path, monkeypatch):
+    from olearning_sim_b200.deviceflow import config_parser as cp
+    monkeypatch.setenv("DF_HOST", "10.1.2.3")
+    f = tmp_path / "deviceflow_config.yaml"
+    f.write_text("grpc_service_address: ${DF_HOST}\nport: 50099\nsource_topic: t_in\nshelfroom_namespace: ns/shelf\n")
+    assert cp.get_grpc_service_address(str(f)) == "10.1.2.3" and cp.get_port(str(f)) == 50099
+    assert cp.get_source_topic(str(f)) == "t_in" and cp.get_shelfroom_namespace(str(f)) == "ns/shelf"
+    assert cp.get_max_workers(str(f)) == 10 and cp.get_shelfroom_url(str(f)) == "mem://local"     # typed defaults
