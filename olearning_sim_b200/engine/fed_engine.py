@@ -457,6 +457,8 @@ class FedEngine:
         else:
             res = self._torch_round(round_idx)
         res.wall_s = time.perf_counter() - t0
+        # reference semantics (task_manager.py:743-748): a round with more failed clients than dynamic_nums is a failure
+        res.extras["within_tolerance"] = res.failed <= self.cfg.dynamic_nums
         if self.cfg.profile:
             res.extras["phases_ms"] = self.timer.collect(self.group, self.world)
         if stream_inputs:

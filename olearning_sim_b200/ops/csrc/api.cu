@@ -116,6 +116,8 @@ constexpr int BATCH = 32;
 using Conv1FwdCfg = FwdCfg<32, 1, 32, 32, 32, BATCH, false, EPI_POOL, 12, 2, 2>;
 using Conv2FwdCfg = FwdFoldCfg<32, 64, 16, BATCH, 7>;
 using Conv2DgradCfg = DgradFoldCfg<32, 64, 16, BATCH, 4>;
+#define CONV2_FWD_SHIFT conv_fwd_shift_kernel<32, 64, 16, 16, BATCH, 6>
+using Conv2FwdShiftCfg = FwdShiftCfg<32, 64, 16, 16, BATCH, 6>;
 #define CONV2_DGRAD_PAIR conv_dgrad_pair_kernel<32, 64, 16, BATCH, 6>
 using Conv2DgradPairCfg = DgradPairCfg<32, 64, 16, BATCH, 6>;
 //                              XROWB NKW YROWB H   W   BATCH NSS SYNTH_Y
@@ -131,6 +133,7 @@ int g_x5_rows = 1;       // 1: X5 is stored pre-swizzled and fetched with 512-by
 // conv2 data gradient on CTA pairs (cta_group::2, weight operand split across the pair): 0 never, 1 always,
 // -1 auto = when a rank holds fewer than 400 clients (measured: 139 vs 151 us at 160 clients, 380 vs 379 at 592)
 int g_dgrad_pair = -1;
+int g_fwd2_shift = 0;    // 1: conv2 forward as 25 shifted-view MMAs per tile (16x8 tiles, weight-stationary pairs)
 int g_wgrad2_ws = 1;     // 1: weight-stationary (B-collector) MMAs in the conv2 weight gradient
 int g_wgrad2_mode = 1;   // 0: five 12x16 boxes per chunk, 1: one 12x20 box, 2: one box + swizzle base offset
 bool g_attr_set = false;
@@ -139,6 +142,7 @@ int set_attrs() {
   CK(cudaFuncSetAttribute(CONV1_FWD, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv1FwdCfg::SMEM_BYTES));
   CK(cudaFuncSetAttribute(CONV2_FWD, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv2FwdCfg::SMEM_BYTES));
   CK(cudaFuncSetAttribute(CONV2_DGRAD, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv2DgradCfg::SMEM_BYTES));
+  CK(cudaFuncSetAttribute(CONV2_FWD_SHIFT, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv2FwdShiftCfg::SMEM_BYTES));
   CK(cudaFuncSetAttribute(CONV2_DGRAD_PAIR, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv2DgradPairCfg::SMEM_BYTES));
   CK(cudaFuncSetAttribute(CONV2_WGRAD, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv2WgradCfg::SMEM_BYTES));
   CK(cudaFuncSetAttribute(CONV1_WGRAD, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv1WgradCfg::SMEM_BYTES));
@@ -216,8 +220,6 @@ int olsb_conv2_fwd(const void* p1, const void* w2_fwd, const void* master, long 
                    void* p2, void* code2, int nsplit, void* stream) {
   if (int r = olsb_init()) return r;
   CUtensorMap tmA, tmW;
-  if (int r = make_act_map(&tmA, p1, (uint64_t)C * BATCH, 16, 16, 32, kBoxH)) return r;
-  if (int r = make_w_map(&tmW, w2_fwd, (uint64_t)C, 64, 800, 32, 32)) return r;
   FwdParams p;
   memset(&p, 0, sizeof(p));
   p.num_clients = C; p.nsplit = auto_split(C, Conv2FwdCfg::TILES_PER_CLIENT, nsplit);
@@ -226,6 +228,21 @@ int olsb_conv2_fwd(const void* p1, const void* w2_fwd, const void* master, long 
   p.out = (__nv_bfloat16*)p2; p.code = (uint8_t*)code2;
   const int work = C * p.nsplit;
   const int grid = work < g_sms ? work : g_sms;
+  if (g_fwd2_shift) {
+    // 16x8-pixel tiles, one (16+4) x (8+4) halo box per tile; weights as 25 K-major [64][32] blocks
+    using SC = Conv2FwdShiftCfg;
+    if (int r = make_act_map(&tmA, p1, (uint64_t)C * BATCH, 16, 16, 32, SC::BOX_H, SC::BOX_W)) return r;
+    if (int r = make_w_map(&tmW, w2_fwd, (uint64_t)C, 64, 800, 64, 32)) return r;
+    if (SC::TILES_PER_CLIENT % (SC::NT * p.nsplit)) {
+      snprintf(g_err, sizeof(g_err), "conv2 fwd (shift): tiles per work item must be a multiple of %d", SC::NT);
+      return -4;
+    }
+    CONV2_FWD_SHIFT<<<grid, kFoldThreads, SC::SMEM_BYTES, (cudaStream_t)stream>>>(tmA, tmW, p);
+    CK(cudaGetLastError());
+    return 0;
+  }
+  if (int r = make_act_map(&tmA, p1, (uint64_t)C * BATCH, 16, 16, 32, kBoxH)) return r;
+  if (int r = make_w_map(&tmW, w2_fwd, (uint64_t)C, 64, 800, 32, 32)) return r;
   CONV2_FWD<<<grid, kFoldThreads, Conv2FwdCfg::SMEM_BYTES, (cudaStream_t)stream>>>(tmA, tmW, p);
   CK(cudaGetLastError());
   return 0;
@@ -437,6 +454,7 @@ int olsb_fedavg_finish(const void* const* partial_peers, const void* const* wsum
 int olsb_set_option(const char* name, int value) {
   if (!strcmp(name, "x5_rows")) { const int o = g_x5_rows; g_x5_rows = value; return o; }
   if (!strcmp(name, "dgrad_pair")) { const int o = g_dgrad_pair; g_dgrad_pair = value; return o; }
+  if (!strcmp(name, "fwd2_shift")) { const int o = g_fwd2_shift; g_fwd2_shift = value; return o; }
   if (!strcmp(name, "wgrad2_ws")) { const int o = g_wgrad2_ws; g_wgrad2_ws = value; return o; }
   if (!strcmp(name, "wgrad2_mode")) { const int o = g_wgrad2_mode; g_wgrad2_mode = value; return o; }
   return -1;

@@ -59,7 +59,9 @@ enum { EPI_POOL = 0, EPI_GATE = 1 };
 // positive one — which is all ReLU needs (an all-negative window yields 0 whoever wins, and its gradient is gated
 // off downstream).  One integer max therefore carries value and argmax (ties -> smallest position) at one ALU op
 // per element; the sign-fixing key transform this replaces made the conv1 forward kernel ALU-bound (80% pipe).
-// Lane (b0 = lane&1, b4 = lane>>4&1) ends with channels [8*(2*b0+b4), +8): pv = bf16 values, cv = argmax codes.
+// Lane (b0 = lane&1 column parity, b4 = row parity; the row partner is lane ^ ROW_XOR: 16 for 8x16-pixel tiles, 8 for
+// 16x8 tiles) ends with channels [8*(2*b0+b4), +8): pv = bf16 values, cv = argmax codes.
+template <int ROW_XOR = 16>
 __device__ __forceinline__ void pool2x2_relu(const float (&x)[32], int b0, int b4, uint4& pv, uint2& cv) {
   const int tag = 3 - ((b4 << 1) | b0);
   int v[32];
@@ -77,7 +79,7 @@ __device__ __forceinline__ void pool2x2_relu(const float (&x)[32], int b0, int b
   for (int i = 0; i < 8; ++i) {                        // partner lane^16: b4=0 keeps the low 8, b4=1 the high 8
     const int give = b4 ? m16[i] : m16[8 + i];
     const int keep = b4 ? m16[8 + i] : m16[i];
-    m8[i] = max(keep, __shfl_xor_sync(0xffffffffu, give, 16));
+    m8[i] = max(keep, __shfl_xor_sync(0xffffffffu, give, ROW_XOR));
   }
   float f[8];
   uint32_t cd[8];
@@ -1133,6 +1135,205 @@ conv_fwd_fold_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           *reinterpret_cast<uint2*>(p.code + off) = cv;
         }
         tphase ^= 1;
+      }
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == kFoldMmaWarp) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+// ================================================================================================
+// conv2 forward, shifted-operand form
+// ================================================================================================
+// The folded kernel above reads 320 accumulator columns per pixel row back from TMEM (64 B/clk/SM: 2560 cycles per
+// tile) and pays 128 shuffles per lane for the column shift.  Here every tap is its own MMA on a *shifted view* of one
+// halo box instead: tiles are 16 rows x 8 pixels, so the 128 M rows form sixteen 8-pixel groups, one per image row,
+// whose stride is the box pitch — uniform for ANY box width.  That makes both tap directions pure start-address
+// shifts of the K-major A descriptor (kw: one 64-byte pixel, kh: one 12-pixel box row), the accumulator is 64 columns
+// per tile, and the epilogue is just bias + pool.  The price, 50 N=64 MMAs whose weight operand would be re-fetched per
+// tile, is paid once per TWO tiles with weight-stationary MMAs (B collector fill / lastuse).
+template <int CIN, int COUT, int IMG_H, int IMG_W, int BATCH, int NSTAGE>
+struct FwdShiftCfg {
+  static constexpr int TH = 16, TW = 8;                 // tile: 16 rows x 8 pixels
+  static constexpr int BOX_H = TH + 2 * kHalo, BOX_W = TW + 2 * kHalo;
+  static constexpr int ROWB = CIN * 2;
+  static constexpr int PITCH = BOX_W * ROWB;            // bytes per box row = stride between the 8-pixel M groups
+  static constexpr int STAGE_BYTES = BOX_H * PITCH;     // 15360: a multiple of the 512-byte SW64 pattern
+  static constexpr int W_TAP_BYTES = COUT * ROWB;       // [COUT rows][CIN] K-major
+  static constexpr int W_BYTES = 25 * W_TAP_BYTES;
+  static constexpr int TILES_PER_CLIENT = BATCH * (IMG_H / TH) * (IMG_W / TW);
+  static constexpr int NT = 2;                          // tiles per weight-stationary batch
+  static constexpr int NBUF = 2 * NT;                   // accumulator buffers (two batches in flight)
+  static constexpr int TMEM_COLS = 256;
+  static constexpr int SMEM_BYTES = 1024 + W_BYTES + NSTAGE * STAGE_BYTES + (int)sizeof(Barriers);
+  static_assert(ROWB == 64 && COUT == 64 && IMG_H == TH && STAGE_BYTES % 512 == 0 && NSTAGE % NT == 0, "conv2 geometry");
+};
+
+template <int CIN, int COUT, int IMG_H, int IMG_W, int BATCH, int NSTAGE>
+__global__ void __launch_bounds__(kFoldThreads, 1)
+conv_fwd_shift_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+                      const FwdParams p) {
+  using Cfg = FwdShiftCfg<CIN, COUT, IMG_H, IMG_W, BATCH, NSTAGE>;
+  constexpr int ROWB = Cfg::ROWB, NT = Cfg::NT;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* w_sm = smem;
+  uint8_t* a_sm = smem + Cfg::W_BYTES;
+  Barriers* bars = reinterpret_cast<Barriers*>(a_sm + NSTAGE * Cfg::STAGE_BYTES);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NSTAGE; ++i) { mbar_init(&bars->full[i], 1); mbar_init(&bars->empty[i], 1); }
+    mbar_init(&bars->wfull, 1);
+    mbar_init(&bars->wempty, 1);
+    for (int i = 0; i < Cfg::NBUF; ++i) { mbar_init(&bars->tfull[i], 1); mbar_init(&bars->tempty[i], kEpiWarps); }
+    fence_mbar_init();
+  }
+  if (warp == kFoldMmaWarp) { tmem_alloc(&bars->tmem_base, Cfg::TMEM_COLS); tmem_relinquish(); }
+  if (warp == kFoldTmaWarp && lane == 0) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmW); }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = bars->tmem_base;
+  const int num_work = p.num_clients * p.nsplit;
+  const int tiles_per_work = Cfg::TILES_PER_CLIENT / p.nsplit;          // a multiple of NT (host picks nsplit)
+  constexpr int TPS = IMG_W / Cfg::TW;                                    // tiles per sample
+
+  if (warp == kFoldTmaWarp) {
+    const bool leader = elect_one();
+    int stage = 0; uint32_t phase = 0; int cur_client = -1; uint32_t wphase = 0; bool first_w = true;
+    for (int wi = blockIdx.x; wi < num_work; wi += gridDim.x) {
+      const int c = wi / p.nsplit, sp = wi % p.nsplit;
+      if (p.active && !p.active[c]) continue;
+      if (c != cur_client) {
+        if (!first_w) { mbar_wait(&bars->wempty, wphase); wphase ^= 1; }
+        first_w = false; cur_client = c;
+        if (leader) {
+          mbar_arrive_expect_tx(&bars->wfull, Cfg::W_BYTES);
+          // forward weight copy [C][COUT][25*CIN]: one K-major [COUT][CIN] block per tap
+#pragma unroll 1
+          for (int tap = 0; tap < 25; ++tap)
+            tma_load_3d(w_sm + tap * Cfg::W_TAP_BYTES, &tmW, &bars->wfull, tap * CIN, 0, c);
+        }
+      }
+      const int t0 = sp * tiles_per_work;
+      for (int t = t0; t < t0 + tiles_per_work; ++t) {
+        const int s = t / TPS, w0 = (t % TPS) * Cfg::TW;
+        mbar_wait(&bars->empty[stage], phase ^ 1);
+        if (leader) {
+          mbar_arrive_expect_tx(&bars->full[stage], Cfg::STAGE_BYTES);
+          tma_load_4d(a_sm + stage * Cfg::STAGE_BYTES, &tmA, &bars->full[stage], 0, w0 - kHalo, -kHalo,
+                      c * p.a_n_stride + p.a_n_off + s);
+        }
+        if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == kFoldMmaWarp) {
+    const bool leader = elect_one();
+    constexpr uint32_t IDESC = make_idesc_bf16(128, COUT, 0, 0);
+    // A: sixteen 8-pixel groups (one per image row of the tile) at the box pitch; B: [COUT][CIN] per tap
+    const uint64_t a_desc_base = make_smem_desc(smem_u32(a_sm), 16, Cfg::PITCH, LT_SW64);
+    const uint64_t b_desc_base = make_smem_desc(smem_u32(w_sm), 16, 8 * ROWB, LT_SW64);
+    int stage = 0; uint32_t phase = 0; int cur_client = -1; uint32_t wphase = 0;
+    uint32_t bseq = 0;                                   // batches issued: buffers (bseq % 2) * NT + {0, 1}
+    for (int wi = blockIdx.x; wi < num_work; wi += gridDim.x) {
+      const int c = wi / p.nsplit;
+      if (p.active && !p.active[c]) continue;
+      bool last_of_client = true;
+      {
+        const int nwi = wi + gridDim.x;
+        if (nwi < num_work && (nwi / p.nsplit) == c) last_of_client = false;
+      }
+      if (c != cur_client) { mbar_wait(&bars->wfull, wphase); wphase ^= 1; cur_client = c; }
+      for (int b = 0; b < tiles_per_work / NT; ++b, ++bseq) {
+        const int buf0 = (bseq & 1) * NT;
+        const uint32_t tpar = ((bseq >> 1) & 1) ^ 1;
+        mbar_wait(&bars->tempty[buf0], tpar);
+        mbar_wait(&bars->tempty[buf0 + 1], tpar);
+        fence_after_sync();
+        const int stage1 = stage + 1;                     // NSTAGE is a multiple of NT: a batch never wraps the ring
+        mbar_wait(&bars->full[stage], phase);
+        mbar_wait(&bars->full[stage1], phase);
+        fence_after_sync();
+        if (leader) {
+          const uint32_t d0 = tmem_base + buf0 * COUT, d1 = d0 + COUT;
+          const uint64_t a0 = desc_advance(a_desc_base, stage * Cfg::STAGE_BYTES);
+          const uint64_t a1 = desc_advance(a_desc_base, stage1 * Cfg::STAGE_BYTES);
+#pragma unroll
+          for (int tap = 0; tap < 25; ++tap) {
+            const uint32_t aoff = (tap / 5) * Cfg::PITCH + (tap % 5) * ROWB;    // (kh, kw) as a byte shift of the view
+            const uint64_t bt = desc_advance(b_desc_base, tap * Cfg::W_TAP_BYTES);
+#pragma unroll
+            for (int ks = 0; ks < ROWB / 32; ++ks) {
+              const uint32_t acc = (tap | ks) ? 1u : 0u;
+              const uint64_t bd = desc_advance(bt, ks * 32);
+              umma_bf16_ws<WS_FILL>(d0, desc_advance(a0, aoff + ks * 32), bd, IDESC, acc);
+              umma_bf16_ws<WS_LAST>(d1, desc_advance(a1, aoff + ks * 32), bd, IDESC, acc);
+            }
+          }
+          umma_commit(&bars->empty[stage]);
+          umma_commit(&bars->empty[stage1]);
+          umma_commit(&bars->tfull[buf0]);
+          umma_commit(&bars->tfull[buf0 + 1]);
+        }
+        __syncwarp();
+        stage += NT;
+        if (stage == NSTAGE) { stage = 0; phase ^= 1; }
+      }
+      if (last_of_client) {
+        if (leader) umma_commit(&bars->wempty);
+        __syncwarp();
+      }
+    }
+  } else {
+    // epilogue warp set g (warps 4g .. 4g+3) takes tile g of every batch: lane = (row 4q + lane/8, pixel lane%8)
+    const int q = warp & 3, g = warp >> 2;
+    const int b0 = lane & 1, b3 = (lane >> 3) & 1;
+    const int sl = b0 * 2 + b3;
+    float bias_r[COUT];
+    int cur_client = -1;
+    uint32_t bseq = 0;
+    for (int wi = blockIdx.x; wi < num_work; wi += gridDim.x) {
+      const int c = wi / p.nsplit, sp = wi % p.nsplit;
+      if (p.active && !p.active[c]) continue;
+      if (c != cur_client) {
+        cur_client = c;
+        const float* bias = p.bias + (size_t)c * p.bias_stride;
+#pragma unroll
+        for (int k = 0; k < COUT; ++k) bias_r[k] = __ldg(&bias[k]);
+      }
+      const int t0 = sp * tiles_per_work;
+      for (int b = 0; b < tiles_per_work / NT; ++b, ++bseq) {
+        const int t = t0 + b * NT + g;
+        const int s = t / TPS, w0 = (t % TPS) * Cfg::TW;
+        const int buf = (bseq & 1) * NT + g;
+        const size_t n_out = (size_t)c * BATCH + s;
+        const int ph = 2 * q + (lane >> 4), pw = (w0 >> 1) + ((lane & 7) >> 1);
+        const size_t obase = ((n_out * (IMG_H / 2) + ph) * (IMG_W / 2) + pw) * COUT;
+        mbar_wait(&bars->tfull[buf], (bseq >> 1) & 1);
+        fence_after_sync();
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(32 * q) << 16) + buf * COUT;
+        uint32_t va[32], vb[32];
+        tmem_ld32(taddr, va);
+        tmem_ld32(taddr + 32, vb);
+        tmem_ld_wait();
+        fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars->tempty[buf]);          // accumulator is in registers
+        float x[32];
+        uint4 pv;
+        uint2 cv;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) x[i] = __uint_as_float(va[i]) + bias_r[i];
+        pool2x2_relu<8>(x, b0, b3, pv, cv);
+        *reinterpret_cast<uint4*>(p.out + obase + sl * 8) = pv;
+        *reinterpret_cast<uint2*>(p.code + obase + sl * 8) = cv;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) x[i] = __uint_as_float(vb[i]) + bias_r[32 + i];
+        pool2x2_relu<8>(x, b0, b3, pv, cv);
+        *reinterpret_cast<uint4*>(p.out + obase + 32 + sl * 8) = pv;
+        *reinterpret_cast<uint2*>(p.code + obase + 32 + sl * 8) = cv;
       }
     }
   }

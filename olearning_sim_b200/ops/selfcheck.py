@@ -122,6 +122,36 @@ def check_conv2_fwd(c: int) -> Dict:
     return {"err": rel_err(p2.float(), ref), "tol": 1e-2, "code_max": int(code2.max().item())}
 
 
+def check_conv2_fwd_shift(c: int) -> Dict:
+    """conv2 forward as shifted-view MMAs on 16x8 tiles (``fwd2_shift`` switch) vs the folded kernel: numerics (values and
+    argmax codes against each other and the fp32 oracle) and time"""
+    master = _rand_master(c)
+    _, w2f, _ = _operand_copies(master)
+    p1 = (torch.randn(c * B, 16, 16, 32, device="cuda").clamp_min(0)).to(torch.bfloat16)
+    v = reference.cnn2_views(master)
+    a2 = F.relu(_conv_ref(p1.float().reshape(c, B, 16, 16, 32), v["w2"].to(torch.bfloat16).float(), v["b2"]))
+    ref = _pool_ref(a2).reshape(c * B, 8, 8, 64)
+    res: Dict = {"tol": 1e-2, "err": 0.0}
+    outs = {}
+    try:
+        for mode in (0, 1):
+            native.set_option("fwd2_shift", mode)
+            p2 = torch.zeros(c * B, 8, 8, 64, dtype=torch.bfloat16, device="cuda")
+            code2 = torch.full((c * B, 8, 8, 64), 9, dtype=torch.uint8, device="cuda")
+            native.conv2_fwd(p1, w2f, master, c, None, p2, code2)
+            torch.cuda.synchronize()
+            outs[mode] = (p2, code2)
+            res[f"shift{mode}_err"] = rel_err(p2.float(), ref)
+            res[f"shift{mode}_code_max"] = int(code2.max().item())
+            res[f"shift{mode}_us"] = round(_time_us(lambda: native.conv2_fwd(p1, w2f, master, c, None, p2, code2)), 1)
+            res["err"] = max(res["err"], res[f"shift{mode}_err"])
+        res["code_mismatch"] = float((outs[0][1] != outs[1][1]).float().mean().item())
+        res["value_mismatch"] = rel_err(outs[1][0].float(), outs[0][0].float())
+    finally:
+        native.set_option("fwd2_shift", 0)
+    return res
+
+
 def check_head(c: int) -> Dict:
     master = _rand_master(c)
     p2 = torch.randn(c * B, 8, 8, 64, device="cuda").clamp_min(0).to(torch.bfloat16)
@@ -509,7 +539,8 @@ CHECKS: Dict[str, Callable[[int], Dict]] = {
 
 # kernel variants under evaluation: run only when named explicitly with --only
 EXPERIMENTAL: Dict[str, Callable[[int], Dict]] = {"conv2_wgrad_wide": check_conv2_wgrad_wide,
-                                                    "conv2_dgrad_pair": check_conv2_dgrad_pair}
+                                                    "conv2_dgrad_pair": check_conv2_dgrad_pair,
+                                                    "conv2_fwd_shift": check_conv2_fwd_shift}
 
 
 def run_all(clients: List[int], only: List[str] | None = None) -> List[Dict]:
