@@ -133,7 +133,9 @@ int g_x5_rows = 1;       // 1: X5 is stored pre-swizzled and fetched with 512-by
 // conv2 data gradient on CTA pairs (cta_group::2, weight operand split across the pair): 0 never, 1 always,
 // -1 auto = when a rank holds fewer than 400 clients (measured: 139 vs 151 us at 160 clients, 380 vs 379 at 592)
 int g_dgrad_pair = -1;
-int g_fwd2_shift = 0;    // 1: conv2 forward as 25 shifted-view MMAs per tile (16x8 tiles, weight-stationary pairs)
+// conv2 forward as 25 shifted-view MMAs per tile (16x8 tiles, weight-stationary pairs): 0 never, 1 always, -1 auto =
+// when a rank holds fewer than 400 clients (measured: 135 vs 149 us at 160 clients, 397 vs 393 us at 592)
+int g_fwd2_shift = -1;
 int g_wgrad2_ws = 1;     // 1: weight-stationary (B-collector) MMAs in the conv2 weight gradient
 int g_wgrad2_mode = 1;   // 0: five 12x16 boxes per chunk, 1: one 12x20 box, 2: one box + swizzle base offset
 bool g_attr_set = false;
@@ -228,7 +230,7 @@ int olsb_conv2_fwd(const void* p1, const void* w2_fwd, const void* master, long 
   p.out = (__nv_bfloat16*)p2; p.code = (uint8_t*)code2;
   const int work = C * p.nsplit;
   const int grid = work < g_sms ? work : g_sms;
-  if (g_fwd2_shift) {
+  if (g_fwd2_shift > 0 || (g_fwd2_shift < 0 && C < 400)) {
     // 16x8-pixel tiles, one (16+4) x (8+4) halo box per tile; weights as 25 K-major [64][32] blocks
     using SC = Conv2FwdShiftCfg;
     if (int r = make_act_map(&tmA, p1, (uint64_t)C * BATCH, 16, 16, 32, SC::BOX_H, SC::BOX_W)) return r;

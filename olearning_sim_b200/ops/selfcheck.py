@@ -148,7 +148,7 @@ def check_conv2_fwd_shift(c: int) -> Dict:
         res["code_mismatch"] = float((outs[0][1] != outs[1][1]).float().mean().item())
         res["value_mismatch"] = rel_err(outs[1][0].float(), outs[0][0].float())
     finally:
-        native.set_option("fwd2_shift", 0)
+        native.set_option("fwd2_shift", -1)       # default: automatic by client count
     return res
 
 
