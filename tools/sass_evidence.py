@@ -6,7 +6,7 @@ root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 lib = os.path.join(root, "olearning_sim_b200/ops/_olsb200_kernels.so")
 tag = sys.argv[1] if len(sys.argv) > 1 else "r1"
 out = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
-pats = {"UTCHMMA": r"\bUTCHMMA", "UTMALDG": r"\bUTMALDG", "UTMAPF": r"UTMAPF|UTMACCTL", "LDTM": r"\bLDTM",
+pats = {"UTCHMMA": r"\bUTCHMMA", "….WS": r"UTCHMMA\.WS", "….2CTA": r"UTCHMMA\.2CTA", "UTMALDG": r"\bUTMALDG", "UTMAPF": r"UTMAPF|UTMACCTL", "LDTM": r"\bLDTM",
         "UTCBAR": r"\bUTCBAR", "SYNCS": r"\bSYNCS", "UBLKPF": r"UBLKPF|UBLKCP", "HMMA(legacy)": r"\bHMMA", "SHFL": r"\bSHFL"}
 per, cur = collections.OrderedDict(), None
 for line in out.splitlines():
@@ -21,7 +21,7 @@ for line in out.splitlines():
             if re.search(p, line):
                 per[cur][k] += 1
 lines = ["SASS evidence for the sm_100a build (cuobjdump -sass olearning_sim_b200/ops/_olsb200_kernels.so)", "",
-         "UTCHMMA = tcgen05.mma, UTMALDG = TMA tensor load, LDTM = tcgen05.ld (TMEM -> registers), UTCBAR = tcgen05.commit,",
+         "UTCHMMA = tcgen05.mma (.WS = weight-stationary form, .2CTA = cta_group::2 pair MMA), UTMALDG = TMA tensor load, LDTM = tcgen05.ld (TMEM -> registers), UTCBAR = tcgen05.commit,",
          "SYNCS = mbarrier ops, UBLK* = bulk L2 prefetch.  No legacy HMMA (mma.sync) anywhere.", "",
          f"{'kernel':<112} " + " ".join(f"{k:>8}" for k in pats)]
 for k, c in per.items():
