@@ -216,7 +216,7 @@ class RoundRunner:
             eng.local_steps_np = steps
             eng.cfg.hetero_steps = bool((steps != cfg.local_steps).any()) or cfg.hetero_steps
             eng.cfg.p_online = float(pon.min()) if (pon < 1).any() else cfg.p_online
-            if eng.backend == "native":
+            if eng.uses_ws:
                 import torch
                 eng.local_steps_t = torch.from_numpy(steps).to(eng.device)
                 eng.p_online_t = torch.from_numpy(pon).to(eng.device)

@@ -125,10 +125,15 @@ class FedEngine:
         backend = cfg.backend
         native_ok = self.device.type == "cuda" and cfg.model in ("cnn2", "mlp2") and cfg.batch == 32
         if backend == "auto":
-            backend = "native" if native_ok else "torch"
+            # native: hand-written kernels end to end; hybrid: library forward/backward + native FL kernels (broadcast,
+            # masks, fused client SGD, P2P reduce + server optimiser); torch: pure library path (CPU / baseline)
+            backend = "native" if native_ok else ("hybrid" if self.device.type == "cuda" else "torch")
         if backend == "native" and not native_ok:
             raise RuntimeError("the native backend needs CUDA, batch 32 and the cnn2 / mlp2 families")
+        if backend == "hybrid" and self.device.type != "cuda":
+            raise RuntimeError("the hybrid backend needs CUDA")
         self.backend = backend
+        self.uses_ws = backend in ("native", "hybrid")      # state lives in a GPU workspace with the native FL kernels
         self.spec = get_model(cfg.model, **cfg.model_kwargs)
         self.c0, self.c1 = shard_range(cfg.num_clients, world, rank)
         self.C = self.c1 - self.c0
@@ -148,6 +153,8 @@ class FedEngine:
         self.n_samples_np = np.full(self.C, cfg.shard, np.int32)
         if backend == "native":
             self._init_native()
+        elif backend == "hybrid":
+            self._init_hybrid()
         else:
             self._init_torch()
 
@@ -220,6 +227,55 @@ class FedEngine:
         self._graphs: Dict[bool, Any] = {}
         self._graph_ok, self._graph_warm, self.graph_error = True, False, None
 
+    def _init_hybrid(self) -> None:
+        """Library forward/backward (chunked ``vmap(grad_and_value)``) on replicas held in a ``FlatWorkspace``."""
+        from torch.func import grad_and_value, vmap
+        from ..parallel.comm import SymmetricHeap
+        from .flat_native import FlatWorkspace
+        heap = SymmetricHeap(group=self.group, device=self.device)
+        self.P = self.spec.padded_params
+        self.ws = FlatWorkspace(self.C, self.P, device=self.device, heap=heap)
+        self.ws.n_samples = torch.full((self.C,), self.cfg.shard, dtype=torch.int32, device=self.device)
+        self._g0 = self.spec.init(self.cfg.seed)
+        d, S = self.device, self.cfg.local_steps
+        self.p_online_t = torch.full((self.C,), float(self.cfg.p_online), device=d)
+        self.p_online_round = self.p_online_t.clone()
+        self.tick_host = torch.zeros(self.C, dtype=torch.int32).pin_memory()
+        self.tick_dev = torch.zeros(self.C, dtype=torch.int32, device=d)
+        self.local_steps_t = torch.from_numpy(self.local_steps_np).to(d)
+        self.participate = torch.ones(self.C, dtype=torch.uint8, device=d)
+        self.step_active = torch.ones(S, self.C, dtype=torch.uint8, device=d)
+        self.agg_weight = torch.zeros(self.C, device=d)
+        self.counters = torch.zeros(4, dtype=torch.int32, device=d)
+        self.result_host = torch.zeros(8).pin_memory()
+        self.ws.set_global(self._g0)
+        self._graphs, self._graph_ok, self._graph_warm, self.graph_error = {}, False, False, None
+        self.x = self.y = None
+        spec = self.spec
+
+        def loss_fn(flat, x, y):
+            return spec.loss(flat, x, y)
+
+        chunk = self.cfg.torch_chunk or max(1, min(self.C, int(20e9 / (max(self.P, 1) * 48))))
+        self._chunk = chunk if chunk < self.C else None
+        self._grad_loss_fn = vmap(grad_and_value(loss_fn), in_dims=(0, 0, 0), randomness="different",
+                                  chunk_size=self._chunk)
+
+    def _hybrid_local_steps(self, need_mask: bool) -> None:
+        cfg, ws, B = self.cfg, self.ws, self.cfg.batch
+        for s in range(cfg.local_steps):
+            off = (s * B) % cfg.shard
+            g, loss = self._grad_loss_fn(ws.master, self.x[:, off:off + B], self.y[:, off:off + B])
+            act = self.step_active[s] if need_mask else None
+            loss = loss.detach()
+            bad = ~torch.isfinite(loss)
+            if act is not None:
+                on = act.bool()
+                loss, bad = torch.where(on, loss, torch.zeros_like(loss)), bad & on
+            ws.loss_sum += torch.where(bad, torch.zeros_like(loss), loss)
+            ws.nonfinite |= bad.to(torch.int32)
+            ws.sgd_step(g.contiguous(), lr=cfg.lr, mu=cfg.mu, active=act)
+
     def _native_round_body(self, round_idx: int) -> None:
         """All device work of one round on the current stream; no host synchronisation."""
         from ..ops import native
@@ -246,10 +302,13 @@ class FedEngine:
                 ws.master[cid - self.c0].fill_(float("nan"))             # poisoned replica: must be masked by the reduce
                 if hasattr(ws, "master_bf16"):
                     ws.master_bf16[cid - self.c0].fill_(float("nan"))
-                else:
+                elif hasattr(ws, "w1_fwd"):
                     ws.w1_fwd[cid - self.c0].fill_(float("nan"))
         with self.timer.phase("local_steps"):
-            self._local_steps(need_mask)
+            if self.backend == "hybrid":
+                self._hybrid_local_steps(need_mask)
+            else:
+                self._local_steps(need_mask)
         with self.timer.phase("reduce_update"):
             ws.reduce_and_update(self.agg_weight, opt=cfg.server_opt, server_lr=cfg.server_lr,
                                  accounting=(self.participate, self.step_active, self.counters, cfg.local_steps))
@@ -451,7 +510,7 @@ class FedEngine:
             self.faults.at_round_start(round_idx, self.rank)
         if stream_inputs:
             h2d = self.stream_inputs()
-        if self.backend == "native":
+        if self.uses_ws:
             self._native_round_body(round_idx)
             res = self._native_finish(round_idx)
         else:
@@ -463,29 +522,29 @@ class FedEngine:
             res.extras["phases_ms"] = self.timer.collect(self.group, self.world)
         if stream_inputs:
             res.extras["h2d_bytes"] = h2d
-            res.extras["d2h_bytes"] = 32 if self.backend == "native" else 64
+            res.extras["d2h_bytes"] = 32 if self.uses_ws else 64
         self.round_log.append(res)
         return res
 
     def enqueue_round(self, round_idx: int) -> None:
         """Device-only enqueue of a round (no host read-back) — used by the device-timed benchmark."""
-        assert self.backend == "native"
+        assert self.uses_ws
         self._native_round_body(round_idx)
 
     def global_model(self) -> torch.Tensor:
-        return self.ws.get_global() if self.backend == "native" else self.global_w
+        return self.ws.get_global() if self.uses_ws else self.global_w
 
     def spec_flat_global(self) -> torch.Tensor:
         """The global model in the zoo's flat (torch state_dict order) format, whatever the backend's packing."""
         g = self.global_model()
         if self.backend != "native":
-            return g
+            return g                                      # torch / hybrid rows are already in the zoo's flat order
         if self.cfg.model == "cnn2":
             return self.spec.flatten(CNN2.unpack(g))
         return self.spec.flatten(self.spec.unflatten(self.ws.L.unpack(g.cpu())))
 
     def set_global_model(self, flat: torch.Tensor) -> None:
-        if self.backend == "native":
+        if self.uses_ws:
             self.ws.set_global(flat)
         else:
             self.global_w = flat.to(self.device).clone()
@@ -511,11 +570,11 @@ class FedEngine:
         return {"loss": float(out[0] / out[2]), "acc": float(out[1] / out[2])}
 
     def kernel_launches(self) -> int:
-        return self.ws.kernel_launches if self.backend == "native" else 0
+        return self.ws.kernel_launches if self.uses_ws else 0
 
     def state_dict(self) -> Dict[str, Any]:
         sd = {"config": asdict(self.cfg), "global": self.global_model().detach().cpu(), "rounds_done": len(self.round_log)}
-        if self.backend == "native":
+        if self.uses_ws:
             sd["opt_m"], sd["opt_v"] = self.ws.opt_m.cpu(), self.ws.opt_v.cpu()
             sd["server_step"] = self.ws.server_step
         else:
@@ -524,12 +583,12 @@ class FedEngine:
 
     def load_state_dict(self, sd: Dict[str, Any]) -> None:
         self.set_global_model(sd["global"])
-        if self.backend == "native":
+        if self.uses_ws:
             self.ws.opt_m.copy_(sd["opt_m"]); self.ws.opt_v.copy_(sd["opt_v"]); self.ws.server_step = sd["server_step"]
         else:
             self.server_state = {k: (v.to(self.device) if torch.is_tensor(v) else v) for k, v in sd.get("server_state", {}).items()}
 
     def close(self) -> None:
-        if self.backend == "native":
+        if self.uses_ws:
             self._graphs.clear()          # graphs reference workspace memory: drop them before the slabs are freed
             self.ws.close()
