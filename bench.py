@@ -41,6 +41,7 @@ def parse_args():
     ap.add_argument("--phases", action="store_true",
                     help="after the timed regions, run 3 extra rounds with CUDA-event phase timers and report "
                          "broadcast / local / reduce times and the peer-memory bus bandwidth they imply")
+    ap.add_argument("--amp", action="store_true", help="hybrid backend: bf16 autocast for the library forward/backward")
     ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5],
                     help="BASELINE.json config: 2 FedAvg CNN-2 x1024 (flagship, default), 3 FedAvg ResNet-18 x512 with "
                          "online/offline + spike trace, 4 FedProx CNN-2 x4096 heterogeneous steps, 5 FedAvg BERT-mini x256")
@@ -136,7 +137,8 @@ def main() -> int:
     # native FL kernels (broadcast, masks, fused client SGD, peer-memory reduce + server optimiser): backend "hybrid"
     backend = ("native" if native_ok else "hybrid") if args.impl == "ours" else "torch"
     cfg = FedConfig(model=model, num_clients=args.clients, local_steps=args.local_steps, batch=32, shard=args.shard,
-                    lr=0.05, backend=backend, device=str(dev), seed=0, **pre)
+                    lr=0.05, backend=backend, device=str(dev), seed=0, amp_bf16=bool(args.amp and backend == "hybrid"),
+                    **pre)
     eng = FedEngine(cfg, rank, world)
     eng.load_synthetic()
 
@@ -217,7 +219,8 @@ def main() -> int:
         out = {
             "metric": METRIC, "value": value, "unit": "client_steps/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_per_round, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "bf16" if backend == "native" else "fp32 (library forward/backward)", "data": "synthetic",
+            "dtype": "bf16" if backend == "native" else ("bf16 autocast (library forward/backward)" if cfg.amp_bf16
+                                                         else "fp32 (library forward/backward)"), "data": "synthetic",
             "impl": args.impl, "rounds_per_sec": 1e3 / ms_per_round,
             "config": {"id": args.config, "model": MODEL_DESC[model], "algorithm": cfg.algorithm, "backend": backend,
                        "clients": args.clients, "local_steps": args.local_steps, "local_batch": 32,

@@ -60,6 +60,7 @@ class FedConfig:
     deviceflow_strategy: Optional[str] = None
     online_trace: Optional[str] = None
     wave: Optional[int] = None       # clients with resident activations at once (None = auto from free HBM)
+    amp_bf16: bool = False           # hybrid / torch backends: run the library forward/backward under bf16 autocast
     torch_chunk: Optional[int] = None  # torch backend: clients per vmap chunk (None = sized from the parameter count)
     profile: bool = False            # CUDA-event phase timing (mask / broadcast / local / reduce), max over ranks
 
@@ -253,7 +254,12 @@ class FedEngine:
         self.x = self.y = None
         spec = self.spec
 
+        amp = self.cfg.amp_bf16
+
         def loss_fn(flat, x, y):
+            if amp:           # fp32 master replicas, bf16 tensor-core compute, fp32 loss / gradients
+                with torch.autocast("cuda", dtype=torch.bfloat16):
+                    return spec.loss(flat, x, y).float()
             return spec.loss(flat, x, y)
 
         chunk = self.cfg.torch_chunk or max(1, min(self.C, int(20e9 / (max(self.P, 1) * 48))))

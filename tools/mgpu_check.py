@@ -9,8 +9,12 @@ from olearning_sim_b200.parallel.comm import init_distributed
 import torch.distributed as dist
 
 rank, world, local = init_distributed()
-cfg = dict(model="cnn2", num_clients=int(os.environ.get("CLIENTS", "96")), local_steps=2, shard=64, lr=0.05, seed=7,
-           p_online=0.9, drop_probability=0.1, hetero_steps=True, backend="native", device=f"cuda:{local}",
+# MODEL / BACKEND select the path: cnn2 + native (default: hand-written kernels end to end) or any family + hybrid
+# (library forward/backward, native FL kernels) — both use the same peer-memory broadcast / reduce
+MODEL, BACKEND = os.environ.get("MODEL", "cnn2"), os.environ.get("BACKEND", "native")
+cfg = dict(model=MODEL, num_clients=int(os.environ.get("CLIENTS", "96")), local_steps=2,
+           shard=64 if MODEL == "cnn2" else 32, batch=32 if MODEL == "cnn2" else 16, lr=0.05, seed=7,
+           p_online=0.9, drop_probability=0.1, hetero_steps=True, backend=BACKEND, device=f"cuda:{local}",
            server_opt=os.environ.get("OPT", "adam"), server_lr=0.01 if os.environ.get("OPT", "adam") == "adam" else 1.0)
 eng = FedEngine(FedConfig(**cfg), rank, world)
 eng.load_synthetic()
@@ -19,7 +23,7 @@ g = eng.global_model().cpu()
 torch.cuda.synchronize()
 if world > 1:
     dist.barrier()
-out = {"world": world, "rounds": [(r.participants, r.dropped, r.arrived, r.client_steps, round(r.loss, 5)) for r in res]}
+out = {"world": world, "model": MODEL, "backend": BACKEND, "rounds": [(r.participants, r.dropped, r.arrived, r.client_steps, round(r.loss, 5)) for r in res]}
 if rank == 0:
     ref = FedEngine(FedConfig(**cfg), 0, 1, group=None) if world == 1 else None
 if world > 1:
