@@ -41,7 +41,8 @@ def parse_args():
     ap.add_argument("--phases", action="store_true",
                     help="after the timed regions, run 3 extra rounds with CUDA-event phase timers and report "
                          "broadcast / local / reduce times and the peer-memory bus bandwidth they imply")
-    ap.add_argument("--amp", action="store_true", help="hybrid backend: bf16 autocast for the library forward/backward")
+    ap.add_argument("--amp", action="store_true", help="hybrid backend: bf16 autocast for the library forward/backward (default for config 5; it is "
+                         "slower than fp32 for the vmapped ResNet convolutions)")
     ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5],
                     help="BASELINE.json config: 2 FedAvg CNN-2 x1024 (flagship, default), 3 FedAvg ResNet-18 x512 with "
                          "online/offline + spike trace, 4 FedProx CNN-2 x4096 heterogeneous steps, 5 FedAvg BERT-mini x256")
@@ -137,7 +138,7 @@ def main() -> int:
     # native FL kernels (broadcast, masks, fused client SGD, peer-memory reduce + server optimiser): backend "hybrid"
     backend = ("native" if native_ok else "hybrid") if args.impl == "ours" else "torch"
     cfg = FedConfig(model=model, num_clients=args.clients, local_steps=args.local_steps, batch=32, shard=args.shard,
-                    lr=0.05, backend=backend, device=str(dev), seed=0, amp_bf16=bool(args.amp and backend == "hybrid"),
+                    lr=0.05, backend=backend, device=str(dev), seed=0, amp_bf16=bool((args.amp or args.config == 5) and backend == "hybrid"),
                     **pre)
     eng = FedEngine(cfg, rank, world)
     eng.load_synthetic()
