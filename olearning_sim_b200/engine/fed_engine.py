@@ -124,13 +124,13 @@ class FedEngine:
             dev = f"cuda:{torch.cuda.current_device()}" if torch.cuda.is_available() else "cpu"
         self.device = torch.device(dev)
         backend = cfg.backend
-        native_ok = self.device.type == "cuda" and cfg.model in ("cnn2", "mlp2") and cfg.batch == 32
+        native_ok = self.device.type == "cuda" and cfg.model in ("cnn2", "mlp2", "mlp") and cfg.batch == 32
         if backend == "auto":
             # native: hand-written kernels end to end; hybrid: library forward/backward + native FL kernels (broadcast,
             # masks, fused client SGD, P2P reduce + server optimiser); torch: pure library path (CPU / baseline)
             backend = "native" if native_ok else ("hybrid" if self.device.type == "cuda" else "torch")
         if backend == "native" and not native_ok:
-            raise RuntimeError("the native backend needs CUDA, batch 32 and the cnn2 / mlp2 families")
+            raise RuntimeError("the native backend needs CUDA, batch 32 and the cnn2 / mlp2 / mlp families")
         if backend == "hybrid" and self.device.type != "cuda":
             raise RuntimeError("the hybrid backend needs CUDA")
         self.backend = backend
@@ -206,8 +206,8 @@ class FedEngine:
             self._g0 = CNN2.init(self.cfg.seed)
         else:
             from .mlp_native import MlpLayout, MlpWorkspace
-            sh = dict(self.spec.shapes)
-            lay = MlpLayout(sh["fc1.weight"][1], sh["fc1.weight"][0], sh["fc2.weight"][0])
+            ws_ = [shape for name, shape in self.spec.shapes if name.endswith(".weight")]        # fc1 .. fcN
+            lay = MlpLayout(ws_[0][1], [w[0] for w in ws_[:-1]], ws_[-1][0])
             self.ws = MlpWorkspace(self.C, self.cfg.shard, lay, device=self.device, heap=heap)
             self._g0 = lay.pack(self.spec.init(self.cfg.seed))
         d = self.device

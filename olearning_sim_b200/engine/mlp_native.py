@@ -1,9 +1,10 @@
 """GPU-resident state of an MLP client population (fully-connected families) on one rank.
 
 Same structure as ``Cnn2Workspace`` but built from the generic per-client GEMM kernels (``csrc/linear_tc.cuh``):
-a local step of a 2-layer MLP is six launches — fc1 forward (+bias+ReLU), fc2 forward (+bias), softmax-xent
-(+fc2-bias SGD), fc2 data gradient (+ReLU gate, +fc1-bias SGD), fc2 weight gradient (+SGD), fc1 weight gradient (+SGD).
-The packed parameter row is [W1 | b1 | W2 | b2] with every block starting on an 8-element boundary so the bf16 copy
+a local step of an L-layer MLP is 3L launches — L forward GEMMs (+bias, ReLU on hidden layers), softmax-xent (+last
+bias SGD), and per layer from the top a data gradient (+ReLU gate, +bias SGD of the layer below) and a weight gradient
+(+SGD); six for the 2-layer MLP of BASELINE config #1.
+The packed parameter row is [W1 | b1 | W2 | b2 | ...] with every block starting on an 8-element boundary so the bf16 copy
 of the row can be used directly as TMA operand storage.
 """
 from __future__ import annotations
@@ -24,30 +25,45 @@ def _al8(n: int) -> int:
 
 
 class MlpLayout:
-    def __init__(self, in_dim: int = 784, hidden: int = 200, classes: int = 10):
-        assert in_dim % 8 == 0 and hidden % 8 == 0, "row strides must be multiples of 16 bytes for TMA"
-        self.in_dim, self.hidden, self.classes = in_dim, hidden, classes
-        self.W1 = 0
-        self.B1 = _al8(self.W1 + hidden * in_dim)
-        self.W2 = _al8(self.B1 + hidden)
-        self.B2 = _al8(self.W2 + classes * hidden)
-        self.P = _al8(self.B2 + classes)
+    """Packed row of an MLP with any number of hidden layers: [W1 | b1 | W2 | b2 | ...], every block on an 8-element
+    boundary.  ``dims`` = (in_dim, hidden_1, ..., hidden_k, classes); the 2-layer constructor arguments are kept."""
+
+    def __init__(self, in_dim: int = 784, hidden=200, classes: int = 10):
+        hid = [int(hidden)] if isinstance(hidden, (int, float)) else [int(h) for h in hidden]
+        self.dims = [int(in_dim)] + hid + [int(classes)]
+        assert all(d % 8 == 0 for d in self.dims[:-1]), "row strides must be multiples of 16 bytes for TMA"
+        self.in_dim, self.hidden, self.classes = self.dims[0], hid[0], self.dims[-1]
+        self.nlayers = len(self.dims) - 1
+        self.W, self.B = [], []
+        o = 0
+        for l in range(1, len(self.dims)):
+            self.W.append(o)
+            o = _al8(o + self.dims[l] * self.dims[l - 1])
+            self.B.append(o)
+            o = _al8(o + self.dims[l])
+        self.P = o
         self.LD = 16                                     # padded class dimension of logits / dlogits
+        assert self.classes <= self.LD
+        # 2-layer names used by older call sites
+        self.W1, self.B1 = self.W[0], self.B[0]
+        self.W2, self.B2 = (self.W[1], self.B[1]) if self.nlayers > 1 else (self.W[0], self.B[0])
+
+    def _blocks(self):
+        for l in range(self.nlayers):
+            yield self.W[l], self.dims[l + 1] * self.dims[l]
+            yield self.B[l], self.dims[l + 1]
 
     def pack(self, flat_spec: torch.Tensor) -> torch.Tensor:
-        """zoo.mlp2 flat order (fc1.weight, fc1.bias, fc2.weight, fc2.bias) -> aligned packed row."""
+        """zoo flat order (fc1.weight, fc1.bias, fc2.weight, ...) -> aligned packed row."""
         out = torch.zeros(self.P)
-        h, i, c = self.hidden, self.in_dim, self.classes
         o = 0
-        for dst, n in ((self.W1, h * i), (self.B1, h), (self.W2, c * h), (self.B2, c)):
+        for dst, n in self._blocks():
             out[dst:dst + n] = flat_spec[o:o + n]
             o += n
         return out
 
     def unpack(self, row: torch.Tensor) -> torch.Tensor:
-        h, i, c = self.hidden, self.in_dim, self.classes
-        return torch.cat([row[self.W1:self.W1 + h * i], row[self.B1:self.B1 + h], row[self.W2:self.W2 + c * h],
-                          row[self.B2:self.B2 + c]])
+        return torch.cat([row[dst:dst + n] for dst, n in self._blocks()])
 
 
 class MlpWorkspace:
@@ -68,8 +84,10 @@ class MlpWorkspace:
         self.master = torch.zeros(C, P, dtype=f32, device=d)
         self.master_bf16 = torch.zeros(C, P, dtype=bf, device=d)
         self.global_local = torch.zeros(P, dtype=f32, device=d)
-        self.h = torch.zeros(C, B, L.hidden, dtype=bf, device=d)
-        self.dh = torch.zeros(C, B, L.hidden, dtype=bf, device=d)
+        # hidden activations / their gradients, one pair per hidden layer
+        self.acts = [torch.zeros(C, B, h, dtype=bf, device=d) for h in L.dims[1:-1]]
+        self.dacts = [torch.zeros(C, B, h, dtype=bf, device=d) for h in L.dims[1:-1]]
+        self.h, self.dh = self.acts[0], self.dacts[0]
         self.logits = torch.zeros(C, B, L.LD, dtype=bf, device=d)
         self.dlogits = torch.zeros(C, B, L.LD, dtype=bf, device=d)
         self.loss_sum = torch.zeros(C, dtype=f32, device=d)
@@ -123,40 +141,41 @@ class MlpWorkspace:
         self.kernel_launches += 1
 
     def local_step(self, step_idx: int, lr: float, mu: float = 0.0, active: Optional[torch.Tensor] = None) -> None:
+        """One SGD / FedProx step of every client: L forward GEMMs (+bias, ReLU), softmax-xent (+last bias SGD), then per
+        layer from the top: data gradient (+ReLU gate, +bias SGD of the layer below) and weight gradient (+SGD).
+        3L launches for an L-layer MLP."""
         L, P, C = self.L, self.P, self.C
         off = (step_idx * B) % self.shard
         act = native._vp(active)
         gw = self.global_local if mu > 0 else None
         mb, mf = self.master_bf16, self.master
-        op = native.operand
-        X = op(self.x, off * L.in_dim, self.shard * L.in_dim, L.in_dim, B, L.in_dim)
-        W1 = op(mb, L.W1, P, L.in_dim, L.hidden, L.in_dim)
-        W2 = op(mb, L.W2, P, L.hidden, L.classes, L.hidden)
-        H = op(self.h, 0, B * L.hidden, L.hidden, B, L.hidden)
-        DH = op(self.dh, 0, B * L.hidden, L.hidden, B, L.hidden)
-        DL = op(self.dlogits, 0, B * L.LD, L.LD, B, L.LD)
-        vp = native._vp
-        # fc1 forward: H^T[f,s] = W1[f,:].X[s,:] + b1, ReLU
-        self._gemm(variant=native.GEMM_FWD, M=L.hidden, N=B, K=L.in_dim, a=W1, b=X, active=act,
-                   out_t=vp(self.h), out_stride=B * L.hidden, out_ld=L.hidden, bias=vp(mf, L.B1), bias_stride=P, relu=1)
-        # fc2 forward: logits
-        self._gemm(variant=native.GEMM_FWD, M=L.classes, N=B, K=L.hidden, a=W2, b=H, active=act,
-                   out_t=vp(self.logits), out_stride=B * L.LD, out_ld=L.LD, bias=vp(mf, L.B2), bias_stride=P, relu=0)
+        op, vp = native.operand, native._vp
+        d, nl = L.dims, L.nlayers
+        # operands: layer inputs a[0..nl-1], weights, output-side gradients dz[1..nl]
+        a_in = [op(self.x, off * d[0], self.shard * d[0], d[0], B, d[0])] + \
+               [op(t, 0, B * h, h, B, h) for t, h in zip(self.acts, d[1:-1])]
+        w = [op(mb, L.W[l], P, d[l], d[l + 1], d[l]) for l in range(nl)]
+        dz = [op(t, 0, B * h, h, B, h) for t, h in zip(self.dacts, d[1:-1])] + [op(self.dlogits, 0, B * L.LD, L.LD, B, L.LD)]
+        for l in range(nl):                                  # forward
+            last = l == nl - 1
+            out = self.logits if last else self.acts[l]
+            ld = L.LD if last else d[l + 1]
+            self._gemm(variant=native.GEMM_FWD, M=d[l + 1], N=B, K=d[l], a=w[l], b=a_in[l], active=act,
+                       out_t=vp(out), out_stride=B * ld, out_ld=ld, bias=vp(mf, L.B[l]), bias_stride=P, relu=0 if last else 1)
         native.client_xent(C, B, L.classes, L.LD, active, self.logits, self.labels, off, self.dlogits, self.loss_sum,
-                           self.nonfinite, b_master=mf, b_offset=L.B2, b_stride=P, b_global=gw, lr=lr, mu=mu)
+                           self.nonfinite, b_master=mf, b_offset=L.B[nl - 1], b_stride=P, b_global=gw, lr=lr, mu=mu)
         self.kernel_launches += 1
-        # fc2 dgrad: dH^T[i,s] = sum_o W2[o,i] dL[s,o], gated by H>0; fc1-bias SGD on the row sums
-        self._gemm(variant=native.GEMM_DGRAD, M=L.hidden, N=B, K=L.classes, a=W2, b=DL, active=act, lr=lr, mu=mu,
-                   out_t=vp(self.dh), out_stride=B * L.hidden, out_ld=L.hidden, mask_t=vp(self.h),
-                   b_master=vp(mf, L.B1), b_stride=P, b_global=vp(gw, L.B1) if gw is not None else None)
-        # fc2 wgrad + SGD: dW2[o,i] = sum_s dL[s,o] H[s,i]
-        self._gemm(variant=native.GEMM_WGRAD, M=L.classes, N=L.hidden, K=B, a=DL, b=H, active=act, lr=lr, mu=mu,
-                   w_master=vp(mf, L.W2), w_stride=P, w_ld=L.hidden, w_global=vp(gw, L.W2) if gw is not None else None,
-                   w_bf16=vp(mb, L.W2), wb_stride=P)
-        # fc1 wgrad + SGD: dW1[f,i] = sum_s dH[s,f] X[s,i]
-        self._gemm(variant=native.GEMM_WGRAD, M=L.hidden, N=L.in_dim, K=B, a=DH, b=X, active=act, lr=lr, mu=mu,
-                   w_master=vp(mf, L.W1), w_stride=P, w_ld=L.in_dim, w_global=vp(gw, L.W1) if gw is not None else None,
-                   w_bf16=vp(mb, L.W1), wb_stride=P)
+        for l in range(nl - 1, -1, -1):                      # backward, top layer first
+            if l > 0:
+                # dA_{l}^T[i,s] = sum_o W_l[o,i] dZ_l[s,o], gated by A_l > 0; bias SGD of layer l-1 on the row sums
+                self._gemm(variant=native.GEMM_DGRAD, M=d[l], N=B, K=d[l + 1], a=w[l], b=dz[l], active=act, lr=lr, mu=mu,
+                           out_t=vp(self.dacts[l - 1]), out_stride=B * d[l], out_ld=d[l], mask_t=vp(self.acts[l - 1]),
+                           b_master=vp(mf, L.B[l - 1]), b_stride=P,
+                           b_global=vp(gw, L.B[l - 1]) if gw is not None else None)
+            # dW_l[o,i] = sum_s dZ_l[s,o] A_{l-1}[s,i]; fused SGD on the fp32 master + bf16 operand copy
+            self._gemm(variant=native.GEMM_WGRAD, M=d[l + 1], N=d[l], K=B, a=dz[l], b=a_in[l], active=act, lr=lr, mu=mu,
+                       w_master=vp(mf, L.W[l]), w_stride=P, w_ld=d[l], w_global=vp(gw, L.W[l]) if gw is not None else None,
+                       w_bf16=vp(mb, L.W[l]), wb_stride=P)
 
     def reduce_and_update(self, weight: torch.Tensor, opt: str = "avg", server_lr: float = 1.0, beta1: float = 0.9,
                           beta2: float = 0.99, eps: float = 1e-3, accounting=None) -> None:

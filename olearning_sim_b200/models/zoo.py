@@ -80,6 +80,25 @@ def mlp2(in_dim: int = 784, hidden: int = 200, num_classes: int = 10) -> ModelSp
                      apply, (in_dim,), num_classes)
 
 
+def mlp(in_dim: int = 784, hidden=(256, 128), num_classes: int = 10) -> ModelSpec:
+    """MLP with any number of hidden layers (fc1 .. fcN, ReLU between) — native on the GPU through the per-client GEMM
+    family, like ``mlp2``."""
+    dims = [in_dim] + [int(h) for h in hidden] + [num_classes]
+    n = len(dims) - 1
+
+    def apply(p, x):
+        h = x.reshape(x.shape[0], -1)
+        for l in range(1, n + 1):
+            h = F.linear(h, p[f"fc{l}.weight"], p[f"fc{l}.bias"])
+            if l < n:
+                h = F.relu(h)
+        return h
+    shapes = []
+    for l in range(1, n + 1):
+        shapes += [(f"fc{l}.weight", (dims[l], dims[l - 1])), (f"fc{l}.bias", (dims[l],))]
+    return ModelSpec("mlp", shapes, apply, (in_dim,), num_classes)
+
+
 # ---- CNN-2 (CIFAR-shaped) -----------------------------------------------------------------------------
 def cnn2() -> ModelSpec:
     def apply(p, x):  # x [B,3,32,32]
@@ -161,7 +180,7 @@ def bert_mini(vocab: int = 30522, seq: int = 128, hidden: int = 256, layers: int
     return ModelSpec("bert_mini", shapes, apply, (seq,), num_classes, input_dtype=torch.int64)
 
 
-REGISTRY: Dict[str, Callable[..., ModelSpec]] = {"mlp2": mlp2, "cnn2": cnn2, "resnet18": resnet18, "bert_mini": bert_mini}
+REGISTRY: Dict[str, Callable[..., ModelSpec]] = {"mlp2": mlp2, "mlp": mlp, "cnn2": cnn2, "resnet18": resnet18, "bert_mini": bert_mini}
 
 
 def get_model(name: str, **kw) -> ModelSpec:
