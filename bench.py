@@ -203,19 +203,29 @@ def main() -> int:
     if args.phases and backend in ("native", "hybrid"):
         eng.cfg.profile = True
         eng.timer.enabled = True
-        acc = {}
+        acc, accmin = {}, {}
         for r in range(3):
             res = eng.run_round(W + 2 * K + 4 + r)
             for k, v in res.extras["phases_ms"].items():
                 acc[k] = acc.get(k, 0.0) + v / 3
+            for k, v in res.extras["phases_ms_min"].items():
+                accmin[k] = accmin.get(k, 0.0) + v / 3
         P4 = eng.P * 4
         far = (world - 1) / world
         # per rank: broadcast pulls the (world-1)/world remote shards of the model; reduce pulls `groups` partial
         # shards from every peer.  Bus bandwidth = bytes crossing NVLink into this GPU / phase time.
         groups = getattr(eng.ws, "groups", 1)
-        phases = {"ms": acc, "bcast_remote_bytes": int(P4 * far), "reduce_remote_bytes": int(groups * P4 / world * (world - 1)),
-                  "bcast_bus_GBps": P4 * far / max(acc.get("broadcast", 0), 1e-9) / 1e6,
-                  "reduce_bus_GBps": groups * P4 / world * (world - 1) / max(acc.get("reduce_update", 0), 1e-9) / 1e6}
+        # phase times: max over ranks, and min over ranks (= the work itself for phases that begin with a cross-rank
+        # barrier: every rank but the slowest also waits there).  Local HBM traffic of the two fused paths per rank:
+        # broadcast writes C_local replicas, reduce reads them and writes / pulls `groups` partial rows.
+        c_local = eng.C
+        phases = {"ms_max": acc, "ms_min": accmin,
+                  "bcast_remote_bytes": int(P4 * far), "reduce_remote_bytes": int(groups * P4 / world * (world - 1)),
+                  "bcast_hbm_bytes": int(P4 * (c_local + 1)), "reduce_hbm_bytes": int(P4 * (c_local + 2 * groups)),
+                  "bcast_bus_GBps": P4 * far / max(accmin.get("broadcast", 0), 1e-9) / 1e6,
+                  "reduce_bus_GBps": groups * P4 / world * (world - 1) / max(accmin.get("reduce_update", 0), 1e-9) / 1e6,
+                  "bcast_hbm_GBps": P4 * (c_local + 1) / max(accmin.get("broadcast", 0), 1e-9) / 1e6,
+                  "reduce_hbm_GBps": P4 * (c_local + 2 * groups) / max(accmin.get("reduce_update", 0), 1e-9) / 1e6}
     if rank == 0:
         out = {
             "metric": METRIC, "value": value, "unit": "client_steps/s", "n_gpus": world, "steps": K, "warmup": W,

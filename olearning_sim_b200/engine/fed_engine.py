@@ -526,6 +526,7 @@ class FedEngine:
         res.extras["within_tolerance"] = res.failed <= self.cfg.dynamic_nums
         if self.cfg.profile:
             res.extras["phases_ms"] = self.timer.collect(self.group, self.world)
+            res.extras["phases_ms_min"] = dict(self.timer.last_min)
         if stream_inputs:
             res.extras["h2d_bytes"] = h2d
             res.extras["d2h_bytes"] = 32 if self.uses_ws else 64

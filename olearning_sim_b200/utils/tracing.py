@@ -22,6 +22,7 @@ class PhaseTimer:
         self.nvtx = nvtx and self.cuda
         self._open: List = []
         self._done: List = []
+        self.last_min: Dict[str, float] = {}
 
     @contextlib.contextmanager
     def phase(self, name: str):
@@ -46,7 +47,9 @@ class PhaseTimer:
                 torch.cuda.nvtx.range_pop()
 
     def collect(self, group=None, world: int = 1) -> Dict[str, float]:
-        """Resolve the events (call after the round's stream synchronisation); max over ranks per phase."""
+        """Resolve the events (call after the round's stream synchronisation); max over ranks per phase.  ``last_min``
+        keeps the min over ranks: a phase that starts with a cross-rank barrier (the reduce) includes, on every rank but
+        the slowest, the wait for that rank — its min over ranks is the time of the work itself."""
         out: Dict[str, float] = {}
         for name, e0, e1, host_ms in self._done:
             ms = host_ms if host_ms is not None else e0.elapsed_time(e1)
@@ -56,8 +59,13 @@ class PhaseTimer:
             import torch.distributed as dist
             keys = sorted(out)
             t = torch.tensor([out[k] for k in keys], dtype=torch.float64, device="cuda" if self.cuda else "cpu")
+            tmin = t.clone()
             dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+            dist.all_reduce(tmin, op=dist.ReduceOp.MIN, group=group)
             out = {k: float(v) for k, v in zip(keys, t.tolist())}
+            self.last_min = {k: float(v) for k, v in zip(keys, tmin.tolist())}
+        else:
+            self.last_min = dict(out)
         return out
 
 
