@@ -204,6 +204,8 @@ def main() -> int:
         eng.cfg.profile = True
         eng.timer.enabled = True
         acc, accmin = {}, {}
+        eng.run_round(W + 2 * K + 3)       # discarded: the first collect() creates the NCCL communicator used for max/min
+        sync()
         for r in range(3):
             res = eng.run_round(W + 2 * K + 4 + r)
             for k, v in res.extras["phases_ms"].items():
