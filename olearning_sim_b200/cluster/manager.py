@@ -234,6 +234,55 @@ class LocalClusterApi:
             return self._items.pop((k8s_namespace, name), None) is not None
 
 
+class KubeClusterApi:
+    """The same five calls against a Kubernetes API server (custom objects of ``GROUP/VERSION``, plural ``PLURAL``) — the
+    counterpart of the reference's KubeRay client (kuberay_cluster_api.py:37-304).  The ``kubernetes`` client is not part
+    of this image, so the class is gated: constructing it without the package raises a clear error and everything else
+    keeps working on ``LocalClusterApi``.  ``api`` may be injected (tests use a fake ``CustomObjectsApi``)."""
+
+    def __init__(self, api: Optional[Any] = None, group: str = GROUP, version: str = VERSION, plural: str = PLURAL):
+        if api is None:
+            try:
+                from kubernetes import client, config          # type: ignore
+            except ImportError as e:  # pragma: no cover - depends on the deployment image
+                raise RuntimeError("KubeClusterApi needs the 'kubernetes' package; use LocalClusterApi on a single box") from e
+            try:
+                config.load_incluster_config()
+            except Exception:  # noqa: BLE001 - outside a pod: fall back to the user's kubeconfig
+                config.load_kube_config()
+            api = client.CustomObjectsApi()
+        self.api, self.group, self.version, self.plural = api, group, version, plural
+
+    def _call(self, fn, *a, **kw):
+        try:
+            return fn(*a, **kw)
+        except Exception as e:  # noqa: BLE001 - ApiException and transport errors: log and report failure
+            log.error("", "cluster", "KubeClusterApi", f"{getattr(fn, '__name__', fn)} failed: {e}")
+            return None
+
+    def create_ray_cluster(self, body: Dict[str, Any], k8s_namespace: Optional[str] = None) -> Optional[Dict[str, Any]]:
+        ns = k8s_namespace or body["metadata"].get("namespace", "default")
+        return self._call(self.api.create_namespaced_custom_object, group=self.group, version=self.version,
+                          namespace=ns, plural=self.plural, body=body)
+
+    def get_ray_cluster(self, name: str, k8s_namespace: str = "default") -> Optional[Dict[str, Any]]:
+        return self._call(self.api.get_namespaced_custom_object, group=self.group, version=self.version,
+                          namespace=k8s_namespace, plural=self.plural, name=name)
+
+    def list_ray_clusters(self, k8s_namespace: str = "default", label_selector: str = "") -> Dict[str, Any]:
+        out = self._call(self.api.list_namespaced_custom_object, group=self.group, version=self.version,
+                         namespace=k8s_namespace, plural=self.plural, label_selector=label_selector)
+        return out if out is not None else {"items": []}
+
+    def patch_ray_cluster(self, name: str, ray_patch: Dict[str, Any], k8s_namespace: str = "default") -> bool:
+        return self._call(self.api.patch_namespaced_custom_object, group=self.group, version=self.version,
+                          namespace=k8s_namespace, plural=self.plural, name=name, body=ray_patch) is not None
+
+    def delete_ray_cluster(self, name: str, k8s_namespace: str = "default") -> bool:
+        return self._call(self.api.delete_namespaced_custom_object, group=self.group, version=self.version,
+                          namespace=k8s_namespace, plural=self.plural, name=name) is not None
+
+
 class GpuClusterManager:
     """Servicer with the reference's four RPC names (kept verbatim for API parity)."""
 

@@ -144,8 +144,6 @@ class FedEngine:
         from ..utils.tracing import PhaseTimer
         self.faults = FaultInjector.from_env()
         self.timer = PhaseTimer(enabled=cfg.profile, device=self.device)
-        self._graph = None
-        self._graph_key = None
         # per-client static attributes
         rng = np.random.default_rng([cfg.seed, 991])
         all_steps = rng.integers(1, cfg.local_steps + 1, size=cfg.num_clients).astype(np.int32) if cfg.hetero_steps \
@@ -221,7 +219,6 @@ class FedEngine:
         self.step_active = torch.ones(S, self.C, dtype=torch.uint8, device=d)
         self.agg_weight = torch.zeros(self.C, device=d)
         self.counters = torch.zeros(4, dtype=torch.int32, device=d)
-        self.result_dev = torch.zeros(8, device=d)
         self.result_host = torch.zeros(8).pin_memory()
         self.ws.set_global(self._g0)
         self.P = self.ws.P
@@ -454,8 +451,6 @@ class FedEngine:
             self.host_y = self.host_y.pin_memory()
         if self.backend == "native":
             self.ws.load_data(self.host_x.to(self.device, non_blocking=True), self.host_y.to(self.device))
-        elif False:
-            pass
         else:
             x = self.host_x.to(self.device)
             if x.dtype == torch.uint8:

@@ -286,3 +286,34 @@ def test_deviceflow_config_getters(tmp_path, monkeypatch):
     assert cp.get_grpc_service_address(str(f)) == "10.1.2.3" and cp.get_port(str(f)) == 50099
     assert cp.get_source_topic(str(f)) == "t_in" and cp.get_shelfroom_namespace(str(f)) == "ns/shelf"
     assert cp.get_max_workers(str(f)) == 10 and cp.get_shelfroom_url(str(f)) == "mem://local"     # typed defaults
+
+
+def test_kube_cluster_api_with_fake_custom_objects_api():
+    """the Kubernetes backend speaks the CustomObjectsApi verbs; driven here through GpuClusterManager with a fake API"""
+    from olearning_sim_b200.cluster.manager import GpuClusterManager, KubeClusterApi
+
+    class FakeCOA:
+        def __init__(self): self.objs = {}
+        def create_namespaced_custom_object(self, group, version, namespace, plural, body):
+            key = (namespace, body["metadata"]["name"])
+            if key in self.objs: raise RuntimeError("409 AlreadyExists")
+            self.objs[key] = body; return body
+        def get_namespaced_custom_object(self, group, version, namespace, plural, name):
+            return self.objs[(namespace, name)]
+        def list_namespaced_custom_object(self, group, version, namespace, plural, label_selector=""):
+            return {"items": [o for (ns, _), o in self.objs.items() if ns == namespace]}
+        def patch_namespaced_custom_object(self, group, version, namespace, plural, name, body):
+            self.objs[(namespace, name)] = body; return body
+        def delete_namespaced_custom_object(self, group, version, namespace, plural, name):
+            return self.objs.pop((namespace, name))
+
+    api = KubeClusterApi(api=FakeCOA())
+    mgr = GpuClusterManager(api=api)
+    assert mgr.createRayCluster({})["ok"]
+    assert not mgr.createRayCluster({})["ok"]                          # duplicate name -> API error -> reported, not raised
+    d = mgr._d
+    assert api.get_ray_cluster(d.ray_name, d.k8s_namespace)["spec"]["workerGroupSpecs"]
+    assert len(api.list_ray_clusters(d.k8s_namespace)["items"]) == 1
+    assert mgr.modifyRayCluster({"k8s_namespace": d.k8s_namespace, "ray_name": d.ray_name, "ray_label": d.ray_label,
+                                 "worker_min_replicas": 1, "worker_replicas": 2, "worker_max_replicas": 4})["ok"]
+    assert api.delete_ray_cluster("nope") is False and api.delete_ray_cluster(d.ray_name, d.k8s_namespace)
