@@ -89,10 +89,10 @@ int make_w_map(CUtensorMap* tm, const void* base, uint64_t C, int rows, int k, i
 
 // conv1 input X5 [N][32][32][16] stored pre-swizzled by the ingest kernel: 4-D map {256 el = 16 px, 2 halves, 32 rows, N}
 // without TMA swizzling -> a 12-row halo box is 12 box rows of 512 B instead of 192 rows of 32 B
-int make_x5_row_map(CUtensorMap* tm, const void* base, uint64_t n, int box_h) {
+int make_x5_row_map(CUtensorMap* tm, const void* base, uint64_t n, int box_h, int box_planes = 1) {
   const uint64_t dims[4] = {256, 2, 32, n};
   const uint64_t str[3] = {256, 512, 32 * 512};
-  const uint32_t box[4] = {256, 1, (uint32_t)box_h, 1};
+  const uint32_t box[4] = {256, (uint32_t)box_planes, (uint32_t)box_h, 1};
   cuuint64_t gd[4], gs[3];
   cuuint32_t bx[4], es[4];
   for (int i = 0; i < 4; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
@@ -114,6 +114,8 @@ constexpr int BATCH = 32;
 #define CONV2_FWD conv_fwd_fold_kernel<32, 64, 16, BATCH, 7>
 #define CONV2_DGRAD conv_dgrad_fold_kernel<32, 64, 16, BATCH, 4>
 using Conv1FwdCfg = FwdCfg<32, 1, 32, 32, 32, BATCH, false, EPI_POOL, 12, 2, 2>;
+#define CONV1_WINDOW conv1_window_kernel<BATCH, 5>
+using Conv1WinCfgT = Conv1WinCfg<BATCH, 5>;
 using Conv2FwdCfg = FwdFoldCfg<32, 64, 16, BATCH, 7>;
 using Conv2DgradCfg = DgradFoldCfg<32, 64, 16, BATCH, 4>;
 #define CONV2_FWD_SHIFT conv_fwd_shift_kernel<32, 64, 16, 16, BATCH, 6>
@@ -129,7 +131,10 @@ using Conv2WgradWideCfg = WgradCfg<64, 5, 128, 6, 20>;
 using Conv2WgradCfg = WgradCfg<64, 5, 128, 2>;
 using Conv1WgradCfg = WgradCfg<32, 1, 64, 8>;
 
-int g_x5_rows = 1;       // 1: X5 is stored pre-swizzled and fetched with 512-byte box rows, 0: 32-byte swizzled rows
+// conv1 input layout (set before data is ingested): 0 plain rows fetched with 32-byte swizzled TMA rows, 1 pre-swizzled
+// rows fetched as 512-byte box rows, 2 pre-swizzled column-parity planes (conv1_window_kernel: pooling by accumulator
+// layout)
+int g_x5_rows = 1;
 // conv2 data gradient on CTA pairs (cta_group::2, weight operand split across the pair): 0 never, 1 always,
 // -1 auto = when a rank holds fewer than 400 clients (measured: 139 vs 151 us at 160 clients, 380 vs 379 at 592)
 int g_dgrad_pair = -1;
@@ -142,6 +147,7 @@ bool g_attr_set = false;
 int set_attrs() {
   if (g_attr_set) return 0;
   CK(cudaFuncSetAttribute(CONV1_FWD, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv1FwdCfg::SMEM_BYTES));
+  CK(cudaFuncSetAttribute(CONV1_WINDOW, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv1WinCfgT::SMEM_BYTES));
   CK(cudaFuncSetAttribute(CONV2_FWD, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv2FwdCfg::SMEM_BYTES));
   CK(cudaFuncSetAttribute(CONV2_DGRAD, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv2DgradCfg::SMEM_BYTES));
   CK(cudaFuncSetAttribute(CONV2_FWD_SHIFT, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv2FwdShiftCfg::SMEM_BYTES));
@@ -200,6 +206,22 @@ int olsb_conv1_fwd(const void* x5, long long x_total, int x_n_stride, int x_n_of
                    void* stream) {
   if (int r = olsb_init()) return r;
   CUtensorMap tmA, tmW;
+  if (g_x5_rows == 2) {
+    // window form: one 36-row x 2-plane box per image, work items are whole images
+    if (int r = make_x5_row_map(&tmA, x5, (uint64_t)x_total, Conv1WinCfgT::BOX_ROWS, 2)) return r;
+    if (int r = make_w_map(&tmW, w1_fwd, (uint64_t)C, 32, 80, 32, 16)) return r;
+    FwdParams p;
+    memset(&p, 0, sizeof(p));
+    p.num_clients = C; p.nsplit = auto_split(C, BATCH, nsplit);
+    p.a_n_stride = x_n_stride; p.a_n_off = x_n_off; p.active = (const uint8_t*)active;
+    p.bias = (const float*)master + Cnn2Layout::B1; p.bias_stride = (int)P;
+    p.out = (__nv_bfloat16*)p1; p.code = (uint8_t*)code1;
+    const int work = C * p.nsplit;
+    const int grid = work < g_sms ? work : g_sms;
+    CONV1_WINDOW<<<grid, Conv1WinCfgT::THREADS, Conv1WinCfgT::SMEM_BYTES, (cudaStream_t)stream>>>(tmA, tmW, p);
+    CK(cudaGetLastError());
+    return 0;
+  }
   if (int r = g_x5_rows ? make_x5_row_map(&tmA, x5, (uint64_t)x_total, kBoxH)
                         : make_act_map(&tmA, x5, (uint64_t)x_total, 32, 32, 16, kBoxH)) return r;
   if (int r = make_w_map(&tmW, w1_fwd, (uint64_t)C, 32, 80, 32, 16)) return r;
@@ -322,7 +344,8 @@ int olsb_conv1_wgrad(const void* x5, long long x_total, int x_n_stride, int x_n_
                         : make_act_map(&tmX, x5, (uint64_t)x_total, 32, 32, 16, kBoxH)) return r;
   WgradParams p;
   memset(&p, 0, sizeof(p));
-  p.x_rowmap = g_x5_rows;
+  p.x_rowmap = g_x5_rows != 0;
+  p.x_planes = g_x5_rows == 2;
   p.num_clients = C; p.x_n_stride = x_n_stride; p.x_n_off = x_n_off; p.active = (const uint8_t*)active;
   p.w_master = (float*)master; p.w_global = (const float*)global_w; p.p_stride = (size_t)P;
   p.w_off = Cnn2Layout::W1; p.w_fwd = (__nv_bfloat16*)w1_fwd; p.w_dgrad = nullptr;

@@ -450,6 +450,207 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 }
 
 // ================================================================================================
+// conv1 forward, pooling done by the accumulator layout ("window" form)
+// ================================================================================================
+// conv_taps_kernel computes one accumulator row per INPUT pixel and pools across lanes: 150 ALU-pipe instructions
+// per lane (tag / select / shuffle / max), which made it ALU-bound (74-80 % of the pipe at 11-14 % tensor).  Here an
+// accumulator row is a POOLED pixel and its four window positions are four 32-column accumulator groups, so pooling
+// is a max over four registers of the same thread: no shuffles, no selects.
+//
+// That needs the A operand of window position (dy, dx) to be "every second pixel of every second row".  The input is
+// therefore stored as two column-parity planes per image row ([n][h][parity][16 pixels][16 ch], written by the ingest
+// kernel, already 32-byte-swizzled): a plane row holds the pixels 2j+dx contiguously, tiles are 16 pooled rows x 8
+// pooled columns (one 8-pixel group per pooled row -> uniform group stride of two box rows), and (dy, dx, kh) are all
+// start-address shifts of one K-major view of ONE 36-row x 2-plane box per image (36 TMA rows of 512 B).
+template <int BATCH, int NSTAGE>
+struct Conv1WinCfg {
+  static constexpr int COUT = 32, KT = 16, ROWB = 32;
+  static constexpr int IMG = 32, POOLED = 16;
+  static constexpr int BOX_ROWS = IMG + 2 * kHalo;            // whole image + halo rows
+  static constexpr int ROW_PITCH = 2 * 16 * ROWB;             // two parity planes of 16 pixels
+  static constexpr int STAGE_BYTES = BOX_ROWS * ROW_PITCH;    // 36864
+  static constexpr int W_KH_BYTES = COUT * ROWB;              // [32 cout][16 k] per vertical tap
+  static constexpr int W_BYTES = kNKH * W_KH_BYTES;
+  static constexpr int NBUF = 4;                              // accumulator buffers: 2 tiles x 2 images in flight
+  static constexpr int BUF_COLS = 4 * COUT;                   // four window positions
+  static constexpr int TMEM_COLS = 512;
+  static constexpr int THREADS = (8 + 1 + 2) * 32;            // 8 epilogue warps, TMA warp, two MMA issuers
+  static constexpr int SMEM_BYTES = 1024 + 1024 + W_BYTES + NSTAGE * STAGE_BYTES + (int)sizeof(Barriers);
+  static_assert(STAGE_BYTES % 1024 == 0, "stage keeps the swizzle phase");
+};
+
+template <int BATCH, int NSTAGE>
+__global__ void __launch_bounds__(Conv1WinCfg<BATCH, NSTAGE>::THREADS, 1)
+conv1_window_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+                    const FwdParams p) {
+  using Cfg = Conv1WinCfg<BATCH, NSTAGE>;
+  constexpr int kTma = 8, kMma0 = 9;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* w_sm = smem;                                         // 5 KB of weights, stage area starts 1 KB-aligned
+  uint8_t* a_sm = smem + ((Cfg::W_BYTES + 1023) / 1024) * 1024;
+  Barriers* bars = reinterpret_cast<Barriers*>(a_sm + NSTAGE * Cfg::STAGE_BYTES);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NSTAGE; ++i) { mbar_init(&bars->full[i], 1); mbar_init(&bars->empty[i], 2); }
+    mbar_init(&bars->wfull, 1);
+    mbar_init(&bars->wempty, 2);
+    for (int i = 0; i < Cfg::NBUF; ++i) { mbar_init(&bars->tfull[i], 1); mbar_init(&bars->tempty[i], kEpiWarps); }
+    fence_mbar_init();
+  }
+  if (warp == kMma0) { tmem_alloc(&bars->tmem_base, Cfg::TMEM_COLS); tmem_relinquish(); }
+  if (warp == kTma && lane == 0) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmW); }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = bars->tmem_base;
+  const int num_work = p.num_clients * p.nsplit;
+  const int imgs_per_work = BATCH / p.nsplit;
+
+  if (warp == kTma) {
+    const bool leader = elect_one();
+    int stage = 0; uint32_t phase = 0; int cur_client = -1; uint32_t wphase = 0; bool first_w = true;
+    for (int wi = blockIdx.x; wi < num_work; wi += gridDim.x) {
+      const int c = wi / p.nsplit, sp = wi % p.nsplit;
+      if (p.active && !p.active[c]) continue;
+      if (c != cur_client) {
+        if (!first_w) { mbar_wait(&bars->wempty, wphase); wphase ^= 1; }
+        first_w = false; cur_client = c;
+        if (leader) {
+          mbar_arrive_expect_tx(&bars->wfull, Cfg::W_BYTES);
+#pragma unroll 1
+          for (int kh = 0; kh < kNKH; ++kh)
+            tma_load_3d(w_sm + kh * Cfg::W_KH_BYTES, &tmW, &bars->wfull, kh * Cfg::KT, 0, c);
+        }
+      }
+      for (int i = 0; i < imgs_per_work; ++i) {
+        const int n = c * p.a_n_stride + p.a_n_off + sp * imgs_per_work + i;
+        mbar_wait(&bars->empty[stage], phase ^ 1);
+        if (leader) {
+          mbar_arrive_expect_tx(&bars->full[stage], Cfg::STAGE_BYTES);
+          tma_load_4d(a_sm + stage * Cfg::STAGE_BYTES, &tmA, &bars->full[stage], 0, 0, -kHalo, n);
+        }
+        if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp >= kMma0) {
+    // issuer g owns tile g (left / right half) of every image
+    const int g = warp - kMma0;
+    const bool leader = elect_one();
+    constexpr uint32_t IDESC = make_idesc_bf16(128, Cfg::COUT, 0, 0);
+    // A: sixteen 8-pixel groups (one per pooled row) two box rows apart; B: [32 cout][16 k] per vertical tap
+    const uint64_t a_desc_base = make_smem_desc(smem_u32(a_sm) + g * 8 * Cfg::ROWB, 16, 2 * Cfg::ROW_PITCH, LT_SW32);
+    const uint64_t b_desc_base = make_smem_desc(smem_u32(w_sm), 16, 8 * Cfg::ROWB, LT_SW32);
+    int stage = 0; uint32_t phase = 0; int cur_client = -1; uint32_t wphase = 0;
+    uint32_t iseq = 0;                                  // images issued: buffer = (iseq % 2) * 2 + g
+    for (int wi = blockIdx.x; wi < num_work; wi += gridDim.x) {
+      const int c = wi / p.nsplit;
+      if (p.active && !p.active[c]) continue;
+      bool last_of_client = true;
+      {
+        const int nwi = wi + gridDim.x;
+        if (nwi < num_work && (nwi / p.nsplit) == c) last_of_client = false;
+      }
+      if (c != cur_client) { mbar_wait(&bars->wfull, wphase); wphase ^= 1; cur_client = c; }
+      for (int i = 0; i < imgs_per_work; ++i, ++iseq) {
+        const int buf = (iseq & 1) * 2 + g;
+        mbar_wait(&bars->tempty[buf], ((iseq >> 1) & 1) ^ 1);
+        fence_after_sync();
+        mbar_wait(&bars->full[stage], phase);
+        fence_after_sync();
+        if (leader) {
+          const uint32_t d0 = tmem_base + buf * Cfg::BUF_COLS;
+          const uint64_t a_stage = desc_advance(a_desc_base, stage * Cfg::STAGE_BYTES);
+#pragma unroll
+          for (int pos = 0; pos < 4; ++pos) {
+#pragma unroll
+            for (int kh = 0; kh < kNKH; ++kh) {
+              // window position (dy, dx) = (pos >> 1, pos & 1): box row 2*ph + dy + kh, parity plane dx
+              const uint32_t aoff = ((pos >> 1) + kh) * Cfg::ROW_PITCH + (pos & 1) * (Cfg::ROW_PITCH / 2);
+              umma_bf16(d0 + pos * Cfg::COUT, desc_advance(a_stage, aoff),
+                        desc_advance(b_desc_base, kh * Cfg::W_KH_BYTES), IDESC, kh ? 1u : 0u);
+            }
+          }
+          umma_commit(&bars->empty[stage]);
+          umma_commit(&bars->tfull[buf]);
+        }
+        __syncwarp();
+        if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+      }
+      if (last_of_client) {
+        if (leader) umma_commit(&bars->wempty);
+        __syncwarp();
+      }
+    }
+  } else {
+    // epilogue warp set g (warps 4g..4g+3): tile g of every image; lane = pooled pixel (ph = 4q + lane/8, pw = 8g + lane%8)
+    const int q = warp & 3, g = warp >> 2;
+    const int ph = 4 * q + (lane >> 3), pw = 8 * g + (lane & 7);
+    float bias_r[Cfg::COUT];
+    int cur_client = -1;
+    uint32_t iseq = 0;
+    for (int wi = blockIdx.x; wi < num_work; wi += gridDim.x) {
+      const int c = wi / p.nsplit, sp = wi % p.nsplit;
+      if (p.active && !p.active[c]) continue;
+      if (c != cur_client) {
+        cur_client = c;
+        const float* bias = p.bias + (size_t)c * p.bias_stride;
+#pragma unroll
+        for (int k = 0; k < Cfg::COUT; ++k) bias_r[k] = __ldg(&bias[k]);
+      }
+      for (int i = 0; i < imgs_per_work; ++i, ++iseq) {
+        const int buf = (iseq & 1) * 2 + g;
+        const size_t n_out = (size_t)c * BATCH + sp * imgs_per_work + i;
+        const size_t obase = ((n_out * Cfg::POOLED + ph) * Cfg::POOLED + pw) * Cfg::COUT;
+        mbar_wait(&bars->tfull[buf], (iseq >> 1) & 1);
+        fence_after_sync();
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(32 * q) << 16) + buf * Cfg::BUF_COLS;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          uint32_t v[4][16];
+#pragma unroll
+          for (int pos = 0; pos < 4; ++pos) tmem_ld16(taddr + pos * Cfg::COUT + half * 16, v[pos]);
+          tmem_ld_wait();
+          if (half == 1) {                                   // accumulator fully in registers: release the buffer
+            fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars->tempty[buf]);
+          }
+          uint32_t ob[8], oc[4];
+#pragma unroll
+          for (int i2 = 0; i2 < 16; i2 += 2) {
+            float f[2];
+            uint32_t cd[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const float b = bias_r[half * 16 + i2 + e];
+              // raw fp32 bits with (3 - position) in the two LSBs, signed max: see pool2x2_relu
+              int m = (__float_as_int(__uint_as_float(v[0][i2 + e]) + b) & ~3) | 3;
+              m = max(m, (__float_as_int(__uint_as_float(v[1][i2 + e]) + b) & ~3) | 2);
+              m = max(m, (__float_as_int(__uint_as_float(v[2][i2 + e]) + b) & ~3) | 1);
+              m = max(m, (__float_as_int(__uint_as_float(v[3][i2 + e]) + b) & ~3));
+              cd[e] = 3u - (static_cast<uint32_t>(m) & 3u);
+              f[e] = fmaxf(__int_as_float(m & ~3), 0.f);
+            }
+            ob[i2 >> 1] = pack_bf16x2(f[0], f[1]);
+            const int sh = (i2 & 3) * 8;
+            if ((i2 & 3) == 0) oc[i2 >> 2] = 0;
+            oc[i2 >> 2] |= (cd[0] << sh) | (cd[1] << (sh + 8));
+          }
+          *reinterpret_cast<uint4*>(p.out + obase + half * 16) = make_uint4(ob[0], ob[1], ob[2], ob[3]);
+          *reinterpret_cast<uint4*>(p.out + obase + half * 16 + 8) = make_uint4(ob[4], ob[5], ob[6], ob[7]);
+          *reinterpret_cast<uint4*>(p.code + obase + half * 16) = make_uint4(oc[0], oc[1], oc[2], oc[3]);
+        }
+      }
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == kMma0) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+// ================================================================================================
 // Data-gradient kernel, horizontal taps folded into N
 // ================================================================================================
 // dX[h,w,ci] = sum_{kh,kw} dY[h-(kh-2), w-(kw-2), co] * W[kh,kw][co,ci].   A shift of the *input* column is the same
@@ -1359,6 +1560,7 @@ struct WgradParams {
   float* grad_out;               // optional [C][BN*NTAPS*KT] raw gradient (tests); when set no update is applied
   // SYNTH_Y: the dY operand is synthesised from the pooled gradient instead of being loaded by TMA
   int x_rowmap;                  // X tensor map is the no-swizzle row map: x coordinate = w0 / 16
+  int x_planes;                  // X rows are stored as two column-parity planes: tile column index = parity plane
   int mma_ws;                    // 1: weight-stationary MMAs (dY slice latched in the B collector across the M tiles)
   int desc_mode;                 // wide-box variant: 1 = encode the swizzle base offset of unaligned operand starts
   const __nv_bfloat16* dpool;    // [C*BATCH][H/2][W/2][BN]
@@ -1535,13 +1737,18 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       if (SYNTH_Y) {
         // ---- operand synthesis: dY[pix][ch] = (code == pos) ? dpool : 0, written as a SW64 MN-major tile
         const int rr = L >> 4, cc = L & 15;                      // pixel (row, col) inside the 8x16 patch
-        const int posy = ((rr & 1) << 1) | (cc & 1);
+        // plane layout: the 16 pixels of a patch row are the columns 2*cc + plane of the image row
+        auto posy_of = [&](int t) -> uint32_t {
+          const int plane = (t % (TILES_X * TILES_Y)) % TILES_X;
+          return static_cast<uint32_t>(((rr & 1) << 1) | (p.x_planes ? plane : (cc & 1)));
+        };
         auto src_off = [&](int t) -> size_t {
           const int s = t / (TILES_X * TILES_Y);
           const int r = t % (TILES_X * TILES_Y);
           const int h0 = (r / TILES_X) * kTileH, w0 = (r % TILES_X) * kTileW;
           const size_t n = (size_t)c * BATCH + s;
-          return ((n * (IMG_H / 2) + ((h0 + rr) >> 1)) * (IMG_W / 2) + ((w0 + cc) >> 1)) * BN;
+          const int pcol = p.x_planes ? cc : ((w0 + cc) >> 1);
+          return ((n * (IMG_H / 2) + ((h0 + rr) >> 1)) * (IMG_W / 2) + pcol) * BN;
         };
         // register ring, kDepth chunks of global loads in flight per thread (hides ~kDepth x the per-chunk work)
         constexpr int kDepth = 4;
@@ -1569,6 +1776,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             issue(i + kDepth - 1, (u + kDepth - 1) % kDepth);
             const uint32_t* gw = reinterpret_cast<const uint32_t*>(gq[u]);
             const uint32_t* cw = reinterpret_cast<const uint32_t*>(cq[u]);
+            const uint32_t posy = posy_of(first + NEPG * i);
             uint4 o[4];
             uint32_t* ow = reinterpret_cast<uint32_t*>(o);
 #pragma unroll

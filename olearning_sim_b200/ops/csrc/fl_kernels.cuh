@@ -47,7 +47,8 @@ __device__ __forceinline__ float bf2f(__nv_bfloat16 v) { return __bfloat162float
 // uint8 [N][32][32][3]  ->  bf16 [N][32][32][16] with channel = kw*3+c holding x[h][w+kw-2][c] (zero outside).
 // The 5 horizontal taps of conv1 are unrolled into the channel dim once at upload time, so conv1 runs as a
 // 5-tap (vertical) implicit GEMM with K=16 per tap instead of wasting 13/16 of a K=16 MMA on 3 channels.
-// preswizzle: store the pixel's two 16-byte halves swapped when (w & 4).  That is exactly the 32-byte swizzle the
+// preswizzle 2: additionally split every image row into its two column-parity planes (conv1_window_kernel).
+// preswizzle 1: store the pixel's two 16-byte halves swapped when (w & 4).  That is exactly the 32-byte swizzle the
 // tensor core applies to a tile of 32-byte pixel rows (address bit 4 ^= bit 7), done once in HBM, so TMA can fetch a
 // whole 16-pixel image row as ONE 512-byte unswizzled box row instead of sixteen 32-byte rows (TMA cost is per row).
 __global__ void ingest_u8_kernel(const uint8_t* __restrict__ src, __nv_bfloat16* __restrict__ dst, size_t npix,
@@ -68,6 +69,15 @@ __global__ void ingest_u8_kernel(const uint8_t* __restrict__ src, __nv_bfloat16*
     }
   }
   v[15] = __float2bfloat16_rn(0.f);
+  if (preswizzle == 2) {
+    // column-parity planes: [row][w & 1][w >> 1][16]; inside a plane the 32-byte swizzle follows the plane index j
+    const int j = w >> 1;
+    uint4* o = reinterpret_cast<uint4*>(dst + ((i - w) + (w & 1) * 16 + j) * 16);
+    const int sw = (j & 4) ? 1 : 0;
+    o[sw] = reinterpret_cast<uint4*>(v)[0];
+    o[sw ^ 1] = reinterpret_cast<uint4*>(v)[1];
+    return;
+  }
   uint4* o = reinterpret_cast<uint4*>(dst + i * 16);
   const int sw = (preswizzle && (w & 4)) ? 1 : 0;
   o[sw] = reinterpret_cast<uint4*>(v)[0];

@@ -19,15 +19,21 @@ def normalize_u8(x_u8: torch.Tensor) -> torch.Tensor:
     return (x_u8.float() * (1.0 / 255.0) - 0.5) * 2.0
 
 
-def ingest_ref(x_u8: torch.Tensor, preswizzle: bool = False) -> torch.Tensor:
-    """uint8 [N,32,32,3] -> float [N,32,32,16] kw-unrolled conv1 operand.  ``preswizzle``: the device layout, where
-    pixels with (w & 4) store their two 8-channel halves swapped (ingest_u8_kernel)."""
+def ingest_ref(x_u8: torch.Tensor, preswizzle=False) -> torch.Tensor:
+    """uint8 [N,32,32,3] -> float [N,32,32,16] kw-unrolled conv1 operand.  ``preswizzle``: the device layouts of
+    ingest_u8_kernel — 1/True: pixels with (w & 4) store their two 8-channel halves swapped; 2: each row additionally
+    split into its two column-parity planes ([row][w & 1][w >> 1]), halves swapped where (plane index & 4)."""
     x = normalize_u8(x_u8)                        # N,H,W,3
     n = x.shape[0]
     xp = F.pad(x, (0, 0, 2, 2))                   # pad W by 2 on both sides
     out = torch.zeros(n, 32, 32, 16, dtype=torch.float32, device=x.device)
     for kw in range(5):
         out[..., kw * 3:kw * 3 + 3] = xp[:, :, kw:kw + 32, :]
+    if int(preswizzle) == 2:
+        planes = torch.stack([out[:, :, 0::2], out[:, :, 1::2]], dim=2)           # N, H, 2, 16, 16ch
+        sw = (torch.arange(16, device=x.device) & 4).bool()
+        planes[:, :, :, sw] = torch.cat([planes[:, :, :, sw, 8:], planes[:, :, :, sw, :8]], dim=-1)
+        return planes.reshape(n, 32, 32, 16)
     if preswizzle:
         sw = (torch.arange(32, device=x.device) & 4).bool()
         out[:, :, sw] = torch.cat([out[:, :, sw, 8:], out[:, :, sw, :8]], dim=-1)

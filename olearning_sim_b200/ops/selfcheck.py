@@ -68,12 +68,15 @@ def _unpool_with_code(g: torch.Tensor, code: torch.Tensor) -> torch.Tensor:
 
 
 # --------------------------------------------------------------------------------------------------
+X5_DEFAULT = 1          # library default of the ``x5_rows`` switch (conv1 input layout)
+
+
 def check_ingest(c: int) -> Dict:
     n = c * 4
     x = torch.randint(0, 256, (n, 32, 32, 3), dtype=torch.uint8, device="cuda")
     out = torch.empty(n, 32, 32, 16, dtype=torch.bfloat16, device="cuda")
     native.ingest_u8(x, out)
-    ref = reference.ingest_ref(x, preswizzle=True).to(torch.bfloat16)
+    ref = reference.ingest_ref(x, preswizzle=X5_DEFAULT).to(torch.bfloat16)
     return {"err": rel_err(out.float(), ref.float()), "tol": 1e-4}
 
 
@@ -149,6 +152,39 @@ def check_conv2_fwd_shift(c: int) -> Dict:
         res["value_mismatch"] = rel_err(outs[1][0].float(), outs[0][0].float())
     finally:
         native.set_option("fwd2_shift", -1)       # default: automatic by client count
+    return res
+
+
+def check_conv1_window(c: int) -> Dict:
+    """conv1 forward with pooling done by the accumulator layout on the column-parity-plane input (``x5_rows`` = 2) next
+    to the row layout (= 1): ingest layout, forward (values + argmax codes), weight gradient, and the time of both"""
+    res: Dict = {"tol": 1e-2, "err": 0.0}
+    try:
+        for mode in (1, 2):
+            native.set_option("x5_rows", mode)
+            n = 8
+            xi = torch.randint(0, 256, (n, 32, 32, 3), dtype=torch.uint8, device="cuda")
+            out = torch.empty(n, 32, 32, 16, dtype=torch.bfloat16, device="cuda")
+            native.ingest_u8(xi, out)
+            res[f"m{mode}_ingest"] = rel_err(out.float(), reference.ingest_ref(xi, preswizzle=mode).to(torch.bfloat16).float())
+            f = check_conv1_fwd(c)
+            w = check_conv1_wgrad(c)
+            res[f"m{mode}_fwd"], res[f"m{mode}_code"], res[f"m{mode}_wgrad"] = f["err"], f["code_err"], w["err"]
+            res["err"] = max(res["err"], res[f"m{mode}_ingest"] * 100, f["err"], f["code_err"], w["err"])
+            # timing
+            shard, off = 2 * B, B // 2
+            _, x5 = _make_x5(c, shard)
+            master = _rand_master(c)
+            w1f, _, _ = _operand_copies(master)
+            p1 = torch.zeros(c * B, 16, 16, 32, dtype=torch.bfloat16, device="cuda")
+            code1 = torch.zeros(c * B, 16, 16, 32, dtype=torch.uint8, device="cuda")
+            dp1 = (torch.randn(c * B, 16, 16, 32, device="cuda") * 0.1).to(torch.bfloat16)
+            gout = torch.zeros(c, CNN2.W1_N, device="cuda")
+            res[f"m{mode}_fwd_us"] = round(_time_us(lambda: native.conv1_fwd(x5, shard, off, w1f, master, c, None, p1, code1)), 1)
+            res[f"m{mode}_wgrad_us"] = round(_time_us(lambda: native.conv1_wgrad(x5, shard, off, dp1, code1, master, None, c,
+                                                                                None, w1f, 0.1, 0.0, gout)), 1)
+    finally:
+        native.set_option("x5_rows", X5_DEFAULT)
     return res
 
 
@@ -540,7 +576,8 @@ CHECKS: Dict[str, Callable[[int], Dict]] = {
 # kernel variants under evaluation: run only when named explicitly with --only
 EXPERIMENTAL: Dict[str, Callable[[int], Dict]] = {"conv2_wgrad_wide": check_conv2_wgrad_wide,
                                                     "conv2_dgrad_pair": check_conv2_dgrad_pair,
-                                                    "conv2_fwd_shift": check_conv2_fwd_shift}
+                                                    "conv2_fwd_shift": check_conv2_fwd_shift,
+                                                    "conv1_window": check_conv1_window}
 
 
 def run_all(clients: List[int], only: List[str] | None = None) -> List[Dict]:
