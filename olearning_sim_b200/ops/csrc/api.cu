@@ -134,7 +134,7 @@ using Conv1WgradCfg = WgradCfg<32, 1, 64, 8>;
 // conv1 input layout (set before data is ingested): 0 plain rows fetched with 32-byte swizzled TMA rows, 1 pre-swizzled
 // rows fetched as 512-byte box rows, 2 pre-swizzled column-parity planes (conv1_window_kernel: pooling by accumulator
 // layout)
-int g_x5_rows = 1;
+int g_x5_rows = 2;
 // conv2 data gradient on CTA pairs (cta_group::2, weight operand split across the pair): 0 never, 1 always,
 // -1 auto = when a rank holds fewer than 400 clients (measured: 139 vs 151 us at 160 clients, 380 vs 379 at 592)
 int g_dgrad_pair = -1;

@@ -68,7 +68,7 @@ def _unpool_with_code(g: torch.Tensor, code: torch.Tensor) -> torch.Tensor:
 
 
 # --------------------------------------------------------------------------------------------------
-X5_DEFAULT = 1          # library default of the ``x5_rows`` switch (conv1 input layout)
+X5_DEFAULT = 2          # library default of the ``x5_rows`` switch (conv1 input layout)
 
 
 def check_ingest(c: int) -> Dict:
