@@ -9,6 +9,6 @@ echo "=== ncu launches"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 260 --csv --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 3 --no-e2e --clients ${NCU_CLIENTS:-592} > gpurun_out/ncu_launch_run.log 2>&1
 tail -2 gpurun_out/ncu_launch_run.log
 echo "=== ncu full (conv kernels + head)"
-timeout 1500 ncu --set full --clock-control none --import-source on -k regex:'conv_|head_fc|fedavg|bcast' -s 33 -c 12 -o gpurun_out/prof_cnn2 -f python bench.py --steps 1 --warmup 3 --no-e2e --clients ${NCU_CLIENTS:-592} > gpurun_out/ncu_full_run.log 2>&1
+timeout 1500 ncu --set full --clock-control none --import-source on -k regex:'conv|head_fc|fedavg|bcast' -s 33 -c 12 -o gpurun_out/prof_cnn2 -f python bench.py --steps 1 --warmup 3 --no-e2e --clients ${NCU_CLIENTS:-592} > gpurun_out/ncu_full_run.log 2>&1
 tail -2 gpurun_out/ncu_full_run.log; ls -la gpurun_out/
 fi

@@ -10,6 +10,7 @@ MB = 1 << 20
 # algorithmic work per client per launch: (GFLOP, MB moved through HBM)
 work = {
  "conv_taps_kernel<32, 1, 32":      ("conv1 fwd+pool",   32768 * 32 * 75 * 2 * 1e-9,            (B * 32 * 1024 + B * 16 * 16 * 32 * 3) / MB),
+ "conv1_window_kernel":             ("conv1 fwd+pool",   32768 * 32 * 75 * 2 * 1e-9,            (B * 32 * 1024 + B * 16 * 16 * 32 * 3) / MB),
  "conv_fwd_fold_kernel":            ("conv2 fwd+pool",   8192 * 64 * 800 * 2 * 1e-9,            (B * 16 * 16 * 32 * 2 + B * 8 * 8 * 64 * 3 + 102400) / MB),
  "head_fc_xent_kernel":             ("fc+xent+bwd+unpool", 3 * B * 4096 * 10 * 2 * 1e-9,          (B * 4096 * 3 + B * 16 * 16 * 64 * 2 + 2 * 163840) / MB),
  "conv_dgrad_fold_kernel":          ("conv2 dgrad+gate", 8192 * 32 * 1600 * 2 * 1e-9,           (B * 16 * 16 * 64 * 2 + 2 * B * 16 * 16 * 32 * 2 + 102400) / MB),
