@@ -113,6 +113,55 @@ def cluster_mgr_handler(cm: Any):
     })
 
 
+def phone_mgr_handler(pm: Any):
+    """Phone-side ``TaskManager`` service (ols_core/proto/phoneMgr.proto:53-66) — in the reference only the client stubs
+    exist and the server is an external product; mounting the in-process phone manager behind the same method names
+    lets a separate ResourceManager / TaskManager process reach it through ``RemotePhoneMgr``."""
+    return _generic("TaskManager", {
+        "submitTask": lambda r: {"is_success": bool(pm.submitTask(r.get("task", r)))},
+        "getDeviceAvailableResource": lambda r: {"resources": pm.getDeviceAvailableResource()},
+        "requestDeviceResource": lambda r: {"is_success": bool(pm.requestDeviceResource(r["task_id"], r.get("user_id", ""),
+                                                                                    r.get("phones", {})))},
+        "releaseDeviceResource": lambda r: {"is_success": bool(pm.releaseDeviceResource(r["task_id"]))},
+        "stopDevice": lambda r: {"is_success": bool(pm.stopDevice(r["task_id"]))},
+        "getDeviceTaskStatus": lambda r: pm.getDeviceTaskStatus(r["task_id"]),
+    })
+
+
+def phone_manager_handler(pm: Any):
+    """``PhoneManager`` (proto only in the reference): device attach / local inventory."""
+    return _generic("PhoneManager", {
+        "connectMSPDevices": lambda r: {"is_success": bool(pm.connectMSPDevices(r.get("user_id", ""), r.get("devices", {})))},
+        "getLocalDeviceResource": lambda r: {"resources": pm.getLocalDeviceResource()},
+    })
+
+
+class RemotePhoneMgr:
+    """Client-side adapter with ``FakePhoneMgr``'s method surface over gRPC (what the reference's ResourceMgr / TaskMgr hold
+    as phone-manager stubs: resource_manager.py:29-47, task_manager.py:36-60)."""
+
+    def __init__(self, address: str):
+        self._stub = JsonStub(connect(address), "TaskManager")
+
+    def getDeviceAvailableResource(self):
+        return self._stub.getDeviceAvailableResource({})["resources"]
+
+    def requestDeviceResource(self, task_id, user_id, phones):
+        return self._stub.requestDeviceResource({"task_id": task_id, "user_id": user_id, "phones": phones})["is_success"]
+
+    def releaseDeviceResource(self, task_id):
+        return self._stub.releaseDeviceResource({"task_id": task_id})["is_success"]
+
+    def submitTask(self, device_task):
+        return self._stub.submitTask({"task": device_task})["is_success"]
+
+    def stopDevice(self, task_id):
+        return self._stub.stopDevice({"task_id": task_id})["is_success"]
+
+    def getDeviceTaskStatus(self, task_id):
+        return self._stub.getDeviceTaskStatus({"task_id": task_id})
+
+
 def performance_mgr_handler(pm: Any):
     return _generic("PerformanceMgr", {"commitJob": lambda r: pm.commitJob(r)})
 
@@ -134,11 +183,12 @@ def connect(address: str) -> grpc.Channel:
 
 class SimulatorSession:
     """``SimulatorSession(port, services).start()`` — mounts servicers on one gRPC server.
-    ``svc``: 0 all / 1 task / 2 resource / 3 cluster / 4 performance / 5 deviceflow (simu_session.py:34-46)."""
+    ``svc``: 0 all / 1 task / 2 resource / 3 cluster / 4 performance / 5 deviceflow / 6 phone manager
+    (simu_session.py:34-46)."""
 
     def __init__(self, port: int = 60061, task_manager: Any = None, resource_manager: Any = None, deviceflow: Any = None,
                  cluster_manager: Any = None, performance_manager: Any = None, svc: int = 0, max_workers: int = 10,
-                 host: str = "127.0.0.1", session_sleep_time: float = 10.0):
+                 host: str = "127.0.0.1", session_sleep_time: float = 10.0, phone_manager: Any = None):
         self.server = grpc.server(futures.ThreadPoolExecutor(max_workers=max_workers), options=_OPTS)
         mounted = []
         if task_manager is not None and svc in (0, 1):
@@ -149,6 +199,12 @@ class SimulatorSession:
             self.server.add_generic_rpc_handlers((cluster_mgr_handler(cluster_manager),)); mounted.append("RayClusterMgr")
         if performance_manager is not None and svc in (0, 4):
             self.server.add_generic_rpc_handlers((performance_mgr_handler(performance_manager),)); mounted.append("PerformanceMgr")
+        if phone_manager is not None and svc in (0, 6):
+            # the phone-side service is also called "TaskManager" in the reference's proto; it is only mounted next to
+            # the task service when explicitly selected (svc == 6) or when there is no task service on this port
+            if svc == 6 or task_manager is None:
+                self.server.add_generic_rpc_handlers((phone_mgr_handler(phone_manager),)); mounted.append("TaskManager(phone)")
+            self.server.add_generic_rpc_handlers((phone_manager_handler(phone_manager),)); mounted.append("PhoneManager")
         if deviceflow is not None and svc in (0, 5):
             self.server.add_generic_rpc_handlers((deviceflow_handler(deviceflow),)); mounted.append("TaskOperatorOrientedDeviceFlow")
         self.mounted = mounted

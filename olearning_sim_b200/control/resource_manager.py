@@ -120,6 +120,19 @@ class FakePhoneMgr:
                 return {"is_finished": True, "device_result": []}
             return {k: t[k] for k in ("is_finished", "device_result", "device_round", "device_operator")}
 
+    # PhoneManager service (proto only in the reference: phoneMgr.proto connectMSPDevices / getLocalDeviceResource)
+    def connectMSPDevices(self, user_id: str, devices: Dict[str, int]) -> bool:
+        """Attach ``devices`` ({device class: count}) to ``user_id``'s inventory."""
+        with self._lock:
+            inv = self._total.setdefault(user_id, {})
+            for k, n in (devices or {}).items():
+                inv[k] = inv.get(k, 0) + int(n)
+            return True
+
+    def getLocalDeviceResource(self) -> Dict[str, Dict[str, int]]:
+        with self._lock:
+            return {u: dict(v) for u, v in self._total.items()}
+
     # test hook: let a test play the phones' role
     def report(self, task_id: str, device_round: int, device_operator: str, device_result: List[dict],
                is_finished: bool = False) -> None:

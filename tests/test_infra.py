@@ -317,3 +317,26 @@ def test_kube_cluster_api_with_fake_custom_objects_api():
     assert mgr.modifyRayCluster({"k8s_namespace": d.k8s_namespace, "ray_name": d.ray_name, "ray_label": d.ray_label,
                                  "worker_min_replicas": 1, "worker_replicas": 2, "worker_max_replicas": 4})["ok"]
     assert api.delete_ray_cluster("nope") is False and api.delete_ray_cluster(d.ray_name, d.k8s_namespace)
+
+
+def test_phone_manager_service_and_remote_adapter():
+    """the phone-side services over gRPC: a ResourceManager in another process can use them through RemotePhoneMgr"""
+    from olearning_sim_b200.api.grpc_service import JsonStub, RemotePhoneMgr, SimulatorSession, connect
+    from olearning_sim_b200.control.repo import ResTableRepo
+    from olearning_sim_b200.control.resource_manager import FakePhoneMgr, ResourceManager
+    pm = FakePhoneMgr({"u1": {"High": 2}})
+    sess = SimulatorSession(port=0, phone_manager=pm, svc=6).start()
+    try:
+        assert sess.mounted == ["TaskManager(phone)", "PhoneManager"]
+        assert JsonStub(connect(sess.address), "PhoneManager").connectMSPDevices({"user_id": "u1", "devices": {"Low": 3}})["is_success"]
+        remote = RemotePhoneMgr(sess.address)
+        assert remote.getDeviceAvailableResource() == {"u1": {"High": 2, "Low": 3}}
+        rm = ResourceManager(ResTableRepo(), totals={"cpu": 4, "mem": 8, "gpu": 0}, phone_mgr=remote)
+        assert rm.requestResource("t1", "u1", cpu=1, mem=1, phones={"High": 2}, type=0)[0]
+        assert remote.getDeviceAvailableResource()["u1"]["High"] == 0
+        assert not remote.requestDeviceResource("t2", "u1", {"High": 1})
+        assert rm.releaseResource("t1", "u1", phones={"High": 2}, type=0)[0] and pm.getDeviceAvailableResource()["u1"]["High"] == 2
+        assert remote.submitTask({"task_id": "t1"}) and remote.getDeviceTaskStatus("t1")["is_finished"] is False
+        assert remote.stopDevice("t1") and remote.getDeviceTaskStatus("t1")["is_finished"] is True
+    finally:
+        sess.stop()
