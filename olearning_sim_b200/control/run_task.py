@@ -220,7 +220,16 @@ class RoundRunner:
                 import torch
                 eng.local_steps_t = torch.from_numpy(steps).to(eng.device)
                 eng.p_online_t = torch.from_numpy(pon).to(eng.device)
-        eng.load_synthetic() if cfgd.get("data", "synthetic") == "synthetic" else None
+        # data: the task's datasets with the reference's shard contract (client i owns sub-folder i when
+        # data_split_type is true); datasets without a data_path use the synthetic non-IID generator
+        dsets = [{"name": d.get("name", ""), "data_path": d.get("data_path", ""), "data_split_type": d.get("data_split_type", False),
+                  "data_transfer_type": d.get("data_transfer_type", "FILE"),
+                  "num_clients": sum(int(n) for n in d.get("simulation_target", {}).get("nums", []))}
+                 for d in self.params.data]
+        if any(d["data_path"] for d in dsets) and cfgd.get("data", "task") != "synthetic":
+            eng.load_datasets(dsets, work_dir=os.path.join(self.working_dir, "data"))
+        else:
+            eng.load_synthetic()
         if self.checkpoint_dir:
             from ..engine.checkpoint import CheckpointManager
             eng.ckpt = CheckpointManager(self.checkpoint_dir, self.params.task_id, rank=self.rank)

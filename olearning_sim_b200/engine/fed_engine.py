@@ -17,6 +17,8 @@ Backends:  ``native``  hand-written sm_100a kernels (CNN-2 family, CUDA only)
 """
 from __future__ import annotations
 
+import os
+
 import math
 import time
 from dataclasses import asdict, dataclass, field
@@ -441,6 +443,33 @@ class FedEngine:
     def load_synthetic(self) -> None:
         xs, ys = synthetic_client_data(self.cfg.model, self.client_ids, self.cfg.shard, self.cfg.seed, self.spec)
         self.load_client_data(xs, ys)
+
+    def load_datasets(self, datasets: List[Dict[str, Any]], work_dir: str = "/tmp/olsb_data") -> None:
+        """Real data with the reference's shard contract (engine/data.py): ``datasets`` = the task's ``target.data``
+        entries in population order, each ``{"data_path", "data_split_type", "data_transfer_type", "num_clients"}``.
+        A dataset without a path falls back to the synthetic generator for its clients."""
+        from .data import fetch_dataset, load_client_shards
+        image = self.cfg.model in ("cnn2", "resnet18")
+        shape = (32, 32, 3) if image else tuple(self.spec.input_shape)
+        xs_parts, ys_parts, off = [], [], 0
+        for d in datasets:
+            n = int(d["num_clients"])
+            ids = self.client_ids[(self.client_ids >= off) & (self.client_ids < off + n)]
+            if len(ids):
+                root = fetch_dataset(d, os.path.join(work_dir, str(d.get("name", off))))
+                if root:
+                    x, y = load_client_shards(root, ids - off, self.cfg.shard, bool(d.get("data_split_type", False)), n, shape)
+                    if image and x.dtype != np.uint8:
+                        raise ValueError("image families take uint8 NHWC samples")
+                    if not image:
+                        x = x.astype(np.int64 if self.spec.input_dtype == torch.int64 else np.float32)
+                else:
+                    x, y = synthetic_client_data(self.cfg.model, ids, self.cfg.shard, self.cfg.seed, self.spec)
+                xs_parts.append(x); ys_parts.append(y)
+            off += n
+        if off != self.cfg.num_clients:
+            raise ValueError(f"datasets describe {off} clients, the engine simulates {self.cfg.num_clients}")
+        self.load_client_data(np.concatenate(xs_parts), np.concatenate(ys_parts))
 
     def load_client_data(self, xs: np.ndarray, labels: np.ndarray) -> None:
         """xs: uint8 NHWC [C, shard, 32,32,3] for the image families, float/int arrays otherwise."""
