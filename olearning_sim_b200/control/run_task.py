@@ -237,8 +237,70 @@ class RoundRunner:
             if state is not None:
                 eng.load_state_dict(state["engine"])
                 eng.resume_round = state["round"] + 1
+        self._import_model(operator, eng)
         self.engines[name] = eng
         return eng
+
+    # ---- model files (utils_run_task.py:327-397) -------------------------------------------------------
+    # The reference's actors download the model file at the start of every operator; for ``model_for_train`` and
+    # round > 0 the name is ``model_update_style`` with {task_id} / {current_round} substituted (default
+    # "{task_id}_{current_round}_result_model.mnn"), written by the external aggregation service.  Here the engine is the
+    # aggregator: the initial model is read from ``model_path`` and every training round publishes the new global model
+    # under the same naming scheme, next to ``model_path`` (or in the job's working directory).
+    def _model_cfg(self, operator: Dict[str, Any]) -> Dict[str, Any]:
+        return operator.get("model", {}) or {}
+
+    def _model_dir(self, m: Dict[str, Any]) -> str:
+        path = m.get("model_path", "")
+        d = os.path.dirname(path) if path and not path.endswith("/") else path
+        return d or os.path.join(self.working_dir, "models")
+
+    def _import_model(self, operator: Dict[str, Any], eng: Any) -> None:
+        m = self._model_cfg(operator)
+        path = m.get("model_path", "")
+        if not (m.get("use_model") and path):
+            return
+        import torch
+        local = path
+        ttype = str(m.get("model_transfer_type", "FILE")).upper()
+        if ttype != "FILE":
+            from ..utils.file_repo import get_file_repo
+            local = os.path.join(self.working_dir, "models", os.path.basename(path))
+            os.makedirs(os.path.dirname(local), exist_ok=True)
+            if not get_file_repo(ttype, m.get("repo_config")).download_if_missing(path, local):
+                raise FileNotFoundError(f"model {path} ({ttype}) could not be fetched")
+        if not os.path.isfile(local):
+            return                                          # a directory: only the place where results are published
+        obj = torch.load(local, map_location="cpu", weights_only=True)
+        flat = obj["flat"] if isinstance(obj, dict) and "flat" in obj else obj
+        if isinstance(flat, dict):                           # a state_dict in the zoo's parameter names
+            flat = eng.spec.flatten({k: v for k, v in flat.items()})
+        flat = torch.as_tensor(flat, dtype=torch.float32).reshape(-1)
+        if flat.numel() < eng.spec.num_params:
+            raise ValueError(f"model file has {flat.numel()} parameters, {eng.cfg.model} needs {eng.spec.num_params}")
+        full = eng.spec.init(eng.cfg.seed)
+        full[:eng.spec.num_params] = flat[:eng.spec.num_params]
+        if eng.backend == "native":                          # native workspaces keep their own packed layout
+            from ..ops.layout import CNN2
+            full = CNN2.pack(eng.spec.unflatten(full)) if eng.cfg.model == "cnn2" else eng.ws.L.pack(full)
+        eng.set_global_model(full)
+
+    def _export_model(self, operator: Dict[str, Any], eng: Any, round_idx: int) -> Optional[str]:
+        m = self._model_cfg(operator)
+        if not (m.get("use_model") and m.get("model_for_train")):
+            return None
+        import torch
+        style = m.get("model_update_style") or "{task_id}_{current_round}_result_model.mnn"
+        name = style.replace("{task_id}", self.params.task_id).replace("{current_round}", str(round_idx + 1))
+        flat = eng.spec_flat_global().detach().cpu()[:eng.spec.num_params]
+        if self.rank != 0:
+            return None
+        out = os.path.join(self._model_dir(m), os.path.basename(name))
+        os.makedirs(os.path.dirname(out), exist_ok=True)
+        tmp = out + ".tmp"
+        torch.save({"model": eng.cfg.model, "round": round_idx, "flat": flat}, tmp)
+        os.replace(tmp, out)
+        return out
 
     def _run_builtin(self, operator: Dict[str, Any], round_idx: int) -> List[Dict[str, Any]]:
         eng = self._builtin_engine(operator)
@@ -263,6 +325,9 @@ class RoundRunner:
                                                     "t_round_ms": res.wall_s * 1e3, "client_steps": res.client_steps,
                                                     "phases_ms": res.extras.get("phases_ms", {})})
             res_failed = res.failed
+            published = self._export_model(operator, eng, round_idx)
+            if published:
+                rec["model_file"] = published
             if getattr(eng, "ckpt", None) is not None:
                 eng.ckpt.save(round_idx, {"engine": eng.state_dict(), "round": round_idx})
         # per (dataset, class) accounting: a client "fails" only if its computation failed (non-finite update);

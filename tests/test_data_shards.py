@@ -95,3 +95,33 @@ def test_task_with_split_data_runs_through_the_control_plane(tmp_path):
     assert tm.wait_for("realdata", 120) == TaskStatus.SUCCEEDED, tm._executor.get_job_error(repo.get_task_value("realdata", "job_id"))
     res = json.loads(repo.get_task_value("realdata", "logical_result"))["logical_result"][0]["simulation_target"]
     assert res["success_num"] == [5]
+
+
+def test_model_files_initial_model_and_per_round_result(tmp_path):
+    """model contract: the initial global model comes from model_path, every training round publishes
+    {task_id}_{round}_result_model.* (model_update_style) that a later task can start from"""
+    import torch
+    from olearning_sim_b200.control.run_task import RoundRunner
+    from olearning_sim_b200.models.zoo import get_model
+    from tests.helpers import make_task_json
+    spec = get_model("mlp2")
+    init = spec.init(123)
+    mdir = tmp_path / "models"
+    mdir.mkdir()
+    torch.save({"flat": init[:spec.num_params]}, mdir / "init.pt")
+    tj = make_task_json(task_id="mfile", rounds=2, nums=(4,), operator_params={
+        "model": "mlp2", "local_steps": 1, "batch": 8, "shard": 8, "lr": 0.1, "device": "cpu", "backend": "torch"})
+    tj["operatorflow"]["operators"][0]["model"] = {"use_model": True, "model_for_train": True, "model_transfer_type": "FILE",
+                                                   "model_path": str(mdir / "init.pt"),
+                                                   "model_update_style": "{task_id}_{current_round}_result_model.pt"}
+    # the job JSON the TaskRunner hands to the round loop carries simulation_target per dataset
+    tj["target"]["data"][0]["simulation_target"] = {"devices": ["High"], "nums": [4]}
+    rr = RoundRunner(tj, working_dir=str(tmp_path / "job"))
+    eng = rr._builtin_engine(tj["operatorflow"]["operators"][0])
+    assert torch.allclose(eng.global_model()[:spec.num_params], init[:spec.num_params])
+    assert rr.run()
+    files = sorted(os.listdir(mdir))
+    assert files == ["init.pt", "mfile_1_result_model.pt", "mfile_2_result_model.pt"]
+    last = torch.load(mdir / "mfile_2_result_model.pt", weights_only=True)
+    assert last["round"] == 1 and torch.allclose(last["flat"], eng.global_model()[:spec.num_params])
+    assert not torch.allclose(last["flat"], init[:spec.num_params])
