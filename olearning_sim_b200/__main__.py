@@ -23,8 +23,14 @@ def _serve(a) -> int:
     from .utils.misc_repos import PerformanceManager
     cfg = load_config([a.config] if a.config else None, overrides=a.set)
     tm, rm, df = build_control_plane(cfg, start_threads=True)
+    from .utils.metrics import Metrics
+    metrics = Metrics()
+    perf = PerformanceManager(metrics=metrics)
+    tm._job_context["performance_mgr"] = perf              # round records of in-process jobs feed the metrics
+    if a.metrics_port:
+        metrics.start_http_server(a.metrics_port, a.host)
     sess = SimulatorSession(port=a.port or cfg.grpc.taskmgr_port, task_manager=tm, resource_manager=rm, deviceflow=df,
-                            cluster_manager=GpuClusterManager(), performance_manager=PerformanceManager(), svc=a.svc,
+                            cluster_manager=GpuClusterManager(), performance_manager=perf, svc=a.svc,
                             max_workers=cfg.grpc.max_workers, host=a.host, session_sleep_time=cfg.runtime.session_sleep_time)
     print(json.dumps({"address": sess.address, "services": sess.mounted}), flush=True)
     sess.start(block=True)
@@ -87,6 +93,7 @@ def main(argv=None) -> int:
     s.add_argument("--svc", type=int, default=0, help="0 all, 1 task, 2 resource, 3 cluster, 4 performance, 5 deviceflow")
     s.add_argument("--host", default="127.0.0.1")
     s.add_argument("--port", type=int, default=0)
+    s.add_argument("--metrics-port", type=int, default=0, help="expose Prometheus metrics on this port (0 = off)")
     s.set_defaults(fn=_serve)
     for name, fn in (("submit", _submit), ("status", _status), ("stop", _stop), ("queue", _queue)):
         c = sub.add_parser(name)

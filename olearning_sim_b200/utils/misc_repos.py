@@ -147,10 +147,11 @@ class LogUtils:
 class PerformanceManager:
     """``commitJob({task_id, round, t_bcast_ms, t_local_ms, t_reduce_ms, clients, local_steps, bytes_bcast, ...})``"""
 
-    def __init__(self, peaks: Optional[Dict[str, float]] = None):
+    def __init__(self, peaks: Optional[Dict[str, float]] = None, metrics: Optional[Any] = None):
         self._jobs: Dict[str, List[Dict[str, Any]]] = collections.defaultdict(list)
         self._lock = threading.Lock()
         self.peaks = peaks or {}
+        self.metrics = metrics          # utils.metrics.Metrics: every committed record is also exported to Prometheus
 
     def commitJob(self, request: Dict[str, Any]) -> Dict[str, Any]:
         tid = request.get("task_id", "")
@@ -158,6 +159,8 @@ class PerformanceManager:
             return {"is_success": False}
         with self._lock:
             self._jobs[tid].append(dict(request))
+        if self.metrics is not None:
+            self.metrics.observe_round(request)
         return {"is_success": True, "count": len(self._jobs[tid])}
 
     def summary(self, task_id: str) -> Dict[str, Any]:

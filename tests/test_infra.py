@@ -340,3 +340,18 @@ def test_phone_manager_service_and_remote_adapter():
         assert remote.stopDevice("t1") and remote.getDeviceTaskStatus("t1")["is_finished"] is True
     finally:
         sess.stop()
+
+
+def test_prometheus_metrics_from_round_records():
+    from olearning_sim_b200.utils.metrics import Metrics
+    from olearning_sim_b200.utils.misc_repos import PerformanceManager
+    m = Metrics()
+    pm = PerformanceManager(metrics=m)
+    for r in range(3):
+        pm.commitJob({"task_id": "t9", "round": r, "t_round_ms": 20.0, "client_steps": 5120,
+                      "phases_ms": {"broadcast": 0.05, "local_steps": 19.0, "reduce_update": 0.2}})
+    m.observe_tasks({"RUNNING": 1, "QUEUED": 2})
+    text = m.render()
+    assert 'olsb_rounds_total{task_id="t9"} 3.0' in text and 'olsb_client_steps_total{task_id="t9"} 15360.0' in text
+    assert 'olsb_phase_ms{phase="local_steps",task_id="t9"} 19.0' in text and 'olsb_tasks{status="QUEUED"} 2.0' in text
+    assert pm.summary("t9")["rounds"] == 3
