@@ -28,7 +28,17 @@ def _serve(a) -> int:
     perf = PerformanceManager(metrics=metrics)
     tm._job_context["performance_mgr"] = perf              # round records of in-process jobs feed the metrics
     if a.metrics_port:
+        import collections
+        import threading
         metrics.start_http_server(a.metrics_port, a.host)
+
+        def poll_tasks():                                   # tasks-per-status gauge from the task table
+            while True:
+                rows = tm._task_repo.all_rows()
+                counts = collections.Counter(str(r.get("task_status", "")) for r in rows)
+                metrics.observe_tasks({st: counts.get(st, 0) for st in ("UNDONE", "QUEUED", "RUNNING", "SUCCEEDED", "FAILED", "STOPPED")})
+                time.sleep(2.0)
+        threading.Thread(target=poll_tasks, name="metrics-tasks", daemon=True).start()
     sess = SimulatorSession(port=a.port or cfg.grpc.taskmgr_port, task_manager=tm, resource_manager=rm, deviceflow=df,
                             cluster_manager=GpuClusterManager(), performance_manager=perf, svc=a.svc,
                             max_workers=cfg.grpc.max_workers, host=a.host, session_sleep_time=cfg.runtime.session_sleep_time)
