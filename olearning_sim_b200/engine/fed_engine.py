@@ -118,6 +118,23 @@ def synthetic_client_data(model: str, client_ids: np.ndarray, shard: int, seed: 
     return xs, labels
 
 
+def merge_opt_shards(parts: List[torch.Tensor], num_params: int) -> torch.Tensor:
+    """Concatenate equal-length rank shards and cut the tail padding: the full [P] optimiser-state vector."""
+    return torch.cat([p.reshape(-1) for p in parts])[:num_params].clone()
+
+
+def take_opt_shard(full: torch.Tensor, rank: int, shard_len: int, out_len: int) -> torch.Tensor:
+    """This rank's slice of a full optimiser-state vector under the CURRENT sharding, zero-padded to ``out_len``
+    (the last rank's shard extends past P).  Accepts the old per-rank format only when the sharding is unchanged."""
+    full = full.reshape(-1)
+    out = torch.zeros(out_len, dtype=full.dtype)
+    s0 = rank * shard_len
+    n = max(0, min(shard_len, full.numel() - s0, out_len))
+    if n > 0:
+        out[:n] = full[s0:s0 + n]
+    return out
+
+
 class FedEngine:
     def __init__(self, cfg: FedConfig, rank: int = 0, world: int = 1, group: Optional[Any] = None):
         self.cfg, self.rank, self.world, self.group = cfg, rank, world, group
@@ -606,7 +623,9 @@ class FedEngine:
     def state_dict(self) -> Dict[str, Any]:
         sd = {"config": asdict(self.cfg), "global": self.global_model().detach().cpu(), "rounds_done": len(self.round_log)}
         if self.uses_ws:
-            sd["opt_m"], sd["opt_v"] = self.ws.opt_m.cpu(), self.ws.opt_v.cpu()
+            # the server-optimiser state is sharded by rank (ZeRO-1-like); checkpoints store the FULL vectors so a job
+            # restarted on a different number of ranks (elastic shrink) can re-slice them
+            sd["opt_m"], sd["opt_v"] = (self._gather_opt(t) for t in (self.ws.opt_m, self.ws.opt_v))
             sd["server_step"] = self.ws.server_step
         else:
             sd["server_state"] = {k: (v.cpu() if torch.is_tensor(v) else v) for k, v in self.server_state.items()}
@@ -615,9 +634,19 @@ class FedEngine:
     def load_state_dict(self, sd: Dict[str, Any]) -> None:
         self.set_global_model(sd["global"])
         if self.uses_ws:
-            self.ws.opt_m.copy_(sd["opt_m"]); self.ws.opt_v.copy_(sd["opt_v"]); self.ws.server_step = sd["server_step"]
+            for name, dst in (("opt_m", self.ws.opt_m), ("opt_v", self.ws.opt_v)):
+                dst.copy_(take_opt_shard(sd[name], self.rank, self.ws.shard_len, dst.numel()))
+            self.ws.server_step = sd["server_step"]
         else:
             self.server_state = {k: (v.to(self.device) if torch.is_tensor(v) else v) for k, v in sd.get("server_state", {}).items()}
+
+    def _gather_opt(self, shard: torch.Tensor) -> torch.Tensor:
+        """Full optimiser-state vector from the per-rank shards (rank r owns [r*shard_len, (r+1)*shard_len))."""
+        if self.world == 1:
+            return shard.detach().cpu().clone()
+        parts = [torch.empty_like(shard) for _ in range(self.world)]
+        dist.all_gather(parts, shard.contiguous(), group=self.group)
+        return merge_opt_shards([p.cpu() for p in parts], self.P)
 
     def close(self) -> None:
         if self.uses_ws:

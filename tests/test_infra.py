@@ -355,3 +355,20 @@ def test_prometheus_metrics_from_round_records():
     assert 'olsb_rounds_total{task_id="t9"} 3.0' in text and 'olsb_client_steps_total{task_id="t9"} 15360.0' in text
     assert 'olsb_phase_ms{phase="local_steps",task_id="t9"} 19.0' in text and 'olsb_tasks{status="QUEUED"} 2.0' in text
     assert pm.summary("t9")["rounds"] == 3
+
+
+def test_optimizer_state_reshards_across_world_sizes():
+    """checkpoints hold the full server-optimiser vectors; a restart on fewer ranks re-slices them"""
+    import torch
+    from olearning_sim_b200.engine.fed_engine import merge_opt_shards, take_opt_shard
+    P = 22
+    full = torch.arange(P, dtype=torch.float32)
+    def shards(world):
+        sl = ((P // 4 + world - 1) // world) * 4
+        return sl, [take_opt_shard(full, r, sl, sl) for r in range(world)]
+    sl4, s4 = shards(4)                      # shard_len 8: ranks 0..2 hold 8/8/6 values, rank 3 holds none
+    assert sl4 == 8 and s4[2].tolist() == [16, 17, 18, 19, 20, 21, 0, 0] and s4[3].sum() == 0
+    assert torch.equal(merge_opt_shards(s4, P), full)
+    sl3, s3 = shards(3)                      # elastic shrink 4 -> 3 ranks
+    assert torch.equal(merge_opt_shards(s3, P), full) and s3[1][0] == sl3
+    assert torch.equal(take_opt_shard(merge_opt_shards(s4, P), 0, 24, 24)[:P], full)       # ... -> 1 rank
