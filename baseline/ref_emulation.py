@@ -113,7 +113,7 @@ def main() -> int:
             m = shelf.receive(0)
             env = parse_envelope(m.value())
             body = json.loads(env["message"])
-            delta = torch.load(io.BytesIO(base64.b64decode(body["delta"])))
+            delta = torch.load(io.BytesIO(base64.b64decode(body["delta"])), weights_only=True)
             tot += body["n"] * delta
             wsum += body["n"]
             shelf.acknowledge(m)

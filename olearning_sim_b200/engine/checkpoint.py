@@ -84,7 +84,7 @@ class CheckpointManager:
         self.wait()
         for _, p in reversed(self._rounds()):
             try:
-                return torch.load(p, map_location="cpu", weights_only=False)
+                return torch.load(p, map_location="cpu", weights_only=True)   # tensors + plain containers only: no pickle code
             except Exception:  # noqa: BLE001 — torn file from a crash: fall back to the previous round
                 continue
         return None
