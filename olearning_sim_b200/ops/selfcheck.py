@@ -188,6 +188,36 @@ def check_conv1_window(c: int) -> Dict:
     return res
 
 
+def check_zero_round(c: int) -> Dict:
+    """engine-level edge case: a round in which no client is online (availability trace = 0) must leave the global model
+    untouched and finite on the native path, then training resumes; also a round where every update is dropped"""
+    from ..engine.fed_engine import FedConfig, FedEngine
+    res: Dict = {"tol": 0.0, "err": 0.0}
+    e = FedEngine(FedConfig(model="cnn2", num_clients=max(c, 2), local_steps=2, shard=64, backend="native", seed=2,
+                            p_online=1.0, online_trace="0 if t == 1 else 1"))
+    e.load_synthetic()
+    r0 = e.run_round(0)
+    g0 = e.global_model().clone()
+    r1 = e.run_round(1)
+    g1 = e.global_model().clone()
+    r2 = e.run_round(2)
+    res.update(part=[r0.participants, r1.participants, r2.participants], loss=[r0.loss, r1.loss, r2.loss],
+               unchanged=float((g1 - g0).abs().max()), moved=float((e.global_model() - g1).abs().max()),
+               finite=bool(torch.isfinite(e.global_model()).all()))
+    ok = r1.participants == 0 and res["unchanged"] == 0.0 and res["moved"] > 0 and res["finite"] and r1.client_steps == 0
+    e.close()
+    d = FedEngine(FedConfig(model="cnn2", num_clients=max(c, 2), local_steps=1, shard=64, backend="native", seed=2,
+                            drop_probability=1.0))
+    d.load_synthetic()
+    gd = d.global_model().clone()
+    rd = d.run_round(0)
+    res.update(dropped=rd.dropped, arrived=rd.arrived, drop_unchanged=float((d.global_model() - gd).abs().max()))
+    ok = ok and rd.arrived == 0 and rd.dropped == rd.participants and res["drop_unchanged"] == 0.0
+    d.close()
+    res["err"] = 0.0 if ok else 1.0
+    return res
+
+
 def check_head(c: int) -> Dict:
     master = _rand_master(c)
     p2 = torch.randn(c * B, 8, 8, 64, device="cuda").clamp_min(0).to(torch.bfloat16)
@@ -577,7 +607,8 @@ CHECKS: Dict[str, Callable[[int], Dict]] = {
 EXPERIMENTAL: Dict[str, Callable[[int], Dict]] = {"conv2_wgrad_wide": check_conv2_wgrad_wide,
                                                     "conv2_dgrad_pair": check_conv2_dgrad_pair,
                                                     "conv2_fwd_shift": check_conv2_fwd_shift,
-                                                    "conv1_window": check_conv1_window}
+                                                    "conv1_window": check_conv1_window,
+                                                    "zero_round": check_zero_round}
 
 
 def run_all(clients: List[int], only: List[str] | None = None) -> List[Dict]:
