@@ -41,7 +41,8 @@ def _serve(a) -> int:
         threading.Thread(target=poll_tasks, name="metrics-tasks", daemon=True).start()
     sess = SimulatorSession(port=a.port or cfg.grpc.taskmgr_port, task_manager=tm, resource_manager=rm, deviceflow=df,
                             cluster_manager=GpuClusterManager(), performance_manager=perf, svc=a.svc,
-                            max_workers=cfg.grpc.max_workers, host=a.host, session_sleep_time=cfg.runtime.session_sleep_time)
+                            max_workers=cfg.grpc.max_workers, host=a.host, session_sleep_time=cfg.runtime.session_sleep_time,
+                            phone_manager=rm.phone_mgr)
     print(json.dumps({"address": sess.address, "services": sess.mounted}), flush=True)
     sess.start(block=True)
     return 0
@@ -100,7 +101,7 @@ def main(argv=None) -> int:
     s = sub.add_parser("serve", help="start the gRPC services")
     s.add_argument("--config", default=None, help="INI / YAML / JSON config (reference names accepted)")
     s.add_argument("--set", action="append", default=[], metavar="section.key=value")
-    s.add_argument("--svc", type=int, default=0, help="0 all, 1 task, 2 resource, 3 cluster, 4 performance, 5 deviceflow")
+    s.add_argument("--svc", type=int, default=0, help="0 all, 1 task, 2 resource, 3 cluster, 4 performance, 5 deviceflow, 6 phone manager")
     s.add_argument("--host", default="127.0.0.1")
     s.add_argument("--port", type=int, default=0)
     s.add_argument("--metrics-port", type=int, default=0, help="expose Prometheus metrics on this port (0 = off)")

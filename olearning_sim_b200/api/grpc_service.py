@@ -200,10 +200,8 @@ class SimulatorSession:
         if performance_manager is not None and svc in (0, 4):
             self.server.add_generic_rpc_handlers((performance_mgr_handler(performance_manager),)); mounted.append("PerformanceMgr")
         if phone_manager is not None and svc in (0, 6):
-            # the phone-side service is also called "TaskManager" in the reference's proto; it is only mounted next to
-            # the task service when explicitly selected (svc == 6) or when there is no task service on this port
-            if svc == 6 or task_manager is None:
-                self.server.add_generic_rpc_handlers((phone_mgr_handler(phone_manager),)); mounted.append("TaskManager(phone)")
+            # the phone-side service is named "TaskManager" in the reference's proto (the task service is "TaskMgr")
+            self.server.add_generic_rpc_handlers((phone_mgr_handler(phone_manager),)); mounted.append("TaskManager(phone)")
             self.server.add_generic_rpc_handlers((phone_manager_handler(phone_manager),)); mounted.append("PhoneManager")
         if deviceflow is not None and svc in (0, 5):
             self.server.add_generic_rpc_handlers((deviceflow_handler(deviceflow),)); mounted.append("TaskOperatorOrientedDeviceFlow")
