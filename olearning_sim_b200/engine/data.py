@@ -112,3 +112,35 @@ def load_client_shards(root: str, client_ids: Sequence[int], shard: int, split: 
             raise ValueError(f"samples of shape {X.shape[2:]} do not match the model input {tuple(input_shape)}")
         X = X.reshape(X.shape[:2] + tuple(input_shape))
     return X, Y
+
+
+# ---- building shard folders ------------------------------------------------------------------------------------------
+def write_shards(out_dir: str, xs: Sequence[np.ndarray], ys: Sequence[np.ndarray], prefix: str = "client_") -> List[str]:
+    """One sub-folder per client (``client_0000`` ...; zero-padded so the reference's plain ``sorted`` keeps the order),
+    each holding ``data.npz`` — the layout ``load_client_shards(..., split=True)`` reads."""
+    width = max(4, len(str(max(len(xs) - 1, 0))))
+    out = []
+    for i, (x, y) in enumerate(zip(xs, ys)):
+        d = os.path.join(out_dir, f"{prefix}{i:0{width}d}")
+        os.makedirs(d, exist_ok=True)
+        np.savez(os.path.join(d, "data.npz"), x=np.asarray(x), y=np.asarray(y))
+        out.append(d)
+    return out
+
+
+def dirichlet_partition(y: np.ndarray, num_clients: int, alpha: float, seed: int = 0, min_size: int = 1) -> List[np.ndarray]:
+    """Label-skewed non-IID split (the usual FL benchmark protocol): for every class the samples are divided among the
+    clients with proportions drawn from Dir(alpha).  Small alpha -> each client sees few classes; large alpha -> IID.
+    Returns one index array per client (every sample is assigned exactly once)."""
+    rng = np.random.default_rng(seed)
+    y = np.asarray(y).reshape(-1)
+    for _ in range(100):
+        buckets: List[List[int]] = [[] for _ in range(num_clients)]
+        for c in np.unique(y):
+            idx = rng.permutation(np.flatnonzero(y == c))
+            cuts = (np.cumsum(rng.dirichlet(np.full(num_clients, alpha))) * len(idx)).astype(int)[:-1]
+            for b, part in zip(buckets, np.split(idx, cuts)):
+                b.extend(part.tolist())
+        if min(len(b) for b in buckets) >= min_size:
+            break
+    return [np.array(sorted(b), dtype=np.int64) for b in buckets]

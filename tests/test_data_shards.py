@@ -125,3 +125,19 @@ def test_model_files_initial_model_and_per_round_result(tmp_path):
     last = torch.load(mdir / "mfile_2_result_model.pt", weights_only=True)
     assert last["round"] == 1 and torch.allclose(last["flat"], eng.global_model()[:spec.num_params])
     assert not torch.allclose(last["flat"], init[:spec.num_params])
+
+
+def test_dirichlet_partition_and_shard_writer_round_trip(tmp_path):
+    from olearning_sim_b200.engine.data import dirichlet_partition, write_shards
+    rng = np.random.default_rng(0)
+    y = rng.integers(0, 10, 2000)
+    x = rng.standard_normal((2000, 8)).astype(np.float32)
+    parts = dirichlet_partition(y, 12, alpha=0.3, seed=1, min_size=8)
+    allidx = np.concatenate(parts)
+    assert len(parts) == 12 and len(allidx) == 2000 and len(np.unique(allidx)) == 2000          # a partition
+    skew = np.mean([np.bincount(y[p], minlength=10).max() / len(p) for p in parts])
+    iid = np.mean([np.bincount(y[p], minlength=10).max() / len(p) for p in dirichlet_partition(y, 12, alpha=100.0, seed=1)])
+    assert skew > 0.35 > iid                                                                   # small alpha is label-skewed
+    write_shards(str(tmp_path), [x[p] for p in parts], [y[p] for p in parts])
+    xs, ys = load_client_shards(str(tmp_path), [0, 11], shard=8, split=True, total_clients=12, input_shape=(8,))
+    assert np.array_equal(ys[1], y[parts[11]][:8]) and np.array_equal(xs[0], x[parts[0]][:8])
