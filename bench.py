@@ -133,7 +133,7 @@ def main() -> int:
         if "--clients" not in sys.argv: args.clients = pre["clients"]
         if "--local-steps" not in sys.argv: args.local_steps = pre["local_steps"]
     model = pre.pop("model"); pre.pop("clients"); pre.pop("local_steps"); pre.pop("shard")
-    native_ok = model in ("cnn2", "mlp2", "mlp")
+    native_ok = model in ("cnn2", "mlp2", "mlp", "resnet18", "bert_mini")
     # ours: hand-written kernels end to end where they exist (cnn2 / mlp2), otherwise library forward/backward + the
     # native FL kernels (broadcast, masks, fused client SGD, peer-memory reduce + server optimiser): backend "hybrid"
     backend = ("native" if native_ok else "hybrid") if args.impl == "ours" else "torch"

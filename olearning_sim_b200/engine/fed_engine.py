@@ -35,6 +35,9 @@ from ..ops.layout import CNN2
 from ..parallel.comm import shard_range
 
 
+NATIVE_FAMILIES = ("cnn2", "mlp2", "mlp", "resnet18", "bert_mini")      # hand-written sm_100a local step
+
+
 @dataclass
 class FedConfig:
     model: str = "cnn2"
@@ -143,13 +146,13 @@ class FedEngine:
             dev = f"cuda:{torch.cuda.current_device()}" if torch.cuda.is_available() else "cpu"
         self.device = torch.device(dev)
         backend = cfg.backend
-        native_ok = self.device.type == "cuda" and cfg.model in ("cnn2", "mlp2", "mlp") and cfg.batch == 32
+        native_ok = self.device.type == "cuda" and cfg.model in NATIVE_FAMILIES and cfg.batch == 32
         if backend == "auto":
             # native: hand-written kernels end to end; hybrid: library forward/backward + native FL kernels (broadcast,
             # masks, fused client SGD, P2P reduce + server optimiser); torch: pure library path (CPU / baseline)
             backend = "native" if native_ok else ("hybrid" if self.device.type == "cuda" else "torch")
         if backend == "native" and not native_ok:
-            raise RuntimeError("the native backend needs CUDA, batch 32 and the cnn2 / mlp2 / mlp families")
+            raise RuntimeError(f"the native backend needs CUDA, batch 32 and one of {NATIVE_FAMILIES}")
         if backend == "hybrid" and self.device.type != "cuda":
             raise RuntimeError("the hybrid backend needs CUDA")
         self.backend = backend
@@ -221,6 +224,15 @@ class FedEngine:
             from .cnn2_native import Cnn2Workspace
             self.ws = Cnn2Workspace(self.C, self.cfg.shard, device=self.device, heap=heap, wave=self.cfg.wave)
             self._g0 = CNN2.init(self.cfg.seed)
+        elif self.cfg.model == "resnet18":
+            from .resnet_native import ResNetWorkspace
+            self.ws = ResNetWorkspace(self.C, self.cfg.shard, self.spec, device=self.device, heap=heap, wave=self.cfg.wave,
+                                      groups=int(self.cfg.model_kwargs.get("groups", 2)))
+            self._g0 = self.ws.L.pack(self.spec.init(self.cfg.seed))
+        elif self.cfg.model == "bert_mini":
+            from .bert_native import BertWorkspace
+            self.ws = BertWorkspace(self.C, self.cfg.shard, self.spec, device=self.device, heap=heap, wave=self.cfg.wave)
+            self._g0 = self.ws.L.pack(self.spec.init(self.cfg.seed))
         else:
             from .mlp_native import MlpLayout, MlpWorkspace
             ws_ = [shape for name, shape in self.spec.shapes if name.endswith(".weight")]        # fc1 .. fcN
@@ -324,6 +336,8 @@ class FedEngine:
                 ws.master[cid - self.c0].fill_(float("nan"))             # poisoned replica: must be masked by the reduce
                 if hasattr(ws, "master_bf16"):
                     ws.master_bf16[cid - self.c0].fill_(float("nan"))
+                elif hasattr(ws, "wb"):
+                    ws.wb[cid - self.c0].fill_(float("nan"))
                 elif hasattr(ws, "w1_fwd"):
                     ws.w1_fwd[cid - self.c0].fill_(float("nan"))
         with self.timer.phase("local_steps"):
@@ -525,8 +539,8 @@ class FedEngine:
             self.x, self.y = x, self.host_y.to(self.device, non_blocking=True)
             return nbytes
         if self.cfg.model != "cnn2":
-            self.ws.x.copy_(self.host_x.to(self.device, non_blocking=True).reshape(self.ws.x.shape))
-            self.ws.labels.copy_(self.host_y.to(self.device, non_blocking=True))
+            # MLP: bf16 cast; ResNet-18: uint8 -> stem im2col operand; BERT-mini: int32 token ids
+            self.ws.load_data(self.host_x.to(self.device, non_blocking=True), self.host_y.to(self.device, non_blocking=True))
             return nbytes
         if not hasattr(self, "_stage_x"):
             self._copy_stream = torch.cuda.Stream(device=self.device)

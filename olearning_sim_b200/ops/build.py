@@ -16,13 +16,13 @@ HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
 LIB = HERE / "_olsb200_kernels.so"
 STAMP = HERE / "_olsb200_kernels.stamp"
-SOURCES = ["api.cu"]
-HEADERS = ["tc05.cuh", "conv_tc.cuh", "fl_kernels.cuh", "linear_tc.cuh"]
+SOURCES = ["api.cu", "api_nn.cu"]
+HEADERS = ["tc05.cuh", "conv_tc.cuh", "fl_kernels.cuh", "linear_tc.cuh", "bgemm_tc.cuh", "nn_kernels.cuh"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",
-    "--shared", "-Xcompiler", "-fPIC",
+    "--shared", "-Xcompiler", "-fPIC", "--threads", "2",
     "-diag-suppress", "177",
 ]
 

@@ -656,13 +656,15 @@ int olsb_client_xent(int C, int batch, int classes, int ld, const void* active, 
 }
 
 int olsb_bcast_scatter_generic(const void* const* global_peers, int nranks, int shard_len, int P, void* global_local,
-                               void* master, void* master_bf16, int C, const void* participate, void* stream) {
+                               void* master, void* master_bf16, int C, const void* participate, int P_bf16,
+                               long long bf16_stride, void* stream) {
   if (int r = olsb_init()) return r;
   lintc::BcastGenericParams p;
   memset(&p, 0, sizeof(p));
   for (int i = 0; i < nranks && i < 8; ++i) p.global_peers[i] = const_cast<void*>(global_peers[i]);
   p.nranks = nranks; p.shard_len = shard_len; p.P = P; p.global_local = (float*)global_local; p.master = (float*)master;
   p.master_bf16 = (__nv_bfloat16*)master_bf16; p.num_clients = C; p.participate = (const uint8_t*)participate;
+  p.P_bf16 = P_bf16 > 0 ? P_bf16 : P; p.bf16_stride = bf16_stride > 0 ? bf16_stride : P;
   const int th = 256, gx = (P / 4 + th - 1) / th;
   int gy = (4 * g_sms + gx - 1) / gx; if (gy > C) gy = C; if (gy < 1) gy = 1;
   lintc::bcast_scatter_generic_kernel<<<dim3(gx, gy), th, 0, (cudaStream_t)stream>>>(p);

@@ -1,0 +1,460 @@
+// bgemm_tc.cuh — batched ("grouped over clients") tcgen05 GEMM / implicit-GEMM convolution family.
+//
+//     D_b[M, N] = sum_k A_b[M, k] * B_b[N, k]          b = client, or (client, sample, head) for attention
+//
+// One persistent warp-specialised kernel (TMA warp, MMA warp, 4 epilogue warps, TMEM double buffering, NSTAGE-deep
+// shared-memory ring) is instantiated over
+//   * the A loader:  A_K     K-major rows straight from a row-major tensor                      (activations, dY)
+//                    A_MN    MN-major (the tensor is read "transposed" by the tensor core)      (dY^T, P^T, dS^T)
+//                    A_CONV  K-major 128-pixel window of an NHWC activation tensor, one TMA box per (tap, 64-channel
+//                            chunk); padding = TMA out-of-bounds zero fill, stride 2 = TMA elementStrides
+//   * the B loader:  B_K     K-major (torch Linear weight [out][in], conv weight [cout][tap][cin])
+//                    B_MN    MN-major (W read transposed for data gradients, V / K / Q / X for attention / wgrad)
+//                    B_WT    MN-major conv weight for the data gradient: box (64 cin, 1 tap, 64 cout) of the forward copy
+//                    B_CONVX MN-major 64-pixel window of the conv input for the weight gradient; every 64-column block
+//                            of the N tile is its own (tap, cin-chunk) so one MMA accumulates several taps at once
+//   * the epilogue:  E_STORE    bf16 row-major store (+ per-column bias, + addend tensor, ReLU / GELU / GELU-backward)
+//                    E_GNSTAT   store + GroupNorm statistics (sum, sum of squares per image and group, fp32 atomics)
+//                    E_SOFTMAX  row softmax of the 128-wide score tile (a thread owns a whole accumulator row)
+//                    E_DSOFT    softmax backward  dS = P o (dP - rowsum(dP o P)) * scale
+//                    E_SGD      weight gradient -> SGD / FedProx step on the fp32 master + bf16 operand copy
+// This is the per-client training step of the ResNet-18 and BERT-mini families (BASELINE configs 3 and 5): the role
+// of the reference's per-phone subprocess (ols_core/taskMgr/utils/utils_run_task.py:481-514).
+#pragma once
+#include "tc05.cuh"
+
+namespace bg {
+using namespace tc05;
+
+constexpr int kThreads = 192;
+constexpr int kEpiWarps = 4;
+constexpr int KC = 64;                 // K elements per pipeline stage (one 128-byte swizzle row)
+enum { A_K = 0, A_MN = 1, A_CONV = 2 };
+enum { B_K = 0, B_MN = 1, B_CONVX = 2, B_WT = 3 };
+enum { E_STORE = 0, E_GNSTAT = 1, E_SOFTMAX = 2, E_DSOFT = 3, E_SGD = 4 };
+enum { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2, ACT_GELU_BWD = 3 };
+
+struct Bars {
+  uint64_t full[8];
+  uint64_t empty[8];
+  uint64_t tfull[2];
+  uint64_t tempty[2];
+  uint32_t tmem_base;
+  uint32_t pad;
+};
+
+// Plain-old-data; mirrored field by field by ops/bgemm.py (ctypes).  Keep the order in sync.
+struct Params {
+  int batches, M, N, m_tiles, n_tiles, k_chunks;
+  const uint8_t* active; int act_div;          // work of batch bi is skipped unless active[bi / act_div]
+  int a_bdiv, b_bdiv;                          // > 0: 4-D operand map, outer coordinates (bi % bdiv, bi / bdiv)
+  // ---- convolution geometry -------------------------------------------------------------------------
+  int tw_log, th_log;                          // an M tile = 2^tw_log x 2^th_log pixels x (128 >> (tw_log+th_log)) images
+  int tiles_x, tiles_y;                        // tiles per image
+  int imgs;                                    // images per batch entry (samples per client)
+  int src_stride;                              // window step in the source tensor (= elementStrides of its map)
+  int src_cimgs, src_img0;                     // source image index = bi * src_cimgs + src_img0 + image (data shards hold
+                                               // more samples per client than one batch)
+  int cchunks, ntaps, ktap;                    // 64-channel chunks per tap; taps; K elements per tap of the weight operand
+  int tap_dy[9], tap_dx[9], tap_w[9];          // window offset (source pixels) and weight tap index of every tap
+  int kb_h, kb_n, kb_cpi;                      // B_CONVX: a 64-pixel K chunk = full rows x kb_h x kb_n images; chunks / image
+  int nblocks, cin;                            // B_CONVX: valid 64-column blocks (taps * cchunks); source channels
+  // ---- epilogue -------------------------------------------------------------------------------------
+  __nv_bfloat16* out; long long o_bs1, o_bs0; int o_bdiv; int ld;
+  int out_conv, os, py, px, OW, OH;            // out_conv: rows are pixels; output pixel = tile pixel * os + (py, px)
+  const float* bias; long long bias_bs; int bias_div;
+  const __nv_bfloat16* addend;
+  int act; const __nv_bfloat16* aux_in; __nv_bfloat16* aux_out;
+  float scale;
+  float* gn_stats; int gn_groups, gn_cpg;      // [batches * imgs][groups][2]; channels per group
+  float* w_master; long long w_bs; int w_ld; const float* w_global; __nv_bfloat16* w_bf16; long long wb_bs;
+  float* grad_out; long long g_bs; float lr, mu;
+};
+
+template <int AM, int BM, int N_TILE, int NSTAGE>
+struct Cfg {
+  static constexpr int A_BYTES = 128 * 128;                       // 128 rows x 64 bf16 (either major)
+  static constexpr int B_BYTES = (BM == B_K) ? N_TILE * 128 : (N_TILE / 64) * KC * 128;
+  static constexpr int STAGE_BYTES = A_BYTES + ((B_BYTES + 1023) / 1024) * 1024;
+  static constexpr int TMEM_COLS = (2 * N_TILE <= 32) ? 32 : (2 * N_TILE <= 64 ? 64 : (2 * N_TILE <= 128 ? 128 : (2 * N_TILE <= 256 ? 256 : 512)));
+  static constexpr int SMEM_BYTES = 1024 + NSTAGE * STAGE_BYTES + (int)sizeof(Bars);
+  static_assert(N_TILE % 32 == 0 && N_TILE <= 256, "epilogue works on 32-column chunks");
+  static_assert(BM == B_K || N_TILE % 64 == 0, "MN-major B is loaded in 64-column boxes");
+  static_assert(NSTAGE <= 8, "barrier arrays hold 8 stages");
+  static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+};
+
+__device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float gelu_grad_f(float x) {
+  return 0.5f * (1.f + erff(x * 0.70710678118654752f)) + x * 0.39894228040143268f * __expf(-0.5f * x * x);
+}
+__device__ __forceinline__ void unpack8(const uint4& u, float* f) {
+  f[0] = bf16lo(u.x); f[1] = bf16hi(u.x); f[2] = bf16lo(u.y); f[3] = bf16hi(u.y);
+  f[4] = bf16lo(u.z); f[5] = bf16hi(u.z); f[6] = bf16lo(u.w); f[7] = bf16hi(u.w);
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+  uint4 u;
+  u.x = pack_bf16x2(f[0], f[1]); u.y = pack_bf16x2(f[2], f[3]); u.z = pack_bf16x2(f[4], f[5]); u.w = pack_bf16x2(f[6], f[7]);
+  return u;
+}
+// 32 consecutive bf16 (64 bytes, 16-byte aligned) <-> registers
+__device__ __forceinline__ void load32(const __nv_bfloat16* p, float* f) {
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { const uint4 u = q[i]; unpack8(u, f + 8 * i); }
+}
+__device__ __forceinline__ void store32(__nv_bfloat16* p, const float* f) {
+  uint4* q = reinterpret_cast<uint4*>(p);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) q[i] = pack8(f + 8 * i);
+}
+
+struct TileCoord {
+  int bi, mt, nt, m0, n0, img0, ty0, tx0;
+};
+
+template <int AM, int N_TILE>
+__device__ __forceinline__ bool decode_work(const Params& p, int wi, TileCoord& t) {
+  const int tpc = p.m_tiles * p.n_tiles;
+  t.bi = wi / tpc;
+  const int r = wi - t.bi * tpc;
+  t.mt = r / p.n_tiles;
+  t.nt = r - t.mt * p.n_tiles;
+  t.m0 = t.mt * 128;
+  t.n0 = t.nt * N_TILE;
+  if (p.active && !p.active[t.bi / p.act_div]) return false;
+  if (AM == A_CONV || p.out_conv) {
+    const int tpi = p.tiles_x * p.tiles_y;
+    const int tn = 128 >> (p.tw_log + p.th_log);
+    const int ti = t.mt / tpi, rem = t.mt - ti * tpi;
+    t.img0 = ti * tn;
+    t.ty0 = (rem / p.tiles_x) << p.th_log;
+    t.tx0 = (rem % p.tiles_x) << p.tw_log;
+  } else {
+    t.img0 = t.ty0 = t.tx0 = 0;
+  }
+  return true;
+}
+
+template <int AM, int BM, int N_TILE, int EPI, int NSTAGE>
+__global__ void __launch_bounds__(kThreads, 1)
+bgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+             const __grid_constant__ Params p) {
+  using C = Cfg<AM, BM, N_TILE, NSTAGE>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  Bars* bars = reinterpret_cast<Bars*>(smem + NSTAGE * C::STAGE_BYTES);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NSTAGE; ++i) { mbar_init(&bars->full[i], 1); mbar_init(&bars->empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&bars->tfull[i], 1); mbar_init(&bars->tempty[i], kEpiWarps); }
+    fence_mbar_init();
+  }
+  if (warp == 5) { tmem_alloc(&bars->tmem_base, C::TMEM_COLS); tmem_relinquish(); }
+  if (warp == 4 && lane == 0) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = bars->tmem_base;
+  const int num_work = p.batches * p.m_tiles * p.n_tiles;
+
+  if (warp == 4) {
+    // ================================================================ TMA producer
+    const bool leader = elect_one();
+    int stage = 0; uint32_t phase = 0;
+    for (int wi = blockIdx.x; wi < num_work; wi += gridDim.x) {
+      TileCoord t;
+      if (!decode_work<AM, N_TILE>(p, wi, t)) continue;
+      for (int kc = 0; kc < p.k_chunks; ++kc) {
+        mbar_wait(&bars->empty[stage], phase ^ 1);
+        if (leader) {
+          uint8_t* a_dst = smem + stage * C::STAGE_BYTES;
+          uint8_t* b_dst = a_dst + C::A_BYTES;
+          uint64_t* bar = &bars->full[stage];
+          mbar_arrive_expect_tx(bar, C::A_BYTES + C::B_BYTES);
+          int tap = 0, ch0 = 0;
+          if (AM == A_CONV) { tap = kc / p.cchunks; ch0 = (kc - tap * p.cchunks) * 64; }
+          // ---- A
+          if (AM == A_K) {
+            if (p.a_bdiv) tma_load_4d(a_dst, &tmA, bar, kc * KC, t.m0, t.bi % p.a_bdiv, t.bi / p.a_bdiv);
+            else tma_load_3d(a_dst, &tmA, bar, kc * KC, t.m0, t.bi);
+          } else if (AM == A_MN) {
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              if (p.a_bdiv) tma_load_4d(a_dst + j * KC * 128, &tmA, bar, t.m0 + 64 * j, kc * KC, t.bi % p.a_bdiv, t.bi / p.a_bdiv);
+              else tma_load_3d(a_dst + j * KC * 128, &tmA, bar, t.m0 + 64 * j, kc * KC, t.bi);
+            }
+          } else {
+            tma_load_4d(a_dst, &tmA, bar, ch0, t.tx0 * p.src_stride + p.tap_dx[tap], t.ty0 * p.src_stride + p.tap_dy[tap],
+                        t.bi * p.src_cimgs + p.src_img0 + t.img0);
+          }
+          // ---- B
+          if (BM == B_K) {
+            const int kb = (AM == A_CONV) ? p.tap_w[tap] * p.ktap + ch0 : kc * KC;
+            if (p.b_bdiv) tma_load_4d(b_dst, &tmB, bar, kb, t.n0, t.bi % p.b_bdiv, t.bi / p.b_bdiv);
+            else tma_load_3d(b_dst, &tmB, bar, kb, t.n0, t.bi);
+          } else if (BM == B_MN) {
+#pragma unroll
+            for (int j = 0; j < N_TILE / 64; ++j) {
+              if (p.b_bdiv) tma_load_4d(b_dst + j * KC * 128, &tmB, bar, t.n0 + 64 * j, kc * KC, t.bi % p.b_bdiv, t.bi / p.b_bdiv);
+              else tma_load_3d(b_dst + j * KC * 128, &tmB, bar, t.n0 + 64 * j, kc * KC, t.bi);
+            }
+          } else if (BM == B_WT) {
+#pragma unroll
+            for (int j = 0; j < N_TILE / 64; ++j)
+              tma_load_4d(b_dst + j * KC * 128, &tmB, bar, t.n0 + 64 * j, p.tap_w[tap], ch0, t.bi);
+          } else {  // B_CONVX
+            const int ci = kc / p.kb_cpi;
+            const int img = ci * p.kb_n, y0 = (kc - ci * p.kb_cpi) * p.kb_h;
+#pragma unroll
+            for (int j = 0; j < N_TILE / 64; ++j) {
+              const int blk = t.nt * (N_TILE / 64) + j;
+              int tp = blk / p.cchunks;
+              int c0 = (blk - tp * p.cchunks) * 64;
+              if (blk >= p.nblocks) { tp = 0; c0 = p.cin + 64; }           // padding block: out of bounds -> zeros
+              tma_load_4d(b_dst + j * KC * 128, &tmB, bar, c0, p.tap_dx[tp], y0 * p.src_stride + p.tap_dy[tp],
+                          t.bi * p.src_cimgs + p.src_img0 + img);
+            }
+          }
+        }
+        if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 5) {
+    // ================================================================ MMA issuer
+    const bool leader = elect_one();
+    constexpr uint32_t IDESC = make_idesc_bf16(128, N_TILE, AM == A_MN ? 1 : 0, BM == B_K ? 0 : 1);
+    const uint32_t sbase = smem_u32(smem);
+    const uint64_t a_desc0 = (AM == A_MN) ? make_smem_desc(sbase, KC * 128, 1024, LT_SW128) : make_smem_desc(sbase, 16, 1024, LT_SW128);
+    const uint64_t b_desc0 = (BM != B_K) ? make_smem_desc(sbase + C::A_BYTES, KC * 128, 1024, LT_SW128)
+                                         : make_smem_desc(sbase + C::A_BYTES, 16, 1024, LT_SW128);
+    constexpr uint32_t A_STEP = (AM == A_MN) ? 2048 : 32, B_STEP = (BM != B_K) ? 2048 : 32;
+    int stage = 0; uint32_t phase = 0; int buf = 0; uint32_t tphase0 = 0, tphase1 = 0;
+    for (int wi = blockIdx.x; wi < num_work; wi += gridDim.x) {
+      TileCoord t;
+      if (!decode_work<AM, N_TILE>(p, wi, t)) continue;
+      mbar_wait(&bars->tempty[buf], (buf ? tphase1 : tphase0) ^ 1);
+      fence_after_sync();
+      const uint32_t d_tmem = tmem_base + buf * N_TILE;
+      for (int kc = 0; kc < p.k_chunks; ++kc) {
+        mbar_wait(&bars->full[stage], phase);
+        fence_after_sync();
+        if (leader) {
+          const uint64_t a_s = desc_advance(a_desc0, stage * C::STAGE_BYTES);
+          const uint64_t b_s = desc_advance(b_desc0, stage * C::STAGE_BYTES);
+#pragma unroll
+          for (int ks = 0; ks < KC / 16; ++ks)
+            umma_bf16(d_tmem, desc_advance(a_s, ks * A_STEP), desc_advance(b_s, ks * B_STEP), IDESC, (kc | ks) ? 1u : 0u);
+          umma_commit(&bars->empty[stage]);
+        }
+        __syncwarp();
+        if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+      }
+      if (leader) umma_commit(&bars->tfull[buf]);
+      __syncwarp();
+      if (buf) tphase1 ^= 1; else tphase0 ^= 1;
+      buf ^= 1;
+    }
+  } else {
+    // ================================================================ epilogue (4 warps, one accumulator row per thread)
+    int buf = 0; uint32_t tphase0 = 0, tphase1 = 0;
+    const int q = warp;
+    for (int wi = blockIdx.x; wi < num_work; wi += gridDim.x) {
+      TileCoord t;
+      if (!decode_work<AM, N_TILE>(p, wi, t)) continue;
+      const int row = 32 * q + lane;
+      const int m = t.m0 + row;
+      const bool rvalid = m < p.M;
+      // ---- output row base
+      size_t obase;
+      int gimg = 0;
+      if (p.out_conv) {
+        const int tx = row & ((1 << p.tw_log) - 1), ty = (row >> p.tw_log) & ((1 << p.th_log) - 1);
+        const int tn = row >> (p.tw_log + p.th_log);
+        const int y = (t.ty0 + ty) * p.os + p.py, x = (t.tx0 + tx) * p.os + p.px;
+        gimg = t.bi * p.imgs + t.img0 + tn;
+        obase = ((size_t)gimg * p.OH * p.OW + (size_t)y * p.OW + x) * p.ld;
+      } else {
+        obase = (size_t)(t.bi / p.o_bdiv) * p.o_bs1 + (size_t)(t.bi % p.o_bdiv) * p.o_bs0 + (size_t)m * p.ld;
+      }
+      mbar_wait(&bars->tfull[buf], buf ? tphase1 : tphase0);
+      fence_after_sync();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(32 * q) << 16) + buf * N_TILE;
+
+      if (EPI == E_STORE || EPI == E_GNSTAT) {
+        float gs = 0.f, gq = 0.f;
+        int gcur = -1;
+        const int rows_per_img = 1 << (p.tw_log + p.th_log);
+        auto flush = [&](int g) {
+          // reduce over the rows of one image held by this warp (whole warp, or 16-lane halves for 4x4 images)
+          if (rows_per_img >= 32) {
+#pragma unroll
+            for (int o = 16; o; o >>= 1) { gs += __shfl_xor_sync(0xffffffffu, gs, o); gq += __shfl_xor_sync(0xffffffffu, gq, o); }
+            if (lane == 0) {
+              float* st = p.gn_stats + ((size_t)gimg * p.gn_groups + g) * 2;
+              atomicAdd(st, gs); atomicAdd(st + 1, gq);
+            }
+          } else {
+#pragma unroll
+            for (int o = 8; o; o >>= 1) { gs += __shfl_xor_sync(0xffffffffu, gs, o); gq += __shfl_xor_sync(0xffffffffu, gq, o); }
+            if ((lane & 15) == 0) {
+              float* st = p.gn_stats + ((size_t)gimg * p.gn_groups + g) * 2;
+              atomicAdd(st, gs); atomicAdd(st + 1, gq);
+            }
+          }
+          gs = gq = 0.f;
+        };
+#pragma unroll 1
+        for (int j = 0; j < N_TILE / 32; ++j) {
+          const int nb = t.n0 + j * 32;
+          if (nb >= p.N) break;                         // warp-uniform
+          uint32_t v[32];
+          tmem_ld32(taddr + j * 32, v);
+          tmem_ld_wait();
+          float f[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+          if (EPI == E_GNSTAT) {
+            const int g = nb / p.gn_cpg;
+            if (g != gcur) { if (gcur >= 0) flush(gcur); gcur = g; }
+#pragma unroll
+            for (int i = 0; i < 32; ++i) { gs += f[i]; gq += f[i] * f[i]; }
+          }
+          if (EPI == E_STORE) {
+            if (p.bias) {
+              const float4* bp = reinterpret_cast<const float4*>(p.bias + (size_t)(t.bi / p.bias_div) * p.bias_bs + nb);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) { const float4 b = __ldg(bp + i); f[4 * i] += b.x; f[4 * i + 1] += b.y; f[4 * i + 2] += b.z; f[4 * i + 3] += b.w; }
+            }
+            if (p.addend && rvalid) {
+              float a[32];
+              load32(p.addend + obase + nb, a);
+#pragma unroll
+              for (int i = 0; i < 32; ++i) f[i] += a[i];
+            }
+            if (p.act == ACT_RELU) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
+            } else if (p.act == ACT_GELU) {
+              if (rvalid && p.aux_out) store32(p.aux_out + obase + nb, f);
+#pragma unroll
+              for (int i = 0; i < 32; ++i) f[i] = gelu_f(f[i]);
+            } else if (p.act == ACT_GELU_BWD) {
+              float a[32];
+              if (rvalid) load32(p.aux_in + obase + nb, a);
+#pragma unroll
+              for (int i = 0; i < 32; ++i) f[i] = rvalid ? f[i] * gelu_grad_f(a[i]) : 0.f;
+            }
+          }
+          if (rvalid) store32(p.out + obase + nb, f);
+        }
+        if (EPI == E_GNSTAT && gcur >= 0) flush(gcur);
+      } else if (EPI == E_SOFTMAX) {
+        // scores tile: N_TILE == N; softmax over the row this thread owns (three passes over TMEM)
+        const float sc = p.scale * 1.4426950408889634f;
+        float mx = -3.0e38f;
+#pragma unroll 1
+        for (int j = 0; j < N_TILE / 32; ++j) {
+          uint32_t v[32];
+          tmem_ld32(taddr + j * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+        }
+        float sum = 0.f;
+#pragma unroll 1
+        for (int j = 0; j < N_TILE / 32; ++j) {
+          uint32_t v[32];
+          tmem_ld32(taddr + j * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) sum += exp2f((__uint_as_float(v[i]) - mx) * sc);
+        }
+        const float inv = 1.f / sum;
+#pragma unroll 1
+        for (int j = 0; j < N_TILE / 32; ++j) {
+          uint32_t v[32];
+          tmem_ld32(taddr + j * 32, v);
+          tmem_ld_wait();
+          float f[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) f[i] = exp2f((__uint_as_float(v[i]) - mx) * sc) * inv;
+          if (rvalid) store32(p.out + obase + t.n0 + j * 32, f);
+        }
+      } else if (EPI == E_DSOFT) {
+        float dot = 0.f;
+#pragma unroll 1
+        for (int j = 0; j < N_TILE / 32; ++j) {
+          uint32_t v[32];
+          tmem_ld32(taddr + j * 32, v);
+          tmem_ld_wait();
+          float a[32];
+          if (rvalid) load32(p.aux_in + obase + t.n0 + j * 32, a);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) dot += rvalid ? __uint_as_float(v[i]) * a[i] : 0.f;
+        }
+#pragma unroll 1
+        for (int j = 0; j < N_TILE / 32; ++j) {
+          uint32_t v[32];
+          tmem_ld32(taddr + j * 32, v);
+          tmem_ld_wait();
+          float a[32], f[32];
+          if (rvalid) load32(p.aux_in + obase + t.n0 + j * 32, a);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) f[i] = rvalid ? a[i] * (__uint_as_float(v[i]) - dot) * p.scale : 0.f;
+          if (rvalid) store32(p.out + obase + t.n0 + j * 32, f);
+        }
+      } else {  // E_SGD: W[b][m][n] -= lr * (g + mu (w - w_global)), bf16 operand copy refreshed in the same pass
+#pragma unroll 1
+        for (int j = 0; j < N_TILE / 32; ++j) {
+          const int nb = t.n0 + j * 32;
+          if (nb >= p.N) break;
+          uint32_t v[32];
+          tmem_ld32(taddr + j * 32, v);
+          tmem_ld_wait();
+          if (rvalid && p.grad_out) {
+            float4* gp = reinterpret_cast<float4*>(p.grad_out + (size_t)t.bi * p.g_bs + (size_t)m * p.w_ld + nb);
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              gp[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+          } else if (rvalid) {
+            float4* wp = reinterpret_cast<float4*>(p.w_master + (size_t)t.bi * p.w_bs + (size_t)m * p.w_ld + nb);
+            float4 wv[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) wv[i] = wp[i];                                    // all loads before any store
+            float w[32];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { w[4 * i] = wv[i].x; w[4 * i + 1] = wv[i].y; w[4 * i + 2] = wv[i].z; w[4 * i + 3] = wv[i].w; }
+            if (p.w_global) {
+              const float4* ap = reinterpret_cast<const float4*>(p.w_global + (size_t)m * p.w_ld + nb);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float4 a = __ldg(ap + i);
+                w[4 * i] -= p.lr * (__uint_as_float(v[4 * i]) + p.mu * (w[4 * i] - a.x));
+                w[4 * i + 1] -= p.lr * (__uint_as_float(v[4 * i + 1]) + p.mu * (w[4 * i + 1] - a.y));
+                w[4 * i + 2] -= p.lr * (__uint_as_float(v[4 * i + 2]) + p.mu * (w[4 * i + 2] - a.z));
+                w[4 * i + 3] -= p.lr * (__uint_as_float(v[4 * i + 3]) + p.mu * (w[4 * i + 3] - a.w));
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) w[i] -= p.lr * __uint_as_float(v[i]);
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) wp[i] = make_float4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+            store32(p.w_bf16 + (size_t)t.bi * p.wb_bs + (size_t)m * p.w_ld + nb, w);
+          }
+        }
+      }
+      fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->tempty[buf]);
+      if (buf) tphase1 ^= 1; else tphase0 ^= 1;
+      buf ^= 1;
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 5) tmem_dealloc(tmem_base, C::TMEM_COLS);
+}
+
+}  // namespace bg

@@ -315,6 +315,7 @@ __global__ void client_xent_kernel(const XentParams p) {
 struct BcastGenericParams {
   void* global_peers[8]; int nranks, shard_len, P;
   float* global_local; float* master; __nv_bfloat16* master_bf16; int num_clients; const uint8_t* participate;
+  int P_bf16; long long bf16_stride;     // the bf16 operand copy covers elements [0, P_bf16) of every row
 };
 __global__ void bcast_scatter_generic_kernel(const BcastGenericParams p) {
   const int i4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
@@ -328,7 +329,7 @@ __global__ void bcast_scatter_generic_kernel(const BcastGenericParams p) {
   for (int c = blockIdx.y; c < p.num_clients; c += gridDim.y) {
     if (p.participate && !p.participate[c]) continue;
     *reinterpret_cast<float4*>(p.master + (size_t)c * p.P + i4) = v;
-    if (p.master_bf16) *reinterpret_cast<uint2*>(p.master_bf16 + (size_t)c * p.P + i4) = o;
+    if (p.master_bf16 && i4 < p.P_bf16) *reinterpret_cast<uint2*>(p.master_bf16 + (size_t)c * p.bf16_stride + i4) = o;
   }
 }
 

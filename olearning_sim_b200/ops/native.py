@@ -261,11 +261,13 @@ def client_xent(num_clients, batch, classes, ld, active, logits, labels, label_o
 
 
 def bcast_scatter_generic(global_peer_ptrs: Sequence[int], shard_len: int, P: int, global_local, master, master_bf16,
-                          participate) -> None:
+                          participate, p_bf16: int = 0, bf16_stride: int = 0) -> None:
+    """``p_bf16`` / ``bf16_stride``: the bf16 operand copy holds only the leading ``p_bf16`` elements of every row
+    (the tensor-core operands), rows ``bf16_stride`` apart; 0 = the whole row."""
     n = len(global_peer_ptrs)
     _ck(require().olsb_bcast_scatter_generic(_ptr_array(global_peer_ptrs), C.c_int(n), C.c_int(shard_len), C.c_int(P),
                                              _p(global_local), _p(master), _p(master_bf16), C.c_int(master.shape[0]),
-                                             _p(participate), _stream()))
+                                             _p(participate), C.c_int(p_bf16), C.c_longlong(bf16_stride), _stream()))
 
 
 assert CNN2.P % 4 == 0
