@@ -125,10 +125,11 @@ class SubprocessJobExecutor(JobExecutor):
         self._lock = threading.Lock()
         os.makedirs(self.workdir, exist_ok=True)
 
-    def _launch(self, job_id: str, path: str, nproc: int, attempt: int):
-        with self._lock:
-            port = self._port
-            self._port += 1
+    def _launch(self, job_id: str, path: str, nproc: int, attempt: int, port: Optional[int] = None):
+        if port is None:
+            with self._lock:
+                port = self._port
+                self._port += 1
         if nproc > 1:
             cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}",
                    "--master-addr", "127.0.0.1", "--master-port", str(port), "-m",
@@ -141,35 +142,62 @@ class SubprocessJobExecutor(JobExecutor):
         env = dict(os.environ, **(self.env or {}))
         return subprocess.Popen(cmd, stdout=log, stderr=subprocess.STDOUT, start_new_session=True, env=env), log.name
 
+    @staticmethod
+    def _json_context(context: Optional[Dict[str, Any]]) -> Dict[str, Any]:
+        """The context crosses a process boundary as JSON: live objects the in-process executor hands to the runner
+        (the task repo, the DeviceFlow service) are dropped — the child re-opens the repo from ``repo_path`` and talks
+        to DeviceFlow through its own client."""
+        out: Dict[str, Any] = {}
+        for k, v in (context or {}).items():
+            try:
+                json.dumps(v)
+            except (TypeError, ValueError):
+                continue
+            out[k] = v
+        return out
+
     def submit_job(self, task_json, context=None) -> str:
         job_id = f"job_{uuid.uuid4().hex[:12]}"
         path = os.path.join(self.workdir, f"{job_id}.json")
+        ctx = self._json_context(context)
+        if self.repo_path is not None or "repo_path" not in ctx:
+            ctx["repo_path"] = self.repo_path
+        # ranks = GPUs granted by the ResourceManager (context["gpus"]) capped by the executor's configured width
+        granted = ctx.get("gpus")
+        nproc = max(1, min(int(granted), self.nproc)) if isinstance(granted, (int, float)) and granted else self.nproc
         with open(path, "w") as f:
-            json.dump({"task": task_json, "context": {**(context or {}), "repo_path": self.repo_path}}, f)
-        proc, logname = self._launch(job_id, path, self.nproc, 0)
+            json.dump({"task": task_json, "context": ctx}, f)
+        proc, logname = self._launch(job_id, path, nproc, 0)
         with self._lock:
-            self._jobs[job_id] = {"proc": proc, "stopped": False, "log": logname, "path": path, "nproc": self.nproc,
+            self._jobs[job_id] = {"proc": proc, "stopped": False, "log": logname, "path": path, "nproc": nproc,
                                   "restarts": 0}
         return job_id
 
     def get_job_status(self, job_id: str) -> str:
+        # poll + relaunch decision + process swap are one critical section: the reaper thread and a getTaskStatus RPC
+        # may observe the same dead process group, and only one of them may start its replacement
         with self._lock:
             rec = self._jobs.get(job_id)
-        if rec is None:
-            raise KeyError(job_id)
-        rc = rec["proc"].poll()
-        if rc is None:
-            return JobStatus.RUNNING
-        if rec["stopped"]:
-            return JobStatus.STOPPED
-        if rc != 0 and rec["restarts"] < self.max_restarts:
+            if rec is None:
+                raise KeyError(job_id)
+            rc = rec["proc"].poll()
+            if rc is None:
+                return JobStatus.RUNNING
+            if rec["stopped"]:
+                return JobStatus.STOPPED
+            if rc == 0:
+                return JobStatus.SUCCEEDED
+            if rec["restarts"] >= self.max_restarts:
+                return JobStatus.FAILED
             # elastic recovery: relaunch from the last checkpoint, optionally without the lost rank
             rec["restarts"] += 1
             if self.shrink and rec["nproc"] > 1:
                 rec["nproc"] -= 1
-            rec["proc"], _ = self._launch(job_id, rec["path"], rec["nproc"], rec["restarts"])
+            attempt, nproc, path = rec["restarts"], rec["nproc"], rec["path"]
+            port = self._port
+            self._port += 1
+            rec["proc"], _ = self._launch(job_id, path, nproc, attempt, port=port)
             return JobStatus.RUNNING
-        return JobStatus.SUCCEEDED if rc == 0 else JobStatus.FAILED
 
     def get_job_error(self, job_id: str) -> str:
         with self._lock:

@@ -199,27 +199,27 @@ class RoundRunner:
                 classes += [f"{d.get('name', '')}/{dev}"] * int(n)
         fields = {k: v for k, v in cfgd.items() if k in FedConfig.__dataclass_fields__}
         fields["num_clients"] = len(classes)
+        # DeviceFlow: the operator's dispatch strategy decides which client updates reach the aggregator (reference:
+        # run_task.py:233-281 injects the inbound endpoint so every update traverses sorter -> shelf -> dispatcher)
+        bc = operator.get("operation_behavior_controller", {}) or {}
+        if bc.get("use_gradient_house") and bc.get("strategy_gradient_house") and not fields.get("deviceflow_strategy"):
+            fields["deviceflow_strategy"] = bc["strategy_gradient_house"]
         cfg = FedConfig(**fields)
         eng = FedEngine(cfg, self.rank, self.world)
         eng.client_class = classes
         # device classes -> heterogeneity (stragglers / availability), e.g. {"Low": {"local_steps": 2, "p_online": 0.8}}
-        dc = cfgd.get("device_classes", {})
-        if dc:
-            import numpy as np
-            steps = eng.local_steps_np.copy()
-            pon = np.full(eng.C, cfg.p_online, np.float32)
-            for i in range(eng.C):
-                dev = classes[eng.c0 + i].split("/", 1)[1]
-                if dev in dc:
-                    steps[i] = min(int(dc[dev].get("local_steps", steps[i])), cfg.local_steps)
-                    pon[i] = float(dc[dev].get("p_online", pon[i]))
-            eng.local_steps_np = steps
-            eng.cfg.hetero_steps = bool((steps != cfg.local_steps).any()) or cfg.hetero_steps
-            eng.cfg.p_online = float(pon.min()) if (pon < 1).any() else cfg.p_online
-            if eng.uses_ws:
-                import torch
-                eng.local_steps_t = torch.from_numpy(steps).to(eng.device)
-                eng.p_online_t = torch.from_numpy(pon).to(eng.device)
+        import numpy as np
+        dc = cfgd.get("device_classes", {}) or {}
+        steps = np.full(len(classes), cfg.local_steps, np.int32)
+        steps[eng.c0:eng.c1] = eng.local_steps_np
+        pon = np.full(len(classes), cfg.p_online, np.float32)
+        for i, cname in enumerate(classes):
+            dev = cname.split("/", 1)[1]
+            if dev in dc:
+                steps[i] = min(int(dc[dev].get("local_steps", steps[i])), cfg.local_steps)
+                pon[i] = float(dc[dev].get("p_online", pon[i]))
+        if classes:
+            eng.set_client_classes(classes, p_online=pon, local_steps=steps if (dc or cfg.hetero_steps) else None)
         # data: the task's datasets with the reference's shard contract (client i owns sub-folder i when
         # data_split_type is true); datasets without a data_path use the synthetic non-IID generator
         dsets = [{"name": d.get("name", ""), "data_path": d.get("data_path", ""), "data_split_type": d.get("data_split_type", False),
@@ -305,6 +305,7 @@ class RoundRunner:
     def _run_builtin(self, operator: Dict[str, Any], round_idx: int) -> List[Dict[str, Any]]:
         eng = self._builtin_engine(operator)
         kind = parse_builtin(operator.get("logical_simulation", {}).get("operator_code_path", ""))
+        class_failed: Dict[str, int] = {}
         if getattr(eng, "resume_round", 0) > round_idx:
             res_failed = 0                                  # round already done before the restart
         elif kind == "evaluate":
@@ -325,20 +326,30 @@ class RoundRunner:
                                                     "t_round_ms": res.wall_s * 1e3, "client_steps": res.client_steps,
                                                     "phases_ms": res.extras.get("phases_ms", {})})
             res_failed = res.failed
+            class_failed = res.extras.get("class_failed", {})
+            if "class_participants" in res.extras:
+                rec["class_participants"], rec["class_failed"] = res.extras["class_participants"], class_failed
+            rec["late"] = res.late
+            self._df_report(operator, round_idx, res)
             published = self._export_model(operator, eng, round_idx)
             if published:
                 rec["model_file"] = published
             if getattr(eng, "ckpt", None) is not None:
                 eng.ckpt.save(round_idx, {"engine": eng.state_dict(), "round": round_idx})
         # per (dataset, class) accounting: a client "fails" only if its computation failed (non-finite update);
-        # offline / dropped-in-flight clients behaved as the trace prescribed and count as successes.
+        # offline / dropped-in-flight clients behaved as the trace prescribed and count as successes.  The per-class
+        # failure counts are reduced on the device with the rest of the round record (round_stats_kernel).
         out: Dict[Tuple[str, str], List[int]] = {}
         for d in self.params.data:
             st = d.get("simulation_target", {})
             for dev, n in zip(st.get("devices", []), st.get("nums", [])):
                 out[(d.get("name", ""), dev)] = [int(n), 0]
-        if res_failed:
-            # attribute failures to classes (rank-local flags are reduced inside the engine for the total only)
+        for cname, nf in (class_failed or {}).items():
+            key = tuple(cname.split("/", 1))
+            if key in out and nf:
+                out[key][0] -= min(int(nf), out[key][0])
+                out[key][1] += int(nf)
+        if res_failed and not class_failed and out:            # engine without class labels: job-wide count only
             key = next(iter(out))
             out[key][0] -= min(res_failed, out[key][0])
             out[key][1] += res_failed

@@ -227,20 +227,44 @@ class Strategy:
                 carry = tmp
         return out
 
-    def _get_interval_params(self, total: int, intervals, domains, functions, drop: Dict[str, Any]) -> Schedule:
+    @staticmethod
+    def interval_samples(interval: List[int], domain: List[float], func: str) -> np.ndarray:
+        """f sampled at the 101 trapezoid nodes of every 1-second bin: float64 [bins, 101] — the input of the on-device
+        integrator (``rate_curve_area_kernel``), which reproduces ``interval_areas`` bit for bit."""
+        f = safe_expr.compile_expr(func)
+        t_int = list(range(interval[0], interval[1] + 1))
+        length, dlen = interval[1] - interval[0], domain[1] - domain[0]
+        t_dom = [domain[0] + dlen / length * (t - t_int[0]) for t in t_int]
+        out = np.empty((len(t_dom) - 1, AREA_CALCULATION_NUM + 1), np.float64)
+        for i in range(len(t_dom) - 1):
+            ts = np.linspace(t_dom[i], t_dom[i + 1], num=AREA_CALCULATION_NUM + 1).tolist()
+            out[i] = [f(t) for t in ts]
+        return out
+
+    def _interval_sends(self, total: int, intervals, domains, functions,
+                        area_fn: Optional[Callable[[np.ndarray], np.ndarray]] = None):
+        """deterministic part of the rate-curve analysis: per-second send counts of every interval"""
         t_list, area_list = [], []
         for iv, dom, fn in zip(intervals, domains, functions):
-            t, a = self.interval_areas(iv, dom, fn)
+            if area_fn is None:
+                t, a = self.interval_areas(iv, dom, fn)
+            else:
+                t = list(range(iv[0], iv[1]))
+                a = [float(v) for v in area_fn(self.interval_samples(iv, dom, fn))]
             t_list.append(t)
             area_list.append(a)
         totals = [sum(a) for a in area_list]
         total_area = sum(totals)
         if total_area <= 0:
-            return _EMPTY
+            return None
         amounts = [round(t / total_area * total) for t in totals]
         amounts[-1] = total - sum(amounts[:-1])
         sends = [self.diffuse([a / totals[i] * amounts[i] for a in area_list[i]]) if totals[i] > 0
                  else [0] * len(area_list[i]) for i in range(len(amounts))]
+        return t_list, sends
+
+    def _interval_finish(self, t_list, sends, drop: Dict[str, Any]) -> Schedule:
+        """random part: expand the per-interval drop rule to per-second slots and draw the drop lists"""
         drop = copy.deepcopy(drop)
         if "drop_probability" in drop:
             dp = drop.get("drop_probability", [])
@@ -271,6 +295,65 @@ class Strategy:
         timing = [origin[0]] + [origin[i] - origin[i - 1] for i in range(1, len(origin))]
         drops = self._generate_drop_simulation_list(amount, drop) if drop else [[] for _ in amount]
         return timing, amount, drops
+
+    def _get_interval_params(self, total: int, intervals, domains, functions, drop: Dict[str, Any]) -> Schedule:
+        det = self._interval_sends(total, intervals, domains, functions)
+        if det is None:
+            return _EMPTY
+        return self._interval_finish(det[0], det[1], drop)
+
+    # ---- per-task plan: parse + integrate once, draw drops per round --------------------------------------
+    @staticmethod
+    def is_round_invariant(strategy: Any) -> bool:
+        """True for relative-time flow strategies: slots and amounts are the same in every round."""
+        fd = _loads(strategy).get("flow_dispatch", {})
+        st, si = fd.get("specific_timing", {}), fd.get("specific_interval", {})
+        sec = st if st.get("use", False) else si
+        return bool(fd.get("use_strategy", False)) and sec.get("time_type", "relative") == "relative"
+
+    @staticmethod
+    def flow_plan(strategy: Any, flow_id: str = "plan_x_0",
+                  area_fn: Optional[Callable[[np.ndarray], np.ndarray]] = None) -> Dict[str, Any]:
+        """Round-invariant part of a relative-time flow strategy ({"timing", "amount", ...}); ``area_fn`` integrates the
+        rate-curve samples (the GPU engine passes the on-device integrator).  ``draw_drops`` adds the per-round part; the
+        pair reproduces ``flow_strategy_analysis`` exactly, including the order in which the RNG is consumed."""
+        fd = _loads(strategy).get("flow_dispatch", {})
+        empty = {"kind": "empty", "timing": [], "amount": []}
+        total = fd.get("total_dispatch_amount", 0)
+        st, si = fd.get("specific_timing", {}), fd.get("specific_interval", {})
+        use_t, use_i = bool(st.get("use", False)), bool(si.get("use", False))
+        if not fd.get("use_strategy", False) or total <= 0 or use_t == use_i:
+            return empty
+        s = Strategy()
+        if use_t:
+            timing, amount = list(st.get("timings", [])), [int(a) for a in st.get("amounts", [])]
+            drop = st.get("drop_simulation", {})
+            if len(timing) != len(amount) or not timing or (drop and len(drop) != 1):
+                return empty
+            return {"kind": "timing", "timing": timing, "amount": amount, "drop": copy.deepcopy(drop)}
+        intervals = si.get("intervals", [])
+        rules = si.get("dispatch_rules", {})
+        domains, functions = rules.get("domains", []), rules.get("functions", [])
+        drop = si.get("drop_simulation", {})
+        if len(intervals) != len(domains) or len(domains) != len(functions) or not intervals or (drop and len(drop) != 1):
+            return empty
+        det = s._interval_sends(total, intervals, domains, functions, area_fn)
+        if det is None:
+            return empty
+        t_list, sends = det
+        origin = [t for ts in t_list for t in ts]
+        return {"kind": "interval", "t_list": t_list, "sends": sends, "drop": copy.deepcopy(drop),
+                "amount": [n for el in sends for n in el],
+                "timing": [origin[0]] + [origin[i] - origin[i - 1] for i in range(1, len(origin))]}
+
+    @staticmethod
+    def draw_drops(plan: Dict[str, Any], rng: Optional[random.Random] = None) -> List[List[int]]:
+        s = Strategy(rng)
+        if plan["kind"] == "timing":
+            return s._generate_drop_simulation_list(plan["amount"], plan["drop"]) if plan["drop"] else [[] for _ in plan["amount"]]
+        if plan["kind"] == "interval":
+            return s._interval_finish(plan["t_list"], plan["sends"], plan["drop"])[2]
+        return []
 
 
 # --------------------------------------------------------------------------------------------------------

@@ -83,9 +83,9 @@ class Cnn2Workspace:
         h.alloc("wsum", max(self.groups, 64) * 4)
         h.alloc("flags", 256)
         h.alloc("round", 256)
-        self.round_rec = h.tensor("round", f32, (8,))
+        self.round_rec = h.tensor("round", f32, (native.ROUND_REC,))
         self.round_rec.zero_()
-        self.round_out = torch.zeros(8, dtype=f32, device=d)
+        self.round_out = torch.zeros(native.ROUND_REC, dtype=f32, device=d)
         self.global_w = h.tensor("global", f32, (P,))
         self.partial = h.tensor("partial", f32, (self.groups, P))
         self.wsum = h.tensor("wsum", f32, (self.groups,))
@@ -158,9 +158,10 @@ class Cnn2Workspace:
         """FedAvg reduce (masked, weighted) + server optimiser; publishes the new global shard to all peers."""
         if accounting is not None:
             # (participate, step_active, counters, local_steps): 8-float record, summed over ranks by the finish kernel
-            part, step_active, counters, nsteps = accounting
+            part, step_active, counters, nsteps = accounting[:4]
+            class_id, nclass = (accounting[4], accounting[5]) if len(accounting) > 4 else (None, 0)
             native.round_stats(self.loss_sum, self.nonfinite, part, step_active, counters, self.C, step_active.shape[0],
-                               1.0 / nsteps, self.round_rec)
+                               1.0 / nsteps, self.round_rec, class_id, nclass)
         native.fedavg_partial(self.master, self.global_local, weight, self.nonfinite, self.groups, self.partial,
                               self.wsum)
         self.epoch += 1
@@ -170,7 +171,8 @@ class Cnn2Workspace:
                              hb["flags"].peer_ptrs if self.world > 1 else None, self.rank, self.groups, self.P,
                              self.shard_len, self.epoch, self.global_w, self.opt_m, self.opt_v,
                              OPT_CODES[opt], server_lr, beta1, beta2, eps, self.server_step, self.stats,
-                             self.arrive_ctr, hb["round"].peer_ptrs if accounting is not None else None, self.round_out)
+                             self.arrive_ctr, hb["round"].peer_ptrs if accounting is not None else None, self.round_out,
+                             8 + 2 * (accounting[5] if accounting is not None and len(accounting) > 4 else 0))
         self.kernel_launches += 2 + (accounting is not None)
 
     def reset_round_stats(self) -> None:

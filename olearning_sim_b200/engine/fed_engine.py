@@ -121,6 +121,11 @@ def synthetic_client_data(model: str, client_ids: np.ndarray, shard: int, seed: 
     return xs, labels
 
 
+def native_round_rec() -> int:
+    from ..ops.native import ROUND_REC
+    return ROUND_REC
+
+
 def merge_opt_shards(parts: List[torch.Tensor], num_params: int) -> torch.Tensor:
     """Concatenate equal-length rank shards and cut the tail padding: the full [P] optimiser-state vector."""
     return torch.cat([p.reshape(-1) for p in parts])[:num_params].clone()
@@ -172,6 +177,12 @@ class FedEngine:
             else np.full(cfg.num_clients, cfg.local_steps, np.int32)
         self.local_steps_np = all_steps[self.c0:self.c1]
         self.n_samples_np = np.full(self.C, cfg.shard, np.int32)
+        # single source of truth for availability: one probability per GLOBAL client (every rank holds the full vector so
+        # the flow schedule, which orders all participants, is computed identically everywhere)
+        self.p_online_np = np.full(cfg.num_clients, cfg.p_online, np.float32)
+        self.class_names: List[str] = []
+        self.class_of_client = np.zeros(cfg.num_clients, np.int32)
+        self._flow_cache: Dict[str, Any] = {}
         if backend == "native":
             self._init_native()
         elif backend == "hybrid":
@@ -182,6 +193,58 @@ class FedEngine:
     # ==================================================================================================
     # DeviceFlow -> per-round masks
     # ==================================================================================================
+    def set_client_classes(self, classes: List[str], p_online: Optional[np.ndarray] = None,
+                           local_steps: Optional[np.ndarray] = None) -> None:
+        """Per-client (dataset, device class) labels in global client order, with optional per-client online
+        probabilities / local-step budgets (device classes -> heterogeneity).  Drives the per-class success / failed
+        accounting of every round (reference: run_task.py:149-210)."""
+        assert len(classes) == self.cfg.num_clients
+        names: List[str] = []
+        idx = np.empty(len(classes), np.int32)
+        for i, c in enumerate(classes):
+            if c not in names:
+                names.append(c)
+            idx[i] = names.index(c)
+        self.class_names, self.class_of_client = names, idx
+        if p_online is not None:
+            self.p_online_np = np.asarray(p_online, np.float32).copy()
+        if local_steps is not None:
+            steps = np.minimum(np.asarray(local_steps, np.int32), self.cfg.local_steps)
+            self.local_steps_np = steps[self.c0:self.c1].copy()
+            self.cfg.hetero_steps = bool((steps != self.cfg.local_steps).any()) or self.cfg.hetero_steps
+        if self.uses_ws:
+            d = self.device
+            self.local_steps_t = torch.from_numpy(self.local_steps_np).to(d)
+            self.p_online_t = torch.from_numpy(self.p_online_np[self.c0:self.c1].copy()).to(d)
+            self.class_id_t = torch.from_numpy(idx[self.c0:self.c1].copy()).to(d)
+
+    def _flow_schedule(self, round_idx: int):
+        """(amounts per slot, drop lists) of the operator's flow strategy for this round.  Relative-time strategies do
+        not depend on the round: the JSON is parsed and the rate curves integrated ONCE per task (on the GPU through
+        ``rate_curve_area_kernel`` when the workspace backend is active); only the drop draws are per round."""
+        import random as _random
+        from ..deviceflow.strategy import Strategy
+        st = self.cfg.deviceflow_strategy
+        rng = _random.Random(f"{self.cfg.seed}:{round_idx}")
+        flow_id = f"engine_train_{round_idx}"
+        if not Strategy.is_round_invariant(st):
+            _, amount, drops = Strategy.flow_strategy_analysis(st, flow_id, rng=rng)
+            return amount, drops
+        plan = self._flow_cache.get("plan")
+        if plan is None:
+            area_fn = None
+            if self.uses_ws:
+                from ..ops import native
+
+                def area_fn(y):                      # y: float64 [bins, 101] samples of the rate function
+                    yt = torch.from_numpy(np.ascontiguousarray(y, np.float64)).to(self.device)
+                    out = torch.empty(y.shape[0], dtype=torch.float64, device=self.device)
+                    native.rate_curve_area(yt, out)
+                    return out.cpu().numpy()
+            plan = Strategy.flow_plan(st, flow_id, area_fn=area_fn)
+            self._flow_cache["plan"] = plan
+        return plan["amount"], Strategy.draw_drops(plan, rng)
+
     def _round_flow(self, round_idx: int):
         """(p_online_scale, drop_probability, arrive_tick[C_local] | None, max_tick) for this round.
         Flow strategies: the k-th *finishing* participant (order = Philox stream 2) is message k on the shelf; the
@@ -193,19 +256,15 @@ class FedEngine:
             scale = float(min(max(safe_expr.evaluate(cfg.online_trace, float(round_idx)), 0.0), 1.0))
         drop_p, ticks, max_tick = cfg.drop_probability, None, 0
         if cfg.deviceflow_strategy:
-            import json as _json
-            import random as _random
             from ..deviceflow.strategy import Strategy, schedule_to_ticks
             st = cfg.deviceflow_strategy
             if Strategy.check_real_time_dispatch(st):
                 _, drop_p = Strategy.real_time_strategy_analysis(st)
             else:
-                flow_id = f"engine_train_{round_idx}"
-                _, amount, drops = Strategy.flow_strategy_analysis(st, flow_id, rng=_random.Random(f"{cfg.seed}:{round_idx}"))
+                amount, drops = self._flow_schedule(round_idx)
                 n = cfg.num_clients
                 u = philox.round_uniforms(n, 0, cfg.seed, round_idx)
-                pon = np.full(n, cfg.p_online * scale, np.float32)
-                part = u[0] < pon
+                part = u[0] < self.p_online_np * scale
                 order = np.argsort(np.where(part, u[2], 2.0), kind="stable")        # finishing order of participants
                 slot_of_msg = schedule_to_ticks(amount, drops, int(part.sum()))
                 t_all = np.full(n, -1, np.int32)
@@ -241,8 +300,9 @@ class FedEngine:
             self._g0 = lay.pack(self.spec.init(self.cfg.seed))
         d = self.device
         S = self.cfg.local_steps
-        self.p_online_t = torch.full((self.C,), float(self.cfg.p_online), device=d)
+        self.p_online_t = torch.from_numpy(self.p_online_np[self.c0:self.c1].copy()).to(d)
         self.p_online_round = self.p_online_t.clone()
+        self.class_id_t = torch.zeros(self.C, dtype=torch.int32, device=d)
         self.tick_host = torch.zeros(self.C, dtype=torch.int32).pin_memory()
         self.tick_dev = torch.zeros(self.C, dtype=torch.int32, device=d)
         self.local_steps_t = torch.from_numpy(self.local_steps_np).to(d)
@@ -250,7 +310,7 @@ class FedEngine:
         self.step_active = torch.ones(S, self.C, dtype=torch.uint8, device=d)
         self.agg_weight = torch.zeros(self.C, device=d)
         self.counters = torch.zeros(4, dtype=torch.int32, device=d)
-        self.result_host = torch.zeros(8).pin_memory()
+        self.result_host = torch.zeros(native_round_rec()).pin_memory()
         self.ws.set_global(self._g0)
         self.P = self.ws.P
         self._graphs: Dict[bool, Any] = {}
@@ -267,8 +327,9 @@ class FedEngine:
         self.ws.n_samples = torch.full((self.C,), self.cfg.shard, dtype=torch.int32, device=self.device)
         self._g0 = self.spec.init(self.cfg.seed)
         d, S = self.device, self.cfg.local_steps
-        self.p_online_t = torch.full((self.C,), float(self.cfg.p_online), device=d)
+        self.p_online_t = torch.from_numpy(self.p_online_np[self.c0:self.c1].copy()).to(d)
         self.p_online_round = self.p_online_t.clone()
+        self.class_id_t = torch.zeros(self.C, dtype=torch.int32, device=d)
         self.tick_host = torch.zeros(self.C, dtype=torch.int32).pin_memory()
         self.tick_dev = torch.zeros(self.C, dtype=torch.int32, device=d)
         self.local_steps_t = torch.from_numpy(self.local_steps_np).to(d)
@@ -276,7 +337,7 @@ class FedEngine:
         self.step_active = torch.ones(S, self.C, dtype=torch.uint8, device=d)
         self.agg_weight = torch.zeros(self.C, device=d)
         self.counters = torch.zeros(4, dtype=torch.int32, device=d)
-        self.result_host = torch.zeros(8).pin_memory()
+        self.result_host = torch.zeros(native_round_rec()).pin_memory()
         self.ws.set_global(self._g0)
         self._graphs, self._graph_ok, self._graph_warm, self.graph_error = {}, False, False, None
         self.x = self.y = None
@@ -316,7 +377,7 @@ class FedEngine:
         cfg, ws = self.cfg, self.ws
         ws.reset_round_stats()
         scale, drop_p, ticks, max_tick = self._round_flow(round_idx)
-        sampled = cfg.p_online * scale < 1.0
+        sampled = bool(self.p_online_np.size and float(self.p_online_np.min()) * scale < 1.0)
         if sampled:
             self.p_online_round.copy_(self.p_online_t).mul_(scale)
         tick_t = None
@@ -347,7 +408,8 @@ class FedEngine:
                 self._local_steps(need_mask)
         with self.timer.phase("reduce_update"):
             ws.reduce_and_update(self.agg_weight, opt=cfg.server_opt, server_lr=cfg.server_lr,
-                                 accounting=(self.participate, self.step_active, self.counters, cfg.local_steps))
+                                 accounting=(self.participate, self.step_active, self.counters, cfg.local_steps,
+                                             self.class_id_t if self.class_names else None, len(self.class_names)))
 
     def _local_steps(self, need_mask: bool) -> None:
         """The S x (6 kernels x waves) local-step block.  Every kernel argument of the block is round-invariant (buffer
@@ -389,9 +451,13 @@ class FedEngine:
         torch.cuda.current_stream().synchronize()
         vals = self.result_host.tolist()
         part_n = int(vals[1])
-        return RoundResult(round=round_idx, participants=int(vals[2]), dropped=int(vals[3]), late=int(vals[4]),
-                           arrived=int(vals[5]), failed=int(vals[6]),
-                           loss=float(vals[0] / max(part_n, 1)), client_steps=int(vals[7]))
+        res = RoundResult(round=round_idx, participants=int(vals[2]), dropped=int(vals[3]), late=int(vals[4]),
+                          arrived=int(vals[5]), failed=int(vals[6]),
+                          loss=float(vals[0] / max(part_n, 1)), client_steps=int(vals[7]))
+        if self.class_names:
+            res.extras["class_failed"] = {n: int(vals[8 + 2 * k]) for k, n in enumerate(self.class_names)}
+            res.extras["class_participants"] = {n: int(vals[9 + 2 * k]) for k, n in enumerate(self.class_names)}
+        return res
 
     # ==================================================================================================
     # generic torch backend (CPU/gloo or CUDA; library path)
@@ -409,7 +475,12 @@ class FedEngine:
         self.y = None
         spec = self.spec
 
+        amp = self.cfg.amp_bf16 and d.type == "cuda"
+
         def loss_fn(flat, x, y):
+            if amp:           # library arm at the product's precision: bf16 tensor-core compute, fp32 masters / loss
+                with torch.autocast("cuda", dtype=torch.bfloat16):
+                    return spec.loss(flat, x, y).float()
             return spec.loss(flat, x, y)
 
         from torch.func import grad_and_value
@@ -422,9 +493,9 @@ class FedEngine:
     def _torch_round(self, round_idx: int) -> RoundResult:
         cfg = self.cfg
         scale, drop_p, ticks, max_tick = self._round_flow(round_idx)
-        sampled = cfg.p_online * scale < 1.0
+        sampled = bool(self.p_online_np.size and float(self.p_online_np.min()) * scale < 1.0)
         m = philox.round_mask(self.C, self.c0, cfg.seed, round_idx,
-                              np.full(self.C, cfg.p_online * scale, np.float32) if sampled else None,
+                              (self.p_online_np[self.c0:self.c1] * np.float32(scale)).astype(np.float32) if sampled else None,
                               drop_p, ticks, max_tick, self.n_samples_np,
                               self.local_steps_np if cfg.hetero_steps else None, cfg.local_steps)
         d = self.device
@@ -464,9 +535,19 @@ class FedEngine:
         self.global_w = reference.server_update(self.global_w, pack[:-1], float(pack[-1]), cfg.server_opt,
                                                 self.server_state, cfg.server_lr)
         n = max(int(stats[1]), 1)
-        return RoundResult(round=round_idx, participants=int(stats[2]), dropped=int(stats[3]), late=int(stats[4]),
-                           arrived=int(stats[5]), failed=int(stats[6]), loss=float(stats[0]) / n,
-                           client_steps=int(stats[7]))
+        res = RoundResult(round=round_idx, participants=int(stats[2]), dropped=int(stats[3]), late=int(stats[4]),
+                          arrived=int(stats[5]), failed=int(stats[6]), loss=float(stats[0]) / n,
+                          client_steps=int(stats[7]))
+        if self.class_names:
+            K = len(self.class_names)
+            cls = torch.from_numpy(self.class_of_client[self.c0:self.c1].astype(np.int64)).to(d)
+            cnt = torch.stack([torch.bincount(cls[~finite], minlength=K), torch.bincount(cls[part], minlength=K)]).double()
+            if self.world > 1:
+                dist.all_reduce(cnt, group=self.group)
+            cnt = cnt.cpu()
+            res.extras["class_failed"] = {nm: int(cnt[0, k]) for k, nm in enumerate(self.class_names)}
+            res.extras["class_participants"] = {nm: int(cnt[1, k]) for k, nm in enumerate(self.class_names)}
+        return res
 
     # ==================================================================================================
     # public API
@@ -584,7 +665,7 @@ class FedEngine:
             res.extras["phases_ms_min"] = dict(self.timer.last_min)
         if stream_inputs:
             res.extras["h2d_bytes"] = h2d
-            res.extras["d2h_bytes"] = 32 if self.uses_ws else 64
+            res.extras["d2h_bytes"] = 4 * native_round_rec() if self.uses_ws else 64
         self.round_log.append(res)
         return res
 

@@ -97,9 +97,9 @@ class MlpWorkspace:
         hp = self.heap
         hp.alloc("global", P * 4); hp.alloc("partial", self.groups * P * 4); hp.alloc("wsum", 64 * 4); hp.alloc("flags", 256)
         hp.alloc("round", 256)
-        self.round_rec = hp.tensor("round", f32, (8,))
+        self.round_rec = hp.tensor("round", f32, (native.ROUND_REC,))
         self.round_rec.zero_()
-        self.round_out = torch.zeros(8, dtype=f32, device=d)
+        self.round_out = torch.zeros(native.ROUND_REC, dtype=f32, device=d)
         self.global_w = hp.tensor("global", f32, (P,))
         self.partial = hp.tensor("partial", f32, (self.groups, P))
         self.wsum = hp.tensor("wsum", f32, (self.groups,))
@@ -181,9 +181,10 @@ class MlpWorkspace:
                           beta2: float = 0.99, eps: float = 1e-3, accounting=None) -> None:
         if accounting is not None:
             # (participate, step_active, counters, local_steps): 8-float record, summed over ranks by the finish kernel
-            part, step_active, counters, nsteps = accounting
+            part, step_active, counters, nsteps = accounting[:4]
+            class_id, nclass = (accounting[4], accounting[5]) if len(accounting) > 4 else (None, 0)
             native.round_stats(self.loss_sum, self.nonfinite, part, step_active, counters, self.C, step_active.shape[0],
-                               1.0 / nsteps, self.round_rec)
+                               1.0 / nsteps, self.round_rec, class_id, nclass)
         native.fedavg_partial(self.master, self.global_local, weight, self.nonfinite, self.groups, self.partial, self.wsum)
         self.epoch += 1
         self.server_step += 1
@@ -191,7 +192,8 @@ class MlpWorkspace:
         native.fedavg_finish(hb["partial"].peer_ptrs, hb["wsum"].peer_ptrs, hb["flags"].peer_ptrs if self.world > 1 else None,
                              self.rank, self.groups, self.P, self.shard_len, self.epoch, self.global_w, self.opt_m,
                              self.opt_v, OPT_CODES[opt], server_lr, beta1, beta2, eps, self.server_step, self.stats,
-                             self.arrive_ctr, hb["round"].peer_ptrs if accounting is not None else None, self.round_out)
+                             self.arrive_ctr, hb["round"].peer_ptrs if accounting is not None else None, self.round_out,
+                             8 + 2 * (accounting[5] if accounting is not None and len(accounting) > 4 else 0))
         self.kernel_launches += 2 + (accounting is not None)
 
     def reset_round_stats(self) -> None:

@@ -187,6 +187,7 @@ int olsb_init() {
   return set_attrs();
 }
 int olsb_num_sms() { return g_sms; }
+int olsb_round_record_len() { return flk::kRoundRec; }
 int olsb_cnn2_param_count() { return Cnn2Layout::P; }
 int olsb_cnn2_batch() { return BATCH; }
 
@@ -447,7 +448,8 @@ int olsb_fedavg_partial(const void* master, const void* global_w, const void* we
 int olsb_fedavg_finish(const void* const* partial_peers, const void* const* wsum_peers, const void* const* flag_peers,
                        int nranks, int rank, int groups, int P, int shard_len, unsigned epoch, void* global_w,
                        void* opt_m, void* opt_v, int opt, float server_lr, float beta1, float beta2, float eps, int step,
-                       void* stats, void* arrive_ctr, const void* const* round_peers, void* round_out, void* stream) {
+                       void* stats, void* arrive_ctr, const void* const* round_peers, void* round_out, int round_len,
+                       void* stream) {
   if (int r = olsb_init()) return r;
   flk::FinishParams p;
   memset(&p, 0, sizeof(p));
@@ -463,6 +465,7 @@ int olsb_fedavg_finish(const void* const* partial_peers, const void* const* wsum
   if (round_peers && round_out) {
     for (int i = 0; i < nranks && i < flk::kMaxPeers; ++i) p.round_peers.p[i] = const_cast<void*>(round_peers[i]);
     p.round_out = (float*)round_out;
+    p.round_len = round_len > 0 ? (round_len < flk::kRoundRec ? round_len : flk::kRoundRec) : 8;
   }
   CK(cudaMemsetAsync(arrive_ctr, 0, 2 * sizeof(uint32_t), (cudaStream_t)stream));
   CK(cudaMemsetAsync(stats, 0, 4 * sizeof(float), (cudaStream_t)stream));
@@ -486,10 +489,12 @@ int olsb_set_option(const char* name, int value) {
 }
 
 int olsb_round_stats(const void* loss_sum, const void* nonfinite, const void* participate, const void* step_active,
-                     const void* counters, int C, int S, float inv_steps, void* out, void* stream) {
+                     const void* counters, int C, int S, float inv_steps, void* out, const void* class_id, int nclass,
+                     void* stream) {
   flk::round_stats_kernel<<<1, 512, 0, (cudaStream_t)stream>>>((const float*)loss_sum, (const int*)nonfinite,
                                                                (const uint8_t*)participate, (const uint8_t*)step_active,
-                                                               (const int*)counters, C, S, inv_steps, (float*)out);
+                                                               (const int*)counters, C, S, inv_steps, (float*)out,
+                                                               (const int*)class_id, nclass);
   CK(cudaGetLastError());
   return 0;
 }
@@ -511,7 +516,7 @@ int olsb_deviceflow_mask(int C, int client_base, unsigned long long seed, unsign
 }
 
 int olsb_rate_curve_area(const void* y, void* area, int bins, void* stream) {
-  flk::rate_curve_area_kernel<<<(bins + 127) / 128, 128, 0, (cudaStream_t)stream>>>((const float*)y, (float*)area,
+  flk::rate_curve_area_kernel<<<(bins + 127) / 128, 128, 0, (cudaStream_t)stream>>>((const double*)y, (double*)area,
                                                                                       bins);
   CK(cudaGetLastError());
   return 0;

@@ -497,8 +497,9 @@ struct FinishParams {
   int step;                 // Adam step (1-based)
   float* stats;             // [4]: total weight, |delta|^2 of owned shard, participants(unused), spare
   uint32_t* arrive_ctr;     // [2] zero-initialised scratch for the intra-grid barriers
-  PeerPtrs round_peers;     // float* [8] per rank: this round's local accounting (round_stats_kernel) or null
-  float* round_out;         // [8] sum over ranks of round_peers (every rank gets the job-wide numbers)
+  PeerPtrs round_peers;     // float* [round_len] per rank: this round's local accounting (round_stats_kernel) or null
+  float* round_out;         // [round_len] sum over ranks of round_peers (every rank gets the job-wide numbers)
+  int round_len;            // 8 (+ 2 per device class)
 };
 
 __device__ __forceinline__ void grid_gate(uint32_t* ctr, uint32_t nblocks) {
@@ -572,7 +573,7 @@ __global__ void fedavg_finish_kernel(const FinishParams p) {
   if ((threadIdx.x & 31) == 0 && dn != 0.f) atomicAdd(&p.stats[1], dn);
   if (blockIdx.x == 0 && threadIdx.x == 0) p.stats[0] = wtot;
   // job-wide round accounting: sum the 8-float records of all ranks (they were complete before the entry barrier)
-  if (blockIdx.x == 0 && threadIdx.x < 8 && p.round_out) {
+  if (blockIdx.x == 0 && (int)threadIdx.x < p.round_len && p.round_out) {
     float a = 0.f;
     for (int r = 0; r < p.nranks; ++r) a += static_cast<const float*>(p.round_peers.p[r])[threadIdx.x];
     p.round_out[threadIdx.x] = a;
@@ -590,16 +591,31 @@ __global__ void fedavg_finish_kernel(const FinishParams p) {
 // 8-float record: [masked loss sum / local_steps, finite participants, counters[0..3], non-finite clients,
 // client-steps executed].  fedavg_finish_kernel then adds the records of all ranks.
 // ---------------------------------------------------------------------------------------------
+// With `class_id` (one small integer per client = its (dataset, device class) index) the record is followed by
+// 2 floats per class: [failed_k, participants_k] — the per-class success / failed numbers the task status is computed
+// from (ols_core/taskMgr/run_task.py:164-197, task_manager.py:739-754).
+constexpr int kMaxClasses = 24;
+constexpr int kRoundRec = 8 + 2 * kMaxClasses;      // floats per rank record
 __global__ void round_stats_kernel(const float* __restrict__ loss_sum, const int* __restrict__ nonfinite,
                                    const uint8_t* __restrict__ participate, const uint8_t* __restrict__ step_active,
                                    const int* __restrict__ counters, int C, int S, float inv_steps,
-                                   float* __restrict__ out) {
+                                   float* __restrict__ out, const int* __restrict__ class_id, int nclass) {
   float loss = 0.f, ok = 0.f, bad = 0.f, steps = 0.f;
+  __shared__ float s_cls[2 * kMaxClasses];
+  for (int i = threadIdx.x; i < 2 * kMaxClasses; i += blockDim.x) s_cls[i] = 0.f;
+  __syncthreads();
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     const bool nf = nonfinite[c] != 0;
     const bool part = participate[c] != 0;
     if (part && !nf) { loss += loss_sum[c]; ok += 1.f; }
     if (nf) bad += 1.f;
+    if (class_id) {
+      const int k = class_id[c];
+      if (k >= 0 && k < nclass && k < kMaxClasses) {
+        if (nf) atomicAdd(&s_cls[2 * k], 1.f);
+        if (part) atomicAdd(&s_cls[2 * k + 1], 1.f);
+      }
+    }
   }
   for (int i = threadIdx.x; i < C * S; i += blockDim.x) steps += step_active[i] ? 1.f : 0.f;
   __shared__ float red[4][32];
@@ -619,6 +635,7 @@ __global__ void round_stats_kernel(const float* __restrict__ loss_sum, const int
     out[slot] = threadIdx.x == 0 ? x * inv_steps : x;
   }
   if (threadIdx.x >= 4 && threadIdx.x < 8) out[threadIdx.x - 2] = (float)counters[threadIdx.x - 4];
+  if (threadIdx.x < 2 * kMaxClasses) out[8 + threadIdx.x] = s_cls[threadIdx.x];
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -680,17 +697,20 @@ __global__ void deviceflow_mask_kernel(const MaskParams p) {
   if (arrived) atomicAdd(&p.counters[3], 1);
 }
 
-// Rate-curve integration (DeviceFlow specific_interval): area of max(f,0)-clipped trapezoids per 1-second bin.
-// `y` holds f sampled at 101 points per bin (bins*100+1 samples are NOT shared between bins to match the
-// reference's per-bin linspace exactly).  out[b] = sum_j 0.5*(y[j]+y[j-1])/100 over segments with positive area.
-__global__ void rate_curve_area_kernel(const float* __restrict__ y, float* __restrict__ area, int bins) {
+// Rate-curve integration (DeviceFlow specific_interval, ols_core/deviceflow/non_grpc/strategy.py:339-349): area of the
+// positive trapezoids of every 1-second bin.  `y` holds f sampled at the 101 nodes of each bin (nodes are NOT shared
+// between bins, matching the reference's per-bin linspace).  Double precision with explicitly rounded operations in the
+// python loop's order (no FMA contraction), so the result is bit-identical to Strategy.interval_areas on the host and a
+// schedule derived from it is the same on CPU and GPU.
+__global__ void rate_curve_area_kernel(const double* __restrict__ y, double* __restrict__ area, int bins) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= bins) return;
-  const float* yy = y + (size_t)b * 101;
-  float a = 0.f;
+  const double* yy = y + (size_t)b * 101;
+  double a = 0.0;
+  const double w = 1.0 / 100.0;
   for (int j = 1; j <= 100; ++j) {
-    const float s = 0.5f * (yy[j] + yy[j - 1]) * 0.01f;
-    if (s > 0.f) a += s;
+    const double s = __dmul_rn(__dmul_rn(0.5, __dadd_rn(yy[j], yy[j - 1])), w);
+    if (s > 0.0) a = __dadd_rn(a, s);
   }
   area[b] = a;
 }

@@ -158,7 +158,7 @@ def fedavg_partial(master, global_w, weight, nonfinite, groups: int, partial, ws
 
 def fedavg_finish(partial_peer_ptrs, wsum_peer_ptrs, flag_peer_ptrs, rank: int, groups: int, P: int, shard_len: int,
                   epoch: int, global_w, opt_m, opt_v, opt: int, server_lr: float, beta1: float, beta2: float,
-                  eps: float, step: int, stats, arrive_ctr, round_peer_ptrs=None, round_out=None) -> None:
+                  eps: float, step: int, stats, arrive_ctr, round_peer_ptrs=None, round_out=None, round_len: int = 8) -> None:
     n = len(partial_peer_ptrs)
     flags = _ptr_array(flag_peer_ptrs) if flag_peer_ptrs is not None else None
     rnd = _ptr_array(round_peer_ptrs) if round_peer_ptrs is not None else None
@@ -167,7 +167,7 @@ def fedavg_finish(partial_peer_ptrs, wsum_peer_ptrs, flag_peer_ptrs, rank: int, 
                                      C.c_uint(epoch), _p(global_w), _p(opt_m), _p(opt_v), C.c_int(opt),
                                      C.c_float(server_lr), C.c_float(beta1), C.c_float(beta2), C.c_float(eps),
                                      C.c_int(step), _p(stats), _p(arrive_ctr), rnd,
-                                     _p(round_out) if rnd is not None else None, _stream()))
+                                     _p(round_out) if rnd is not None else None, C.c_int(round_len), _stream()))
 
 
 def set_option(name: str, value: int) -> int:
@@ -178,11 +178,16 @@ def set_option(name: str, value: int) -> int:
     return int(old)
 
 
+ROUND_REC = 56        # floats per rank record: 8 job-wide + 2 per (dataset, device class), up to 24 classes
+
+
 def round_stats(loss_sum, nonfinite, participate, step_active, counters, num_clients: int, steps: int, inv_steps: float,
-                out) -> None:
-    """8-float per-rank round record: [loss, finite participants, counters[0..3], non-finite clients, client-steps]"""
+                out, class_id=None, nclass: int = 0) -> None:
+    """Per-rank round record: [loss, finite participants, counters[0..3], non-finite clients, client-steps] followed by
+    [failed_k, participants_k] for every device class k (``class_id``: int32 class index per local client)."""
     _ck(require().olsb_round_stats(_p(loss_sum), _p(nonfinite), _p(participate), _p(step_active), _p(counters),
-                                   C.c_int(num_clients), C.c_int(steps), C.c_float(inv_steps), _p(out), _stream()))
+                                   C.c_int(num_clients), C.c_int(steps), C.c_float(inv_steps), _p(out), _p(class_id),
+                                   C.c_int(nclass), _stream()))
 
 
 def deviceflow_mask(num_clients, client_base, seed, round_idx, p_online, drop_probability, arrive_tick, max_tick,
@@ -195,6 +200,8 @@ def deviceflow_mask(num_clients, client_base, seed, round_idx, p_online, drop_pr
 
 
 def rate_curve_area(y: torch.Tensor, area: torch.Tensor) -> None:
+    """y: float64 [bins, 101] rate-function samples; area: float64 [bins] positive-trapezoid integrals."""
+    assert y.dtype == torch.float64 and area.dtype == torch.float64 and y.shape[-1] == 101
     _ck(require().olsb_rate_curve_area(_p(y), _p(area), C.c_int(area.numel()), _stream()))
 
 

@@ -296,9 +296,27 @@ def _compare_round(a, b, g0, tol):
 
 
 def test_resnet18_native_round_vs_torch():
+    """20 convolution layers with bf16 activations: the deviation from the fp32 library grows towards the stem.  The
+    bound is therefore relative to what the LIBRARY shows at the same precision (bf16 autocast vs fp32)."""
+    from olearning_sim_b200.engine.fed_engine import FedConfig, FedEngine
     a, b, g0 = _engine_pair("resnet18", 4, 2, hetero_steps=True)
     assert a.backend == "native"
-    _compare_round(a, b, g0, 6e-2)
+    c = FedEngine(FedConfig(backend="torch", device="cuda", amp_bf16=True, model="resnet18", num_clients=4, local_steps=2,
+                            shard=64, lr=0.05, seed=3, hetero_steps=True))
+    c.load_synthetic(); c.set_global_model(g0)
+    ra, rb_, rc = a.run_round(0), b.run_round(0), c.run_round(0)
+    assert (ra.participants, ra.arrived, ra.client_steps) == (rb_.participants, rb_.arrived, rb_.client_steps)
+    assert abs(ra.loss - rb_.loss) < 2e-2 * max(1.0, abs(rb_.loss)), (ra.loss, rb_.loss)
+    da = a.spec_flat_global().cpu() - g0
+    db, dc = b.global_model().cpu() - g0, c.global_model().cpu() - g0
+    e_native, e_lib = rel(da, db), rel(dc, db)
+    print("resnet18 round delta vs fp32 library: native", e_native, "bf16-autocast library", e_lib)
+    assert e_native < 4e-2 and e_native < 1.5 * e_lib + 5e-3, (e_native, e_lib)
+    ga, gb = a.spec.unflatten(a.spec_flat_global().cpu()), a.spec.unflatten(b.global_model().cpu())
+    g0d = a.spec.unflatten(g0)
+    for k in ga:
+        r = rel(ga[k] - g0d[k], gb[k] - g0d[k])
+        assert r < 0.12, (k, r)
     a.close()
 
 
@@ -312,7 +330,7 @@ def test_bert_mini_native_round_vs_torch():
 def test_resnet18_fedprox_sampled_round_runs():
     from olearning_sim_b200.engine.fed_engine import FedConfig, FedEngine
     eng = FedEngine(FedConfig(model="resnet18", num_clients=6, local_steps=2, shard=64, backend="native", algorithm="fedprox",
-                              mu=0.01, p_online=0.7, drop_probability=0.1, wave=4))
+                              mu=0.01, p_online=0.7, drop_probability=0.1, wave=4, lr=0.01))
     eng.load_synthetic()
     r0, r1, r2 = eng.run_round(0), eng.run_round(1), eng.run_round(2)
     assert r2.loss == r2.loss and r2.loss < r0.loss + 0.5 and r0.failed == 0
