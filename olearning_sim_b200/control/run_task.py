@@ -82,38 +82,133 @@ def construct_run_params(data: Dict[str, Any], resource_request: Dict[str, Any])
 
 
 class ScriptActor:
-    """One worker ("actor"): runs its simulated phones sequentially, one subprocess each."""
+    """One worker ("actor"): fetches its data and model once, then runs its simulated phones sequentially, one
+    subprocess each (ols_core/taskMgr/utils/utils_run_task.py:146-577)."""
 
     def __init__(self, params: Params, operator: Dict[str, Any], working_dir: str, round_idx: int,
-                 deviceflow_info: Dict[str, Any], stop_event: threading.Event):
+                 deviceflow_info: Dict[str, Any], stop_event: threading.Event, file_repo: Any = None,
+                 actor_id: Optional[str] = None):
         self.p, self.op, self.wd, self.round, self.df, self.stop = params, operator, working_dir, round_idx, deviceflow_info, stop_event
+        self.file_repo = file_repo
+        import uuid
+        self.actor_id = actor_id or f"actor_{uuid.uuid4().hex[:12]}"
+        self.save_dir = os.path.join(working_dir, "actors", self.actor_id)
 
-    def construct_params_for_phones(self, run_params: Dict[str, Any], data: Dict[str, Any]) -> List[Dict[str, Any]]:
-        model = self.op.get("model", {})
+    # ---- downloads (utils_run_task.py:174-428) -------------------------------------------------------
+    def _repo(self, ttype: str, cfg: Optional[Dict[str, Any]] = None):
+        if self.file_repo is not None:
+            return self.file_repo
+        from ..utils.file_repo import get_file_repo
+        return get_file_repo(ttype, cfg)
+
+    def download_data_files(self, data: Dict[str, Any], split_index: List[int], simulation_num: int) -> Dict[str, Any]:
+        """Resolve the dataset to local per-phone paths.  ``data_split_type`` false: every phone gets the one shared folder
+        (or file); true: the unpacked data must hold exactly ``simulation_num`` entries, which are sorted and indexed by
+        each phone's ``split_index`` — client i owns shard i (:248-263, :294-310).  ``dataconfig.json`` rides along."""
+        out: Dict[str, Any] = {"local_data_path_list": [], "dataconfig": {}}
+        if not self.op.get("use_data", True) or not data.get("data_path"):
+            return out
+        from ..engine.data import fetch_dataset
+        ttype = str(data.get("data_transfer_type", "FILE")).upper()
+        repo = None if ttype == "FILE" else self._repo(ttype, data.get("repo_config"))
+        root = fetch_dataset(data, os.path.join(self.save_dir, "data"), file_repo=repo)
+        if not root or not os.path.exists(root):
+            raise FileNotFoundError(f"dataset {data.get('data_path')} is not reachable")
+        cfg_path = os.path.join(root, "dataconfig.json")
+        if os.path.isfile(cfg_path):
+            try:
+                with open(cfg_path) as f:
+                    out["dataconfig"] = json.load(f)
+            except ValueError:
+                out["dataconfig"] = {}
+        if data.get("data_split_type", False):
+            entries = sorted(e for e in os.listdir(root) if e not in ("dataconfig.json", ".unpacked"))
+            if len(entries) != simulation_num:
+                raise ValueError(f"data_split_type is true but the data holds {len(entries)} shards for {simulation_num} simulated devices")
+            out["local_data_path_list"] = [os.path.join(root, entries[i]) for i in split_index]
+        else:
+            entries = [e for e in os.listdir(root) if e not in ("dataconfig.json", ".unpacked")] if os.path.isdir(root) else []
+            shared = os.path.join(root, entries[0]) if len(entries) == 1 and os.path.isdir(os.path.join(root, entries[0])) else root
+            out["local_data_path_list"] = [shared for _ in split_index]
+        return out
+
+    def model_object_path(self) -> str:
+        model = self.op.get("model", {}) or {}
         path = model.get("model_path", "")
         if model.get("use_model") and model.get("model_for_train") and self.round > 0 and model.get("model_update_style"):
-            # per-round global model written by the aggregator: "{task_id}_{current_round}_result_model..." (utils_run_task.py:335-350)
+            # per-round global model written by the aggregator: "{task_id}_{current_round}_result_model..." (:335-350)
             name = model["model_update_style"].replace("{task_id}", self.p.task_id).replace("{current_round}", str(self.round))
             path = os.path.join(os.path.dirname(path), name)
+        return path
+
+    def download_model_files(self) -> Dict[str, Any]:
+        model = self.op.get("model", {}) or {}
+        path = self.model_object_path()
+        if not model.get("use_model") or not path:
+            return {"local_model_path": ""}
+        ttype = str(model.get("model_transfer_type", "FILE")).upper()
+        if ttype == "FILE":
+            return {"local_model_path": path}
+        local = os.path.join(self.save_dir, "model", os.path.basename(path))
+        os.makedirs(os.path.dirname(local), exist_ok=True)
+        if not self._repo(ttype, model.get("repo_config")).download_file(path, local):
+            raise FileNotFoundError(f"model {path} ({ttype}) could not be fetched")
+        return {"local_model_path": local}
+
+    # ---- per-phone parameters (utils_run_task.py:430-479; operator contract base_operator.py:12-53) ------------
+    def construct_params_for_phones(self, run_params: Dict[str, Any], data: Dict[str, Any],
+                                    downloads: Optional[Dict[str, Any]] = None) -> List[Dict[str, Any]]:
+        model = dict(self.op.get("model", {}) or {})
         info = self.op.get("logical_simulation", {})
         try:
             user_params = json.loads(info.get("operator_params") or "{}")
         except ValueError:
             user_params = {}
-        return [{"task_id": self.p.task_id, "operator_name": self.op.get("name", ""), "round": self.round,
-                 "device_type": run_params["device_type"], "split_index": idx,
-                 "data": {"name": data.get("name", ""), "path": data.get("data_path", ""),
-                          "split_type": data.get("data_split_type", False)},
-                 "model": {"use_model": model.get("use_model", False), "for_train": model.get("model_for_train", False), "path": path},
-                 "operator_params": user_params, "deviceflow": self.df} for idx in run_params["split_index"]]
+        downloads = downloads or {}
+        paths = downloads.get("data", {}).get("local_data_path_list", [])
+        local_model = downloads.get("model", {}).get("local_model_path", "") or self.model_object_path()
+        sim_num = sum(int(n) for n in data.get("simulation_target", {}).get("nums", []))
+        phone_model = {"use_model": model.get("use_model", False), "model_path": local_model}
+        phone_op = {"name": self.op.get("name", ""), "input": self.op.get("input", []),
+                    "operation_behavior_controller": self.op.get("operation_behavior_controller", {}),
+                    "use_data": self.op.get("use_data", True), "model": phone_model,
+                    "operator_params": info.get("operator_params", "")}
+        out = []
+        for i, idx in enumerate(run_params["split_index"]):
+            dpath = paths[i] if i < len(paths) else data.get("data_path", "")
+            out.append({
+                # reference contract
+                "task_id": self.p.task_id, "current_round": self.round,
+                "config": {"working_dir": self.wd, "deviceflow": self.df},
+                "data": {"name": data.get("name", ""), "data_path": dpath, "data_split_type": data.get("data_split_type", False),
+                         "task_type": data.get("task_type", ""), "dataconfig": downloads.get("data", {}).get("dataconfig", {}),
+                         "path": dpath, "split_type": data.get("data_split_type", False)},
+                "operator": phone_op, "simulation_num": sim_num, "split_index": idx, "actor_save_dir": self.save_dir,
+                "actor_simulation_num": len(run_params["split_index"]), "params": user_params,
+                # flat aliases kept for operators written against round 1 of this framework
+                "operator_name": self.op.get("name", ""), "round": self.round, "device_type": run_params["device_type"],
+                "model": {"use_model": model.get("use_model", False), "for_train": model.get("model_for_train", False),
+                          "path": local_model},
+                "operator_params": user_params, "deviceflow": self.df})
+        return out
 
     def run(self, run_params: Dict[str, Any], data: Dict[str, Any]) -> Dict[str, Any]:
         info = self.op.get("logical_simulation", {})
         entry = os.path.join(self.wd, self.op.get("name", ""), info.get("operator_entry_file", ""))
         ok = bad = 0
+        n_phones = len(run_params["split_index"])
+        os.makedirs(self.save_dir, exist_ok=True)
         tmp = tempfile.mkdtemp(prefix="olsb_actor_")
         try:
-            for i, prm in enumerate(self.construct_params_for_phones(run_params, data)):
+            try:
+                sim_num = sum(int(n) for n in data.get("simulation_target", {}).get("nums", []))
+                downloads = {"data": self.download_data_files(data, run_params["split_index"], sim_num),
+                             "model": self.download_model_files()}
+            except Exception as e:  # noqa: BLE001 - a failed download fails every phone of this actor (:549-559)
+                logger.error(self.p.task_id, "TaskMgr", "run_task", f"[Actor.run]: download failed: {e}")
+                return {"data_name": run_params["data_name"], "device_type": run_params["device_type"], "success": 0,
+                        "failed": n_phones}
+            for i, prm in enumerate(self.construct_params_for_phones(run_params, data, downloads)):
                 if self.stop.is_set():
                     break
                 f = os.path.join(tmp, f"params_{i}.json")
@@ -123,6 +218,7 @@ class ScriptActor:
                 ok, bad = (ok + 1, bad) if rc == 0 else (ok, bad + 1)
         finally:
             shutil.rmtree(tmp, ignore_errors=True)
+            shutil.rmtree(self.save_dir, ignore_errors=True)       # delete_tmp_results (:569-577)
         return {"data_name": run_params["data_name"], "device_type": run_params["device_type"], "success": ok, "failed": bad}
 
 
@@ -130,7 +226,7 @@ class RoundRunner:
     def __init__(self, task_json: Dict[str, Any], stop_event: Optional[threading.Event] = None, repo: Any = None,
                  deviceflow: Any = None, working_dir: Optional[str] = None, gate_params: Optional[Dict[str, Any]] = None,
                  rank: int = 0, world: int = 1, checkpoint_dir: Optional[str] = None, trace_path: Optional[str] = None,
-                 performance_mgr: Any = None, **_: Any):
+                 performance_mgr: Any = None, file_repo: Any = None, **_: Any):
         self.params = Params(task_json)
         self.stop_event = stop_event or threading.Event()
         self.repo, self.deviceflow, self.working_dir = repo, deviceflow, working_dir or tempfile.mkdtemp(prefix="olsb_job_")
@@ -145,6 +241,7 @@ class RoundRunner:
             from ..utils.tracing import TraceWriter
             self.trace = TraceWriter(trace_path)
         self.performance_mgr = performance_mgr
+        self.file_repo = file_repo
 
     # ---- deviceflow wiring (utils_run_task.py:53-144) ----------------------------------------------------
     def _df_start(self, operator: Dict[str, Any], round_idx: int) -> Dict[str, Any]:
@@ -166,6 +263,20 @@ class RoundRunner:
         return {"use": True, "routing_key": routing_key, "compute_resource": "logical_simulation",
                 "inbound": self.deviceflow.GetDeviceflowPulsarClient(),
                 "websocket_url": self.deviceflow.GetDeviceflowWebsocket().get("url", "")}
+
+    def _df_report(self, operator: Dict[str, Any], round_idx: int, res: Any) -> None:
+        """Tell the DeviceFlow service what the on-device dispatch of this round did (see ReportDeviceDispatch)."""
+        bc = operator.get("operation_behavior_controller", {}) or {}
+        if not bc.get("use_gradient_house") or self.deviceflow is None or self.rank != 0:
+            return
+        if not hasattr(self.deviceflow, "ReportDeviceDispatch"):
+            return
+        flow_id = f"{self.params.task_id}_{operator.get('name', '')}_{round_idx}"
+        summary = {"participants": res.participants, "forwarded": res.arrived, "dropped": res.dropped, "late": res.late}
+        plan = res.extras.get("flow_plan")
+        if plan:
+            summary.update(timing=plan.get("timing", []), amount=plan.get("amount", []))
+        self.deviceflow.ReportDeviceDispatch(self.params.task_id, flow_id, "logical_simulation", summary)
 
     def _df_stop(self, df_info: Dict[str, Any]) -> None:
         if df_info.get("use") and self.rank == 0:
@@ -364,7 +475,8 @@ class RoundRunner:
                 jobs.append((rp, d))
         results = []
         with concurrent.futures.ThreadPoolExecutor(max_workers=max(1, min(len(jobs), os.cpu_count() or 1))) as pool:
-            futs = [pool.submit(ScriptActor(self.params, operator, self.working_dir, round_idx, df_info, self.stop_event).run, rp, d)
+            futs = [pool.submit(ScriptActor(self.params, operator, self.working_dir, round_idx, df_info, self.stop_event,
+                                            file_repo=self.file_repo).run, rp, d)
                     for rp, d in jobs]
             for f in futs:
                 results.append(f.result())

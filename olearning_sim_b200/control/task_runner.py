@@ -182,52 +182,174 @@ def fix_device_task_json(task_json: Dict[str, Any]) -> Dict[str, Any]:
 
 
 class HybridDataSplitter:
-    """Splits one dataset between the logical and the device side (utils_runner.py:178-476): either by
-    ``device_ratio`` over samples (the reference uses sklearn ``train_test_split``) or, for pre-split data
-    (``data_split_type``), by handing the first ``logical`` client sub-folders to the servers and the rest to phones."""
+    """Splits one dataset between the logical (server) and the device (phone) side of a hybrid task
+    (ols_core/taskMgr/utils/utils_runner.py:178-476).
 
-    def __init__(self, task_id: str, task_type: str = "classification", split_id: str = "", seed: int = 0):
+    The dataset is a zip — fetched through the task's transfer type (FILE / HTTP / S3 / MINIO) — holding an optional
+    ``dataconfig.json`` next to the sample folders:
+
+    * ``data_split_type = false``: ONE shared folder.  Its sample files are split row-wise with
+      ``device_ratio = device / (logical + device)``: ``*_features.csv`` / ``*_labels.csv`` pairs (the reference's CSV
+      contract; train files only, test files are copied to both sides, as in the reference) and ``x.npy`` / ``y.npy`` /
+      ``data.npz`` arrays (the built-in GPU operators' format).  Rows are assigned with scikit-learn's
+      ``train_test_split(random_state=42)`` when available — the reference's call — otherwise a seeded permutation.
+    * ``data_split_type = true``: ``logical + device`` client sub-folders; the first ``logical`` go to the servers, the
+      rest to the phones (:340-364).
+
+    Both halves are re-zipped (folder entries + ``dataconfig.json``) and written to ``data_path_logical`` /
+    ``data_path_device`` — uploaded through the same store for S3 / MINIO (:400-476), plain files otherwise."""
+
+    def __init__(self, task_id: str, task_type: str = "classification", split_id: str = "", seed: int = 42,
+                 file_repo: Optional[Any] = None):
         self.task_id, self.task_type, self.split_id, self.seed = task_id, task_type, split_id, seed
+        self.file_repo = file_repo
 
-    def split(self, data: Dict[str, Any], workdir: Optional[str] = None) -> bool:
+    # ---- helpers -----------------------------------------------------------------------------------
+    def _repo_for(self, data: Dict[str, Any]):
+        if self.file_repo is not None:
+            return self.file_repo
+        ttype = str(data.get("data_transfer_type", "FILE")).upper()
+        if ttype == "FILE":
+            return None
+        from ..utils.file_repo import get_file_repo
+        return get_file_repo(ttype, data.get("repo_config"))
+
+    def download_data(self, data: Dict[str, Any], tmp: str) -> Optional[str]:
         src = data.get("data_path", "")
+        repo = self._repo_for(data)
+        if repo is None:
+            return src if os.path.exists(src) else None
+        local = os.path.join(tmp, os.path.basename(src) or "data.zip")
+        return local if repo.download_file(src, local) else None
+
+    def _rows_split(self, n: int, device_ratio: float) -> Tuple[List[int], List[int]]:
+        idx = list(range(n))
+        try:
+            from sklearn.model_selection import train_test_split
+            a, b = train_test_split(idx, test_size=device_ratio, random_state=self.seed)
+            return sorted(a), sorted(b)
+        except Exception:  # noqa: BLE001 - sklearn missing or degenerate ratio
+            rng = random.Random(self.seed)
+            rng.shuffle(idx)
+            k = n - int(round(n * device_ratio))
+            return sorted(idx[:k]), sorted(idx[k:])
+
+    def _split_shared_folder(self, folder: str, out_l: str, out_d: str, device_ratio: float) -> None:
+        import numpy as np
+        os.makedirs(out_l, exist_ok=True); os.makedirs(out_d, exist_ok=True)
+        names = sorted(os.listdir(folder))
+        done = set()
+        # CSV pairs: <stem>_features.csv + <stem>_labels.csv share one row split (header kept on both sides)
+        for f in names:
+            if f.endswith("_features.csv") and f.startswith("train"):
+                lab = f.replace("_features.csv", "_labels.csv")
+                rows_f = open(os.path.join(folder, f)).read().splitlines()
+                rows_l = open(os.path.join(folder, lab)).read().splitlines() if lab in names else None
+                keep_l, keep_d = self._rows_split(len(rows_f) - 1, device_ratio)
+                for dst, keep in ((out_l, keep_l), (out_d, keep_d)):
+                    with open(os.path.join(dst, f), "w") as fh:
+                        fh.write("\n".join([rows_f[0]] + [rows_f[1 + i] for i in keep]) + "\n")
+                    if rows_l is not None:
+                        with open(os.path.join(dst, lab), "w") as fh:
+                            fh.write("\n".join([rows_l[0]] + [rows_l[1 + i] for i in keep]) + "\n")
+                done.update({f, lab})
+        # array shards of the built-in operators
+        if "data.npz" in names:
+            z = np.load(os.path.join(folder, "data.npz"))
+            keep_l, keep_d = self._rows_split(len(z["y"]), device_ratio)
+            for dst, keep in ((out_l, keep_l), (out_d, keep_d)):
+                np.savez(os.path.join(dst, "data.npz"), **{k: z[k][keep] for k in z.files})
+            done.add("data.npz")
+        elif "x.npy" in names and "y.npy" in names:
+            x, y = np.load(os.path.join(folder, "x.npy")), np.load(os.path.join(folder, "y.npy"))
+            keep_l, keep_d = self._rows_split(len(y), device_ratio)
+            for dst, keep in ((out_l, keep_l), (out_d, keep_d)):
+                np.save(os.path.join(dst, "x.npy"), x[keep]); np.save(os.path.join(dst, "y.npy"), y[keep])
+            done.update({"x.npy", "y.npy"})
+        for f in names:                                    # everything else (test files, configs) goes to both sides
+            if f not in done:
+                src = os.path.join(folder, f)
+                for dst in (out_l, out_d):
+                    (shutil.copytree(src, os.path.join(dst, f), dirs_exist_ok=True) if os.path.isdir(src)
+                     else shutil.copy2(src, os.path.join(dst, f)))
+
+    @staticmethod
+    def _zip_dir(root: str, dst_zip: str) -> None:
+        os.makedirs(os.path.dirname(dst_zip) or ".", exist_ok=True)
+        with zipfile.ZipFile(dst_zip, "w", zipfile.ZIP_DEFLATED) as z:
+            for base, dirs, files in os.walk(root):
+                for dname in dirs:
+                    z.write(os.path.join(base, dname), os.path.relpath(os.path.join(base, dname), root))
+                for f in files:
+                    full = os.path.join(base, f)
+                    z.write(full, os.path.relpath(full, root))
+
+    def _publish(self, data: Dict[str, Any], local_zip: str, dst: str) -> bool:
+        repo = self._repo_for(data)
+        if repo is None:
+            os.makedirs(os.path.dirname(dst) or ".", exist_ok=True)
+            shutil.copyfile(local_zip, dst)
+            return True
+        return bool(repo.upload_file(local_zip, dst))
+
+    # ---- entry -------------------------------------------------------------------------------------
+    def split(self, data: Dict[str, Any], workdir: Optional[str] = None) -> bool:
         dl, dd = data.get("data_path_logical", ""), data.get("data_path_device", "")
-        if not src or not dl or not dd:
+        if not data.get("data_path") or not dl or not dd:
             return False
         al = data.get("allocation", {})
-        n_log, n_dev = sum(al.get("logical_simulation", [])), sum(al.get("device_simulation", []))
+        n_log = sum(al.get("logical_simulation", []))
+        n_dev = sum(al.get("device_simulation", [])) + sum(al.get("running_response", {}).get("nums", []))
         if n_log + n_dev == 0:
             return False
-        tmp = workdir or tempfile.mkdtemp(prefix="olsb_split_")
+        tmp = workdir or tempfile.mkdtemp(prefix=f"olsb_split_{self.split_id}")
         try:
+            src = self.download_data(data, tmp)
+            if src is None:
+                logger.error(self.task_id, "TaskMgr", "task_runner", f"[HybridDataSplitter]: download of {data.get('data_path')} failed")
+                return False
             root = os.path.join(tmp, "src")
             if os.path.isdir(src):
                 shutil.copytree(src, root, dirs_exist_ok=True)
             else:
                 with zipfile.ZipFile(src) as z:
+                    for m in z.namelist():
+                        if os.path.isabs(m) or ".." in m.split("/"):
+                            raise ValueError(f"zip entry escapes the dataset folder: {m}")
                     z.extractall(root)
-            entries = sorted(os.listdir(root))
+            entries = sorted(e for e in os.listdir(root) if e != "dataconfig.json")
+            out_l, out_d = os.path.join(tmp, "logical"), os.path.join(tmp, "device")
+            os.makedirs(out_l); os.makedirs(out_d)
+            if os.path.exists(os.path.join(root, "dataconfig.json")):
+                shutil.copy2(os.path.join(root, "dataconfig.json"), out_l)
+                shutil.copy2(os.path.join(root, "dataconfig.json"), out_d)
             if data.get("data_split_type", False):
-                part_l, part_d = entries[:n_log], entries[n_log:n_log + n_dev]
-            else:
-                rng = random.Random(self.seed)
-                shuffled = entries[:]
-                rng.shuffle(shuffled)
-                k = round(len(shuffled) * n_log / (n_log + n_dev))
-                part_l, part_d = sorted(shuffled[:k]), sorted(shuffled[k:])
-            for part, dst in ((part_l, dl), (part_d, dd)):
-                os.makedirs(os.path.dirname(dst) or ".", exist_ok=True)
-                with zipfile.ZipFile(dst, "w", zipfile.ZIP_DEFLATED) as z:
+                folders = [e for e in entries if os.path.isdir(os.path.join(root, e))]
+                if len(folders) < n_log + n_dev:
+                    logger.error(self.task_id, "TaskMgr", "task_runner",
+                                 f"[HybridDataSplitter]: {len(folders)} client folders for {n_log + n_dev} simulated clients")
+                    return False
+                for part, dst in ((folders[:n_log], out_l), (folders[n_log:n_log + n_dev], out_d)):
                     for e in part:
-                        p = os.path.join(root, e)
-                        if os.path.isdir(p):
-                            for base, _, files in os.walk(p):
-                                for f in files:
-                                    full = os.path.join(base, f)
-                                    z.write(full, os.path.relpath(full, root))
-                        else:
-                            z.write(p, e)
-            return True
+                        shutil.copytree(os.path.join(root, e), os.path.join(dst, e))
+            else:
+                folders = [e for e in entries if os.path.isdir(os.path.join(root, e))]
+                if len(folders) != 1:
+                    # a flat zip (sample files at the top level) is treated as the one shared folder
+                    if folders:
+                        logger.error(self.task_id, "TaskMgr", "task_runner",
+                                     f"[HybridDataSplitter]: unsplit data must hold exactly one sample folder, found {folders}")
+                        return False
+                    self._split_shared_folder(root, out_l, out_d, n_dev / (n_log + n_dev))
+                else:
+                    self._split_shared_folder(os.path.join(root, folders[0]), os.path.join(out_l, folders[0]),
+                                              os.path.join(out_d, folders[0]), n_dev / (n_log + n_dev))
+            ok = True
+            for part, dst in ((out_l, dl), (out_d, dd)):
+                z = os.path.join(tmp, os.path.basename(part) + ".zip")
+                self._zip_dir(part, z)
+                ok = self._publish(data, z, dst) and ok
+            return ok
         except Exception as e:  # noqa: BLE001
             logger.error(self.task_id, "TaskMgr", "task_runner", f"[HybridDataSplitter.split]: {e}")
             return False
@@ -239,11 +361,12 @@ class HybridDataSplitter:
 class TaskRunner:
     def __init__(self, task: TaskConfig, repo: Any, executor: JobExecutor, deviceflow: Optional[Any] = None,
                  phone_mgr: Optional[Any] = None, job_context: Optional[Dict[str, Any]] = None,
-                 file_repo: Optional[Any] = None):
+                 file_repo: Optional[Any] = None, dashboard: Optional[Any] = None):
         self._task, self._repo, self._executor = task, repo, executor
         self._deviceflow, self._phone_mgr = deviceflow, phone_mgr
         self._job_context = job_context or {}
         self._file_repo = file_repo
+        self._dashboard = dashboard if dashboard is not None else getattr(deviceflow, "dashboard", None)
 
     def submit_job(self, submitter: JobSubmitter) -> Optional[str]:
         """``submit_rayjob``: stage operator code into a working dir, then hand the round-loop driver to the executor."""
@@ -273,10 +396,14 @@ class TaskRunner:
         data_list = opt.fix_data_parameters()
         # write the (possibly optimised) allocation back so status accounting sees it
         tj["target"]["data"] = [{k: v for k, v in d.items() if k not in ("data_path_logical", "data_path_device")} for d in data_list]
+        def _reachable(d):
+            remote = str(d.get("data_transfer_type", "FILE")).upper() != "FILE" and (self._file_repo is not None or d.get("repo_config"))
+            return remote or os.path.exists(d.get("data_path", ""))
         both = [d for d in data_list if d.get("data_path_logical") and d.get("data_path_device")
-                and d["data_path_logical"] != d.get("data_path") and os.path.exists(d.get("data_path", ""))]
+                and d["data_path_logical"] != d.get("data_path") and _reachable(d)]
         for d in both:
-            if not HybridDataSplitter(tid, d.get("task_type", "classification")).split(d):
+            if not HybridDataSplitter(tid, d.get("task_type", "classification"), split_id=tid,
+                                      file_repo=self._file_repo).split(d):
                 logger.error(tid, "TaskMgr", "task_runner", "[submit]: hybrid data split failed")
                 return False, None
         logical, device = JobSubmitter("logical_simulation"), JobSubmitter("device_simulation")
@@ -307,13 +434,15 @@ class TaskRunner:
         return True, job_id
 
     def temp_write_table(self, data_list: List[Dict[str, Any]]) -> Dict[str, int]:
-        """Dashboard row task_target(task_id, high, middle, low) (task_runner.py:226-256).  Returned (and logged)
-        instead of written through a hard-coded DSN."""
-        tot = {"high": 0, "middle": 0, "low": 0}
-        for d in data_list:
-            for dev, n in zip(d.get("total_simulation", {}).get("devices", []), d.get("total_simulation", {}).get("nums", [])):
-                k = str(dev).lower()
-                if k in tot:
-                    tot[k] += int(n)
+        """Dashboard row task_target(task_id, high, middle, low) (task_runner.py:226-256): written to the dashboard repo
+        when the deployment has one (``DashboardRepo``; the reference uses a hard-coded MySQL DSN), always logged."""
+        from ..deviceflow.dashboard import task_target_row
+        tj = {"task_id": self._task.task_id, "target": {"data": data_list}}
+        tot = {"high": 0, "middle": 0, "low": 0, **task_target_row(tj)}
+        if self._dashboard is not None:
+            try:
+                self._dashboard.write_task_target(tj)
+            except Exception as e:  # noqa: BLE001 - display only
+                logger.warning(self._task.task_id, "TaskMgr", "task_runner", f"[task_target]: dashboard write failed: {e}")
         logger.info(self._task.task_id, "TaskMgr", "task_runner", f"[task_target]: {json.dumps(tot)}")
         return tot

@@ -87,8 +87,9 @@ class Dispatcher:
                  outbound_service: Dict[str, Dict[str, Any]], is_finished: bool = False,
                  clock: Optional[Clock] = None, rng: Optional[random.Random] = None,
                  default_bus: Optional[InMemoryBus] = None, now: Optional[Callable] = None,
-                 timeout_millis: int = TIMEOUT_MILLIS):
+                 timeout_millis: int = TIMEOUT_MILLIS, dashboard: Optional[Any] = None):
         self._task_id, self._flow_id, self._shelf_room = task_id, flow_id, shelf_room
+        self._dashboard = dashboard
         self._strategy, self._outbound_service = strategy, outbound_service
         self._is_finished = is_finished
         self._consumer: Consumer = shelf_room.get_consumer(flow_id)
@@ -175,6 +176,12 @@ class Dispatcher:
         if len(timing) != len(amount) or not timing:
             self.clean_remain_message()
             return
+        if self._dashboard is not None:
+            # display tables of the dispatch curve (dispatcher.py:254-395); failures never stop the dispatch
+            try:
+                self._dashboard.write_dispatch_curves(self._task_id, timing, amount, self._strategy)
+            except Exception as e:  # noqa: BLE001
+                logger.warning(self._task_id, "Deviceflow", "Dispatcher", f"[dashboard]: writing the curve tables failed: {e}")
         if timing[0] > 0:
             self._clock.sleep(timing[0])
         with concurrent.futures.ThreadPoolExecutor(max_workers=1) as ex:   # slots stay ordered

@@ -56,8 +56,11 @@ class NotifyRequest:
 class DeviceFlowService:
     def __init__(self, bus: Optional[InMemoryBus] = None, repo: Optional[FlowTableRepo] = None,
                  config: Optional[DeviceFlowConfig] = None, clock: Optional[Clock] = None, seed: Optional[int] = None,
-                 now=None, dispatcher_timeout_millis: int = 1000):
+                 now=None, dispatcher_timeout_millis: int = 1000, dashboard: Optional[Any] = None):
         self.config = config or DeviceFlowConfig()
+        self.dashboard = dashboard
+        self._device_reports: Dict[str, Dict[str, Any]] = {}      # flow_id -> on-device dispatch summary
+        self.finished_flows: Dict[str, Dict[str, Any]] = {}       # flow_id -> final counts of device-dispatched flows
         self.bus = bus or InMemoryBus()
         self._repo = repo or FlowTableRepo()
         self._clock = clock or Clock()
@@ -88,7 +91,7 @@ class DeviceFlowService:
         return Dispatcher(task_id=task_id, flow_id=f["flow_id"], shelf_room=self._deviceflow._shelf_room,
                           strategy=f["strategy"], outbound_service=f["outbound_service"], is_finished=is_finished,
                           clock=self._clock, rng=self._rng(flow_id), default_bus=self.bus, now=self._now,
-                          timeout_millis=self._dtimeout)
+                          timeout_millis=self._dtimeout, dashboard=self.dashboard)
 
     # ---- restart recovery (deviceflow_server.py:83-164) ---------------------------------------------------
     def initiate_from_repo(self) -> None:
@@ -182,6 +185,32 @@ class DeviceFlowService:
                 self._dispatcher[flow_id] = self._new_dispatcher(task_id, flow_id)
             return True
 
+    def ReportDeviceDispatch(self, task_id: str, flow_id: str, compute_resource: str, summary: Dict[str, Any]) -> bool:
+        """GPU-native operators apply the flow's strategy on the device (``deviceflow_mask_kernel``): the client updates
+        never travel over the bus, so instead of messages the engine reports what the dispatcher would have counted —
+        ``{"participants", "forwarded", "dropped", "late", ...}`` for this flow.  When every compute resource has called
+        NotifyComplete the flow is closed with these numbers (no shelf to drain) and
+        ``CheckDeviceflowDispatchFinished`` sees it as finished, exactly as after a bus-driven dispatch."""
+        with self._lock:
+            if flow_id not in self._flow or self._flow[flow_id]["task_id"] != task_id:
+                return False
+            rep = self._device_reports.setdefault(flow_id, {"task_id": task_id, "by_resource": {}})
+            rep["by_resource"][compute_resource] = dict(summary)
+            for k in ("participants", "forwarded", "dropped", "late"):
+                rep[k] = sum(int(v.get(k, 0)) for v in rep["by_resource"].values())
+            if self.dashboard is not None and summary.get("amount"):
+                try:
+                    self.dashboard.write_dispatch_curves(task_id, summary.get("timing", []), summary["amount"],
+                                                         self._flow[flow_id]["strategy"])
+                except Exception as e:  # noqa: BLE001
+                    logger.warning(task_id, "Deviceflow", "ReportDeviceDispatch", f"dashboard write failed: {e}")
+            return True
+
+    def device_report(self, flow_id: str) -> Optional[Dict[str, Any]]:
+        with self._lock:
+            r = self._device_reports.get(flow_id)
+            return None if r is None else json.loads(json.dumps(r))
+
     def NotifyComplete(self, req: NotifyRequest) -> bool:
         task_id, flow_id = req.task_id, req.routing_key
         if req.compute_resource not in ComputeResource.__members__:
@@ -191,6 +220,20 @@ class DeviceFlowService:
             if not ok:
                 self.stop(task_id=task_id, flow_id=flow_id, delete_flow_id=True)
                 return False
+            all_done = task_id in self._registry and DeviceFlow.check_all_notify_complete(self._registry[task_id], params)
+            if all_done and flow_id in self._device_reports and \
+                    set(self._device_reports[flow_id]["by_resource"]) >= set(params["notify_complete_called"]):
+                # dispatched on the device: nothing on the shelf, close the flow with the reported numbers
+                params["isFinished"] = True
+                params["device_dispatch"] = {k: self._device_reports[flow_id].get(k, 0)
+                                             for k in ("participants", "forwarded", "dropped", "late")}
+                self._deviceflow.update_flow(flow_id, task_id, params)
+                self.finished_flows[flow_id] = dict(params["device_dispatch"], task_id=task_id)
+                d = self._dispatcher.pop(flow_id, None)
+                if d is not None:
+                    d.stop_dispatch()
+                self.stop(task_id=task_id, flow_id=flow_id, delete_flow_id=True)
+                return True
             if task_id in self._registry and DeviceFlow.check_all_notify_complete(self._registry[task_id], params):
                 if Strategy.check_real_time_dispatch(params["strategy"]):
                     self._dispatcher[flow_id].release_dispatch()
@@ -296,4 +339,5 @@ class DeviceFlowService:
             return {"registered": sorted(self._registry), "flows": sorted(self._flow),
                     "dispatchers": {k: {"forwarded": d.forwarded, "dropped": d.dropped, "discarded": d.discarded,
                                         "finished": d.is_finished} for k, d in self._dispatcher.items()},
-                    "sorter": {"shelved": self._sorter.shelved, "discarded": self._sorter.discarded}}
+                    "sorter": {"shelved": self._sorter.shelved, "discarded": self._sorter.discarded},
+                    "device_dispatched": dict(self.finished_flows)}

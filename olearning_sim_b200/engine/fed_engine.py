@@ -660,6 +660,8 @@ class FedEngine:
         res.wall_s = time.perf_counter() - t0
         # reference semantics (task_manager.py:743-748): a round with more failed clients than dynamic_nums is a failure
         res.extras["within_tolerance"] = res.failed <= self.cfg.dynamic_nums
+        if self._flow_cache.get("plan"):
+            res.extras["flow_plan"] = {k: self._flow_cache["plan"].get(k, []) for k in ("timing", "amount")}
         if self.cfg.profile:
             res.extras["phases_ms"] = self.timer.collect(self.group, self.world)
             res.extras["phases_ms_min"] = dict(self.timer.last_min)

@@ -114,54 +114,100 @@ class HttpFileRepo(FileRepo):
 
 
 class S3FileRepo(FileRepo):
-    def __init__(self, endpoint_url: str, access_key: str, secret_key: str, bucket: str, region: Optional[str] = None):
+    """S3-compatible object store through a boto3 client (ofl_commons/.../s3_file_repo.py:1-64).  ``client`` injects a
+    ready client (tests use an in-memory fake with the boto3 method names); otherwise ``boto3`` is imported lazily."""
+
+    def __init__(self, endpoint_url: str = "", access_key: str = "", secret_key: str = "", bucket: str = "",
+                 region: Optional[str] = None, client: Any = None):
+        if client is None:
+            try:
+                import boto3  # type: ignore
+            except ImportError as e:
+                raise RuntimeError("S3 transfer needs the boto3 client, which is not installed on this box") from e
+            client = boto3.client("s3", endpoint_url=endpoint_url, aws_access_key_id=access_key,
+                                  aws_secret_access_key=secret_key, region_name=region)
+        self._s3, self._bucket = client, bucket
+
+    def upload_file(self, local_path, object_name) -> bool:
         try:
-            import boto3  # type: ignore
-        except ImportError as e:  # pragma: no cover - not installed offline
-            raise RuntimeError("S3 transfer needs the boto3 client, which is not installed on this box") from e
-        self._s3 = boto3.client("s3", endpoint_url=endpoint_url, aws_access_key_id=access_key,
-                                aws_secret_access_key=secret_key, region_name=region)
-        self._bucket = bucket
+            self._s3.upload_file(local_path, self._bucket, object_name)
+            return True
+        except Exception:  # noqa: BLE001
+            return False
 
-    def upload_file(self, local_path, object_name) -> bool:  # pragma: no cover
-        self._s3.upload_file(local_path, self._bucket, object_name)
-        return True
+    def download_file(self, object_name, local_path) -> bool:
+        try:
+            os.makedirs(os.path.dirname(local_path) or ".", exist_ok=True)
+            self._s3.download_file(self._bucket, object_name, local_path)
+            return True
+        except Exception:  # noqa: BLE001
+            if os.path.exists(local_path) and os.path.getsize(local_path) == 0:
+                os.remove(local_path)
+            return False
 
-    def download_file(self, object_name, local_path) -> bool:  # pragma: no cover
-        self._s3.download_file(self._bucket, object_name, local_path)
-        return True
+    def delete_file(self, object_name) -> bool:
+        try:
+            self._s3.delete_object(Bucket=self._bucket, Key=object_name)
+            return True
+        except Exception:  # noqa: BLE001
+            return False
 
-    def delete_file(self, object_name) -> bool:  # pragma: no cover
-        self._s3.delete_object(Bucket=self._bucket, Key=object_name)
-        return True
+    def download_payload(self, object_name):
+        try:
+            return self._s3.get_object(Bucket=self._bucket, Key=object_name)["Body"].read()
+        except Exception:  # noqa: BLE001
+            return None
 
-    def download_payload(self, object_name):  # pragma: no cover
-        return self._s3.get_object(Bucket=self._bucket, Key=object_name)["Body"].read()
+    def listdir_object_name(self, prefix: str) -> List[str]:
+        out, token = [], None
+        while True:
+            kw = {"Bucket": self._bucket, "Prefix": prefix}
+            if token:
+                kw["ContinuationToken"] = token
+            page = self._s3.list_objects_v2(**kw)
+            out += [o["Key"] for o in page.get("Contents", [])]
+            token = page.get("NextContinuationToken")
+            if not page.get("IsTruncated") or not token:
+                return sorted(out)
 
 
 class MinioFileRepo(FileRepo):
-    def __init__(self, endpoint: str, access_key: str, secret_key: str, bucket: str, secure: bool = False):
+    """MinIO through the ``minio`` client (ofl_commons/.../minio_file_repo.py:1-89); ``client`` as for S3."""
+
+    def __init__(self, endpoint: str = "", access_key: str = "", secret_key: str = "", bucket: str = "",
+                 secure: bool = False, client: Any = None):
+        if client is None:
+            try:
+                from minio import Minio  # type: ignore
+            except ImportError as e:
+                raise RuntimeError("MINIO transfer needs the minio client, which is not installed on this box") from e
+            client = Minio(endpoint, access_key=access_key, secret_key=secret_key, secure=secure)
+        self._c, self._bucket = client, bucket
+
+    def upload_file(self, local_path, object_name) -> bool:
         try:
-            from minio import Minio  # type: ignore
-        except ImportError as e:  # pragma: no cover
-            raise RuntimeError("MINIO transfer needs the minio client, which is not installed on this box") from e
-        self._c = Minio(endpoint, access_key=access_key, secret_key=secret_key, secure=secure)
-        self._bucket = bucket
+            self._c.fput_object(self._bucket, object_name, local_path)
+            return True
+        except Exception:  # noqa: BLE001
+            return False
 
-    def upload_file(self, local_path, object_name) -> bool:  # pragma: no cover
-        self._c.fput_object(self._bucket, object_name, local_path)
-        return True
+    def download_file(self, object_name, local_path) -> bool:
+        try:
+            os.makedirs(os.path.dirname(local_path) or ".", exist_ok=True)
+            self._c.fget_object(self._bucket, object_name, local_path)
+            return True
+        except Exception:  # noqa: BLE001
+            return False
 
-    def download_file(self, object_name, local_path) -> bool:  # pragma: no cover
-        self._c.fget_object(self._bucket, object_name, local_path)
-        return True
+    def delete_file(self, object_name) -> bool:
+        try:
+            self._c.remove_object(self._bucket, object_name)
+            return True
+        except Exception:  # noqa: BLE001
+            return False
 
-    def delete_file(self, object_name) -> bool:  # pragma: no cover
-        self._c.remove_object(self._bucket, object_name)
-        return True
-
-    def listdir_object_name(self, prefix: str) -> List[str]:  # pragma: no cover
-        return [o.object_name for o in self._c.list_objects(self._bucket, prefix=prefix, recursive=True)]
+    def listdir_object_name(self, prefix: str) -> List[str]:
+        return sorted(o.object_name for o in self._c.list_objects(self._bucket, prefix=prefix, recursive=True))
 
 
 def get_file_repo(transfer_type: Any, config: Optional[Dict[str, Any]] = None) -> Optional[FileRepo]:
@@ -174,10 +220,12 @@ def get_file_repo(transfer_type: Any, config: Optional[Dict[str, Any]] = None) -
         return HttpFileRepo(cfg.get("base_url", ""))
     if name == "S3":
         c = cfg.get("s3", cfg)
-        return S3FileRepo(c["endpoint_url"], c["access_key"], c["secret_key"], c["bucket"])
+        return S3FileRepo(c.get("endpoint_url", ""), c.get("access_key", ""), c.get("secret_key", ""), c.get("bucket", ""),
+                          client=c.get("client"))
     if name == "MINIO":
         c = cfg.get("minio", cfg)
-        return MinioFileRepo(c["endpoint"], c["access_key"], c["secret_key"], c["bucket"])
+        return MinioFileRepo(c.get("endpoint", ""), c.get("access_key", ""), c.get("secret_key", ""), c.get("bucket", ""),
+                             client=c.get("client"))
     raise ValueError(f"unknown transfer type {transfer_type!r}")
 
 

@@ -94,7 +94,11 @@ def test_task_with_deviceflow_real_time_strategy():
     tm.schedule_once(inline=True)
     assert tm.wait_for("dft", 120) == TaskStatus.SUCCEEDED
     assert df.stats()["registered"] == ["dft"]
-    assert sorted(df.stats()["flows"]) == ["dft_training_0", "dft_training_1"]
+    # built-in operators apply the strategy on the device and report the dispatch counts: each (operator, round) flow is
+    # closed at NotifyComplete with the numbers the dispatcher would have produced
+    done = df.stats()["device_dispatched"]
+    assert sorted(done) == ["dft_training_0", "dft_training_1"] and df.stats()["flows"] == []
+    assert all(v["participants"] == 8 and v["forwarded"] + v["dropped"] + v["late"] == 8 for v in done.values())
     df.pump(); df.pump()
     assert df.CheckDeviceflowDispatchFinished("dft")
     assert tm.reap_once() == ["dft"]
