@@ -11,10 +11,15 @@ Services / methods (ols_core/proto/*.proto):
     RayClusterMgr (-> GpuClusterMgr) createRayCluster deleteRayCluster modifyRayCluster queryRayCluster
     PerformanceMgr                   commitJob
 
-``grpc_tools`` (protoc) is not available offline, so instead of generated ``*_pb2`` classes the wire format is a JSON
-object per message (UTF-8) routed through ``grpc.method_handlers_generic_handler`` — same fully-qualified method paths
-(``/TaskMgr/submitTask`` ...), same 100 MiB message cap (ols_core/config/config.conf:2-3), insecure port like the
-reference (ols_core/simu_session.py:31-47).  ``JsonStub`` is the matching client.
+Two codecs share every method path (``/TaskMgr/submitTask``, ``/deviceflow.TaskOperatorOrientedDeviceFlow/NotifyStart`` ...):
+
+* **protobuf** — the reference's messages with their field numbers (``api/wire.py`` builds the descriptors without
+  ``protoc``): what a client generated from ols_core/proto/*.proto sends.  This is the default codec.
+* **JSON** — one UTF-8 JSON object per message; chosen when the call carries the metadata ``x-olsb-codec: json`` (``JsonStub``
+  sends it) or the payload starts like a JSON document.
+
+Same 100 MiB message cap (ols_core/config/config.conf:2-3), insecure port like the reference (ols_core/simu_session.py:
+31-47).  ``JsonStub`` / ``ProtoStub`` are the matching clients.
 """
 from __future__ import annotations
 
@@ -44,17 +49,31 @@ def _de(b: bytes) -> Any:
     return json.loads(b.decode("utf-8")) if b else {}
 
 
-def _generic(service: str, methods: Dict[str, Callable[[Dict[str, Any]], Any]]):
-    def wrap(fn):
-        def handler(request, context):
+JSON_CODEC_MD = ("x-olsb-codec", "json")
+
+
+def _raw(b: bytes) -> bytes:
+    return b
+
+
+def _generic(service: str, methods: Dict[str, Callable[[Dict[str, Any]], Any]], mount_as: Optional[str] = None):
+    from . import wire
+
+    def wrap(name, fn):
+        def handler(payload: bytes, context):
+            md = dict(context.invocation_metadata() or ())
+            use_json = md.get(JSON_CODEC_MD[0]) == JSON_CODEC_MD[1] or wire.looks_like_json(payload or b"") or \
+                name not in wire.SERVICES.get(service, {})
             try:
-                return fn(request or {})
+                if use_json:
+                    return _ser(fn(_de(payload) or {}))
+                return wire.encode_response(service, name, fn(wire.decode_request(service, name, payload or b"") or {}))
             except Exception as e:  # noqa: BLE001
                 context.set_code(grpc.StatusCode.INTERNAL)
                 context.set_details(f"{type(e).__name__}: {e}")
-                return {"is_success": False, "error": str(e)}
-        return grpc.unary_unary_rpc_method_handler(handler, request_deserializer=_de, response_serializer=_ser)
-    return grpc.method_handlers_generic_handler(service, {m: wrap(f) for m, f in methods.items()})
+                return _ser({"is_success": False, "error": str(e)}) if use_json else b""
+        return grpc.unary_unary_rpc_method_handler(handler, request_deserializer=_raw, response_serializer=_raw)
+    return grpc.method_handlers_generic_handler(mount_as or service, {m: wrap(m, f) for m, f in methods.items()})
 
 
 # ---- servicers ---------------------------------------------------------------------------------------------
@@ -86,7 +105,7 @@ def resource_mgr_handler(rm: Any):
     })
 
 
-def deviceflow_handler(df: Any):
+def deviceflow_handler(df: Any, mount_as: Optional[str] = None):
     from ..deviceflow.service import NotifyRequest
 
     def req(r):
@@ -101,7 +120,7 @@ def deviceflow_handler(df: Any):
         "UnRegisterTask": lambda r: {"is_success": bool(df.UnRegisterTask(r["task_id"]))},
         "GetTotalComputeResources": lambda r: {"total_compute_resources": df.GetTotalComputeResources(r["task_id"])},
         "CheckDeviceflowDispatchFinished": lambda r: {"is_success": bool(df.CheckDeviceflowDispatchFinished(r["task_id"]))},
-    })
+    }, mount_as=mount_as)
 
 
 def cluster_mgr_handler(cm: Any):
@@ -174,7 +193,25 @@ class JsonStub:
 
     def __getattr__(self, method: str):
         call = self._channel.unary_unary(f"/{self._service}/{method}", request_serializer=_ser, response_deserializer=_de)
-        return lambda request=None, timeout=30: call(request or {}, timeout=timeout)
+        return lambda request=None, timeout=30: call(request or {}, timeout=timeout, metadata=(JSON_CODEC_MD,))
+
+
+class ProtoStub:
+    """Client speaking the reference's protobuf messages — what code generated from ols_core/proto/*.proto does:
+    ``ProtoStub(channel, "TaskMgr").submitTask(wire.task_json_to_pb(task_json))`` returns an ``OperationStatus``."""
+
+    def __init__(self, channel: grpc.Channel, service: str):
+        from . import wire
+        self._channel, self._service, self._wire = channel, service, wire
+        pkg = wire.SERVICE_PACKAGE.get(service)
+        self._path = f"{pkg}.{service}" if pkg else service
+
+    def __getattr__(self, method: str):
+        req_t, resp_t = self._wire.SERVICES[self._service][method]
+        resp_cls = self._wire.msg(resp_t)
+        call = self._channel.unary_unary(f"/{self._path}/{method}", request_serializer=lambda m: m.SerializeToString(),
+                                         response_deserializer=resp_cls.FromString)
+        return lambda request=None, timeout=30: call(request if request is not None else self._wire.msg(req_t)(), timeout=timeout)
 
 
 def connect(address: str) -> grpc.Channel:
@@ -205,6 +242,8 @@ class SimulatorSession:
             self.server.add_generic_rpc_handlers((phone_manager_handler(phone_manager),)); mounted.append("PhoneManager")
         if deviceflow is not None and svc in (0, 5):
             self.server.add_generic_rpc_handlers((deviceflow_handler(deviceflow),)); mounted.append("TaskOperatorOrientedDeviceFlow")
+            # the reference's proto declares `package deviceflow;` — generated clients use the qualified path
+            self.server.add_generic_rpc_handlers((deviceflow_handler(deviceflow, "deviceflow.TaskOperatorOrientedDeviceFlow"),))
         self.mounted = mounted
         self.port = self.server.add_insecure_port(f"{host}:{port}")
         self.address = f"{host}:{self.port}"

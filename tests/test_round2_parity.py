@@ -1,0 +1,437 @@
+"""Round-2 parity items: protobuf wire contract, dashboard tables, hybrid splitter over object stores, script-actor data /
+model fetch, object-store adapters against fake clients, cached flow plans, per-class accounting, subprocess executor."""
+import io
+import json
+import os
+import random
+import sys
+import time
+import zipfile
+
+import numpy as np
+import pytest
+
+from olearning_sim_b200.api import wire
+from olearning_sim_b200.api.schema import TaskStatus
+from tests.helpers import make_task_json
+
+
+# ---------------------------------------------------------------------------------------------------------
+# protobuf wire contract (ols_core/proto/*.proto)
+# ---------------------------------------------------------------------------------------------------------
+def _varint_fields(b: bytes):
+    """minimal wire-format walk: (field number, wire type) of the top-level fields"""
+    out, i = [], 0
+    while i < len(b):
+        key, shift = 0, 0
+        while True:
+            c = b[i]; i += 1
+            key |= (c & 0x7F) << shift; shift += 7
+            if not c & 0x80:
+                break
+        fn, wt = key >> 3, key & 7
+        out.append((fn, wt))
+        if wt == 0:
+            while b[i] & 0x80:
+                i += 1
+            i += 1
+        elif wt == 2:
+            ln, shift = 0, 0
+            while True:
+                c = b[i]; i += 1
+                ln |= (c & 0x7F) << shift; shift += 7
+                if not c & 0x80:
+                    break
+            i += ln
+        elif wt == 5:
+            i += 4
+        elif wt == 1:
+            i += 8
+    return out
+
+
+def test_taskconfig_uses_the_reference_field_numbers_and_round_trips():
+    strategy = {"real_time_dispatch": {"use_strategy": True, "dispatch_batch_sizes": [3], "drop_simulation": {"drop_probability": 0.1}},
+                "flow_dispatch": {"use_strategy": False}}
+    tj = make_task_json(task_id="w1", nums=(4, 2), devices=("High", "Low"), dynamic=(1, 0), use_df=True, strategy=strategy,
+                        num_request=(2, 1))
+    m = wire.task_json_to_pb(tj)
+    b = m.SerializeToString()
+    # taskService.proto:4-11 — userID=1 string, taskID=2 msg, target=3, operatorFlow=4, logicalSimulation=5, deviceSimulation=6
+    assert _varint_fields(b) == [(1, 2), (2, 2), (3, 2), (4, 2), (5, 2), (6, 2)]
+    assert m.taskID.taskID == "w1" and m.target.targetData[0].totalSimulation.numTotalSimulation == [4, 2]
+    op = m.operatorFlow.operator[0]
+    assert op.operationBehaviorController.useController and json.loads(op.operationBehaviorController.strategyBehaviorController) == strategy
+    back = wire.task_pb_to_json(wire.msg("TaskConfig").FromString(b))
+    want = {k: v for k, v in tj.items() if k != "engine"}
+    assert json.loads(json.dumps(back)) == json.loads(json.dumps(want))
+    # enums travel as numbers on the wire and names in JSON
+    assert wire.msg("TaskStatus")(taskStatus=7).SerializeToString() == b"\x08\x07"
+    assert wire.to_dict(wire.msg("TaskStatus").FromString(b"\x08\x07")) == {"taskStatus": "QUEUED"}
+    # deviceflow.proto lives in package `deviceflow`
+    assert wire.msg("deviceflow.NotifyRequest").DESCRIPTOR.full_name == "deviceflow.NotifyRequest"
+
+
+def test_grpc_server_speaks_protobuf_to_reference_clients():
+    from olearning_sim_b200.api.grpc_service import JsonStub, ProtoStub, SimulatorSession, connect
+    from olearning_sim_b200.control.jobs import InProcessJobExecutor
+    from olearning_sim_b200.control.repo import FlowTableRepo, ResTableRepo, TaskTableRepo
+    from olearning_sim_b200.control.resource_manager import FakePhoneMgr, ResourceManager
+    from olearning_sim_b200.control.task_manager import TaskManager
+    from olearning_sim_b200.deviceflow.bus import FakeClock, InMemoryBus
+    from olearning_sim_b200.deviceflow.service import DeviceFlowService
+    from tests.test_control_plane import StubRunner
+    StubRunner.gate = None
+    rm = ResourceManager(ResTableRepo(), totals={"cpu": 4, "mem": 8, "gpu": 0}, phone_mgr=FakePhoneMgr({"u1": {"High": 2}}))
+    df = DeviceFlowService(bus=InMemoryBus(virtual_time=True), repo=FlowTableRepo(), clock=FakeClock())
+    tm = TaskManager(repo=TaskTableRepo(), resource_manager=rm, deviceflow=df, executor=InProcessJobExecutor(runner_factory=StubRunner))
+    sess = SimulatorSession(port=0, task_manager=tm, resource_manager=rm, deviceflow=df).start()
+    try:
+        ch = connect(sess.address)
+        t, r, d = ProtoStub(ch, "TaskMgr"), ProtoStub(ch, "ResourceMgr"), ProtoStub(ch, "TaskOperatorOrientedDeviceFlow")
+        ok = t.submitTask(wire.task_json_to_pb(make_task_json(task_id="p1")))
+        assert ok.is_success is True
+        assert [x.taskID for x in t.getTaskQueue().tasks] == ["p1"]                       # Empty request, protobuf reply
+        assert wire.to_dict(t.getTaskStatus(wire.msg("TaskID")(taskID="p1"))) == {"taskStatus": "QUEUED"}
+        assert t.getTaskStatus(wire.msg("TaskID")(taskID="nope")).taskStatus == 5            # MISSING
+        res = r.getResource()
+        assert res.clusterRes.cores == 4 and res.phoneRes.userDeviceAvailableResource[0].deviceResourceInfo[0].phoneType == "High"
+        st = r.requestClusterResource(wire.msg("ServerClusterReq")(taskId="x", cores=9, mem=1))
+        assert wire.to_dict(st) == {"status": "NOT_ENOUGH_RES"}
+        rq = wire.from_dict("ResReq", {"type": 0, "clusterReq": {"taskId": "x", "cores": 1, "mem": 1},
+                                       "phoneReq": {"taskID": "x", "userID": "u1", "deviceResourceInfo": [{"phoneType": "High", "num": 1}]}})
+        got = r.requestResource(rq)
+        assert got.clusterStatus.status == 0 and got.phoneStatus.isSuccess
+        assert r.releaseResource(wire.msg("ResRelease")(type=0, taskId="x")).clusterStatus.status == 0
+        # DeviceFlow under its package-qualified path
+        assert d.RegisterTask(wire.from_dict("deviceflow.RegisterRequest", {"task_id": "p1", "total_compute_resources": ["logical_simulation"]})).is_success
+        assert list(d.GetTotalComputeResources(wire.msg("deviceflow.TotalComputeResourcesRequest")(task_id="p1")).total_compute_resources) == ["logical_simulation"]
+        nr = wire.from_dict("deviceflow.NotifyRequest", {"task_id": "p1", "routing_key": "p1_training_0", "compute_resource": "logical_simulation",
+                                                         "strategy": json.dumps({"real_time_dispatch": {"use_strategy": True, "dispatch_batch_sizes": [1],
+                                                                                                        "drop_simulation": {"drop_probability": 0.0}},
+                                                                                 "flow_dispatch": {"use_strategy": False}}),
+                                                         "outbound_service": {"pulsar_client": {"url": "mem://local", "topic": "agg"}}})
+        assert d.NotifyStart(nr).is_success
+        assert d.GetDeviceflowPulsarClient().topic
+        # the JSON codec still works on the same server
+        assert JsonStub(ch, "TaskMgr").getTaskQueue() == {"tasks": ["p1"]}
+    finally:
+        sess.stop()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# dashboard tables (dispatcher.py:254-395, task_runner.py:226-256)
+# ---------------------------------------------------------------------------------------------------------
+def test_dashboard_curves_follow_the_reference_rules():
+    from olearning_sim_b200.deviceflow import dashboard as db
+    timing, amount = [3, 2, 4], [1000, 2000, 300]
+    assert db.operation_rows(timing, amount, "relative") == [(0, 0), (3, 1000), (5, 2000), (9, 300)]
+    assert db.operation_rows(timing, amount, "absolute") == [(0, 1000), (2, 2000), (6, 300)]
+    acc = dict(db.accumulated_rows(timing, amount, "relative"))
+    assert acc[0] == 0 and acc[1] == 0 and acc[2] == 0          # silence before the first slot
+    assert acc[3] == 750 and acc[4] == 1000                      # a 1000-message burst ramps at 750 / s
+    assert acc[5] == 1750 and acc[6] == 2500 and acc[7] == 3000 and acc[8] == 3000
+    assert acc[9] == 3300 and max(acc) == 10                     # tail of max(2, (9-5)//2) seconds after the last slot
+    st = {"flow_dispatch": {"use_strategy": True, "total_dispatch_amount": 3300,
+                            "specific_timing": {"use": True, "time_type": "relative", "timings": timing, "amounts": amount}}}
+    repo = db.DashboardRepo()
+    assert repo.write_dispatch_curves("t", timing, amount, json.dumps(st))
+    assert repo.curve("t", "operation")[1] == (3.0, 1000) and repo.curve("t")[-1][1] == 3300
+    repo.write_dispatch_curves("t", [1], [5], json.dumps(st))                           # replace, not append
+    assert len(repo.curve("t", "operation")) == 2
+    assert not repo.write_dispatch_curves("t", [1], [5], json.dumps({"real_time_dispatch": {"use_strategy": True}}))
+    tj = make_task_json(task_id="tt", nums=(4, 2), devices=("High", "Low"), dynamic=(0, 0))
+    assert db.task_target_row(tj) == {"high": 4, "low": 2}
+    repo.write_task_target(tj)
+    assert repo.target.get_item_value("task_id", "tt", "high") in (4, "4")
+
+
+def test_dispatcher_and_task_runner_write_the_dashboard():
+    from olearning_sim_b200.control.jobs import InProcessJobExecutor
+    from olearning_sim_b200.control.repo import FlowTableRepo, ResTableRepo, TaskTableRepo
+    from olearning_sim_b200.control.resource_manager import FakePhoneMgr, ResourceManager
+    from olearning_sim_b200.control.task_manager import TaskManager
+    from olearning_sim_b200.deviceflow.bus import FakeClock, InMemoryBus
+    from olearning_sim_b200.deviceflow.dashboard import DashboardRepo
+    from olearning_sim_b200.deviceflow.service import DeviceFlowService
+    dash = DashboardRepo()
+    st = {"real_time_dispatch": {"use_strategy": False},
+          "flow_dispatch": {"use_strategy": True, "total_dispatch_amount": 8,
+                            "specific_timing": {"use": True, "time_type": "relative", "timings": [1, 2], "amounts": [5, 3]}}}
+    df = DeviceFlowService(bus=InMemoryBus(virtual_time=True), repo=FlowTableRepo(), clock=FakeClock(), seed=0,
+                           dispatcher_timeout_millis=0, dashboard=dash)
+    rm = ResourceManager(ResTableRepo(), totals={"cpu": 8, "mem": 32, "gpu": 0}, phone_mgr=FakePhoneMgr())
+    tm = TaskManager(repo=TaskTableRepo(), resource_manager=rm, deviceflow=df, executor=InProcessJobExecutor())
+    tj = make_task_json(task_id="dsh", rounds=1, use_df=True, strategy=st, nums=(8,),
+                        operator_params={"model": "mlp2", "local_steps": 1, "batch": 8, "shard": 8, "lr": 0.1, "device": "cpu"})
+    assert tm.submitTask(tj)
+    tm.schedule_once(inline=True)
+    assert tm.wait_for("dsh", 120) == TaskStatus.SUCCEEDED
+    assert dash.target.get_item_value("task_id", "dsh", "high") in (8, "8")             # task_target row
+    # the GPU/CPU engine applied the 5 + 3 schedule itself and reported it: curves are on the dashboard, flow is closed
+    assert dash.curve("dsh", "operation") == [(0.0, 0), (1.0, 5), (3.0, 3)]
+    rep = df.stats()["device_dispatched"]["dsh_training_0"]
+    assert rep["participants"] == 8 and rep["forwarded"] == 8 and rep["late"] == 0
+    assert df.CheckDeviceflowDispatchFinished("dsh")
+
+
+# ---------------------------------------------------------------------------------------------------------
+# object stores against fake clients; hybrid splitter through them
+# ---------------------------------------------------------------------------------------------------------
+class FakeBoto:
+    """the subset of the boto3 S3 client the adapter uses"""
+
+    def __init__(self):
+        self.objects = {}
+
+    def upload_file(self, local, bucket, key):
+        self.objects[(bucket, key)] = open(local, "rb").read()
+
+    def download_file(self, bucket, key, local):
+        if (bucket, key) not in self.objects:
+            raise KeyError(key)
+        with open(local, "wb") as f:
+            f.write(self.objects[(bucket, key)])
+
+    def delete_object(self, Bucket, Key):
+        self.objects.pop((Bucket, Key))
+
+    def get_object(self, Bucket, Key):
+        return {"Body": io.BytesIO(self.objects[(Bucket, Key)])}
+
+    def list_objects_v2(self, Bucket, Prefix, ContinuationToken=None):
+        keys = sorted(k for (b, k) in self.objects if b == Bucket and k.startswith(Prefix))
+        start = int(ContinuationToken or 0)
+        page = keys[start:start + 2]
+        more = start + 2 < len(keys)
+        return {"Contents": [{"Key": k} for k in page], "IsTruncated": more, **({"NextContinuationToken": str(start + 2)} if more else {})}
+
+
+class FakeMinio:
+    class _Obj:
+        def __init__(self, n):
+            self.object_name = n
+
+    def __init__(self):
+        self.objects = {}
+
+    def fput_object(self, bucket, name, local):
+        self.objects[(bucket, name)] = open(local, "rb").read()
+
+    def fget_object(self, bucket, name, local):
+        with open(local, "wb") as f:
+            f.write(self.objects[(bucket, name)])
+
+    def remove_object(self, bucket, name):
+        del self.objects[(bucket, name)]
+
+    def list_objects(self, bucket, prefix="", recursive=False):
+        return [self._Obj(n) for (b, n) in sorted(self.objects) if b == bucket and n.startswith(prefix)]
+
+
+@pytest.mark.parametrize("kind", ["S3", "MINIO"])
+def test_object_store_adapters_against_fake_clients(tmp_path, kind):
+    from olearning_sim_b200.utils.file_repo import get_file_repo
+    client = FakeBoto() if kind == "S3" else FakeMinio()
+    repo = get_file_repo(kind, {"bucket": "bk", "client": client})
+    src = tmp_path / "a.bin"
+    src.write_bytes(b"hello")
+    for name in ("d/a.bin", "d/b.bin", "d/c.bin", "e/z.bin"):
+        assert repo.upload_file(str(src), name)
+    assert repo.listdir_object_name("d/") == ["d/a.bin", "d/b.bin", "d/c.bin"]           # S3: paginated listing
+    assert repo.download_file("d/b.bin", str(tmp_path / "out" / "b.bin")) and (tmp_path / "out" / "b.bin").read_bytes() == b"hello"
+    assert repo.download_payload("d/a.bin") == b"hello"
+    assert not repo.download_file("missing", str(tmp_path / "m.bin"))
+    assert repo.delete_file("d/a.bin") and not repo.delete_file("d/a.bin")
+    assert repo.download_if_missing("d/c.bin", str(tmp_path / "out" / "b.bin"))          # local copy short-circuits
+
+
+def _make_zip(path, files):
+    with zipfile.ZipFile(path, "w") as z:
+        for name, data in files.items():
+            z.writestr(name, data)
+
+
+def test_hybrid_splitter_ratio_split_through_an_object_store(tmp_path):
+    """unsplit data (one shared folder, CSV contract): rows are split by device_ratio, both halves re-zipped and uploaded"""
+    from olearning_sim_b200.control.task_runner import HybridDataSplitter
+    from olearning_sim_b200.utils.file_repo import S3FileRepo
+    client = FakeBoto()
+    repo = S3FileRepo(bucket="bk", client=client)
+    feats = "f0,f1\n" + "\n".join(f"{i},{i * 2}" for i in range(40)) + "\n"
+    labs = "y\n" + "\n".join(str(i % 3) for i in range(40)) + "\n"
+    z = tmp_path / "d.zip"
+    _make_zip(z, {"dataconfig.json": "{\"k\": 1}", "shared/train_features.csv": feats, "shared/train_labels.csv": labs,
+                  "shared/test_features.csv": "f0,f1\n1,2\n", "shared/test_labels.csv": "y\n0\n"})
+    repo.upload_file(str(z), "in/d.zip")
+    data = {"name": "d", "data_path": "in/d.zip", "data_split_type": False, "data_transfer_type": "S3",
+            "data_path_logical": "out/d_logical.zip", "data_path_device": "out/d_device.zip",
+            "allocation": {"logical_simulation": [6], "device_simulation": [2], "running_response": {"devices": [], "nums": []}}}
+    assert HybridDataSplitter("t", file_repo=repo).split(data)
+    rows = {}
+    for side in ("logical", "device"):
+        zz = zipfile.ZipFile(io.BytesIO(client.objects[("bk", f"out/d_{side}.zip")]))
+        names = set(zz.namelist())
+        assert {"dataconfig.json", "shared/train_features.csv", "shared/train_labels.csv", "shared/test_features.csv"} <= names
+        f = zz.read("shared/train_features.csv").decode().splitlines()
+        l = zz.read("shared/train_labels.csv").decode().splitlines()
+        assert f[0] == "f0,f1" and l[0] == "y" and len(f) == len(l)
+        assert all(int(a.split(",")[0]) % 3 == int(b) for a, b in zip(f[1:], l[1:]))       # features and labels stay paired
+        rows[side] = {int(a.split(",")[0]) for a in f[1:]}
+        assert zz.read("shared/test_features.csv").decode() == "f0,f1\n1,2\n"            # test files copied to both sides
+    assert len(rows["device"]) == 10 and len(rows["logical"]) == 30 and not (rows["device"] & rows["logical"])
+    assert rows["device"] | rows["logical"] == set(range(40))
+
+
+def test_hybrid_splitter_presplit_folders_and_array_shards(tmp_path):
+    from olearning_sim_b200.control.task_runner import HybridDataSplitter
+    z = tmp_path / "p.zip"
+    _make_zip(z, {f"c{i:02d}/x.txt": str(i) for i in range(5)})
+    data = {"name": "p", "data_path": str(z), "data_split_type": True, "data_transfer_type": "FILE",
+            "data_path_logical": str(tmp_path / "pl.zip"), "data_path_device": str(tmp_path / "pd.zip"),
+            "allocation": {"logical_simulation": [3], "device_simulation": [2]}}
+    assert HybridDataSplitter("t").split(data)
+    assert {n.split("/")[0] for n in zipfile.ZipFile(tmp_path / "pl.zip").namelist()} == {"c00", "c01", "c02"}
+    assert {n.split("/")[0] for n in zipfile.ZipFile(tmp_path / "pd.zip").namelist()} == {"c03", "c04"}
+    # built-in operators' array format
+    import io as _io
+    buf = _io.BytesIO()
+    np.savez(buf, x=np.arange(20).reshape(20, 1), y=np.arange(20))
+    z2 = tmp_path / "a.zip"
+    _make_zip(z2, {"shared/data.npz": buf.getvalue()})
+    d2 = {"name": "a", "data_path": str(z2), "data_split_type": False, "data_transfer_type": "FILE",
+          "data_path_logical": str(tmp_path / "al.zip"), "data_path_device": str(tmp_path / "ad.zip"),
+          "allocation": {"logical_simulation": [3], "device_simulation": [1]}}
+    assert HybridDataSplitter("t").split(d2)
+    yl = np.load(_io.BytesIO(zipfile.ZipFile(tmp_path / "al.zip").read("shared/data.npz")))["y"]
+    yd = np.load(_io.BytesIO(zipfile.ZipFile(tmp_path / "ad.zip").read("shared/data.npz")))["y"]
+    assert len(yd) == 5 and len(yl) == 15 and set(yl) | set(yd) == set(range(20))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# script operators: per-actor download / unzip / split_index folders / per-round model file
+# ---------------------------------------------------------------------------------------------------------
+def test_script_actor_fetches_sharded_data_and_round_model_over_http(tmp_path):
+    import http.server
+    import socketserver
+    import threading
+    from olearning_sim_b200.control.run_task import RoundRunner
+    www = tmp_path / "www"
+    www.mkdir()
+    _make_zip(www / "shards.zip", {"dataconfig.json": "{\"classes\": 3}", **{f"dev{i}/sample.txt": f"shard {i}" for i in range(4)}})
+    (www / "tsk_1_result_model.bin").write_bytes(b"round-1-model")
+    (www / "init_model.bin").write_bytes(b"init-model")
+    handler = lambda *a, **k: http.server.SimpleHTTPRequestHandler(*a, directory=str(www), **k)  # noqa: E731
+    srv = socketserver.TCPServer(("127.0.0.1", 0), handler)
+    threading.Thread(target=srv.serve_forever, daemon=True).start()
+    base = f"http://127.0.0.1:{srv.server_address[1]}"
+    op = tmp_path / "ops" / "training"
+    op.mkdir(parents=True)
+    log = tmp_path / "seen.jsonl"
+    (op / "train.py").write_text(
+        "import json, os, sys\n"
+        "p = json.load(open(sys.argv[sys.argv.index('--params') + 1]))\n"
+        "rec = {'round': p['current_round'], 'idx': p['split_index'], 'shard': open(os.path.join(p['data']['data_path'], 'sample.txt')).read(),\n"
+        "       'cfg': p['data']['dataconfig'], 'model': open(p['operator']['model']['model_path'], 'rb').read().decode(),\n"
+        "       'n': p['simulation_num'], 'actor_n': p['actor_simulation_num'], 'save': os.path.isdir(p['actor_save_dir'])}\n"
+        f"open({str(log)!r}, 'a').write(json.dumps(rec) + '\\n')\n")
+    tj = make_task_json(task_id="tsk", rounds=2, nums=(4,), num_request=(2,), code_path=str(op), operator_params={})
+    tj["target"]["data"][0].update(data_path=f"{base}/shards.zip", data_split_type=True, data_transfer_type="HTTP")
+    tj["target"]["data"][0]["simulation_target"] = {"devices": ["High"], "nums": [4]}
+    tj["operatorflow"]["operators"][0]["model"] = {"use_model": True, "model_for_train": True, "model_transfer_type": "HTTP",
+                                                   "model_path": f"{base}/init_model.bin",
+                                                   "model_update_style": "{task_id}_{current_round}_result_model.bin"}
+    wd = tmp_path / "job"
+    (wd / "training").mkdir(parents=True)
+    (wd / "training" / "train.py").write_text((op / "train.py").read_text())
+    try:
+        assert RoundRunner(tj, working_dir=str(wd)).run()
+    finally:
+        srv.shutdown()
+    seen = [json.loads(l) for l in log.read_text().splitlines()]
+    assert len(seen) == 8
+    r0 = sorted((s for s in seen if s["round"] == 0), key=lambda s: s["idx"])
+    assert [s["shard"] for s in r0] == [f"shard {i}" for i in range(4)]                   # client i owns shard i
+    assert all(s["cfg"] == {"classes": 3} and s["n"] == 4 and s["actor_n"] == 2 and s["save"] for s in seen)
+    assert {s["model"] for s in seen if s["round"] == 0} == {"init-model"}
+    assert {s["model"] for s in seen if s["round"] == 1} == {"round-1-model"}             # {task_id}_{current_round}_result_model
+
+
+# ---------------------------------------------------------------------------------------------------------
+# flow plan cache == per-round analysis; per-class accounting; subprocess executor context
+# ---------------------------------------------------------------------------------------------------------
+def test_flow_plan_plus_draws_reproduce_the_per_round_analysis():
+    from olearning_sim_b200.deviceflow.strategy import Strategy
+    for drop in ({"drop_probability": [0.3, 0.0]}, {"drop_amounts": [7, 2]}, {}):
+        st = {"flow_dispatch": {"use_strategy": True, "total_dispatch_amount": 100,
+                                "specific_interval": {"use": True, "time_type": "relative", "intervals": [[0, 6], [8, 12]],
+                                                      "dispatch_rules": {"domains": [[0, 3.14], [0, 1]], "functions": ["math.sin(t)+0.2", "2*t"]},
+                                                      **({"drop_simulation": drop} if drop else {})}}}
+        assert Strategy.is_round_invariant(st)
+        plan = Strategy.flow_plan(st)
+        for r in range(3):
+            timing, amount, drops = Strategy.flow_strategy_analysis(st, f"x_y_{r}", rng=random.Random(r))
+            assert plan["amount"] == amount and plan["timing"] == timing
+            assert Strategy.draw_drops(plan, random.Random(r)) == drops
+        # an injected integrator (the GPU kernel's stand-in) sees the 101-node samples of every bin
+        ref = {}
+
+        def area_fn(y):
+            assert y.shape[1] == 101 and y.dtype == np.float64
+            out = []
+            for row in y:
+                a = 0.0
+                for j in range(1, 101):
+                    s = 0.5 * (row[j] + row[j - 1]) * (1 / 100)
+                    if s > 0:
+                        a += s
+                out.append(a)
+            ref["called"] = True
+            return np.array(out)
+        assert Strategy.flow_plan(st, area_fn=area_fn)["amount"] == plan["amount"] and ref["called"]
+    absolute = {"flow_dispatch": {"use_strategy": True, "total_dispatch_amount": 1,
+                                  "specific_timing": {"use": True, "time_type": "absolute", "timings": [["2030-01-01 00:00:00"]], "amounts": [1]}}}
+    assert not Strategy.is_round_invariant(absolute)
+
+
+def test_per_class_failures_are_charged_to_the_right_class(monkeypatch):
+    """a poisoned Low client: FAILED must show up under Low, not under the first class (run_task.py:149-210)"""
+    from olearning_sim_b200.control.run_task import RoundRunner
+    monkeypatch.setenv("OLSB_FAULTS", "corrupt:client=5,round=0")          # global client 5 = the second Low client
+    tj = make_task_json(task_id="pc", rounds=1, nums=(4, 3), devices=("High", "Low"), dynamic=(0, 1),
+                        operator_params={"model": "mlp2", "local_steps": 1, "batch": 8, "shard": 8, "lr": 0.1, "device": "cpu",
+                                         "device_classes": {"Low": {"p_online": 1.0, "local_steps": 1}}})
+    from olearning_sim_b200.control.repo import TaskTableRepo
+    tj["target"]["data"][0]["simulation_target"] = {"devices": ["High", "Low"], "nums": [4, 3]}     # as the JobSubmitter writes it
+    repo = TaskTableRepo()
+    repo.create_task("pc")
+    rr = RoundRunner(tj, repo=repo)
+    assert rr.run()
+    rec = rr.history[-1]
+    assert rec["class_failed"] == {"data_0/High": 0, "data_0/Low": 1} and rec["class_participants"] == {"data_0/High": 4, "data_0/Low": 3}
+    got = json.loads(repo.get_task_value("pc", "logical_result"))["logical_result"][0]["simulation_target"]
+    assert got == {"devices": ["High", "Low"], "success_num": [4, 2], "failed_num": [0, 1]}
+
+
+def test_subprocess_executor_serialises_the_control_plane_context(tmp_path):
+    """build_control_plane(job_executor='subprocess') hands live repo / deviceflow objects to the
+    executor; they must not reach json.dump, and the task must run to SUCCEEDED in the child process."""
+    from olearning_sim_b200 import build_control_plane
+    from olearning_sim_b200.utils.config import OlsbConfig
+    cfg = OlsbConfig()
+    cfg.cluster.job_executor = "subprocess"
+    cfg.cluster.gpus = 1
+    cfg.storage.task_table = str(tmp_path / "tasks.db")
+    tm, rm, df = build_control_plane(cfg)
+    tj = make_task_json(task_id="sp", rounds=1, operator_params={"model": "mlp2", "local_steps": 1, "batch": 8, "shard": 8,
+                                                                 "lr": 0.1, "device": "cpu", "backend": "torch"})
+    assert tm.submitTask(tj)
+    tm.schedule_once(inline=True)
+    deadline = time.time() + 240
+    st = None
+    while time.time() < deadline:
+        st = tm.getTaskStatus("sp")
+        if st in TaskStatus.TERMINAL:
+            break
+        time.sleep(0.5)
+    assert st == TaskStatus.SUCCEEDED, (st, tm._executor.get_job_error(tm._task_running.get("sp", {}).get("job_id", "")) if hasattr(tm, "_task_running") else "")
