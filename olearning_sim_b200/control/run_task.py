@@ -344,7 +344,7 @@ class RoundRunner:
         if self.checkpoint_dir:
             from ..engine.checkpoint import CheckpointManager
             eng.ckpt = CheckpointManager(self.checkpoint_dir, self.params.task_id, rank=self.rank)
-            state = eng.ckpt.load_latest()
+            state = eng.ckpt.load_agreed(eng.group, self.world)       # same resume round on every rank
             if state is not None:
                 eng.load_state_dict(state["engine"])
                 eng.resume_round = state["round"] + 1

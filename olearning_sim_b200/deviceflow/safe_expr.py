@@ -77,7 +77,7 @@ def compile_expr(src: str) -> Callable[[float], float]:
         if isinstance(n, ast.Constant):
             if isinstance(n.value, bool) or not isinstance(n.value, (int, float)):
                 raise UnsafeExpression("only numeric literals are allowed")
-            v = n.value
+            v = float(n.value)                  # float arithmetic only: no unbounded Python big-int intermediates
             return lambda t: v
         if isinstance(n, (ast.Name, ast.Attribute)):
             kind, val = _resolve_name(n)
@@ -90,12 +90,15 @@ def compile_expr(src: str) -> Callable[[float], float]:
             op, a, b = _BINOPS[type(n.op)], build(n.left), build(n.right)
             if isinstance(n.op, ast.Pow):
                 def powf(t, a=a, b=b):
-                    x, y = a(t), b(t)
+                    x, y = float(a(t)), float(b(t))
                     if abs(y) > 64 and abs(x) > 1:
                         raise UnsafeExpression("exponent too large")
-                    return x ** y
+                    r = x ** y
+                    if isinstance(r, complex):
+                        raise UnsafeExpression("complex result")
+                    return r
                 return powf
-            return lambda t: op(a(t), b(t))
+            return lambda t, op=op, a=a, b=b: op(float(a(t)), float(b(t)))
         if isinstance(n, ast.UnaryOp) and type(n.op) in _UNOPS:
             op, a = _UNOPS[type(n.op)], build(n.operand)
             return lambda t: op(a(t))
@@ -117,10 +120,26 @@ def compile_expr(src: str) -> Callable[[float], float]:
             if kind != "func":
                 raise UnsafeExpression("only whitelisted functions can be called")
             args = [build(a) for a in n.args]
-            return lambda t: fn(*[a(t) for a in args])
+
+            def call(t, fn=fn, args=args):
+                r = fn(*[a(t) for a in args])
+                # int() / round() / floor() return Python ints: bring them back to float so later ** and * stay bounded
+                return float(r) if isinstance(r, int) and not isinstance(r, bool) else r
+            return call
         raise UnsafeExpression(f"syntax element {type(n).__name__} is not allowed")
 
-    return build(tree)
+    f = build(tree)
+
+    def guarded(t: float):
+        """every arithmetic failure of a request-supplied expression surfaces as UnsafeExpression (never a bare
+        OverflowError / ZeroDivisionError / ValueError out of the service)"""
+        try:
+            return f(float(t))
+        except UnsafeExpression:
+            raise
+        except (OverflowError, ZeroDivisionError, ValueError, TypeError) as e:
+            raise UnsafeExpression(f"evaluation failed: {type(e).__name__}: {e}") from None
+    return guarded
 
 
 def evaluate(src: str, t: float) -> float:

@@ -80,14 +80,48 @@ class CheckpointManager:
             except OSError:
                 pass
 
-    def load_latest(self) -> Optional[Dict[str, Any]]:
+    def _load(self, p: str) -> Optional[Dict[str, Any]]:
+        try:
+            return torch.load(p, map_location="cpu", weights_only=True)       # tensors + plain containers only: no pickle code
+        except Exception:  # noqa: BLE001 — torn file from a crash
+            return None
+
+    def load_latest(self, max_round: Optional[int] = None) -> Optional[Dict[str, Any]]:
+        """Newest loadable checkpoint (of round <= ``max_round`` when given); a torn file falls back to the previous round."""
         self.wait()
-        for _, p in reversed(self._rounds()):
-            try:
-                return torch.load(p, map_location="cpu", weights_only=True)   # tensors + plain containers only: no pickle code
-            except Exception:  # noqa: BLE001 — torn file from a crash: fall back to the previous round
+        for r, p in reversed(self._rounds()):
+            if max_round is not None and r > max_round:
                 continue
+            st = self._load(p)
+            if st is not None:
+                return st
         return None
+
+    def newest_loadable_round(self) -> int:
+        """Round index of the newest checkpoint of THIS rank that actually loads, -1 if none."""
+        st = self.load_latest()
+        return int(st["round"]) if st is not None and "round" in st else -1
+
+    def load_agreed(self, group=None, world: int = 1) -> Optional[Dict[str, Any]]:
+        """Multi-rank resume: writes are asynchronous and per rank, so a crash can leave rank 0 at round r and rank 1 at
+        r-1 (or with a torn newest file).  Every rank therefore loads the MINIMUM over ranks of the newest loadable
+        round (``keep >= 2`` retains it), so all ranks re-enter the collectives at the same round with the same state."""
+        mine = self.newest_loadable_round()
+        agreed = mine
+        if world > 1:
+            import torch.distributed as dist
+            t = torch.tensor([mine], dtype=torch.int64)
+            if dist.get_backend(group) == "nccl":
+                t = t.cuda()
+            dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+            agreed = int(t.item())
+        if agreed < 0:
+            return None
+        st = self.load_latest(max_round=agreed)
+        if st is None or int(st.get("round", -2)) != agreed:
+            raise RuntimeError(f"rank {self.rank}: no loadable checkpoint of the agreed resume round {agreed} "
+                               f"(newest here: {mine}); increase `keep`")
+        return st
 
 
 def _to_host(obj: Any) -> Any:

@@ -435,3 +435,64 @@ def test_subprocess_executor_serialises_the_control_plane_context(tmp_path):
             break
         time.sleep(0.5)
     assert st == TaskStatus.SUCCEEDED, (st, tm._executor.get_job_error(tm._task_running.get("sp", {}).get("job_id", "")) if hasattr(tm, "_task_running") else "")
+
+
+# ---------------------------------------------------------------------------------------------------------
+# bounded expression evaluation, cross-rank resume agreement, relaunch under lock
+# ---------------------------------------------------------------------------------------------------------
+def test_safe_expr_is_float_only_and_maps_arithmetic_errors():
+    from olearning_sim_b200.deviceflow import safe_expr as se
+    t0 = time.time()
+    for bad in ("(((((2)**64)**64)**64)**64)**64", "((((((3)**60)**60)**60)**60)**60)**60", "1/(t-t)", "math.log(-1)", "math.exp(10000)"):
+        with pytest.raises(se.UnsafeExpression):
+            se.evaluate(bad, 2.0)
+    assert time.time() - t0 < 1.0                                   # no big-int blow-up
+    assert se.evaluate("int(t)*2+round(2.7)", 3.9) == 9.0 and abs(se.evaluate("math.sin(t)+1", 0.5) - 1.479425538604203) < 1e-12
+    assert isinstance(se.evaluate("2**10", 0.0), float)
+
+
+def test_resume_round_is_the_minimum_loadable_round(tmp_path):
+    import torch
+    from olearning_sim_b200.engine.checkpoint import CheckpointManager
+    r0 = CheckpointManager(str(tmp_path), "tk", rank=0, keep=2, asynchronous=False)
+    r1 = CheckpointManager(str(tmp_path), "tk", rank=1, keep=2, asynchronous=False)
+    for rd in range(3):
+        r0.save(rd, {"round": rd, "engine": {"w": torch.full((2,), float(rd))}})
+    for rd in range(2):                                               # rank 1 crashed before writing round 2
+        r1.save(rd, {"round": rd, "engine": {"w": torch.full((2,), float(rd))}})
+    assert r0.newest_loadable_round() == 2 and r1.newest_loadable_round() == 1
+    agreed = min(r0.newest_loadable_round(), r1.newest_loadable_round())
+    assert int(r0.load_latest(max_round=agreed)["round"]) == 1 and int(r1.load_latest(max_round=agreed)["round"]) == 1
+    # a torn newest file on rank 1 falls back one more round
+    with open(r1.path(1), "wb") as f:
+        f.write(b"torn")
+    assert r1.newest_loadable_round() == 0
+    # single-rank agreement path
+    assert int(r0.load_agreed(None, 1)["round"]) == 2
+
+
+def test_subprocess_relaunch_happens_once_under_concurrent_polls(tmp_path, monkeypatch):
+    import threading
+    from olearning_sim_b200.control.jobs import JobStatus, SubprocessJobExecutor
+    ex = SubprocessJobExecutor(nproc_per_node=4, workdir=str(tmp_path), max_restarts=1)
+    launches = []
+
+    class P:
+        def __init__(self, rc):
+            self.rc, self.pid = rc, 0
+
+        def poll(self):
+            return self.rc
+
+    def fake_launch(job_id, path, nproc, attempt, port=None):
+        launches.append((nproc, attempt))
+        time.sleep(0.05)
+        return P(1 if attempt == 0 else None), str(tmp_path / "x.log")
+    monkeypatch.setattr(ex, "_launch", fake_launch)
+    jid = ex.submit_job({"task_id": "x"}, {"repo": object(), "deviceflow": object(), "gpus": 2, "checkpoint_dir": None})
+    blob = json.load(open(tmp_path / f"{jid}.json"))
+    assert "repo" not in blob["context"] and "deviceflow" not in blob["context"] and launches == [(2, 0)]      # granted GPUs -> ranks
+    out = []
+    ths = [threading.Thread(target=lambda: out.append(ex.get_job_status(jid))) for _ in range(6)]
+    [t.start() for t in ths]; [t.join() for t in ths]
+    assert out == [JobStatus.RUNNING] * 6 and launches == [(2, 0), (2, 1)]                                     # exactly one relaunch
