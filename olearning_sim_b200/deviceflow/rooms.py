@@ -204,9 +204,14 @@ class PulsarClientProducer(MessageProducerBase):
         self._default, self._producer = default_bus, None
 
     def get_producer(self, outbound_params: Dict[str, Any]) -> None:
-        bus = self.buses.get(outbound_params.get("url", ""), self._default)
+        url = outbound_params.get("url", "")
+        bus = self.buses.get(url)
+        if bus is None and url.startswith(("pulsar://", "pulsar+ssl://")):
+            from .pulsar_bus import PulsarBus           # a real broker URL: connect once, keep the bus for later flows
+            bus = self.buses[url] = PulsarBus(url)
+        bus = bus or self._default
         if bus is None:
-            raise DeviceFlowError(f"no bus registered for url {outbound_params.get('url')!r}")
+            raise DeviceFlowError(f"no bus registered for url {url!r}")
         self._producer = bus.create_producer(outbound_params["topic"])
 
     def send(self, message: bytes) -> None:

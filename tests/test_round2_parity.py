@@ -496,3 +496,177 @@ def test_subprocess_relaunch_happens_once_under_concurrent_polls(tmp_path, monke
     ths = [threading.Thread(target=lambda: out.append(ex.get_job_status(jid))) for _ in range(6)]
     [t.start() for t in ths]; [t.join() for t in ths]
     assert out == [JobStatus.RUNNING] * 6 and launches == [(2, 0), (2, 1)]                                     # exactly one relaunch
+
+
+# ---------------------------------------------------------------------------------------------------------
+# broker / database adapters against fake servers
+# ---------------------------------------------------------------------------------------------------------
+class FakePulsarClient:
+    """pulsar.Client surface used by PulsarBus: topics with named Shared subscriptions, ack / redelivery, Timeout"""
+
+    class Timeout(Exception):
+        pass
+
+    class _Msg:
+        def __init__(self, mid, data):
+            self._id, self._d = mid, data
+
+        def data(self):
+            return self._d
+
+        def message_id(self):
+            return self._id
+
+    class _Producer:
+        def __init__(self, c, topic):
+            self.c, self.topic = c, topic
+
+        def send(self, payload):
+            self.c._n += 1
+            for sub in self.c.subs.setdefault(self.topic, {}).values():
+                sub["pending"].append(FakePulsarClient._Msg(self.c._n, payload))
+            self.c.log.setdefault(self.topic, []).append(payload)
+
+        def close(self):
+            pass
+
+    class _Consumer:
+        def __init__(self, c, topic, name):
+            self.sub = c.subs.setdefault(topic, {}).setdefault(name, {"pending": [], "inflight": {}})
+
+        def receive(self, timeout_millis=None):
+            if not self.sub["pending"]:
+                raise FakePulsarClient.Timeout("Pulsar error: TimeOut")
+            m = self.sub["pending"].pop(0)
+            self.sub["inflight"][m.message_id()] = m
+            return m
+
+        def acknowledge(self, m):
+            self.sub["inflight"].pop(m.message_id(), None)
+
+        def close(self):
+            self.sub["pending"][:0] = list(self.sub["inflight"].values())
+            self.sub["inflight"].clear()
+
+    def __init__(self):
+        self.subs, self.log, self._n = {}, {}, 0
+
+    def create_producer(self, topic):
+        return self._Producer(self, topic)
+
+    def subscribe(self, topic, subscription_name, consumer_type=None):
+        return self._Consumer(self, topic, subscription_name)
+
+    def close(self):
+        pass
+
+
+def test_deviceflow_service_runs_on_the_pulsar_transport():
+    """sorter -> shelf -> dispatcher -> outbound, every hop through PulsarBus (fake broker client)"""
+    from olearning_sim_b200.control.repo import FlowTableRepo
+    from olearning_sim_b200.deviceflow.bus import BusTimeout, FakeClock
+    from olearning_sim_b200.deviceflow.pulsar_bus import PulsarBus
+    from olearning_sim_b200.deviceflow.rooms import PulsarClientProducer
+    from olearning_sim_b200.deviceflow.service import DeviceFlowService, NotifyRequest
+    client = FakePulsarClient()
+    bus = PulsarBus("pulsar://fake:6650", client=client)
+    bus.virtual_time = True                 # inline pump(): a receive timeout ends the dispatcher pass instead of polling
+    PulsarClientProducer.buses["pulsar://fake:6650"] = bus
+    df = DeviceFlowService(bus=bus, repo=FlowTableRepo(), clock=FakeClock(), seed=1, dispatcher_timeout_millis=0)
+    st = json.dumps({"real_time_dispatch": {"use_strategy": True, "dispatch_batch_sizes": [2], "drop_simulation": {"drop_probability": 0.0}},
+                     "flow_dispatch": {"use_strategy": False}})
+    assert df.RegisterTask("pt", ["logical_simulation"])
+    out = {"pulsar_client": {"url": "pulsar://fake:6650", "topic": "agg"}}
+    assert df.NotifyStart(NotifyRequest("pt", "pt_training_0", "logical_simulation", st, out))
+    inbound = bus.create_producer(df.config.source_topic)
+    for i in range(5):
+        inbound.send(json.dumps({"routing_key": "pt_training_0", "compute_resource": "logical_simulation", "message": f"u{i}"}))
+    inbound.send(json.dumps({"routing_key": "other_flow_0", "compute_resource": "logical_simulation", "message": "stray"}))
+    df._sorter.drain()                                              # inbound -> shelf (sorter thread in a live service)
+    assert df.NotifyComplete(NotifyRequest("pt", "pt_training_0", "logical_simulation"))
+    df.pump(); df.pump()
+    full = bus._full("agg")
+    assert [m.decode() for m in client.log[full]] == [f"u{i}" for i in range(5)]          # 2 + 2 + flushed 1
+    assert df.CheckDeviceflowDispatchFinished("pt") and df.stats()["sorter"]["discarded"] == 1
+    c = bus.subscribe("empty_topic", "s")
+    with pytest.raises(BusTimeout):
+        c.receive(timeout_millis=1)
+    del PulsarClientProducer.buses["pulsar://fake:6650"]
+
+
+class FakeMySql:
+    """DB-API connection factory in the pymysql dialect (%s placeholders, backticks, AUTO_INCREMENT) backed by sqlite;
+    the first statement after `drop_next` raises an operational error, as a dropped server connection would"""
+
+    class OperationalError(Exception):
+        pass
+
+    def __init__(self):
+        import sqlite3
+        self.db = sqlite3.connect(":memory:", check_same_thread=False, isolation_level=None)
+        self.drop_next = False
+        self.connects = 0
+        self.seen = []
+
+    def connect(self):
+        outer = self
+        outer.connects += 1
+
+        class Cur:
+            def execute(self, q, params=()):
+                if outer.drop_next:
+                    outer.drop_next = False
+                    raise FakeMySql.OperationalError("(2006, 'MySQL server has gone away')")
+                assert "?" not in q and '"' not in q, q
+                outer.seen.append(q)
+                q2 = (q.replace("`", '"').replace("%s", "?").replace("BIGINT PRIMARY KEY AUTO_INCREMENT", "INTEGER PRIMARY KEY AUTOINCREMENT")
+                      .replace("LONGTEXT", "TEXT").replace("DOUBLE", "REAL"))
+                self._c = outer.db.execute(q2, params)
+                self.rowcount, self.description = self._c.rowcount, self._c.description
+                return self
+
+            def fetchone(self):
+                return self._c.fetchone()
+
+            def fetchall(self):
+                return self._c.fetchall()
+
+        class Conn:
+            def cursor(self):
+                return Cur()
+
+            def commit(self):
+                pass
+
+            def close(self):
+                pass
+        return Conn()
+
+
+def test_mysql_repos_translate_dialect_and_reconnect_once():
+    from olearning_sim_b200.control.mysql_repo import MySqlConnection, MySqlResTableRepo, MySqlTaskTableRepo, translate
+    assert translate('SELECT "a" FROM "t" WHERE "b"=?') == "SELECT `a` FROM `t` WHERE `b`=%s"
+    srv = FakeMySql()
+    conn = MySqlConnection(connect=srv.connect, operational_errors=(FakeMySql.OperationalError,))
+    tasks, res = MySqlTaskTableRepo(conn), MySqlResTableRepo(conn)
+    assert any("AUTO_INCREMENT" in q and "`taskmgr_table`" in q for q in srv.seen)
+    assert tasks.create_task("m1", "u") and not tasks.create_task("m1", "u")
+    assert tasks.set_task_value("m1", "task_status", "QUEUED") and tasks.get_task_value("m1", "task_status") == "QUEUED"
+    srv.drop_next = True                                                # server went away: reconnect once and retry
+    assert tasks.get_task_value("m1", "task_status") == "QUEUED" and conn.reconnects == 1 and srv.connects == 2
+    assert res.insert_data("m1", 2.0, 4.0, 1.0) and res.held()[0]["cpu"] == 2.0
+    assert res.delete_by_taskid("m1") and res.held() == []
+    # the control plane runs unchanged on top of it
+    from olearning_sim_b200.control.resource_manager import FakePhoneMgr, ResourceManager
+    rm = ResourceManager(res, totals={"cpu": 4, "mem": 8, "gpu": 0}, phone_mgr=FakePhoneMgr())
+    assert rm.requestClusterResource("x", 3, 1).name == "SUCCESS" and rm.requestClusterResource("y", 3, 1).name == "NOT_ENOUGH_RES"
+    srv.drop_next = True
+    with pytest.raises(FakeMySql.OperationalError):                     # two failures in a row are not swallowed
+        srv_drop_again = [True]
+
+        class Twice:
+            def __call__(self):
+                c = srv.connect()
+                srv.drop_next = True
+                return c
+        MySqlConnection(connect=Twice(), operational_errors=(FakeMySql.OperationalError,)).execute('SELECT 1')
