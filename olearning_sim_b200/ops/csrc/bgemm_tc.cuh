@@ -26,8 +26,9 @@
 namespace bg {
 using namespace tc05;
 
-constexpr int kThreads = 192;
-constexpr int kEpiWarps = 4;
+constexpr int kThreads = 320;          // warps 0-7 epilogue (group g = warp / 4 owns accumulator buffer g), 8 TMA, 9 MMA
+constexpr int kEpiWarps = 4;          // warps per epilogue group = TMEM lane quadrants
+constexpr int kTmaWarp = 8, kMmaWarp = 9;
 constexpr int KC = 64;                 // K elements per pipeline stage (one 128-byte swizzle row)
 enum { A_K = 0, A_MN = 1, A_CONV = 2 };
 enum { B_K = 0, B_MN = 1, B_CONVX = 2, B_WT = 3 };
@@ -84,10 +85,24 @@ struct Cfg {
   static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 };
 
-__device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
-__device__ __forceinline__ float gelu_grad_f(float x) {
-  return 0.5f * (1.f + erff(x * 0.70710678118654752f)) + x * 0.39894228040143268f * __expf(-0.5f * x * x);
+// GELU (erf form, torch's default) and its derivative.  erf(|x|/sqrt2) = 1 - poly(t) * exp(-x^2/2), t = 1/(1 + p|x|/sqrt2)
+// (Abramowitz-Stegun 7.1.26, |error| < 1.5e-7 — far below bf16 resolution); the exponential is the Gaussian density's too,
+// so value + derivative cost one MUFU.EX2 + one MUFU.RCP + a dozen FMAs instead of two erff() + expf() calls: the GELU
+// epilogues were ALU-bound at 5x the MMA time of their tile.
+__device__ __forceinline__ void gelu_parts(float x, float& cdf, float& pdf_x) {
+  const float ax = fabsf(x);
+  const float e = exp2f(-0.72134752044448170f * x * x);                     // exp(-x^2 / 2)
+  const float t = __frcp_rn(fmaf(0.23164189f, ax, 1.f));                    // p / sqrt2 = 0.3275911 / 1.41421356
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float erf_abs = 1.f - poly * t * e;                                 // erf(|x| / sqrt2)
+  cdf = 0.5f * (1.f + copysignf(erf_abs, x));
+  pdf_x = x * 0.39894228040143268f * e;
 }
+__device__ __forceinline__ float gelu_f(float x) { float c, d; gelu_parts(x, c, d); return x * c; }
+__device__ __forceinline__ float gelu_grad_f(float x) { float c, d; gelu_parts(x, c, d); return c + d; }
 __device__ __forceinline__ void unpack8(const uint4& u, float* f) {
   f[0] = bf16lo(u.x); f[1] = bf16hi(u.x); f[2] = bf16lo(u.y); f[3] = bf16hi(u.y);
   f[4] = bf16lo(u.z); f[5] = bf16hi(u.z); f[6] = bf16lo(u.w); f[7] = bf16hi(u.w);
@@ -150,15 +165,15 @@ bgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     for (int i = 0; i < 2; ++i) { mbar_init(&bars->tfull[i], 1); mbar_init(&bars->tempty[i], kEpiWarps); }
     fence_mbar_init();
   }
-  if (warp == 5) { tmem_alloc(&bars->tmem_base, C::TMEM_COLS); tmem_relinquish(); }
-  if (warp == 4 && lane == 0) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); }
+  if (warp == kMmaWarp) { tmem_alloc(&bars->tmem_base, C::TMEM_COLS); tmem_relinquish(); }
+  if (warp == kTmaWarp && lane == 0) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); }
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem_base = bars->tmem_base;
   const int num_work = p.batches * p.m_tiles * p.n_tiles;
 
-  if (warp == 4) {
+  if (warp == kTmaWarp) {
     // ================================================================ TMA producer
     const bool leader = elect_one();
     int stage = 0; uint32_t phase = 0;
@@ -220,7 +235,7 @@ bgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == kMmaWarp) {
     // ================================================================ MMA issuer
     const bool leader = elect_one();
     constexpr uint32_t IDESC = make_idesc_bf16(128, N_TILE, AM == A_MN ? 1 : 0, BM == B_K ? 0 : 1);
@@ -256,12 +271,17 @@ bgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       buf ^= 1;
     }
   } else {
-    // ================================================================ epilogue (4 warps, one accumulator row per thread)
-    int buf = 0; uint32_t tphase0 = 0, tphase1 = 0;
-    const int q = warp;
+    // ================================================================ epilogue: two groups of 4 warps; group g drains accumulator
+    // buffer g, i.e. every other tile — the epilogues of consecutive tiles overlap each other as well as the MMAs (the
+    // forward GEMMs with K = 256 were epilogue-bound at 9 % tensor-pipe utilisation with a single group)
+    const int group = warp >> 2, q = warp & 3;
+    const int buf = group;
+    uint32_t tphase = 0;
+    int tile_n = 0;
     for (int wi = blockIdx.x; wi < num_work; wi += gridDim.x) {
       TileCoord t;
       if (!decode_work<AM, N_TILE>(p, wi, t)) continue;
+      if ((tile_n++ & 1) != group) continue;
       const int row = 32 * q + lane;
       const int m = t.m0 + row;
       const bool rvalid = m < p.M;
@@ -277,7 +297,13 @@ bgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       } else {
         obase = (size_t)(t.bi / p.o_bdiv) * p.o_bs1 + (size_t)(t.bi % p.o_bdiv) * p.o_bs0 + (size_t)m * p.ld;
       }
-      mbar_wait(&bars->tfull[buf], buf ? tphase1 : tphase0);
+      if (EPI == E_SGD && rvalid && !p.grad_out) {
+        // the fp32 master rows this thread is going to update: pull them into L2 while the tile's MMAs run
+        const char* wr = reinterpret_cast<const char*>(p.w_master + (size_t)t.bi * p.w_bs + (size_t)m * p.w_ld + t.n0);
+        const int nbytes = min(N_TILE, p.N - t.n0) * 4;
+        for (int o = 0; o < nbytes; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(wr + o));
+      }
+      mbar_wait(&bars->tfull[buf], tphase);
       fence_after_sync();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(32 * q) << 16) + buf * N_TILE;
 
@@ -304,16 +330,17 @@ bgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           }
           gs = gq = 0.f;
         };
+        uint32_t v[32];
+        tmem_ld32(taddr, v);
 #pragma unroll 1
         for (int j = 0; j < N_TILE / 32; ++j) {
           const int nb = t.n0 + j * 32;
           if (nb >= p.N) break;                         // warp-uniform
-          uint32_t v[32];
-          tmem_ld32(taddr + j * 32, v);
           tmem_ld_wait();
           float f[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+          if (j + 1 < N_TILE / 32 && nb + 32 < p.N) tmem_ld32(taddr + (j + 1) * 32, v);   // next chunk in flight
           if (EPI == E_GNSTAT) {
             const int g = nb / p.gn_cpg;
             if (g != gcur) { if (gcur >= 0) flush(gcur); gcur = g; }
@@ -405,13 +432,17 @@ bgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           if (rvalid) store32(p.out + obase + t.n0 + j * 32, f);
         }
       } else {  // E_SGD: W[b][m][n] -= lr * (g + mu (w - w_global)), bf16 operand copy refreshed in the same pass
+        uint32_t vn[32];
+        tmem_ld32(taddr, vn);
 #pragma unroll 1
         for (int j = 0; j < N_TILE / 32; ++j) {
           const int nb = t.n0 + j * 32;
           if (nb >= p.N) break;
-          uint32_t v[32];
-          tmem_ld32(taddr + j * 32, v);
           tmem_ld_wait();
+          uint32_t v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = vn[i];
+          if (j + 1 < N_TILE / 32 && nb + 32 < p.N) tmem_ld32(taddr + (j + 1) * 32, vn);   // next chunk in flight
           if (rvalid && p.grad_out) {
             float4* gp = reinterpret_cast<float4*>(p.grad_out + (size_t)t.bi * p.g_bs + (size_t)m * p.w_ld + nb);
 #pragma unroll
@@ -448,13 +479,12 @@ bgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->tempty[buf]);
-      if (buf) tphase1 ^= 1; else tphase0 ^= 1;
-      buf ^= 1;
+      tphase ^= 1;
     }
   }
   fence_before_sync();
   __syncthreads();
-  if (warp == 5) tmem_dealloc(tmem_base, C::TMEM_COLS);
+  if (warp == kMmaWarp) tmem_dealloc(tmem_base, C::TMEM_COLS);
 }
 
 }  // namespace bg
