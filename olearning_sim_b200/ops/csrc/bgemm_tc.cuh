@@ -78,7 +78,8 @@ struct Cfg {
   static constexpr int B_BYTES = (BM == B_K) ? N_TILE * 128 : (N_TILE / 64) * KC * 128;
   static constexpr int STAGE_BYTES = A_BYTES + ((B_BYTES + 1023) / 1024) * 1024;
   static constexpr int TMEM_COLS = (2 * N_TILE <= 32) ? 32 : (2 * N_TILE <= 64 ? 64 : (2 * N_TILE <= 128 ? 128 : (2 * N_TILE <= 256 ? 256 : 512)));
-  static constexpr int SMEM_BYTES = 1024 + NSTAGE * STAGE_BYTES + (int)sizeof(Bars);
+  static constexpr int SCRATCH_BYTES = 8 * 4096;                 // one 32-row x 128-byte staging block per epilogue warp
+  static constexpr int SMEM_BYTES = 1024 + NSTAGE * STAGE_BYTES + SCRATCH_BYTES + (int)sizeof(Bars);
   static_assert(N_TILE % 32 == 0 && N_TILE <= 256, "epilogue works on 32-column chunks");
   static_assert(BM == B_K || N_TILE % 64 == 0, "MN-major B is loaded in 64-column boxes");
   static_assert(NSTAGE <= 8, "barrier arrays hold 8 stages");
@@ -124,6 +125,57 @@ __device__ __forceinline__ void store32(__nv_bfloat16* p, const float* f) {
   for (int i = 0; i < 4; ++i) q[i] = pack8(f + 8 * i);
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Warp-private staging transposes.  A thread of the epilogue owns one accumulator ROW, so a direct store makes every
+// warp-level instruction write 32 scattered 16-byte pieces (half sectors): measured at ~6x the per-byte cost of reads,
+// it made the output-heavy GEMMs (K = 256) run at a third of their HBM roofline.  Rows are therefore exchanged through a
+// 4 KB swizzled block per warp so that each global instruction touches four full 128-byte lines (8 lanes per row).
+// Slot (row, c) holds 16-byte piece c of a 128-byte row segment at sc[row * 8 + (c ^ (row & 7))]: conflict-free both for
+// the row-owner access (lane = row) and for the transposed access (8 lanes per row).
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void stage_rows_out(uint4* sc, int lane, const uint4* pk, int nq, char* dst_base, size_t row_off,
+                                               bool rvalid) {
+  // pk[0..nq): this thread's row segment (nq <= 8 pieces); dst = dst_base + row_off(row) for every row of the warp
+  __syncwarp();
+#pragma unroll
+  for (int c = 0; c < 8; ++c)
+    if (c < nq) sc[lane * 8 + (c ^ (lane & 7))] = pk[c];
+  __syncwarp();
+  const int c = lane & 7;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int row = 4 * i + (lane >> 3);
+    const uint32_t lo = __shfl_sync(0xffffffffu, static_cast<uint32_t>(row_off), row);
+    const uint32_t hi = __shfl_sync(0xffffffffu, static_cast<uint32_t>(row_off >> 32), row);
+    const int ok = __shfl_sync(0xffffffffu, rvalid ? 1 : 0, row);
+    if (ok && c < nq)
+      *reinterpret_cast<uint4*>(dst_base + ((static_cast<size_t>(hi) << 32) | lo) + c * 16) = sc[row * 8 + (c ^ (row & 7))];
+  }
+}
+__device__ __forceinline__ void stage_rows_in(uint4* sc, int lane, uint4* pk, int nq, const char* src_base, size_t row_off,
+                                              bool rvalid) {
+  __syncwarp();
+  const int c = lane & 7;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int row = 4 * i + (lane >> 3);
+    const uint32_t lo = __shfl_sync(0xffffffffu, static_cast<uint32_t>(row_off), row);
+    const uint32_t hi = __shfl_sync(0xffffffffu, static_cast<uint32_t>(row_off >> 32), row);
+    const int ok = __shfl_sync(0xffffffffu, rvalid ? 1 : 0, row);
+    if (ok && c < nq)
+      sc[row * 8 + (c ^ (row & 7))] = *reinterpret_cast<const uint4*>(src_base + ((static_cast<size_t>(hi) << 32) | lo) + c * 16);
+  }
+  __syncwarp();
+#pragma unroll
+  for (int cc = 0; cc < 8; ++cc)
+    if (cc < nq) pk[cc] = sc[lane * 8 + (cc ^ (lane & 7))];
+}
+// 32 fp32 values of this thread's row -> 4 packed bf16 pieces
+__device__ __forceinline__ void pack32(const float* f, uint4* pk) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) pk[i] = pack8(f + 8 * i);
+}
+
 struct TileCoord {
   int bi, mt, nt, m0, n0, img0, ty0, tx0;
 };
@@ -152,13 +204,14 @@ __device__ __forceinline__ bool decode_work(const Params& p, int wi, TileCoord& 
 }
 
 template <int AM, int BM, int N_TILE, int EPI, int NSTAGE>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __maxnreg__(200)
 bgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
              const __grid_constant__ Params p) {
   using C = Cfg<AM, BM, N_TILE, NSTAGE>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  Bars* bars = reinterpret_cast<Bars*>(smem + NSTAGE * C::STAGE_BYTES);
+  uint4* scratch_all = reinterpret_cast<uint4*>(smem + NSTAGE * C::STAGE_BYTES);
+  Bars* bars = reinterpret_cast<Bars*>(smem + NSTAGE * C::STAGE_BYTES + C::SCRATCH_BYTES);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int i = 0; i < NSTAGE; ++i) { mbar_init(&bars->full[i], 1); mbar_init(&bars->empty[i], 1); }
@@ -276,6 +329,7 @@ bgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     // forward GEMMs with K = 256 were epilogue-bound at 9 % tensor-pipe utilisation with a single group)
     const int group = warp >> 2, q = warp & 3;
     const int buf = group;
+    uint4* scratch = scratch_all + warp * 256;
     uint32_t tphase = 0;
     int tile_n = 0;
     for (int wi = blockIdx.x; wi < num_work; wi += gridDim.x) {
@@ -332,48 +386,62 @@ bgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         };
         uint32_t v[32];
         tmem_ld32(taddr, v);
+        const int nchunks = min(N_TILE / 32, (p.N - t.n0 + 31) / 32);          // warp-uniform
 #pragma unroll 1
-        for (int j = 0; j < N_TILE / 32; ++j) {
-          const int nb = t.n0 + j * 32;
-          if (nb >= p.N) break;                         // warp-uniform
-          tmem_ld_wait();
-          float f[32];
+        for (int jp = 0; jp < N_TILE / 64; ++jp) {
+          if (2 * jp >= nchunks) break;
+          uint4 pko[8], pka[8];                          // packed output / packed GELU pre-activation of a 64-column pair
 #pragma unroll
-          for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
-          if (j + 1 < N_TILE / 32 && nb + 32 < p.N) tmem_ld32(taddr + (j + 1) * 32, v);   // next chunk in flight
-          if (EPI == E_GNSTAT) {
-            const int g = nb / p.gn_cpg;
-            if (g != gcur) { if (gcur >= 0) flush(gcur); gcur = g; }
+          for (int half = 0; half < 2; ++half) {
+            const int j = 2 * jp + half;
+            if (j < nchunks) {
+              const int nb = t.n0 + j * 32;
+              tmem_ld_wait();
+              float f[32];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) { gs += f[i]; gq += f[i] * f[i]; }
+              for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+              if (j + 1 < nchunks) tmem_ld32(taddr + (j + 1) * 32, v);       // next chunk in flight
+              if (EPI == E_GNSTAT) {
+                const int g = nb / p.gn_cpg;
+                if (g != gcur) { if (gcur >= 0) flush(gcur); gcur = g; }
+#pragma unroll
+                for (int i = 0; i < 32; ++i) { gs += f[i]; gq += f[i] * f[i]; }
+              }
+              if (EPI == E_STORE) {
+                if (p.bias) {
+                  const float4* bp = reinterpret_cast<const float4*>(p.bias + (size_t)(t.bi / p.bias_div) * p.bias_bs + nb);
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) { const float4 b = __ldg(bp + i); f[4 * i] += b.x; f[4 * i + 1] += b.y; f[4 * i + 2] += b.z; f[4 * i + 3] += b.w; }
+                }
+                if (p.addend && rvalid) {
+                  float a[32];
+                  load32(p.addend + obase + nb, a);
+#pragma unroll
+                  for (int i = 0; i < 32; ++i) f[i] += a[i];
+                }
+                if (p.act == ACT_RELU) {
+#pragma unroll
+                  for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
+                } else if (p.act == ACT_GELU) {
+                  pack32(f, pka + 4 * half);
+#pragma unroll
+                  for (int i = 0; i < 32; ++i) f[i] = gelu_f(f[i]);
+                } else if (p.act == ACT_GELU_BWD) {
+                  float a[32];
+                  if (rvalid) load32(p.aux_in + obase + nb, a);
+#pragma unroll
+                  for (int i = 0; i < 32; ++i) f[i] = rvalid ? f[i] * gelu_grad_f(a[i]) : 0.f;
+                }
+              }
+              pack32(f, pko + 4 * half);
+            }
           }
-          if (EPI == E_STORE) {
-            if (p.bias) {
-              const float4* bp = reinterpret_cast<const float4*>(p.bias + (size_t)(t.bi / p.bias_div) * p.bias_bs + nb);
-#pragma unroll
-              for (int i = 0; i < 8; ++i) { const float4 b = __ldg(bp + i); f[4 * i] += b.x; f[4 * i + 1] += b.y; f[4 * i + 2] += b.z; f[4 * i + 3] += b.w; }
-            }
-            if (p.addend && rvalid) {
-              float a[32];
-              load32(p.addend + obase + nb, a);
-#pragma unroll
-              for (int i = 0; i < 32; ++i) f[i] += a[i];
-            }
-            if (p.act == ACT_RELU) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
-            } else if (p.act == ACT_GELU) {
-              if (rvalid && p.aux_out) store32(p.aux_out + obase + nb, f);
-#pragma unroll
-              for (int i = 0; i < 32; ++i) f[i] = gelu_f(f[i]);
-            } else if (p.act == ACT_GELU_BWD) {
-              float a[32];
-              if (rvalid) load32(p.aux_in + obase + nb, a);
-#pragma unroll
-              for (int i = 0; i < 32; ++i) f[i] = rvalid ? f[i] * gelu_grad_f(a[i]) : 0.f;
-            }
-          }
-          if (rvalid) store32(p.out + obase + nb, f);
+          // rows of the warp x 64 (or a trailing 32) columns of the pair, written as full 128-byte lines
+          const int nq = (2 * jp + 1 < nchunks) ? 8 : 4;
+          const size_t off = (obase + (size_t)(t.n0 + jp * 64)) * 2;
+          stage_rows_out(scratch, lane, pko, nq, reinterpret_cast<char*>(p.out), off, rvalid);
+          if (EPI == E_STORE && p.act == ACT_GELU && p.aux_out)
+            stage_rows_out(scratch, lane, pka, nq, reinterpret_cast<char*>(p.aux_out), off, rvalid);
         }
         if (EPI == E_GNSTAT && gcur >= 0) flush(gcur);
       } else if (EPI == E_SOFTMAX) {
@@ -406,7 +474,9 @@ bgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           float f[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) f[i] = exp2f((__uint_as_float(v[i]) - mx) * sc) * inv;
-          if (rvalid) store32(p.out + obase + t.n0 + j * 32, f);
+          uint4 pk[4];
+          pack32(f, pk);
+          stage_rows_out(scratch, lane, pk, 4, reinterpret_cast<char*>(p.out), (obase + t.n0 + j * 32) * 2, rvalid);
         }
       } else if (EPI == E_DSOFT) {
         float dot = 0.f;
@@ -429,7 +499,9 @@ bgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           if (rvalid) load32(p.aux_in + obase + t.n0 + j * 32, a);
 #pragma unroll
           for (int i = 0; i < 32; ++i) f[i] = rvalid ? a[i] * (__uint_as_float(v[i]) - dot) * p.scale : 0.f;
-          if (rvalid) store32(p.out + obase + t.n0 + j * 32, f);
+          uint4 pk[4];
+          pack32(f, pk);
+          stage_rows_out(scratch, lane, pk, 4, reinterpret_cast<char*>(p.out), (obase + t.n0 + j * 32) * 2, rvalid);
         }
       } else {  // E_SGD: W[b][m][n] -= lr * (g + mu (w - w_global)), bf16 operand copy refreshed in the same pass
         uint32_t vn[32];
@@ -448,15 +520,18 @@ bgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 #pragma unroll
             for (int i = 0; i < 8; ++i)
               gp[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
-          } else if (rvalid) {
-            float4* wp = reinterpret_cast<float4*>(p.w_master + (size_t)t.bi * p.w_bs + (size_t)m * p.w_ld + nb);
-            float4 wv[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) wv[i] = wp[i];                                    // all loads before any store
+          } else if (!p.grad_out) {
+            // fp32 master rows: coalesced read through the staging block, update, coalesced write back + bf16 operand copy
+            const size_t woff = (size_t)t.bi * p.w_bs + (size_t)m * p.w_ld + nb;
+            uint4 wq[8];
+            stage_rows_in(scratch, lane, wq, 8, reinterpret_cast<const char*>(p.w_master), woff * 4, rvalid);
             float w[32];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) { w[4 * i] = wv[i].x; w[4 * i + 1] = wv[i].y; w[4 * i + 2] = wv[i].z; w[4 * i + 3] = wv[i].w; }
-            if (p.w_global) {
+            for (int i = 0; i < 8; ++i) {
+              w[4 * i] = __uint_as_float(wq[i].x); w[4 * i + 1] = __uint_as_float(wq[i].y);
+              w[4 * i + 2] = __uint_as_float(wq[i].z); w[4 * i + 3] = __uint_as_float(wq[i].w);
+            }
+            if (p.w_global && rvalid) {
               const float4* ap = reinterpret_cast<const float4*>(p.w_global + (size_t)m * p.w_ld + nb);
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
@@ -471,8 +546,13 @@ bgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               for (int i = 0; i < 32; ++i) w[i] -= p.lr * __uint_as_float(v[i]);
             }
 #pragma unroll
-            for (int i = 0; i < 8; ++i) wp[i] = make_float4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
-            store32(p.w_bf16 + (size_t)t.bi * p.wb_bs + (size_t)m * p.w_ld + nb, w);
+            for (int i = 0; i < 8; ++i)
+              wq[i] = make_uint4(__float_as_uint(w[4 * i]), __float_as_uint(w[4 * i + 1]), __float_as_uint(w[4 * i + 2]), __float_as_uint(w[4 * i + 3]));
+            stage_rows_out(scratch, lane, wq, 8, reinterpret_cast<char*>(p.w_master), woff * 4, rvalid);
+            uint4 pk[4];
+            pack32(w, pk);
+            stage_rows_out(scratch, lane, pk, 4, reinterpret_cast<char*>(p.w_bf16),
+                           ((size_t)t.bi * p.wb_bs + (size_t)m * p.w_ld + nb) * 2, rvalid);
           }
         }
       }

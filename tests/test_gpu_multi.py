@@ -22,3 +22,18 @@ def test_two_ranks_match_single_rank(opt):
     assert lines, out.stderr[-2000:]
     res = json.loads(lines[-1])
     assert res["world"] == 2 and res["ok"], res
+
+
+@pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
+@pytest.mark.parametrize("model,opt", [("cnn2", "avg"), ("cnn2", "adam"), ("mlp2", "momentum"), ("resnet18", "avg"), ("bert_mini", "avg")])
+def test_native_ranks_match_the_nccl_oracle(model, opt):
+    """native P2P broadcast / reduce + hand-written local step on 2 ranks vs the fp32 torch backend over NCCL all-reduce"""
+    env = dict(os.environ, MODEL=model, OPT=opt)
+    port = 29540 + abs(hash((model, opt))) % 40
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(ROOT, "tools", "mgpu_oracle.py")]
+    out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=900, cwd=ROOT)
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert lines, out.stderr[-2000:]
+    res = json.loads(lines[-1])
+    assert res["world"] == 2 and res["ok"], res
