@@ -204,7 +204,7 @@ __device__ __forceinline__ bool decode_work(const Params& p, int wi, TileCoord& 
 }
 
 template <int AM, int BM, int N_TILE, int EPI, int NSTAGE>
-__global__ void __maxnreg__(200)
+__global__ void __maxnreg__(192)
 bgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
              const __grid_constant__ Params p) {
   using C = Cfg<AM, BM, N_TILE, NSTAGE>;
