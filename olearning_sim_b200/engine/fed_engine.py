@@ -181,6 +181,7 @@ class FedEngine:
         # the flow schedule, which orders all participants, is computed identically everywhere)
         self.p_online_np = np.full(cfg.num_clients, cfg.p_online, np.float32)
         self.class_names: List[str] = []
+        self.device_flow_ticks = True       # workspace backends: rank flow-dispatch arrivals on the GPU (False: host twin)
         self.class_of_client = np.zeros(cfg.num_clients, np.int32)
         self._flow_cache: Dict[str, Any] = {}
         if backend == "native":
@@ -244,6 +245,50 @@ class FedEngine:
             plan = Strategy.flow_plan(st, flow_id, area_fn=area_fn)
             self._flow_cache["plan"] = plan
         return plan["amount"], Strategy.draw_drops(plan, rng)
+
+    def _device_flow(self, round_idx: int, scale: float) -> bool:
+        """Flow strategy of a workspace backend: fill ``self.tick_dev`` on the device (flow_*_kernel) from the per-task
+        plan.  Host work per round: nothing, or — when the strategy drops messages — drawing the drop lists with the
+        round's seeded RNG (the reference's algorithm) and uploading them as a per-message byte map."""
+        cfg = self.cfg
+        from ..deviceflow.strategy import Strategy
+        st = cfg.deviceflow_strategy
+        if not (self.uses_ws and st and not Strategy.check_real_time_dispatch(st) and Strategy.is_round_invariant(st)):
+            return False
+        from ..ops import native
+        amount, drops = self._flow_schedule(round_idx)
+        fc = self._flow_cache
+        if "dev" not in fc:
+            d, n = self.device, cfg.num_clients
+            cum = np.cumsum(np.asarray(amount, np.int64)).astype(np.int32)
+            fc["dev"] = {"cum": torch.from_numpy(cum).to(d) if len(cum) else torch.zeros(1, dtype=torch.int32, device=d),
+                         "nslots": len(amount), "total": int(cum[-1]) if len(cum) else 0,
+                         "p_all": torch.from_numpy(self.p_online_np.copy()).to(d),
+                         "scratch": {"keys": torch.empty(n, dtype=torch.int32, device=d), "hist": torch.zeros(4096, dtype=torch.int32, device=d),
+                                     "start": torch.zeros(4097, dtype=torch.int32, device=d), "cursor": torch.zeros(4096, dtype=torch.int32, device=d),
+                                     "items": torch.empty(max(n, 1), dtype=torch.int32, device=d)},
+                         "dropmap": None, "drop_host": None}
+        dv = fc["dev"]
+        dropmap = None
+        if any(len(x) for x in drops):
+            if dv["dropmap"] is None:
+                dv["dropmap"] = torch.zeros(max(dv["total"], 1), dtype=torch.uint8, device=self.device)
+                dv["drop_host"] = torch.zeros(max(dv["total"], 1), dtype=torch.uint8).pin_memory()
+            hm = dv["drop_host"].numpy()
+            hm[:] = 0
+            k = 0
+            for slot, nmsg in enumerate(amount):
+                if slot < len(drops) and drops[slot]:
+                    idx = np.asarray(drops[slot], np.int64)
+                    hm[k + idx[idx < nmsg]] = 1
+                k += nmsg
+            dv["dropmap"].copy_(dv["drop_host"], non_blocking=True)
+            dropmap = dv["dropmap"]
+        native.flow_ticks(cfg.num_clients, self.c0, self.C, cfg.seed, round_idx, dv["p_all"], float(scale), dv["scratch"], dv["cum"],
+                          dv["nslots"], dropmap, self.tick_dev)
+        self.ws.kernel_launches += 4
+        self._max_tick = max(dv["nslots"] - 1, 0)
+        return True
 
     def _round_flow(self, round_idx: int):
         """(p_online_scale, drop_probability, arrive_tick[C_local] | None, max_tick) for this round.
@@ -376,11 +421,21 @@ class FedEngine:
         from ..ops import native
         cfg, ws = self.cfg, self.ws
         ws.reset_round_stats()
-        scale, drop_p, ticks, max_tick = self._round_flow(round_idx)
+        on_device = False
+        if cfg.deviceflow_strategy and self.device_flow_ticks:
+            scale = 1.0
+            if cfg.online_trace:
+                from ..deviceflow import safe_expr
+                scale = float(min(max(safe_expr.evaluate(cfg.online_trace, float(round_idx)), 0.0), 1.0))
+            on_device = self._device_flow(round_idx, scale)
+        if on_device:
+            drop_p, ticks, max_tick = cfg.drop_probability, None, self._max_tick
+        else:
+            scale, drop_p, ticks, max_tick = self._round_flow(round_idx)
         sampled = bool(self.p_online_np.size and float(self.p_online_np.min()) * scale < 1.0)
         if sampled:
             self.p_online_round.copy_(self.p_online_t).mul_(scale)
-        tick_t = None
+        tick_t = self.tick_dev if on_device else None
         if ticks is not None:
             self.tick_host.copy_(torch.from_numpy(ticks))
             self.tick_dev.copy_(self.tick_host, non_blocking=True)

@@ -515,6 +515,23 @@ int olsb_deviceflow_mask(int C, int client_base, unsigned long long seed, unsign
   return 0;
 }
 
+// flow-dispatch ticks of this rank's clients, computed on the device (see fl_kernels.cuh: flow_*_kernel)
+int olsb_flow_ticks(int N, int c0, int C, unsigned long long seed, unsigned round, const void* p_online_all, float scale,
+                    void* keys, void* hist, void* start, void* cursor, void* items, const void* cum, int nslots,
+                    const void* dropmap, void* tick, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  CK(cudaMemsetAsync(hist, 0, flk::kFlowBuckets * sizeof(int), st));
+  const int th = 256, gn = (N + th - 1) / th;
+  flk::flow_keys_kernel<<<gn, th, 0, st>>>(N, (uint32_t)seed, (uint32_t)(seed >> 32), round, (const float*)p_online_all, scale,
+                                            (uint32_t*)keys, (int*)hist);
+  flk::flow_scan_kernel<<<1, 1024, 0, st>>>((const int*)hist, (int*)start, (int*)cursor);
+  flk::flow_scatter_kernel<<<gn, th, 0, st>>>(N, (const uint32_t*)keys, (const int*)start, (int*)cursor, (int*)items);
+  flk::flow_ticks_kernel<<<(C + th - 1) / th, th, 0, st>>>(c0, C, (const uint32_t*)keys, (const int*)start, (const int*)items,
+                                                           (const int*)cum, nslots, (const uint8_t*)dropmap, (int32_t*)tick);
+  CK(cudaGetLastError());
+  return 0;
+}
+
 int olsb_rate_curve_area(const void* y, void* area, int bins, void* stream) {
   flk::rate_curve_area_kernel<<<(bins + 127) / 128, 128, 0, (cudaStream_t)stream>>>((const double*)y, (double*)area,
                                                                                       bins);

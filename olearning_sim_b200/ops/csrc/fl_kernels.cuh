@@ -697,6 +697,83 @@ __global__ void deviceflow_mask_kernel(const MaskParams p) {
   if (arrived) atomicAdd(&p.counters[3], 1);
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Flow-dispatch schedule on the device (DeviceFlow flow mode, ols_core/deviceflow/non_grpc/dispatcher.py:174-252):
+// message k of a flow's shelf is the k-th FINISHING participant of the round; slot s forwards amount[s] messages, the
+// indices in its drop list are consumed but not forwarded, and whatever is left on the shelf after the last slot is
+// discarded.  The host used to rank all clients with numpy every round (philox + argsort + H2D copy); these four
+// kernels do it on the GPU from the per-task plan (cumulative amounts, uploaded once):
+//   flow_keys     Philox stream of every GLOBAL client -> participation, 24-bit finishing key, histogram of the top 12 bits
+//   flow_scan     exclusive scan of the 4096 buckets (one CTA)
+//   flow_scatter  participants grouped by bucket
+//   flow_ticks    rank inside the bucket (ties by client id = the stable argsort of the host twin) -> message index ->
+//                 slot via binary search in the cumulative amounts -> arrive_tick of this rank's clients
+// Every rank computes the same global ranking (counter-based RNG, no communication).
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kFlowBuckets = 4096;
+__global__ void flow_keys_kernel(int N, uint32_t seed_lo, uint32_t seed_hi, uint32_t round, const float* __restrict__ p_online,
+                                 float scale, uint32_t* __restrict__ keys, int* __restrict__ hist) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  uint32_t r[4];
+  philox4x32_10(round, (uint32_t)i, 0u, 0u, seed_lo, seed_hi, r);
+  const float u_on = (r[0] >> 8) * (1.f / 16777216.f);
+  const bool part = u_on < p_online[i] * scale;
+  const uint32_t key = r[2] >> 8;
+  keys[i] = part ? key : 0xFFFFFFFFu;
+  if (part) atomicAdd(&hist[key >> 12], 1);
+}
+__global__ void flow_scan_kernel(const int* __restrict__ hist, int* __restrict__ start, int* __restrict__ cursor) {
+  // 4096 buckets, 1024 threads x 4; start[kFlowBuckets] = number of participants
+  __shared__ int s_part[1024];
+  const int t = threadIdx.x;
+  int v[4], sum = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { v[k] = hist[t * 4 + k]; sum += v[k]; }
+  s_part[t] = sum;
+  __syncthreads();
+  for (int o = 1; o < 1024; o <<= 1) {
+    const int add = t >= o ? s_part[t - o] : 0;
+    __syncthreads();
+    s_part[t] += add;
+    __syncthreads();
+  }
+  int base = s_part[t] - sum;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { start[t * 4 + k] = base; cursor[t * 4 + k] = 0; base += v[k]; }
+  if (t == 1023) start[kFlowBuckets] = s_part[1023];
+}
+__global__ void flow_scatter_kernel(int N, const uint32_t* __restrict__ keys, const int* __restrict__ start,
+                                    int* __restrict__ cursor, int* __restrict__ items) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const uint32_t k = keys[i];
+  if (k == 0xFFFFFFFFu) return;
+  const int b = k >> 12;
+  items[start[b] + atomicAdd(&cursor[b], 1)] = i;
+}
+__global__ void flow_ticks_kernel(int c0, int C, const uint32_t* __restrict__ keys, const int* __restrict__ start,
+                                  const int* __restrict__ items, const int* __restrict__ cum, int nslots,
+                                  const uint8_t* __restrict__ dropmap, int32_t* __restrict__ tick) {
+  const int li = blockIdx.x * blockDim.x + threadIdx.x;
+  if (li >= C) return;
+  const int i = c0 + li;
+  const uint32_t k = keys[i];
+  if (k == 0xFFFFFFFFu) { tick[li] = -1; return; }
+  const int b = k >> 12, s0 = start[b], s1 = start[b + 1];
+  int rank = s0;
+  for (int j = s0; j < s1; ++j) {
+    const int o = items[j];
+    const uint32_t ko = keys[o];
+    rank += (ko < k || (ko == k && o < i)) ? 1 : 0;
+  }
+  const int total = nslots > 0 ? cum[nslots - 1] : 0;
+  if (rank >= total) { tick[li] = -1; return; }          // beyond the schedule: left on the shelf, discarded
+  int lo = 0, hi = nslots - 1;                            // first slot with cum[slot] > rank
+  while (lo < hi) { const int mid = (lo + hi) >> 1; if (cum[mid] > rank) hi = mid; else lo = mid + 1; }
+  tick[li] = (dropmap && dropmap[rank]) ? -1 : lo;
+}
+
 // Rate-curve integration (DeviceFlow specific_interval, ols_core/deviceflow/non_grpc/strategy.py:339-349): area of the
 // positive trapezoids of every 1-second bin.  `y` holds f sampled at the 101 nodes of each bin (nodes are NOT shared
 // between bins, matching the reference's per-bin linspace).  Double precision with explicitly rounded operations in the

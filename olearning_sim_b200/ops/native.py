@@ -199,6 +199,15 @@ def deviceflow_mask(num_clients, client_base, seed, round_idx, p_online, drop_pr
                                        _p(counters), _stream()))
 
 
+def flow_ticks(num_clients_total: int, c0: int, num_local: int, seed: int, round_idx: int, p_online_all, scale: float, scratch: dict,
+               cum, nslots: int, dropmap, tick) -> None:
+    """arrive_tick of this rank's clients for a flow-dispatch schedule, ranked on the device (4 launches)."""
+    _ck(require().olsb_flow_ticks(C.c_int(num_clients_total), C.c_int(c0), C.c_int(num_local), C.c_ulonglong(seed), C.c_uint(round_idx),
+                                  _p(p_online_all), C.c_float(scale), _p(scratch["keys"]), _p(scratch["hist"]), _p(scratch["start"]),
+                                  _p(scratch["cursor"]), _p(scratch["items"]), _p(cum), C.c_int(nslots), _p(dropmap), _p(tick),
+                                  _stream()))
+
+
 def rate_curve_area(y: torch.Tensor, area: torch.Tensor) -> None:
     """y: float64 [bins, 101] rate-function samples; area: float64 [bins] positive-trapezoid integrals."""
     assert y.dtype == torch.float64 and area.dtype == torch.float64 and y.shape[-1] == 101

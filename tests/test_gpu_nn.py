@@ -342,3 +342,48 @@ def test_resnet18_fedprox_sampled_waves_track_the_torch_backend():
         assert abs(ra.loss - rb_.loss) < 4e-2 * max(1.0, abs(rb_.loss)), (r, ra.loss, rb_.loss)
     assert rel(a.spec_flat_global().cpu() - g0, b.global_model().cpu() - g0) < 8e-2
     a.close()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# DeviceFlow on the device: rate-curve integration (K8) and flow-dispatch ranking vs their host twins
+# ---------------------------------------------------------------------------------------------------------
+def test_rate_curve_kernel_is_bit_identical_to_the_host_integrator():
+    import numpy as np
+    from olearning_sim_b200.deviceflow.strategy import Strategy
+    from olearning_sim_b200.ops import native
+    for iv, dom, fn in (([0, 40], [0.0, 6.283], "math.sin(t)+0.3"), ([5, 17], [-1.0, 2.0], "t*t-0.5"), ([0, 3], [0, 1], "2*t")):
+        y = Strategy.interval_samples(iv, dom, fn)
+        yt = torch.from_numpy(np.ascontiguousarray(y)).to(DEV)
+        out = torch.empty(y.shape[0], dtype=torch.float64, device=DEV)
+        native.rate_curve_area(yt, out)
+        _, want = Strategy.interval_areas(iv, dom, fn)
+        assert out.cpu().tolist() == want                              # exact: same operations in the same order
+
+
+@pytest.mark.parametrize("drop", [None, {"drop_probability": [0.3, 0.0]}, {"drop_amounts": [5, 2]}])
+def test_flow_ticks_on_device_match_the_host_ranking(drop):
+    import json as _json
+    from olearning_sim_b200.engine.fed_engine import FedConfig, FedEngine
+    si = {"use": True, "time_type": "relative", "intervals": [[0, 6], [8, 12]],
+          "dispatch_rules": {"domains": [[0, 3.14], [0, 1]], "functions": ["math.sin(t)+0.2", "2*t"]}}
+    if drop:
+        si["drop_simulation"] = drop
+    st = {"real_time_dispatch": {"use_strategy": False}, "flow_dispatch": {"use_strategy": True, "total_dispatch_amount": 150, "specific_interval": si}}
+    eng = FedEngine(FedConfig(model="cnn2", num_clients=257, local_steps=1, shard=64, backend="native", p_online=0.85,
+                              online_trace="0.7+0.3*math.cos(t)", deviceflow_strategy=_json.dumps(st), seed=5))
+    eng.load_synthetic()
+    for r in range(3):
+        scale, _, ticks, max_tick = eng._round_flow(r)                  # host twin: philox + stable argsort + schedule_to_ticks
+        assert eng._device_flow(r, scale) and eng._max_tick == max_tick
+        torch.cuda.synchronize()
+        assert eng.tick_dev.cpu().tolist() == ticks.tolist(), r
+    # and the whole round agrees with the host path end to end
+    a = eng.run_round(5)
+    eng.device_flow_ticks = False
+    eng2 = FedEngine(FedConfig(model="cnn2", num_clients=257, local_steps=1, shard=64, backend="native", p_online=0.85,
+                               online_trace="0.7+0.3*math.cos(t)", deviceflow_strategy=_json.dumps(st), seed=5))
+    eng2.device_flow_ticks = False
+    eng2.load_synthetic()
+    b = eng2.run_round(5)
+    assert (a.participants, a.arrived, a.late, a.dropped) == (b.participants, b.arrived, b.late, b.dropped) and a.late > 0
+    eng.close(); eng2.close()
