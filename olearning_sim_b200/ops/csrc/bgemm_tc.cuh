@@ -133,42 +133,44 @@ __device__ __forceinline__ void store32(__nv_bfloat16* p, const float* f) {
 // Slot (row, c) holds 16-byte piece c of a 128-byte row segment at sc[row * 8 + (c ^ (row & 7))]: conflict-free both for
 // the row-owner access (lane = row) and for the transposed access (8 lanes per row).
 // ---------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void stage_rows_out(uint4* sc, int lane, const uint4* pk, int nq, char* dst_base, size_t row_off,
-                                               bool rvalid) {
-  // pk[0..nq): this thread's row segment (nq <= 8 pieces); dst = dst_base + row_off(row) for every row of the warp
+template <int NQ>   // 16-byte pieces per row segment: 8 (128 B: fp32 chunk) or 4 (64 B: bf16 chunk)
+__device__ __forceinline__ int stage_slot(int row, int c) {
+  return NQ == 8 ? row * 8 + (c ^ (row & 7)) : row * 4 + (c ^ ((row >> 1) & 3));
+}
+template <int NQ>
+__device__ __forceinline__ void stage_rows_out(uint4* sc, int lane, const uint4* pk, char* dst_base, size_t row_off, bool rvalid) {
+  // pk[0..NQ): this thread's row segment; dst = dst_base + row_off(row) for every row of the warp
   __syncwarp();
 #pragma unroll
-  for (int c = 0; c < 8; ++c)
-    if (c < nq) sc[lane * 8 + (c ^ (lane & 7))] = pk[c];
+  for (int c = 0; c < NQ; ++c) sc[stage_slot<NQ>(lane, c)] = pk[c];
   __syncwarp();
-  const int c = lane & 7;
+  constexpr int RPI = 32 / NQ;                       // rows per instruction
+  const int c = lane % NQ;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int row = 4 * i + (lane >> 3);
+  for (int i = 0; i < NQ; ++i) {
+    const int row = RPI * i + lane / NQ;
     const uint32_t lo = __shfl_sync(0xffffffffu, static_cast<uint32_t>(row_off), row);
     const uint32_t hi = __shfl_sync(0xffffffffu, static_cast<uint32_t>(row_off >> 32), row);
     const int ok = __shfl_sync(0xffffffffu, rvalid ? 1 : 0, row);
-    if (ok && c < nq)
-      *reinterpret_cast<uint4*>(dst_base + ((static_cast<size_t>(hi) << 32) | lo) + c * 16) = sc[row * 8 + (c ^ (row & 7))];
+    if (ok) *reinterpret_cast<uint4*>(dst_base + ((static_cast<size_t>(hi) << 32) | lo) + c * 16) = sc[stage_slot<NQ>(row, c)];
   }
 }
-__device__ __forceinline__ void stage_rows_in(uint4* sc, int lane, uint4* pk, int nq, const char* src_base, size_t row_off,
-                                              bool rvalid) {
+template <int NQ>
+__device__ __forceinline__ void stage_rows_in(uint4* sc, int lane, uint4* pk, const char* src_base, size_t row_off, bool rvalid) {
   __syncwarp();
-  const int c = lane & 7;
+  constexpr int RPI = 32 / NQ;
+  const int c = lane % NQ;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int row = 4 * i + (lane >> 3);
+  for (int i = 0; i < NQ; ++i) {
+    const int row = RPI * i + lane / NQ;
     const uint32_t lo = __shfl_sync(0xffffffffu, static_cast<uint32_t>(row_off), row);
     const uint32_t hi = __shfl_sync(0xffffffffu, static_cast<uint32_t>(row_off >> 32), row);
     const int ok = __shfl_sync(0xffffffffu, rvalid ? 1 : 0, row);
-    if (ok && c < nq)
-      sc[row * 8 + (c ^ (row & 7))] = *reinterpret_cast<const uint4*>(src_base + ((static_cast<size_t>(hi) << 32) | lo) + c * 16);
+    if (ok) sc[stage_slot<NQ>(row, c)] = *reinterpret_cast<const uint4*>(src_base + ((static_cast<size_t>(hi) << 32) | lo) + c * 16);
   }
   __syncwarp();
 #pragma unroll
-  for (int cc = 0; cc < 8; ++cc)
-    if (cc < nq) pk[cc] = sc[lane * 8 + (cc ^ (lane & 7))];
+  for (int cc = 0; cc < NQ; ++cc) pk[cc] = sc[stage_slot<NQ>(lane, cc)];
 }
 // 32 fp32 values of this thread's row -> 4 packed bf16 pieces
 __device__ __forceinline__ void pack32(const float* f, uint4* pk) {
@@ -204,7 +206,7 @@ __device__ __forceinline__ bool decode_work(const Params& p, int wi, TileCoord& 
 }
 
 template <int AM, int BM, int N_TILE, int EPI, int NSTAGE>
-__global__ void __maxnreg__(192)
+__global__ void __launch_bounds__(kThreads, 1)   // 10 warps are allocated as 12: 168 registers per thread
 bgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
              const __grid_constant__ Params p) {
   using C = Cfg<AM, BM, N_TILE, NSTAGE>;
@@ -388,60 +390,53 @@ bgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         tmem_ld32(taddr, v);
         const int nchunks = min(N_TILE / 32, (p.N - t.n0 + 31) / 32);          // warp-uniform
 #pragma unroll 1
-        for (int jp = 0; jp < N_TILE / 64; ++jp) {
-          if (2 * jp >= nchunks) break;
-          uint4 pko[8], pka[8];                          // packed output / packed GELU pre-activation of a 64-column pair
+        for (int j = 0; j < nchunks; ++j) {
+          const int nb = t.n0 + j * 32;
+          tmem_ld_wait();
+          float f[32];
 #pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            const int j = 2 * jp + half;
-            if (j < nchunks) {
-              const int nb = t.n0 + j * 32;
-              tmem_ld_wait();
-              float f[32];
+          for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+          if (j + 1 < nchunks) tmem_ld32(taddr + (j + 1) * 32, v);           // next chunk in flight
+          if (EPI == E_GNSTAT) {
+            const int g = nb / p.gn_cpg;
+            if (g != gcur) { if (gcur >= 0) flush(gcur); gcur = g; }
 #pragma unroll
-              for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
-              if (j + 1 < nchunks) tmem_ld32(taddr + (j + 1) * 32, v);       // next chunk in flight
-              if (EPI == E_GNSTAT) {
-                const int g = nb / p.gn_cpg;
-                if (g != gcur) { if (gcur >= 0) flush(gcur); gcur = g; }
+            for (int i = 0; i < 32; ++i) { gs += f[i]; gq += f[i] * f[i]; }
+          }
+          const size_t off = (obase + (size_t)nb) * 2;
+          uint4 pk[4];
+          if (EPI == E_STORE) {
+            if (p.bias) {
+              const float4* bp = reinterpret_cast<const float4*>(p.bias + (size_t)(t.bi / p.bias_div) * p.bias_bs + nb);
 #pragma unroll
-                for (int i = 0; i < 32; ++i) { gs += f[i]; gq += f[i] * f[i]; }
+              for (int i = 0; i < 8; ++i) { const float4 b = __ldg(bp + i); f[4 * i] += b.x; f[4 * i + 1] += b.y; f[4 * i + 2] += b.z; f[4 * i + 3] += b.w; }
+            }
+            if (p.addend && rvalid) {
+              float a[32];
+              load32(p.addend + obase + nb, a);
+#pragma unroll
+              for (int i = 0; i < 32; ++i) f[i] += a[i];
+            }
+            if (p.act == ACT_RELU) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
+            } else if (p.act == ACT_GELU) {
+              if (p.aux_out) {
+                pack32(f, pk);
+                stage_rows_out<4>(scratch, lane, pk, reinterpret_cast<char*>(p.aux_out), off, rvalid);
               }
-              if (EPI == E_STORE) {
-                if (p.bias) {
-                  const float4* bp = reinterpret_cast<const float4*>(p.bias + (size_t)(t.bi / p.bias_div) * p.bias_bs + nb);
 #pragma unroll
-                  for (int i = 0; i < 8; ++i) { const float4 b = __ldg(bp + i); f[4 * i] += b.x; f[4 * i + 1] += b.y; f[4 * i + 2] += b.z; f[4 * i + 3] += b.w; }
-                }
-                if (p.addend && rvalid) {
-                  float a[32];
-                  load32(p.addend + obase + nb, a);
+              for (int i = 0; i < 32; ++i) f[i] = gelu_f(f[i]);
+            } else if (p.act == ACT_GELU_BWD) {
+              float a[32];
+              if (rvalid) load32(p.aux_in + obase + nb, a);
 #pragma unroll
-                  for (int i = 0; i < 32; ++i) f[i] += a[i];
-                }
-                if (p.act == ACT_RELU) {
-#pragma unroll
-                  for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
-                } else if (p.act == ACT_GELU) {
-                  pack32(f, pka + 4 * half);
-#pragma unroll
-                  for (int i = 0; i < 32; ++i) f[i] = gelu_f(f[i]);
-                } else if (p.act == ACT_GELU_BWD) {
-                  float a[32];
-                  if (rvalid) load32(p.aux_in + obase + nb, a);
-#pragma unroll
-                  for (int i = 0; i < 32; ++i) f[i] = rvalid ? f[i] * gelu_grad_f(a[i]) : 0.f;
-                }
-              }
-              pack32(f, pko + 4 * half);
+              for (int i = 0; i < 32; ++i) f[i] = rvalid ? f[i] * gelu_grad_f(a[i]) : 0.f;
             }
           }
-          // rows of the warp x 64 (or a trailing 32) columns of the pair, written as full 128-byte lines
-          const int nq = (2 * jp + 1 < nchunks) ? 8 : 4;
-          const size_t off = (obase + (size_t)(t.n0 + jp * 64)) * 2;
-          stage_rows_out(scratch, lane, pko, nq, reinterpret_cast<char*>(p.out), off, rvalid);
-          if (EPI == E_STORE && p.act == ACT_GELU && p.aux_out)
-            stage_rows_out(scratch, lane, pka, nq, reinterpret_cast<char*>(p.aux_out), off, rvalid);
+          // 32 rows x 64 bytes of the warp, written as full sectors (8 rows x 64 contiguous bytes per instruction)
+          pack32(f, pk);
+          stage_rows_out<4>(scratch, lane, pk, reinterpret_cast<char*>(p.out), off, rvalid);
         }
         if (EPI == E_GNSTAT && gcur >= 0) flush(gcur);
       } else if (EPI == E_SOFTMAX) {
@@ -476,7 +471,7 @@ bgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           for (int i = 0; i < 32; ++i) f[i] = exp2f((__uint_as_float(v[i]) - mx) * sc) * inv;
           uint4 pk[4];
           pack32(f, pk);
-          stage_rows_out(scratch, lane, pk, 4, reinterpret_cast<char*>(p.out), (obase + t.n0 + j * 32) * 2, rvalid);
+          stage_rows_out<4>(scratch, lane, pk, reinterpret_cast<char*>(p.out), (obase + t.n0 + j * 32) * 2, rvalid);
         }
       } else if (EPI == E_DSOFT) {
         float dot = 0.f;
@@ -501,7 +496,7 @@ bgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           for (int i = 0; i < 32; ++i) f[i] = rvalid ? a[i] * (__uint_as_float(v[i]) - dot) * p.scale : 0.f;
           uint4 pk[4];
           pack32(f, pk);
-          stage_rows_out(scratch, lane, pk, 4, reinterpret_cast<char*>(p.out), (obase + t.n0 + j * 32) * 2, rvalid);
+          stage_rows_out<4>(scratch, lane, pk, reinterpret_cast<char*>(p.out), (obase + t.n0 + j * 32) * 2, rvalid);
         }
       } else {  // E_SGD: W[b][m][n] -= lr * (g + mu (w - w_global)), bf16 operand copy refreshed in the same pass
         uint32_t vn[32];
@@ -524,7 +519,7 @@ bgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             // fp32 master rows: coalesced read through the staging block, update, coalesced write back + bf16 operand copy
             const size_t woff = (size_t)t.bi * p.w_bs + (size_t)m * p.w_ld + nb;
             uint4 wq[8];
-            stage_rows_in(scratch, lane, wq, 8, reinterpret_cast<const char*>(p.w_master), woff * 4, rvalid);
+            stage_rows_in<8>(scratch, lane, wq, reinterpret_cast<const char*>(p.w_master), woff * 4, rvalid);
             float w[32];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
@@ -548,10 +543,10 @@ bgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 #pragma unroll
             for (int i = 0; i < 8; ++i)
               wq[i] = make_uint4(__float_as_uint(w[4 * i]), __float_as_uint(w[4 * i + 1]), __float_as_uint(w[4 * i + 2]), __float_as_uint(w[4 * i + 3]));
-            stage_rows_out(scratch, lane, wq, 8, reinterpret_cast<char*>(p.w_master), woff * 4, rvalid);
+            stage_rows_out<8>(scratch, lane, wq, reinterpret_cast<char*>(p.w_master), woff * 4, rvalid);
             uint4 pk[4];
             pack32(w, pk);
-            stage_rows_out(scratch, lane, pk, 4, reinterpret_cast<char*>(p.w_bf16),
+            stage_rows_out<4>(scratch, lane, pk, reinterpret_cast<char*>(p.w_bf16),
                            ((size_t)t.bi * p.wb_bs + (size_t)m * p.w_ld + nb) * 2, rvalid);
           }
         }
