@@ -126,22 +126,22 @@ int olsb_bgemm(const OlsbBgemm* g, void* stream) {
   const int key = g->am * 1000000 + g->bm * 100000 + g->n_tile * 100 + g->epi;
   switch (key) {
     // ---- plain batched GEMMs (fully-connected layers, attention)
-    case A_K * 1000000 + B_K * 100000 + 256 * 100 + E_STORE: return launch<A_K, B_K, 256, E_STORE, 3>(g, st);
-    case A_K * 1000000 + B_MN * 100000 + 256 * 100 + E_STORE: return launch<A_K, B_MN, 256, E_STORE, 3>(g, st);
-    case A_MN * 1000000 + B_MN * 100000 + 256 * 100 + E_SGD: return launch<A_MN, B_MN, 256, E_SGD, 3>(g, st);
-    case A_K * 1000000 + B_K * 100000 + 128 * 100 + E_SOFTMAX: return launch<A_K, B_K, 128, E_SOFTMAX, 5>(g, st);
-    case A_K * 1000000 + B_K * 100000 + 128 * 100 + E_DSOFT: return launch<A_K, B_K, 128, E_DSOFT, 5>(g, st);
-    case A_K * 1000000 + B_MN * 100000 + 64 * 100 + E_STORE: return launch<A_K, B_MN, 64, E_STORE, 7>(g, st);
-    case A_MN * 1000000 + B_MN * 100000 + 64 * 100 + E_STORE: return launch<A_MN, B_MN, 64, E_STORE, 7>(g, st);
-    case A_K * 1000000 + B_K * 100000 + 64 * 100 + E_STORE: return launch<A_K, B_K, 64, E_STORE, 7>(g, st);
+    case A_K * 1000000 + B_K * 100000 + 256 * 100 + E_STORE: return launch<A_K, B_K, 256, E_STORE, 4>(g, st);
+    case A_K * 1000000 + B_MN * 100000 + 256 * 100 + E_STORE: return launch<A_K, B_MN, 256, E_STORE, 4>(g, st);
+    case A_MN * 1000000 + B_MN * 100000 + 256 * 100 + E_SGD: return launch<A_MN, B_MN, 256, E_SGD, 4>(g, st);
+    case A_K * 1000000 + B_K * 100000 + 128 * 100 + E_SOFTMAX: return launch<A_K, B_K, 128, E_SOFTMAX, 6>(g, st);
+    case A_K * 1000000 + B_K * 100000 + 128 * 100 + E_DSOFT: return launch<A_K, B_K, 128, E_DSOFT, 6>(g, st);
+    case A_K * 1000000 + B_MN * 100000 + 64 * 100 + E_STORE: return launch<A_K, B_MN, 64, E_STORE, 8>(g, st);
+    case A_MN * 1000000 + B_MN * 100000 + 64 * 100 + E_STORE: return launch<A_MN, B_MN, 64, E_STORE, 8>(g, st);
+    case A_K * 1000000 + B_K * 100000 + 64 * 100 + E_STORE: return launch<A_K, B_K, 64, E_STORE, 8>(g, st);
     // ---- implicit-GEMM convolutions
-    case A_CONV * 1000000 + B_K * 100000 + 64 * 100 + E_GNSTAT: return launch<A_CONV, B_K, 64, E_GNSTAT, 7>(g, st);
-    case A_CONV * 1000000 + B_K * 100000 + 128 * 100 + E_GNSTAT: return launch<A_CONV, B_K, 128, E_GNSTAT, 5>(g, st);
-    case A_CONV * 1000000 + B_K * 100000 + 256 * 100 + E_GNSTAT: return launch<A_CONV, B_K, 256, E_GNSTAT, 3>(g, st);
-    case A_CONV * 1000000 + B_WT * 100000 + 64 * 100 + E_STORE: return launch<A_CONV, B_WT, 64, E_STORE, 7>(g, st);
-    case A_CONV * 1000000 + B_WT * 100000 + 128 * 100 + E_STORE: return launch<A_CONV, B_WT, 128, E_STORE, 5>(g, st);
-    case A_CONV * 1000000 + B_WT * 100000 + 256 * 100 + E_STORE: return launch<A_CONV, B_WT, 256, E_STORE, 3>(g, st);
-    case A_MN * 1000000 + B_CONVX * 100000 + 192 * 100 + E_SGD: return launch<A_MN, B_CONVX, 192, E_SGD, 4>(g, st);
+    case A_CONV * 1000000 + B_K * 100000 + 64 * 100 + E_GNSTAT: return launch<A_CONV, B_K, 64, E_GNSTAT, 8>(g, st);
+    case A_CONV * 1000000 + B_K * 100000 + 128 * 100 + E_GNSTAT: return launch<A_CONV, B_K, 128, E_GNSTAT, 6>(g, st);
+    case A_CONV * 1000000 + B_K * 100000 + 256 * 100 + E_GNSTAT: return launch<A_CONV, B_K, 256, E_GNSTAT, 4>(g, st);
+    case A_CONV * 1000000 + B_WT * 100000 + 64 * 100 + E_STORE: return launch<A_CONV, B_WT, 64, E_STORE, 8>(g, st);
+    case A_CONV * 1000000 + B_WT * 100000 + 128 * 100 + E_STORE: return launch<A_CONV, B_WT, 128, E_STORE, 6>(g, st);
+    case A_CONV * 1000000 + B_WT * 100000 + 256 * 100 + E_STORE: return launch<A_CONV, B_WT, 256, E_STORE, 4>(g, st);
+    case A_MN * 1000000 + B_CONVX * 100000 + 192 * 100 + E_SGD: return launch<A_MN, B_CONVX, 192, E_SGD, 5>(g, st);
     default:
       snprintf(g_err, sizeof(g_err), "bgemm: no instantiation for am %d bm %d n_tile %d epi %d", g->am, g->bm, g->n_tile, g->epi);
       return -5;

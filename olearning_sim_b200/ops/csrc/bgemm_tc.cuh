@@ -78,7 +78,7 @@ struct Cfg {
   static constexpr int B_BYTES = (BM == B_K) ? N_TILE * 128 : (N_TILE / 64) * KC * 128;
   static constexpr int STAGE_BYTES = A_BYTES + ((B_BYTES + 1023) / 1024) * 1024;
   static constexpr int TMEM_COLS = (2 * N_TILE <= 32) ? 32 : (2 * N_TILE <= 64 ? 64 : (2 * N_TILE <= 128 ? 128 : (2 * N_TILE <= 256 ? 256 : 512)));
-  static constexpr int SCRATCH_BYTES = 8 * 4096;                 // one 32-row x 128-byte staging block per epilogue warp
+  static constexpr int SCRATCH_BYTES = 8 * 3072;                 // per epilogue warp: 32 rows x 64 B staging block + 1 KB bias row
   static constexpr int SMEM_BYTES = 1024 + NSTAGE * STAGE_BYTES + SCRATCH_BYTES + (int)sizeof(Bars);
   static_assert(N_TILE % 32 == 0 && N_TILE <= 256, "epilogue works on 32-column chunks");
   static_assert(BM == B_K || N_TILE % 64 == 0, "MN-major B is loaded in 64-column boxes");
@@ -331,7 +331,8 @@ bgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     // forward GEMMs with K = 256 were epilogue-bound at 9 % tensor-pipe utilisation with a single group)
     const int group = warp >> 2, q = warp & 3;
     const int buf = group;
-    uint4* scratch = scratch_all + warp * 256;
+    uint4* scratch = scratch_all + warp * 192;                       // [0,128) staging block, [128,192) bias row of the tile
+    float* sbias = reinterpret_cast<float*>(scratch + 128);
     uint32_t tphase = 0;
     int tile_n = 0;
     for (int wi = blockIdx.x; wi < num_work; wi += gridDim.x) {
@@ -358,6 +359,14 @@ bgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         const char* wr = reinterpret_cast<const char*>(p.w_master + (size_t)t.bi * p.w_bs + (size_t)m * p.w_ld + t.n0);
         const int nbytes = min(N_TILE, p.N - t.n0) * 4;
         for (int o = 0; o < nbytes; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(wr + o));
+      }
+      if (EPI == E_STORE && p.bias) {
+        // the tile's bias row -> shared memory while the MMAs run (one cold L2 access per tile instead of one per chunk)
+        const float* bp = p.bias + (size_t)(t.bi / p.bias_div) * p.bias_bs + t.n0;
+        __syncwarp();
+        for (int i = lane * 4; i < N_TILE; i += 128)
+          if (t.n0 + i < p.N) *reinterpret_cast<float4*>(sbias + i) = __ldg(reinterpret_cast<const float4*>(bp + i));
+        __syncwarp();
       }
       mbar_wait(&bars->tfull[buf], tphase);
       fence_after_sync();
@@ -407,9 +416,9 @@ bgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           uint4 pk[4];
           if (EPI == E_STORE) {
             if (p.bias) {
-              const float4* bp = reinterpret_cast<const float4*>(p.bias + (size_t)(t.bi / p.bias_div) * p.bias_bs + nb);
+              const float4* bp = reinterpret_cast<const float4*>(sbias + j * 32);
 #pragma unroll
-              for (int i = 0; i < 8; ++i) { const float4 b = __ldg(bp + i); f[4 * i] += b.x; f[4 * i + 1] += b.y; f[4 * i + 2] += b.z; f[4 * i + 3] += b.w; }
+              for (int i = 0; i < 8; ++i) { const float4 b = bp[i]; f[4 * i] += b.x; f[4 * i + 1] += b.y; f[4 * i + 2] += b.z; f[4 * i + 3] += b.w; }
             }
             if (p.addend && rvalid) {
               float a[32];
@@ -515,18 +524,15 @@ bgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 #pragma unroll
             for (int i = 0; i < 8; ++i)
               gp[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
-          } else if (!p.grad_out) {
-            // fp32 master rows: coalesced read through the staging block, update, coalesced write back + bf16 operand copy
-            const size_t woff = (size_t)t.bi * p.w_bs + (size_t)m * p.w_ld + nb;
-            uint4 wq[8];
-            stage_rows_in<8>(scratch, lane, wq, reinterpret_cast<const char*>(p.w_master), woff * 4, rvalid);
+          } else if (rvalid) {
+            float4* wp = reinterpret_cast<float4*>(p.w_master + (size_t)t.bi * p.w_bs + (size_t)m * p.w_ld + nb);
+            float4 wv[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) wv[i] = wp[i];                                    // all loads before any store
             float w[32];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              w[4 * i] = __uint_as_float(wq[i].x); w[4 * i + 1] = __uint_as_float(wq[i].y);
-              w[4 * i + 2] = __uint_as_float(wq[i].z); w[4 * i + 3] = __uint_as_float(wq[i].w);
-            }
-            if (p.w_global && rvalid) {
+            for (int i = 0; i < 8; ++i) { w[4 * i] = wv[i].x; w[4 * i + 1] = wv[i].y; w[4 * i + 2] = wv[i].z; w[4 * i + 3] = wv[i].w; }
+            if (p.w_global) {
               const float4* ap = reinterpret_cast<const float4*>(p.w_global + (size_t)m * p.w_ld + nb);
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
@@ -541,13 +547,8 @@ bgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               for (int i = 0; i < 32; ++i) w[i] -= p.lr * __uint_as_float(v[i]);
             }
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
-              wq[i] = make_uint4(__float_as_uint(w[4 * i]), __float_as_uint(w[4 * i + 1]), __float_as_uint(w[4 * i + 2]), __float_as_uint(w[4 * i + 3]));
-            stage_rows_out<8>(scratch, lane, wq, reinterpret_cast<char*>(p.w_master), woff * 4, rvalid);
-            uint4 pk[4];
-            pack32(w, pk);
-            stage_rows_out<4>(scratch, lane, pk, reinterpret_cast<char*>(p.w_bf16),
-                           ((size_t)t.bi * p.wb_bs + (size_t)m * p.w_ld + nb) * 2, rvalid);
+            for (int i = 0; i < 8; ++i) wp[i] = make_float4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+            store32(p.w_bf16 + (size_t)t.bi * p.wb_bs + (size_t)m * p.w_ld + nb, w);
           }
         }
       }
