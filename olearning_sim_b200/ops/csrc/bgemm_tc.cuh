@@ -49,6 +49,7 @@ struct Params {
   int batches, M, N, m_tiles, n_tiles, k_chunks;
   const uint8_t* active; int act_div;          // work of batch bi is skipped unless active[bi / act_div]
   int a_bdiv, b_bdiv;                          // > 0: 4-D operand map, outer coordinates (bi % bdiv, bi / bdiv)
+  int pf_ahead;                                // L2 prefetch distance in pipeline chunks (0 = off)
   // ---- convolution geometry -------------------------------------------------------------------------
   int tw_log, th_log;                          // an M tile = 2^tw_log x 2^th_log pixels x (128 >> (tw_log+th_log)) images
   int tiles_x, tiles_y;                        // tiles per image
@@ -207,6 +208,63 @@ __device__ __forceinline__ bool decode_work(const Params& p, int wi, TileCoord& 
   return true;
 }
 
+// One pipeline chunk of operands for tile `t`: TMA loads into (a_dst, b_dst) signalling `bar`, or — PF — the same boxes as
+// L2 prefetches.  The producer runs the prefetches `kPrefetchAhead` chunks in front of the loads: with at most ~190 KB of
+// loads in flight per SM (the shared-memory ring) a kernel whose operands come from HBM is bound by bytes-in-flight /
+// latency; prefetched boxes are L2 hits when their load is issued.
+template <int AM, int BM, int N_TILE, bool PF>
+__device__ __forceinline__ void issue_chunk(const Params& p, const CUtensorMap* tmA, const CUtensorMap* tmB, const TileCoord& t,
+                                            int kc, uint8_t* a_dst, uint8_t* b_dst, uint64_t* bar) {
+  auto op3 = [&](uint8_t* dst, const CUtensorMap* tm, int c0, int c1, int c2) {
+    if (PF) tma_prefetch_3d(tm, c0, c1, c2); else tma_load_3d(dst, tm, bar, c0, c1, c2);
+  };
+  auto op4 = [&](uint8_t* dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3) {
+    if (PF) tma_prefetch_4d(tm, c0, c1, c2, c3); else tma_load_4d(dst, tm, bar, c0, c1, c2, c3);
+  };
+  int tap = 0, ch0 = 0;
+  if (AM == A_CONV) { tap = kc / p.cchunks; ch0 = (kc - tap * p.cchunks) * 64; }
+  // ---- A
+  if (AM == A_K) {
+    if (p.a_bdiv) op4(a_dst, tmA, kc * KC, t.m0, t.bi % p.a_bdiv, t.bi / p.a_bdiv);
+    else op3(a_dst, tmA, kc * KC, t.m0, t.bi);
+  } else if (AM == A_MN) {
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      if (p.a_bdiv) op4(a_dst + j * KC * 128, tmA, t.m0 + 64 * j, kc * KC, t.bi % p.a_bdiv, t.bi / p.a_bdiv);
+      else op3(a_dst + j * KC * 128, tmA, t.m0 + 64 * j, kc * KC, t.bi);
+    }
+  } else {
+    op4(a_dst, tmA, ch0, t.tx0 * p.src_stride + p.tap_dx[tap], t.ty0 * p.src_stride + p.tap_dy[tap],
+        t.bi * p.src_cimgs + p.src_img0 + t.img0);
+  }
+  // ---- B
+  if (BM == B_K) {
+    const int kb = (AM == A_CONV) ? p.tap_w[tap] * p.ktap + ch0 : kc * KC;
+    if (p.b_bdiv) op4(b_dst, tmB, kb, t.n0, t.bi % p.b_bdiv, t.bi / p.b_bdiv);
+    else op3(b_dst, tmB, kb, t.n0, t.bi);
+  } else if (BM == B_MN) {
+#pragma unroll
+    for (int j = 0; j < N_TILE / 64; ++j) {
+      if (p.b_bdiv) op4(b_dst + j * KC * 128, tmB, t.n0 + 64 * j, kc * KC, t.bi % p.b_bdiv, t.bi / p.b_bdiv);
+      else op3(b_dst + j * KC * 128, tmB, t.n0 + 64 * j, kc * KC, t.bi);
+    }
+  } else if (BM == B_WT) {
+#pragma unroll
+    for (int j = 0; j < N_TILE / 64; ++j) op4(b_dst + j * KC * 128, tmB, t.n0 + 64 * j, p.tap_w[tap], ch0, t.bi);
+  } else {  // B_CONVX
+    const int ci = kc / p.kb_cpi;
+    const int img = ci * p.kb_n, y0 = (kc - ci * p.kb_cpi) * p.kb_h;
+#pragma unroll
+    for (int j = 0; j < N_TILE / 64; ++j) {
+      const int blk = t.nt * (N_TILE / 64) + j;
+      int tp = blk / p.cchunks;
+      int c0 = (blk - tp * p.cchunks) * 64;
+      if (blk >= p.nblocks) { tp = 0; c0 = p.cin + 64; }           // padding block: out of bounds -> zeros
+      op4(b_dst + j * KC * 128, tmB, c0, p.tap_dx[tp], y0 * p.src_stride + p.tap_dy[tp], t.bi * p.src_cimgs + p.src_img0 + img);
+    }
+  }
+}
+
 template <int AM, int BM, int N_TILE, int EPI, int NSTAGE>
 __global__ void __launch_bounds__(kThreads, 1)   // 10 warps are allocated as 12: 168 registers per thread
 bgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -234,6 +292,20 @@ bgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     // ================================================================ TMA producer
     const bool leader = elect_one();
     int stage = 0; uint32_t phase = 0;
+    // prefetch cursor: (work item, chunk) kPrefetchAhead chunks ahead of the load cursor in this CTA's own sequence
+    const int pf_ahead = p.pf_ahead;
+    int pf_wi = blockIdx.x, pf_kc = 0;
+    TileCoord pt;
+    bool pf_ok = pf_ahead > 0 && pf_wi < num_work && decode_work<AM, N_TILE>(p, pf_wi, pt);
+    auto pf_step = [&]() {                      // advance the prefetch cursor by one chunk (skipping inactive work items)
+      if (pf_wi >= num_work) return;
+      if (pf_ok && leader) issue_chunk<AM, BM, N_TILE, true>(p, &tmA, &tmB, pt, pf_kc, nullptr, nullptr, nullptr);
+      if (!pf_ok || ++pf_kc == p.k_chunks) {
+        pf_kc = 0;
+        do { pf_wi += gridDim.x; } while (pf_wi < num_work && !(pf_ok = decode_work<AM, N_TILE>(p, pf_wi, pt)));
+      }
+    };
+    for (int i = 0; i < pf_ahead; ++i) pf_step();
     for (int wi = blockIdx.x; wi < num_work; wi += gridDim.x) {
       TileCoord t;
       if (!decode_work<AM, N_TILE>(p, wi, t)) continue;
@@ -244,51 +316,9 @@ bgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           uint8_t* b_dst = a_dst + C::A_BYTES;
           uint64_t* bar = &bars->full[stage];
           mbar_arrive_expect_tx(bar, C::A_BYTES + C::B_BYTES);
-          int tap = 0, ch0 = 0;
-          if (AM == A_CONV) { tap = kc / p.cchunks; ch0 = (kc - tap * p.cchunks) * 64; }
-          // ---- A
-          if (AM == A_K) {
-            if (p.a_bdiv) tma_load_4d(a_dst, &tmA, bar, kc * KC, t.m0, t.bi % p.a_bdiv, t.bi / p.a_bdiv);
-            else tma_load_3d(a_dst, &tmA, bar, kc * KC, t.m0, t.bi);
-          } else if (AM == A_MN) {
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-              if (p.a_bdiv) tma_load_4d(a_dst + j * KC * 128, &tmA, bar, t.m0 + 64 * j, kc * KC, t.bi % p.a_bdiv, t.bi / p.a_bdiv);
-              else tma_load_3d(a_dst + j * KC * 128, &tmA, bar, t.m0 + 64 * j, kc * KC, t.bi);
-            }
-          } else {
-            tma_load_4d(a_dst, &tmA, bar, ch0, t.tx0 * p.src_stride + p.tap_dx[tap], t.ty0 * p.src_stride + p.tap_dy[tap],
-                        t.bi * p.src_cimgs + p.src_img0 + t.img0);
-          }
-          // ---- B
-          if (BM == B_K) {
-            const int kb = (AM == A_CONV) ? p.tap_w[tap] * p.ktap + ch0 : kc * KC;
-            if (p.b_bdiv) tma_load_4d(b_dst, &tmB, bar, kb, t.n0, t.bi % p.b_bdiv, t.bi / p.b_bdiv);
-            else tma_load_3d(b_dst, &tmB, bar, kb, t.n0, t.bi);
-          } else if (BM == B_MN) {
-#pragma unroll
-            for (int j = 0; j < N_TILE / 64; ++j) {
-              if (p.b_bdiv) tma_load_4d(b_dst + j * KC * 128, &tmB, bar, t.n0 + 64 * j, kc * KC, t.bi % p.b_bdiv, t.bi / p.b_bdiv);
-              else tma_load_3d(b_dst + j * KC * 128, &tmB, bar, t.n0 + 64 * j, kc * KC, t.bi);
-            }
-          } else if (BM == B_WT) {
-#pragma unroll
-            for (int j = 0; j < N_TILE / 64; ++j)
-              tma_load_4d(b_dst + j * KC * 128, &tmB, bar, t.n0 + 64 * j, p.tap_w[tap], ch0, t.bi);
-          } else {  // B_CONVX
-            const int ci = kc / p.kb_cpi;
-            const int img = ci * p.kb_n, y0 = (kc - ci * p.kb_cpi) * p.kb_h;
-#pragma unroll
-            for (int j = 0; j < N_TILE / 64; ++j) {
-              const int blk = t.nt * (N_TILE / 64) + j;
-              int tp = blk / p.cchunks;
-              int c0 = (blk - tp * p.cchunks) * 64;
-              if (blk >= p.nblocks) { tp = 0; c0 = p.cin + 64; }           // padding block: out of bounds -> zeros
-              tma_load_4d(b_dst + j * KC * 128, &tmB, bar, c0, p.tap_dx[tp], y0 * p.src_stride + p.tap_dy[tp],
-                          t.bi * p.src_cimgs + p.src_img0 + img);
-            }
-          }
+          issue_chunk<AM, BM, N_TILE, false>(p, &tmA, &tmB, t, kc, a_dst, b_dst, bar);
         }
+        if (pf_ahead > 0) pf_step();
         if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
       }
     }

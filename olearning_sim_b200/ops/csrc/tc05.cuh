@@ -102,6 +102,15 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* tm, ui
       : "memory");
 }
 
+// TMA prefetch of a box into L2 (no shared-memory destination, no barrier): run ahead of the loads so they hit L2
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* tm, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(tm), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* tm, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+
 // 1-D bulk copy global -> shared (bytes multiple of 16, both addresses 16-byte aligned); completion is counted in
 // bytes on `bar` (pair with mbar_arrive_expect_tx).
 __device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gptr, uint32_t bytes, uint64_t* bar) {
