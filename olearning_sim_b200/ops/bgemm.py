@@ -165,7 +165,7 @@ def tmap(t: torch.Tensor, elem_off: int, dims: Sequence[int], strides: Sequence[
     return m
 
 
-PF_AHEAD = int(__import__("os").environ.get("OLSB_PF_AHEAD", "8"))       # L2 prefetch distance (pipeline chunks) of the TMA producer
+PF_AHEAD = int(__import__("os").environ.get("OLSB_PF_AHEAD", "0"))       # L2 prefetch distance (pipeline chunks) of the TMA producer
 
 
 def launch(g: Bgemm) -> None:
