@@ -136,16 +136,25 @@ __device__ __forceinline__ void store32(__nv_bfloat16* p, const float* f) {
 // Slot (row, c) holds 16-byte piece c of a 128-byte row segment at sc[row * 8 + (c ^ (row & 7))]: conflict-free both for
 // the row-owner access (lane = row) and for the transposed access (8 lanes per row).
 // ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
 template <int NQ>   // 16-byte pieces per row segment: 8 (128 B: fp32 chunk) or 4 (64 B: bf16 chunk)
-__device__ __forceinline__ int stage_slot(int row, int c) {
-  return NQ == 8 ? row * 8 + (c ^ (row & 7)) : row * 4 + (c ^ ((row >> 1) & 3));
+__device__ __forceinline__ uint32_t stage_slot(int row, int c) {
+  return (NQ == 8 ? row * 8 + (c ^ (row & 7)) : row * 4 + (c ^ ((row >> 1) & 3))) * 16;
 }
 template <int NQ>
-__device__ __forceinline__ void stage_rows_out(uint4* sc, int lane, const uint4* pk, char* dst_base, size_t row_off, bool rvalid) {
+__device__ __forceinline__ void stage_rows_out(uint4* sc_ptr, int lane, const uint4* pk, char* dst_base, size_t row_off, bool rvalid) {
   // pk[0..NQ): this thread's row segment; dst = dst_base + row_off(row) for every row of the warp
+  const uint32_t sc = smem_u32(sc_ptr);              // explicit shared-space accesses (a generic pointer compiles to LD.E / ST.E)
   __syncwarp();
 #pragma unroll
-  for (int c = 0; c < NQ; ++c) sc[stage_slot<NQ>(lane, c)] = pk[c];
+  for (int c = 0; c < NQ; ++c) sts128(sc + stage_slot<NQ>(lane, c), pk[c]);
   __syncwarp();
   constexpr int RPI = 32 / NQ;                       // rows per instruction
   const int c = lane % NQ;
@@ -155,25 +164,8 @@ __device__ __forceinline__ void stage_rows_out(uint4* sc, int lane, const uint4*
     const uint32_t lo = __shfl_sync(0xffffffffu, static_cast<uint32_t>(row_off), row);
     const uint32_t hi = __shfl_sync(0xffffffffu, static_cast<uint32_t>(row_off >> 32), row);
     const int ok = __shfl_sync(0xffffffffu, rvalid ? 1 : 0, row);
-    if (ok) *reinterpret_cast<uint4*>(dst_base + ((static_cast<size_t>(hi) << 32) | lo) + c * 16) = sc[stage_slot<NQ>(row, c)];
+    if (ok) *reinterpret_cast<uint4*>(dst_base + ((static_cast<size_t>(hi) << 32) | lo) + c * 16) = lds128(sc + stage_slot<NQ>(row, c));
   }
-}
-template <int NQ>
-__device__ __forceinline__ void stage_rows_in(uint4* sc, int lane, uint4* pk, const char* src_base, size_t row_off, bool rvalid) {
-  __syncwarp();
-  constexpr int RPI = 32 / NQ;
-  const int c = lane % NQ;
-#pragma unroll
-  for (int i = 0; i < NQ; ++i) {
-    const int row = RPI * i + lane / NQ;
-    const uint32_t lo = __shfl_sync(0xffffffffu, static_cast<uint32_t>(row_off), row);
-    const uint32_t hi = __shfl_sync(0xffffffffu, static_cast<uint32_t>(row_off >> 32), row);
-    const int ok = __shfl_sync(0xffffffffu, rvalid ? 1 : 0, row);
-    if (ok) sc[stage_slot<NQ>(row, c)] = *reinterpret_cast<const uint4*>(src_base + ((static_cast<size_t>(hi) << 32) | lo) + c * 16);
-  }
-  __syncwarp();
-#pragma unroll
-  for (int cc = 0; cc < NQ; ++cc) pk[cc] = sc[stage_slot<NQ>(lane, cc)];
 }
 // 32 fp32 values of this thread's row -> 4 packed bf16 pieces
 __device__ __forceinline__ void pack32(const float* f, uint4* pk) {
