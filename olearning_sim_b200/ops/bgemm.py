@@ -42,7 +42,7 @@ class Params(C.Structure):
     _fields_ = [
         ("batches", C.c_int), ("M", C.c_int), ("N", C.c_int), ("m_tiles", C.c_int), ("n_tiles", C.c_int), ("k_chunks", C.c_int),
         ("active", C.c_void_p), ("act_div", C.c_int),
-        ("a_bdiv", C.c_int), ("b_bdiv", C.c_int), ("pf_ahead", C.c_int),
+        ("a_bdiv", C.c_int), ("b_bdiv", C.c_int), ("pf_ahead", C.c_int), ("direct_store", C.c_int),
         ("tw_log", C.c_int), ("th_log", C.c_int), ("tiles_x", C.c_int), ("tiles_y", C.c_int), ("imgs", C.c_int),
         ("src_stride", C.c_int), ("src_cimgs", C.c_int), ("src_img0", C.c_int), ("cchunks", C.c_int), ("ntaps", C.c_int), ("ktap", C.c_int),
         ("tap_dy", I9), ("tap_dx", I9), ("tap_w", I9),
@@ -168,9 +168,13 @@ def tmap(t: torch.Tensor, elem_off: int, dims: Sequence[int], strides: Sequence[
 PF_AHEAD = int(__import__("os").environ.get("OLSB_PF_AHEAD", "0"))       # L2 prefetch distance (pipeline chunks) of the TMA producer
 
 
+DIRECT_STORE = __import__("os").environ.get("OLSB_DIRECT_STORE", "auto")   # "0" staged, "1" direct, "auto": direct for conv outputs
+
+
 def launch(g: Bgemm) -> None:
     global launches
     g.p.pf_ahead = PF_AHEAD
+    g.p.direct_store = int(DIRECT_STORE) if DIRECT_STORE in ("0", "1") else (1 if g.p.out_conv else 0)
     _ck(_lib().olsb_bgemm(C.byref(g), native._stream()))
     launches += 1
 

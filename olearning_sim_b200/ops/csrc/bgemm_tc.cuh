@@ -50,6 +50,7 @@ struct Params {
   const uint8_t* active; int act_div;          // work of batch bi is skipped unless active[bi / act_div]
   int a_bdiv, b_bdiv;                          // > 0: 4-D operand map, outer coordinates (bi % bdiv, bi / bdiv)
   int pf_ahead;                                // L2 prefetch distance in pipeline chunks (0 = off)
+  int direct_store;                            // 1: every thread stores its own row pieces (no staging transpose)
   // ---- convolution geometry -------------------------------------------------------------------------
   int tw_log, th_log;                          // an M tile = 2^tw_log x 2^th_log pixels x (128 >> (tw_log+th_log)) images
   int tiles_x, tiles_y;                        // tiles per image
@@ -455,8 +456,8 @@ bgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
             } else if (p.act == ACT_GELU) {
               if (p.aux_out) {
-                pack32(f, pk);
-                stage_rows_out<4>(scratch, lane, pk, reinterpret_cast<char*>(p.aux_out), off, rvalid);
+                if (p.direct_store) { if (rvalid) store32(p.aux_out + obase + nb, f); }
+                else { pack32(f, pk); stage_rows_out<4>(scratch, lane, pk, reinterpret_cast<char*>(p.aux_out), off, rvalid); }
               }
 #pragma unroll
               for (int i = 0; i < 32; ++i) f[i] = gelu_f(f[i]);
@@ -468,8 +469,8 @@ bgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             }
           }
           // 32 rows x 64 bytes of the warp, written as full sectors (8 rows x 64 contiguous bytes per instruction)
-          pack32(f, pk);
-          stage_rows_out<4>(scratch, lane, pk, reinterpret_cast<char*>(p.out), off, rvalid);
+          if (p.direct_store) { if (rvalid) store32(p.out + obase + nb, f); }
+          else { pack32(f, pk); stage_rows_out<4>(scratch, lane, pk, reinterpret_cast<char*>(p.out), off, rvalid); }
         }
         if (EPI == E_GNSTAT && gcur >= 0) flush(gcur);
       } else if (EPI == E_SOFTMAX) {

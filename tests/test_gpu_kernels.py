@@ -153,3 +153,22 @@ def test_poisoned_client_masked_on_gpu(monkeypatch):
     assert r.failed == 1 and r.loss == r.loss and bool(torch.isfinite(e.global_model()).all())
     assert set(r.extras["phases_ms"]) == {"broadcast", "local_steps", "reduce_update"}
     e.close()
+
+
+def test_cnn2_round_is_bitwise_deterministic():
+    """racecheck reports the bulk-copy staging ring of head_fc_xent_kernel (async-proxy writes vs generic reads ordered by
+    mbarriers, which the tool does not model — profiles/r1_sanitizer.txt).  A real race there would make the head's outputs
+    timing dependent: two engines with the same seed must therefore produce bit-identical global models and losses, with and
+    without the CUDA graph (different launch timing)."""
+    import torch
+    from olearning_sim_b200.engine.fed_engine import FedConfig, FedEngine
+    outs = []
+    for graph in (True, False, True):
+        e = FedEngine(FedConfig(model="cnn2", num_clients=37, local_steps=3, shard=64, backend="native", seed=9, p_online=0.9,
+                                hetero_steps=True, use_cuda_graph=graph))
+        e.load_synthetic()
+        losses = [e.run_round(r).loss for r in range(3)]
+        outs.append((losses, e.global_model().clone()))
+        e.close()
+    for losses, g in outs[1:]:
+        assert losses == outs[0][0] and torch.equal(g, outs[0][1])
