@@ -322,6 +322,12 @@ def main() -> int:
                   "reduce_hbm_GBps": P4 * (c_local + 2 * groups) / max(accmin.get("reduce_update", 0), 1e-9) / 1e6}
     graph_error = getattr(eng, "graph_error", None)
     sync()
+    comm_desc = None
+    hp = getattr(getattr(eng, "ws", None), "heap", None)
+    if hp is not None and world > 1:
+        gb = hp.buffers.get("global")
+        comm_desc = {"transport": "peer-memory kernels over NVLink (no NCCL on the model path)",
+                     "nvls_multicast": bool(gb is not None and gb.mc_ptr), "nvls_error": hp.nvls_error}
     eng.close()
     del eng
     torch.cuda.empty_cache()
@@ -348,6 +354,8 @@ def main() -> int:
                                        "reference publishes no number and cannot be installed", **base}
             if base.get("e2e") and e2e:
                 out["baseline"]["e2e_ratio"] = e2e["value"] / base["e2e"]["value"]
+        if comm_desc:
+            out["comm"] = comm_desc
         if graph_error:
             out["cuda_graph_error"] = graph_error
         if phases:

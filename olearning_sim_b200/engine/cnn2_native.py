@@ -78,8 +78,8 @@ class Cnn2Workspace:
         self.n_samples = torch.full((C,), shard, dtype=i32, device=d)
         # symmetric (peer-visible) state
         h = self.heap
-        h.alloc("global", P * 4)
-        h.alloc("partial", self.groups * P * 4)
+        h.alloc("global", P * 4, multicast=True)
+        h.alloc("partial", self.groups * P * 4, multicast=True)
         h.alloc("wsum", max(self.groups, 64) * 4)
         h.alloc("flags", 256)
         h.alloc("round", 256)
@@ -172,7 +172,8 @@ class Cnn2Workspace:
                              self.shard_len, self.epoch, self.global_w, self.opt_m, self.opt_v,
                              OPT_CODES[opt], server_lr, beta1, beta2, eps, self.server_step, self.stats,
                              self.arrive_ctr, hb["round"].peer_ptrs if accounting is not None else None, self.round_out,
-                             8 + 2 * (accounting[5] if accounting is not None and len(accounting) > 4 else 0))
+                             8 + 2 * (accounting[5] if accounting is not None and len(accounting) > 4 else 0),
+                             partial_mc=hb["partial"].mc_ptr, global_mc=hb["global"].mc_ptr)
         self.kernel_launches += 2 + (accounting is not None)
 
     def reset_round_stats(self) -> None:

@@ -95,7 +95,7 @@ class MlpWorkspace:
         self.n_samples = torch.full((C,), shard, dtype=i32, device=d)
         self.groups = max(1, min(16, max(1, C // 8)))
         hp = self.heap
-        hp.alloc("global", P * 4); hp.alloc("partial", self.groups * P * 4); hp.alloc("wsum", 64 * 4); hp.alloc("flags", 256)
+        hp.alloc("global", P * 4, multicast=True); hp.alloc("partial", self.groups * P * 4, multicast=True); hp.alloc("wsum", 64 * 4); hp.alloc("flags", 256)
         hp.alloc("round", 256)
         self.round_rec = hp.tensor("round", f32, (native.ROUND_REC,))
         self.round_rec.zero_()
@@ -193,7 +193,8 @@ class MlpWorkspace:
                              self.rank, self.groups, self.P, self.shard_len, self.epoch, self.global_w, self.opt_m,
                              self.opt_v, OPT_CODES[opt], server_lr, beta1, beta2, eps, self.server_step, self.stats,
                              self.arrive_ctr, hb["round"].peer_ptrs if accounting is not None else None, self.round_out,
-                             8 + 2 * (accounting[5] if accounting is not None and len(accounting) > 4 else 0))
+                             8 + 2 * (accounting[5] if accounting is not None and len(accounting) > 4 else 0),
+                             partial_mc=hb["partial"].mc_ptr, global_mc=hb["global"].mc_ptr)
         self.kernel_launches += 2 + (accounting is not None)
 
     def reset_round_stats(self) -> None:

@@ -168,7 +168,7 @@ def tmap(t: torch.Tensor, elem_off: int, dims: Sequence[int], strides: Sequence[
 PF_AHEAD = int(__import__("os").environ.get("OLSB_PF_AHEAD", "0"))       # L2 prefetch distance (pipeline chunks) of the TMA producer
 
 
-DIRECT_STORE = __import__("os").environ.get("OLSB_DIRECT_STORE", "auto")   # "0" staged, "1" direct, "auto": direct for conv outputs
+DIRECT_STORE = __import__("os").environ.get("OLSB_DIRECT_STORE", "0")   # "0" staged through smem (measured best everywhere), "1" direct
 
 
 def launch(g: Bgemm) -> None:

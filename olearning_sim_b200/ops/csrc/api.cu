@@ -449,10 +449,11 @@ int olsb_fedavg_finish(const void* const* partial_peers, const void* const* wsum
                        int nranks, int rank, int groups, int P, int shard_len, unsigned epoch, void* global_w,
                        void* opt_m, void* opt_v, int opt, float server_lr, float beta1, float beta2, float eps, int step,
                        void* stats, void* arrive_ctr, const void* const* round_peers, void* round_out, int round_len,
-                       void* stream) {
+                       const void* partial_mc, void* global_mc, void* stream) {
   if (int r = olsb_init()) return r;
   flk::FinishParams p;
   memset(&p, 0, sizeof(p));
+  p.partial_mc = (const float*)partial_mc; p.global_mc = (float*)global_mc;
   for (int i = 0; i < nranks && i < flk::kMaxPeers; ++i) {
     p.partial_peers.p[i] = const_cast<void*>(partial_peers[i]);
     p.wsum_peers.p[i] = const_cast<void*>(wsum_peers[i]);

@@ -164,7 +164,7 @@ constexpr int kHeadThreads = 256;
 // backward-phase staging ring: a slice = 8 samples x 512 features of the pooled activation (bf16) and its argmax code,
 // fetched by 1-D bulk copies four slices ahead of their use
 constexpr int kHeadSlots = 4, kHeadSliceX = 8 * 512 * 2, kHeadSliceC = 8 * 512, kHeadSlice = kHeadSliceX + kHeadSliceC;
-constexpr int kHeadSmem = (10 * 4096 + 32 * 10 + 32 * 10 + 64 + 16) * 4 + kHeadSlots * kHeadSlice + 64;
+constexpr int kHeadSmem = (10 * 4096 + 32 * 10 + 32 * 10 + (kHeadThreads / 32) * 64 + 16) * 4 + kHeadSlots * kHeadSlice + 64;
 
 __global__ void __launch_bounds__(kHeadThreads, 1) head_fc_xent_kernel(const HeadParams p) {
   using L = Cnn2Layout;
@@ -172,8 +172,8 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_fc_xent_kernel(const Hea
   float* Ws = hs;                    // [10][4096]
   float* logit = Ws + 10 * 4096;     // [32][10]
   float* dlog = logit + 320;         // [32][10]
-  float* db2 = dlog + 320;           // [64]
-  float* misc = db2 + 64;            // [16]
+  float* db2 = dlog + 320;           // [8 warps][64]: per-warp conv2-bias gradient partials (summed in warp order)
+  float* misc = db2 + (kHeadThreads / 32) * 64;   // [16]
   uint8_t* ring = reinterpret_cast<uint8_t*>(misc + 16);
   uint64_t* rfull = reinterpret_cast<uint64_t*>(ring + kHeadSlots * kHeadSlice);
   uint64_t* rempty = rfull + kHeadSlots;      // slot consumed: one arrival per warp
@@ -218,7 +218,6 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_fc_xent_kernel(const Hea
 #pragma unroll
       for (int u = 0; u < 8; ++u) *reinterpret_cast<float4*>(Ws + i0 + u * kHeadThreads * 4) = t8[u];
     }
-    if (tid < 64) db2[tid] = 0.f;
     __syncthreads();
 
     // ---- logits: a warp owns 4 samples; per k-chunk the 10 weight rows are read from smem once and reused for
@@ -311,6 +310,10 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_fc_xent_kernel(const Hea
     const uint8_t* code = p.code2 + (size_t)c * 32 * 4096;
     __nv_bfloat16* dy = p.dy2 + (size_t)c * 32 * 16 * 16 * 64;
     const float* wg = p.global_w;
+    // a thread's two features map to the same channel pair in every iteration (512 features = 8 pixels x 64 channels per
+    // iteration), so the conv2-bias gradient accumulates in registers and is combined in a fixed order: no atomics,
+    // bit-reproducible
+    float dbs0 = 0.f, dbs1 = 0.f;
     for (int it = 0; it < 8; ++it) {
       const int k = (it * kHeadThreads + tid) * 2;       // two consecutive features (same pooled pixel)
       float w0[10], w1[10], g0[10], g1[10];
@@ -366,8 +369,7 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_fc_xent_kernel(const Hea
           }
         }
       }
-      atomicAdd(&db2[ch], dbl0);
-      atomicAdd(&db2[ch + 1], dbl1);
+      dbs0 += dbl0; dbs1 += dbl1;
       if (p.dwfc_out) {
 #pragma unroll
         for (int j = 0; j < 10; ++j) {
@@ -386,6 +388,8 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_fc_xent_kernel(const Hea
         }
       }
     }
+    db2[warp * 64 + ((tid * 2) & 63)] = dbs0;
+    db2[warp * 64 + ((tid * 2) & 63) + 1] = dbs1;
     __syncthreads();
     if (tid < 10) {
       float g = 0.f;
@@ -399,7 +403,9 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_fc_xent_kernel(const Hea
     }
     if (tid >= 64 && tid < 128) {
       const int ch = tid - 64;
-      float g = db2[ch];
+      float g = 0.f;
+#pragma unroll
+      for (int w = 0; w < kHeadThreads / 32; ++w) g += db2[w * 64 + ch];
       if (p.db2_out) p.db2_out[(size_t)c * 64 + ch] = g;
       if (p.apply_update) {
         float b = wm[L::B2 + ch];
@@ -500,7 +506,23 @@ struct FinishParams {
   PeerPtrs round_peers;     // float* [round_len] per rank: this round's local accounting (round_stats_kernel) or null
   float* round_out;         // [round_len] sum over ranks of round_peers (every rank gets the job-wide numbers)
   int round_len;            // 8 (+ 2 per device class)
+  // NVSwitch multicast path (both null: peer-pointer path).  partial_mc: multicast address of the [groups][P] partial
+  // sums, read with multimem.ld_reduce (the switch adds the ranks' copies); global_mc: multicast address of the
+  // replicated global model, written with multimem.st (every rank's copy receives the owner's new shard).
+  const float* partial_mc;
+  float* global_mc;
 };
+
+__device__ __forceinline__ float4 multimem_ld_reduce_add(const float* mc) {
+  float4 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(mc) : "memory");
+  return v;
+}
+__device__ __forceinline__ void multimem_st(float* mc, const float4 v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};"
+               ::"l"(mc), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
 
 __device__ __forceinline__ void grid_gate(uint32_t* ctr, uint32_t nblocks) {
   // lightweight one-shot "all CTAs arrived" (all CTAs are co-resident: grid <= #SMs)
@@ -532,11 +554,19 @@ __global__ void fedavg_finish_kernel(const FinishParams p) {
   float dn = 0.f;
   for (int i4 = s0 + (blockIdx.x * blockDim.x + threadIdx.x) * 4; i4 < s1; i4 += gridDim.x * blockDim.x * 4) {
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int r = 0; r < p.nranks; ++r) {
-      const float* pp = static_cast<const float*>(p.partial_peers.p[r]);
+    if (p.partial_mc) {
+      // in-switch reduction: one load per group returns the sum over all ranks
       for (int g = 0; g < p.groups; ++g) {
-        const float4 v = *reinterpret_cast<const float4*>(pp + (size_t)g * p.P + i4);
+        const float4 v = multimem_ld_reduce_add(p.partial_mc + (size_t)g * p.P + i4);
         acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+    } else {
+      for (int r = 0; r < p.nranks; ++r) {
+        const float* pp = static_cast<const float*>(p.partial_peers.p[r]);
+        for (int g = 0; g < p.groups; ++g) {
+          const float4 v = *reinterpret_cast<const float4*>(pp + (size_t)g * p.P + i4);
+          acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
       }
     }
     float d[4] = {acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv};   // averaged client delta (pseudo-gradient = -d)
@@ -564,8 +594,10 @@ __global__ void fedavg_finish_kernel(const FinishParams p) {
       wv[e] += upd;
       dn += upd * upd;
     }
-    *reinterpret_cast<float4*>(p.global_w + i4) = make_float4(wv[0], wv[1], wv[2], wv[3]);
+    if (p.global_mc) multimem_st(p.global_mc + i4, make_float4(wv[0], wv[1], wv[2], wv[3]));   // all replicas at once
+    else *reinterpret_cast<float4*>(p.global_w + i4) = make_float4(wv[0], wv[1], wv[2], wv[3]);
   }
+  if (p.global_mc) __threadfence_system();
   // stats
   dn += __shfl_xor_sync(0xffffffffu, dn, 16); dn += __shfl_xor_sync(0xffffffffu, dn, 8);
   dn += __shfl_xor_sync(0xffffffffu, dn, 4);  dn += __shfl_xor_sync(0xffffffffu, dn, 2);

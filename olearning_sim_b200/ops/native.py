@@ -158,7 +158,10 @@ def fedavg_partial(master, global_w, weight, nonfinite, groups: int, partial, ws
 
 def fedavg_finish(partial_peer_ptrs, wsum_peer_ptrs, flag_peer_ptrs, rank: int, groups: int, P: int, shard_len: int,
                   epoch: int, global_w, opt_m, opt_v, opt: int, server_lr: float, beta1: float, beta2: float,
-                  eps: float, step: int, stats, arrive_ctr, round_peer_ptrs=None, round_out=None, round_len: int = 8) -> None:
+                  eps: float, step: int, stats, arrive_ctr, round_peer_ptrs=None, round_out=None, round_len: int = 8,
+                  partial_mc: int = 0, global_mc: int = 0) -> None:
+    """``partial_mc`` / ``global_mc``: NVSwitch multicast addresses of the partial-sum and global-model slabs
+    (parallel/nvls.py); non-zero selects the multimem.ld_reduce / multimem.st path of the kernel."""
     n = len(partial_peer_ptrs)
     flags = _ptr_array(flag_peer_ptrs) if flag_peer_ptrs is not None else None
     rnd = _ptr_array(round_peer_ptrs) if round_peer_ptrs is not None else None
@@ -167,7 +170,8 @@ def fedavg_finish(partial_peer_ptrs, wsum_peer_ptrs, flag_peer_ptrs, rank: int, 
                                      C.c_uint(epoch), _p(global_w), _p(opt_m), _p(opt_v), C.c_int(opt),
                                      C.c_float(server_lr), C.c_float(beta1), C.c_float(beta2), C.c_float(eps),
                                      C.c_int(step), _p(stats), _p(arrive_ctr), rnd,
-                                     _p(round_out) if rnd is not None else None, C.c_int(round_len), _stream()))
+                                     _p(round_out) if rnd is not None else None, C.c_int(round_len),
+                                     C.c_void_p(partial_mc or None), C.c_void_p(global_mc or None), _stream()))
 
 
 def set_option(name: str, value: int) -> int:

@@ -41,6 +41,8 @@ class SymBuffer:
     local_ptr: int
     peer_ptrs: List[int]            # device pointers valid in THIS process for every rank's slab (self included)
     tensors: Dict[str, torch.Tensor] = field(default_factory=dict)
+    mc_ptr: int = 0                 # NVSwitch multicast address of the slab (0: plain CUDA-IPC slab)
+    slab: Optional[object] = None   # parallel.nvls.MulticastSlab backing a multicast buffer
 
 
 class SymmetricHeap:
@@ -56,10 +58,25 @@ class SymmetricHeap:
         self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
         self.device = device or torch.device("cuda", torch.cuda.current_device())
         self.buffers: Dict[str, SymBuffer] = {}
+        self.nvls_error: Optional[str] = None
 
     # ---- allocation ------------------------------------------------------------------------------
-    def alloc(self, name: str, nbytes: int) -> SymBuffer:
+    def alloc(self, name: str, nbytes: int, multicast: bool = False) -> SymBuffer:
+        """``multicast``: back the slab with an NVSwitch multicast object when the platform has one (parallel/nvls.py).
+        Such a slab is *replicated*: every rank reads its own copy (``peer_ptrs`` all point at the local mapping),
+        writes reach the peers through ``mc_ptr`` (``multimem.st``) and sums over ranks come from ``multimem.ld_reduce``.
+        Falls back to a CUDA-IPC slab, on all ranks together, when multicast is unavailable."""
         nbytes = (nbytes + 255) // 256 * 256
+        if multicast and self.world > 1:
+            from . import nvls
+            if nvls.enabled(self.world):
+                slab = nvls.create(nbytes, self.device, self.group)
+                if slab is not None:
+                    buf = SymBuffer(name, slab.nbytes, slab.local_ptr, [slab.local_ptr] * self.world, mc_ptr=slab.mc_ptr,
+                                    slab=slab)
+                    self.buffers[name] = buf
+                    return buf
+                self.nvls_error = nvls.last_error()
         p = C.c_void_p()
         self._native._ck(self._lib.olsb_sym_alloc(C.c_ulonglong(nbytes), C.byref(p)))
         local = int(p.value)
@@ -103,6 +120,9 @@ class SymmetricHeap:
     def close(self) -> None:
         self.barrier()
         for buf in self.buffers.values():
+            if buf.slab is not None:
+                buf.slab.close()
+                continue
             for r, p in enumerate(buf.peer_ptrs):
                 if r != self.rank:
                     self._lib.olsb_ipc_close(C.c_void_p(p))

@@ -155,11 +155,12 @@ def test_poisoned_client_masked_on_gpu(monkeypatch):
     e.close()
 
 
-def test_cnn2_round_is_bitwise_deterministic():
+def test_cnn2_round_is_reproducible():
     """racecheck reports the bulk-copy staging ring of head_fc_xent_kernel (async-proxy writes vs generic reads ordered by
-    mbarriers, which the tool does not model — profiles/r1_sanitizer.txt).  A real race there would make the head's outputs
-    timing dependent: two engines with the same seed must therefore produce bit-identical global models and losses, with and
-    without the CUDA graph (different launch timing)."""
+    mbarriers, which the tool does not model — profiles/r1_sanitizer.txt).  A real race there would feed stale activations
+    into the classifier gradients and make a round timing dependent (errors of order 1e-2).  Two engines with the same seed
+    must therefore agree to float rounding (the only run-to-run freedom left is the order of a few fp32 atomics in the
+    statistics kernels), with and without the CUDA graph, i.e. under different launch timing."""
     import torch
     from olearning_sim_b200.engine.fed_engine import FedConfig, FedEngine
     outs = []
@@ -170,5 +171,7 @@ def test_cnn2_round_is_bitwise_deterministic():
         losses = [e.run_round(r).loss for r in range(3)]
         outs.append((losses, e.global_model().clone()))
         e.close()
+    l0, g0 = outs[0]
     for losses, g in outs[1:]:
-        assert losses == outs[0][0] and torch.equal(g, outs[0][1])
+        assert all(abs(a - b) <= 1e-5 * max(1.0, abs(a)) for a, b in zip(losses, l0)), (losses, l0)
+        assert float((g - g0).abs().max()) <= 1e-5 * float(g0.abs().max())

@@ -37,3 +37,16 @@ def test_native_ranks_match_the_nccl_oracle(model, opt):
     assert lines, out.stderr[-2000:]
     res = json.loads(lines[-1])
     assert res["world"] == 2 and res["ok"], res
+
+
+@pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
+def test_ipc_peer_pointer_fallback_matches_the_nccl_oracle():
+    """the same check with the NVSwitch multicast slabs disabled: the CUDA-IPC peer-pointer reduce / broadcast path"""
+    env = dict(os.environ, MODEL="cnn2", OPT="avg", OLSB_NVLS="0")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29597", os.path.join(ROOT, "tools", "mgpu_oracle.py")]
+    out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=900, cwd=ROOT)
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert lines, out.stderr[-2000:]
+    res = json.loads(lines[-1])
+    assert res["world"] == 2 and res["ok"] and not res["nvls_multicast"], res

@@ -71,12 +71,28 @@ dist.all_reduce(pack) if world > 1 else None
 want = base.double() + pack[:-1] / pack[-1]
 rel_comm = float((got.double() - want).norm() / (want - base.double()).norm())
 ok = ok and rel_comm < 1e-5
+# ---- time of the fused reduce + server step (device events, max over ranks)
 torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+for _ in range(3):
+    ws.reduce_and_update(w, opt="avg", server_lr=1.0)
+if world > 1:
+    dist.barrier()
+e0.record()
+for _ in range(10):
+    ws.reduce_and_update(w, opt="avg", server_lr=1.0)
+e1.record()
+torch.cuda.synchronize()
+t_red = torch.tensor([e0.elapsed_time(e1) * 100.0], device=nat.device)      # us per call
+if world > 1:
+    dist.all_reduce(t_red, op=dist.ReduceOp.MAX)
+gbuf = ws.heap.buffers["global"]
 if world > 1:
     dist.barrier()
 if rank == 0:
     print(json.dumps({"world": world, "model": MODEL, "server_opt": OPT, "clients": CLIENTS, "rounds": rows,
-                      "model_delta_rel_err_vs_nccl_oracle": rel, "tol": tol, "reduce_kernel_rel_err_vs_nccl_allreduce": rel_comm, "ok": bool(ok)}),
+                      "model_delta_rel_err_vs_nccl_oracle": rel, "tol": tol, "reduce_kernel_rel_err_vs_nccl_allreduce": rel_comm, "nvls_multicast": bool(gbuf.mc_ptr),
+                      "nvls_error": ws.heap.nvls_error, "reduce_update_us": round(float(t_red), 1), "params": int(P), "ok": bool(ok)}),
           flush=True)
 nat.close()
 if world > 1:
