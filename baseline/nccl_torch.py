@@ -77,7 +77,11 @@ class Cnn2Library:
     def load(self, x_u8: torch.Tensor, labels: torch.Tensor) -> None:
         """x_u8 [C, shard, 32, 32, 3] uint8 (device), labels [C, shard]: fold clients into channels per batch offset."""
         x = reference.normalize_u8(x_u8).permute(0, 1, 4, 2, 3)                       # C, shard, 3, 32, 32
-        self.y = labels.to(self.dev).long()
+        y = labels.to(self.dev).long()
+        if self.y is None or self.y.shape != y.shape:
+            self.y = y
+        else:
+            self.y.copy_(y)                                                              # graph-captured address stays valid
         B = 32
         act_dtype = torch.bfloat16 if self.dtype == "bf16" else torch.float32
         for off in sorted({(s * B) % self.shard for s in range(self.S)}):

@@ -4,6 +4,7 @@
 N=${N:-2}
 mkdir -p gpurun_out
 nvidia-smi topo -m 2>/dev/null | head -12 > gpurun_out/topo_n$N.txt
+if [ -z "$SKIP_ORACLE" ]; then
 : > gpurun_out/mgpu_oracle_n$N.jsonl
 IFS=";" read -ra SPECS_A <<< "${SPECS:-cnn2 avg;cnn2 adam;mlp2 momentum;resnet18 avg;bert_mini avg}"
 for spec in "${SPECS_A[@]}"; do
@@ -16,6 +17,7 @@ for spec in "cnn2 avg" "bert_mini avg"; do
   OLSB_NVLS=0 MODEL=$1 OPT=$2 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29612 tools/mgpu_oracle.py 2>gpurun_out/mgpu_oracle_${1}_$2_p2p.err | grep -E "^\{" >> gpurun_out/mgpu_oracle_n$N.jsonl || tail -5 gpurun_out/mgpu_oracle_${1}_$2_p2p.err
 done
 cat gpurun_out/mgpu_oracle_n$N.jsonl | cut -c1-600
+fi
 for c in ${CONFIGS:-2}; do
   timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 2962$N bench.py --gpus $N --config $c --steps ${STEPS:-10} --warmup 3 --phases > gpurun_out/bench_c${c}_n$N.json 2>gpurun_out/bench_c${c}_n$N.err
   tail -2 gpurun_out/bench_c${c}_n$N.err; grep -h '^{"metric"' gpurun_out/bench_c${c}_n$N.json | python -c "
