@@ -560,7 +560,15 @@ def main(argv: Optional[List[str]] = None) -> int:
         task.setdefault("engine", {})["profile"] = True
     runner = RoundRunner(task, repo=repo, working_dir=ctx.get("working_dir"), rank=rank, world=world,
                          checkpoint_dir=ctx.get("checkpoint_dir"), trace_path=a.profile or ctx.get("trace_path"))
-    ok = runner.run()
+    from ..parallel.comm import PeerLostError
+    try:
+        ok = runner.run()
+    except PeerLostError as e:
+        # a peer GPU/process vanished mid-round: this rank is healthy and its model untouched; leave with EX_TEMPFAIL so the
+        # job executor (control/jobs.py, max_restarts / shrink_on_restart) relaunches from the last agreed checkpoint
+        print(json.dumps({"task_id": runner.params.task_id, "ok": False, "peer_lost": e.peer, "round": e.round_idx,
+                          "rank": rank}), flush=True)
+        os._exit(PeerLostError.exit_code)      # no collective teardown: the peer will never answer it
     if rank == 0:
         print(json.dumps({"task_id": runner.params.task_id, "ok": ok, "history": runner.history[-3:]}))
     return 0 if ok else 1

@@ -85,14 +85,14 @@ class Cnn2Workspace:
         h.alloc("round", 256)
         self.round_rec = h.tensor("round", f32, (native.ROUND_REC,))
         self.round_rec.zero_()
-        self.round_out = torch.zeros(native.ROUND_REC, dtype=f32, device=d)
+        self.round_out = torch.zeros(native.ROUND_REC + 8, dtype=f32, device=d)      # [ROUND_REC] = peer-lost code
         self.global_w = h.tensor("global", f32, (P,))
         self.partial = h.tensor("partial", f32, (self.groups, P))
         self.wsum = h.tensor("wsum", f32, (self.groups,))
         self.opt_m = torch.zeros(self.shard_len, dtype=f32, device=d)
         self.opt_v = torch.zeros(self.shard_len, dtype=f32, device=d)
         self.stats = torch.zeros(4, dtype=f32, device=d)
-        self.arrive_ctr = torch.zeros(2, dtype=i32, device=d)
+        self.arrive_ctr = torch.zeros(4, dtype=i32, device=d)                        # [2] = sticky peer-lost code
         self.epoch = 0
         self.server_step = 0
         self.kernel_launches = 0

@@ -355,7 +355,7 @@ class FedEngine:
         self.step_active = torch.ones(S, self.C, dtype=torch.uint8, device=d)
         self.agg_weight = torch.zeros(self.C, device=d)
         self.counters = torch.zeros(4, dtype=torch.int32, device=d)
-        self.result_host = torch.zeros(native_round_rec()).pin_memory()
+        self.result_host = torch.zeros(native_round_rec() + 8).pin_memory()
         self.ws.set_global(self._g0)
         self.P = self.ws.P
         self._graphs: Dict[bool, Any] = {}
@@ -382,7 +382,7 @@ class FedEngine:
         self.step_active = torch.ones(S, self.C, dtype=torch.uint8, device=d)
         self.agg_weight = torch.zeros(self.C, device=d)
         self.counters = torch.zeros(4, dtype=torch.int32, device=d)
-        self.result_host = torch.zeros(native_round_rec()).pin_memory()
+        self.result_host = torch.zeros(native_round_rec() + 8).pin_memory()
         self.ws.set_global(self._g0)
         self._graphs, self._graph_ok, self._graph_warm, self.graph_error = {}, False, False, None
         self.x = self.y = None
@@ -505,6 +505,12 @@ class FedEngine:
         self.result_host.copy_(self.ws.round_out, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         vals = self.result_host.tolist()
+        lost = int(vals[native_round_rec()])
+        if lost:
+            # a cross-GPU barrier of fedavg_finish_kernel gave up on a peer: the model was not updated, this process and its
+            # CUDA context are intact — the job layer restarts the task on the surviving GPUs from the last checkpoint
+            from ..parallel.comm import PeerLostError
+            raise PeerLostError(lost - 1, round_idx)
         part_n = int(vals[1])
         res = RoundResult(round=round_idx, participants=int(vals[2]), dropped=int(vals[3]), late=int(vals[4]),
                           arrived=int(vals[5]), failed=int(vals[6]),

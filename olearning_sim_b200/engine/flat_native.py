@@ -42,11 +42,11 @@ class FlatWorkspace:
         self.wsum = hp.tensor("wsum", f32, (self.groups,))
         self.round_rec = hp.tensor("round", f32, (native.ROUND_REC,))
         self.round_rec.zero_()
-        self.round_out = torch.zeros(native.ROUND_REC, dtype=f32, device=d)
+        self.round_out = torch.zeros(native.ROUND_REC + 8, dtype=f32, device=d)      # [ROUND_REC] = peer-lost code
         self.opt_m = torch.zeros(self.shard_len, dtype=f32, device=d)
         self.opt_v = torch.zeros(self.shard_len, dtype=f32, device=d)
         self.stats = torch.zeros(4, dtype=f32, device=d)
-        self.arrive_ctr = torch.zeros(2, dtype=i32, device=d)
+        self.arrive_ctr = torch.zeros(4, dtype=i32, device=d)                        # [2] = sticky peer-lost code
         self.epoch = self.server_step = self.kernel_launches = 0
 
     def set_global(self, row: torch.Tensor) -> None:

@@ -142,6 +142,7 @@ int g_dgrad_pair = -1;
 // when a rank holds fewer than 400 clients (measured: 135 vs 149 us at 160 clients, 397 vs 393 us at 592)
 int g_fwd2_shift = -1;
 int g_wgrad2_ws = 1;     // 1: weight-stationary (B-collector) MMAs in the conv2 weight gradient
+unsigned g_peer_spin_limit = 1u << 28;   // polls of a peer flag before a cross-GPU barrier reports the peer as lost
 int g_wgrad2_mode = 1;   // 0: five 12x16 boxes per chunk, 1: one 12x20 box, 2: one box + swizzle base offset
 bool g_attr_set = false;
 int set_attrs() {
@@ -454,6 +455,7 @@ int olsb_fedavg_finish(const void* const* partial_peers, const void* const* wsum
   flk::FinishParams p;
   memset(&p, 0, sizeof(p));
   p.partial_mc = (const float*)partial_mc; p.global_mc = (float*)global_mc;
+  p.spin_limit = g_peer_spin_limit;
   for (int i = 0; i < nranks && i < flk::kMaxPeers; ++i) {
     p.partial_peers.p[i] = const_cast<void*>(partial_peers[i]);
     p.wsum_peers.p[i] = const_cast<void*>(wsum_peers[i]);
@@ -486,6 +488,7 @@ int olsb_set_option(const char* name, int value) {
   if (!strcmp(name, "fwd2_shift")) { const int o = g_fwd2_shift; g_fwd2_shift = value; return o; }
   if (!strcmp(name, "wgrad2_ws")) { const int o = g_wgrad2_ws; g_wgrad2_ws = value; return o; }
   if (!strcmp(name, "wgrad2_mode")) { const int o = g_wgrad2_mode; g_wgrad2_mode = value; return o; }
+  if (!strcmp(name, "peer_spin_limit")) { const int o = (int)(g_peer_spin_limit >> 8); g_peer_spin_limit = (unsigned)value << 8; return o; }
   return -1;
 }
 

@@ -458,7 +458,10 @@ __global__ void fedavg_partial_kernel(const PartialParams p) {
 // ---------------------------------------------------------------------------------------------
 // Device-side barrier across ranks: flags live in peer-mapped memory (one uint32 per (dst, src) pair).
 // Every rank writes `epoch` into slot [rank] of every peer's flag array, then waits until all of its own
-// slots reached `epoch`.  Bounded spin -> trap, so a dead peer fails the launch instead of hanging the box.
+// slots reached `epoch`.  The spin is bounded: when a peer does not show up within `spin_limit` polls the waiting
+// thread records 1 + (peer index) in `*lost` and gives up.  The kernel then returns without touching the model, the
+// CUDA context stays healthy and the host raises PeerLostError (parallel/comm.py) — a dead rank costs the survivors
+// one round, not their process.
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -468,7 +471,8 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
   asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ void peer_barrier(const PeerPtrs& flags, int nranks, int rank, uint32_t epoch) {
+__device__ __forceinline__ void peer_barrier(const PeerPtrs& flags, int nranks, int rank, uint32_t epoch,
+                                             uint32_t spin_limit, uint32_t* lost) {
   // caller: a single CTA-wide call; thread r (< nranks) signals peer r and waits on local slot r
   __syncthreads();
   if ((int)threadIdx.x < nranks) {
@@ -477,7 +481,7 @@ __device__ __forceinline__ void peer_barrier(const PeerPtrs& flags, int nranks, 
     const uint32_t* mine = static_cast<const uint32_t*>(flags.p[rank]) + threadIdx.x;
     uint32_t spins = 0;
     while (ld_acquire_sys(mine) < epoch) {
-      if (++spins > (1u << 28)) { __trap(); }
+      if (++spins > spin_limit) { atomicMax(lost, 1u + threadIdx.x); break; }
     }
   }
   __syncthreads();
@@ -489,6 +493,8 @@ __device__ __forceinline__ void peer_barrier(const PeerPtrs& flags, int nranks, 
 // no NCCL, no staging copy), normalises by the global weight sum, applies server SGD(momentum)/Adam and
 // writes the new global shard in place.  Grid barrier at entry (partials ready) and exit (shard published).
 // ---------------------------------------------------------------------------------------------
+constexpr int kMaxClasses = 24;
+constexpr int kRoundRec = 8 + 2 * kMaxClasses;      // floats per rank record; round_out[kRoundRec] carries the peer-lost code
 struct FinishParams {
   PeerPtrs partial_peers;   // float* [groups][P] per rank
   PeerPtrs wsum_peers;      // float* [groups] per rank
@@ -502,7 +508,8 @@ struct FinishParams {
   float server_lr, beta1, beta2, eps;
   int step;                 // Adam step (1-based)
   float* stats;             // [4]: total weight, |delta|^2 of owned shard, participants(unused), spare
-  uint32_t* arrive_ctr;     // [2] zero-initialised scratch for the intra-grid barriers
+  uint32_t* arrive_ctr;     // [4]: [0],[1] scratch of the intra-grid barriers (zeroed per launch); [2] sticky peer-lost code
+  uint32_t spin_limit;      // polls of a peer flag before the barrier gives up
   PeerPtrs round_peers;     // float* [round_len] per rank: this round's local accounting (round_stats_kernel) or null
   float* round_out;         // [round_len] sum over ranks of round_peers (every rank gets the job-wide numbers)
   int round_len;            // 8 (+ 2 per device class)
@@ -540,8 +547,13 @@ __device__ __forceinline__ void grid_gate(uint32_t* ctr, uint32_t nblocks) {
 __global__ void fedavg_finish_kernel(const FinishParams p) {
   // entry barrier: every rank's partials are complete & visible
   if (p.nranks > 1) {
-    if (blockIdx.x == 0) peer_barrier(p.flags, p.nranks, p.rank, p.epoch * 2 + 1);
+    if (blockIdx.x == 0) peer_barrier(p.flags, p.nranks, p.rank, p.epoch * 2 + 1, p.spin_limit, p.arrive_ctr + 2);
     grid_gate(p.arrive_ctr + 0, gridDim.x);
+    const uint32_t lost = *reinterpret_cast<volatile uint32_t*>(p.arrive_ctr + 2);
+    if (lost != 0u) {       // a peer is gone (now or in an earlier round): leave the model untouched
+      if (blockIdx.x == 0 && threadIdx.x == 0 && p.round_out) p.round_out[kRoundRec] = static_cast<float>(lost);
+      return;
+    }
   }
   float wtot = 0.f;
   for (int r = 0; r < p.nranks; ++r) {
@@ -613,7 +625,11 @@ __global__ void fedavg_finish_kernel(const FinishParams p) {
   // exit barrier: new shard visible to every peer before anyone starts the next broadcast pull
   if (p.nranks > 1) {
     grid_gate(p.arrive_ctr + 1, gridDim.x);
-    if (blockIdx.x == 0) peer_barrier(p.flags, p.nranks, p.rank, p.epoch * 2 + 2);
+    if (blockIdx.x == 0) {
+      peer_barrier(p.flags, p.nranks, p.rank, p.epoch * 2 + 2, p.spin_limit, p.arrive_ctr + 2);
+      if (threadIdx.x == 0 && p.round_out)
+        p.round_out[kRoundRec] = static_cast<float>(*reinterpret_cast<volatile uint32_t*>(p.arrive_ctr + 2));
+    }
   }
 }
 
@@ -626,8 +642,6 @@ __global__ void fedavg_finish_kernel(const FinishParams p) {
 // With `class_id` (one small integer per client = its (dataset, device class) index) the record is followed by
 // 2 floats per class: [failed_k, participants_k] — the per-class success / failed numbers the task status is computed
 // from (ols_core/taskMgr/run_task.py:164-197, task_manager.py:739-754).
-constexpr int kMaxClasses = 24;
-constexpr int kRoundRec = 8 + 2 * kMaxClasses;      // floats per rank record
 __global__ void round_stats_kernel(const float* __restrict__ loss_sum, const int* __restrict__ nonfinite,
                                    const uint8_t* __restrict__ participate, const uint8_t* __restrict__ step_active,
                                    const int* __restrict__ counters, int C, int S, float inv_steps,

@@ -22,6 +22,17 @@ import torch.distributed as dist
 _DTYPE_STR = {torch.float32: "<f4", torch.int32: "<i4", torch.uint8: "|u1", torch.bfloat16: None, torch.uint32: "<u4"}
 
 
+class PeerLostError(RuntimeError):
+    """A rank did not reach a round barrier within the spin budget (``native.set_option("peer_spin_limit", n)``: n * 256
+    polls).  Raised on the host after the round's result read-back; the raising process can still use its GPU."""
+
+    exit_code = 75          # EX_TEMPFAIL: control/jobs.py restarts the job on the surviving ranks
+
+    def __init__(self, peer: int, round_idx: int):
+        super().__init__(f"rank {peer} did not reach the reduce barrier of round {round_idx}")
+        self.peer, self.round_idx = peer, round_idx
+
+
 class _CudaBuffer:
     """Minimal __cuda_array_interface__ holder so torch can wrap a raw device pointer without copying."""
 

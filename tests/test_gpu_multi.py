@@ -50,3 +50,15 @@ def test_ipc_peer_pointer_fallback_matches_the_nccl_oracle():
     assert lines, out.stderr[-2000:]
     res = json.loads(lines[-1])
     assert res["world"] == 2 and res["ok"] and not res["nvls_multicast"], res
+
+
+@pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
+def test_lost_peer_raises_on_the_survivor_and_keeps_its_context():
+    """a rank that stops taking part mid-task: the survivor's reduce barrier gives up, PeerLostError surfaces on the host,
+    the global model is untouched and the CUDA context still works (no device trap)"""
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29598", os.path.join(ROOT, "tools", "peer_loss_check.py")]
+    out = subprocess.run(cmd, env=dict(os.environ, LOST_SLEEP="8"), capture_output=True, text=True, timeout=600, cwd=ROOT)
+    recs = [json.loads(l) for l in out.stdout.splitlines() if l.startswith("{")]
+    surv = [r for r in recs if r.get("role") == "survivor"]
+    assert surv and all(r["ok"] for r in surv), (recs, out.stderr[-1500:])
