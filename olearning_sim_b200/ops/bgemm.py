@@ -25,9 +25,9 @@ import torch
 
 from . import native
 
-A_K, A_MN, A_CONV = 0, 1, 2
+A_K, A_MN, A_CONV, A_HALO, A_HALOW = 0, 1, 2, 3, 4
 B_K, B_MN, B_CONVX, B_WT = 0, 1, 2, 3
-E_STORE, E_GNSTAT, E_SOFTMAX, E_DSOFT, E_SGD = 0, 1, 2, 3, 4
+E_STORE, E_GNSTAT, E_SOFTMAX, E_DSOFT, E_SGD, E_SGD_T = 0, 1, 2, 3, 4, 5
 ACT_NONE, ACT_RELU, ACT_GELU, ACT_GELU_BWD = 0, 1, 2, 3
 
 I9 = C.c_int * 9
@@ -351,6 +351,16 @@ def _n_tile(n: int) -> int:
     return 256 if n >= 256 else (128 if n >= 128 else 64)
 
 
+HALO = __import__("os").environ.get("OLSB_HALO", "1") != "0"      # halo-box form of the 3x3 / 64 -> 64 / 32x32 convolutions
+
+
+HALO_WGRAD = __import__("os").environ.get("OLSB_HALO_WGRAD", "1") != "0"
+
+
+def _halo_ok(H: int, Cin: int, Cout: int, ksize: int, stride: int) -> bool:
+    return HALO and ksize == 3 and stride == 1 and Cin == 64 and Cout == 64 and H % 16 == 0
+
+
 def conv_fwd(C_: int, imgs: int, H: int, Cin: int, Cout: int, ksize: int, stride: int, x: torch.Tensor, wb: torch.Tensor,
              w_off: int, wb_stride: int, raw: torch.Tensor, stats: torch.Tensor, groups: int, active=None,
              x_cimgs: int = 0, x_img0: int = 0) -> None:
@@ -361,9 +371,14 @@ def conv_fwd(C_: int, imgs: int, H: int, Cin: int, Cout: int, ksize: int, stride
     TW, TH = 1 << twl, 1 << thl
     nt = _n_tile(Cout)
     g = Bgemm()
-    g.am, g.bm, g.n_tile, g.epi = A_CONV, B_K, nt, E_GNSTAT
+    halo = _halo_ok(H, Cin, Cout, ksize, stride)
+    g.am, g.bm, g.n_tile, g.epi = A_HALO if halo else A_CONV, B_K, nt, E_GNSTAT
     nimg = x.numel() // (H * H * Cin)
-    g.a = tmap(x, 0, (Cin, H, H, nimg), (Cin, H * Cin, H * H * Cin), (64, TW * stride, TH * stride, tn), (1, stride, stride, 1))
+    if halo:            # 16 x 8-pixel tiles of one image, one (16+2) x (8+2) box each
+        twl, thl, tn, TW, TH = 3, 4, 1, 8, 16
+        g.a = tmap(x, 0, (Cin, H, H, nimg), (Cin, H * Cin, H * H * Cin), (64, TW + 2, TH + 2, 1))
+    else:
+        g.a = tmap(x, 0, (Cin, H, H, nimg), (Cin, H * Cin, H * H * Cin), (64, TW * stride, TH * stride, tn), (1, stride, stride, 1))
     ktot = ksize * ksize * Cin
     g.b = tmap(wb, w_off, (ktot, Cout, C_), (ktot, wb_stride), (64, nt, 1))
     p = g.p
@@ -398,8 +413,13 @@ def conv_dgrad(C_: int, imgs: int, H: int, Cin: int, Cout: int, ksize: int, stri
     classes = [(0, 0)] if stride == 1 else ([(0, 0)] if ksize == 1 else [(0, 0), (0, 1), (1, 0), (1, 1)])
     for (py, px) in classes:
         g = Bgemm()
-        g.am, g.bm, g.n_tile, g.epi = A_CONV, B_WT, nt, E_STORE
-        g.a = tmap(dy, 0, (Cout, OH, OH, C_ * imgs), (Cout, OH * Cout, OH * OH * Cout), (64, TW, TH, tn))
+        halo = _halo_ok(H, Cin, Cout, ksize, stride)
+        g.am, g.bm, g.n_tile, g.epi = A_HALO if halo else A_CONV, B_WT, nt, E_STORE
+        if halo:
+            twl, thl, tn, TW, TH = 3, 4, 1, 8, 16
+            g.a = tmap(dy, 0, (Cout, OH, OH, C_ * imgs), (Cout, OH * Cout, OH * OH * Cout), (64, TW + 2, TH + 2, 1))
+        else:
+            g.a = tmap(dy, 0, (Cout, OH, OH, C_ * imgs), (Cout, OH * Cout, OH * OH * Cout), (64, TW, TH, tn))
         g.b = tmap(wb, w_off, (Cin, ktaps, Cout, C_), (Cin, ktaps * Cin, wb_stride), (64, 1, 64, 1))
         p = g.p
         taps = []
@@ -433,6 +453,26 @@ def conv_wgrad(C_: int, imgs: int, H: int, Cin: int, Cout: int, ksize: int, stri
     pad = ksize // 2
     ktaps = ksize * ksize
     ktot = ktaps * Cin
+    if _halo_ok(H, Cin, Cout, ksize, stride) and HALO_WGRAD:
+        # halo form: work item = (client, set of tap pairs), accumulating over every 16 x 8-pixel tile of the client
+        g = Bgemm()
+        g.am, g.bm, g.n_tile, g.epi = A_HALOW, B_MN, 192, E_SGD_T
+        nimg = x.numel() // (H * H * Cin)
+        g.a = tmap(x, 0, (Cin, H, H, nimg), (Cin, H * Cin, H * H * Cin), (64, 10, 18, 1))
+        g.b = tmap(dy, 0, (Cout, OH, OH, C_ * imgs), (Cout, OH * Cout, OH * OH * Cout), (64, 8, 16, 1))
+        p = g.p
+        p.batches, p.M, p.N, p.m_tiles, p.n_tiles = C_, ktot, Cout, 1, 2
+        p.tw_log, p.th_log, p.tiles_x, p.tiles_y, p.imgs, p.src_stride = 3, 4, H // 8, H // 16, imgs, 1
+        p.src_cimgs, p.src_img0 = x_cimgs or imgs, x_img0
+        p.active, p.act_div = _ptr(active), 1
+        p.w_master, p.w_bs, p.w_ld = _ptr(master, w_off), P, ktot
+        p.w_bf16, p.wb_bs = _ptr(wb, w_off), wb_stride
+        p.w_global = _ptr(global_w, w_off) if (global_w is not None and mu > 0) else None
+        p.lr, p.mu, p.o_bdiv = lr, mu, 1
+        if grad_out is not None:
+            p.grad_out, p.g_bs = _ptr(grad_out), Cout * ktot
+        launch(g)
+        return
     kb_h, kb_n = (64 // OH, 1) if OH * OH >= 64 else (OH, 64 // (OH * OH))
     cpi = max(OH * OH // 64, 1)
     g = Bgemm()

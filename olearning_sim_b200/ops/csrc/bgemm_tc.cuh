@@ -8,6 +8,15 @@
 //                    A_MN    MN-major (the tensor is read "transposed" by the tensor core)      (dY^T, P^T, dS^T)
 //                    A_CONV  K-major 128-pixel window of an NHWC activation tensor, one TMA box per (tap, 64-channel
 //                            chunk); padding = TMA out-of-bounds zero fill, stride 2 = TMA elementStrides
+//                    A_HALO  3x3 / stride 1 / 64 -> 64 channels (ResNet stage 1): ONE 18 x 10-pixel halo box per
+//                            16 x 8-pixel tile; the 128 M rows are sixteen 8-pixel groups at the box pitch, so every tap
+//                            is a start-address shift of the same K-major view, and the client's nine 64 x 64 weight
+//                            blocks stay resident in shared memory while a CTA walks a contiguous range of tiles
+//                            (6x less L2 -> SM operand traffic than one box per tap: that feed bounds the N = 64 tiles)
+//                    A_HALOW the weight gradient of the same layer: the halo box is the MN-major A operand (M = 2 taps x
+//                            64 input channels, the second tap = the descriptor's leading-dimension offset), B = the
+//                            16 x 8-pixel dY tile (MN-major), K = pixels; a work item is (client, set of M tiles) and
+//                            accumulates over ALL tiles of the client in TMEM (E_SGD_T: rows = (tap, cin), columns = cout)
 //   * the B loader:  B_K     K-major (torch Linear weight [out][in], conv weight [cout][tap][cin])
 //                    B_MN    MN-major (W read transposed for data gradients, V / K / Q / X for attention / wgrad)
 //                    B_WT    MN-major conv weight for the data gradient: box (64 cin, 1 tap, 64 cout) of the forward copy
@@ -30,9 +39,9 @@ constexpr int kThreads = 320;          // warps 0-7 epilogue (group g = warp / 4
 constexpr int kEpiWarps = 4;          // warps per epilogue group = TMEM lane quadrants
 constexpr int kTmaWarp = 8, kMmaWarp = 9;
 constexpr int KC = 64;                 // K elements per pipeline stage (one 128-byte swizzle row)
-enum { A_K = 0, A_MN = 1, A_CONV = 2 };
+enum { A_K = 0, A_MN = 1, A_CONV = 2, A_HALO = 3, A_HALOW = 4 };
 enum { B_K = 0, B_MN = 1, B_CONVX = 2, B_WT = 3 };
-enum { E_STORE = 0, E_GNSTAT = 1, E_SOFTMAX = 2, E_DSOFT = 3, E_SGD = 4 };
+enum { E_STORE = 0, E_GNSTAT = 1, E_SOFTMAX = 2, E_DSOFT = 3, E_SGD = 4, E_SGD_T = 5 };
 enum { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2, ACT_GELU_BWD = 3 };
 
 struct Bars {
@@ -40,6 +49,7 @@ struct Bars {
   uint64_t empty[8];
   uint64_t tfull[2];
   uint64_t tempty[2];
+  uint64_t wfull, wempty;                // A_HALO: resident weight blocks of the current client landed / may be overwritten
   uint32_t tmem_base;
   uint32_t pad;
 };
@@ -76,12 +86,22 @@ struct Params {
 
 template <int AM, int BM, int N_TILE, int NSTAGE>
 struct Cfg {
+  static constexpr bool HALO = (AM == A_HALO);
+  static constexpr bool HALOW = (AM == A_HALOW);
+  static constexpr int HALO_W = 10, HALO_H = 18;                  // box of a 16 x 8-pixel tile with a 1-pixel apron
+  static constexpr int HALO_PITCH = HALO_W * 128;                 // bytes per box row = stride between the 8-pixel M groups
+  static constexpr int HALO_BYTES = HALO_H * HALO_PITCH;          // 23040 (TMA transaction size)
+  static constexpr int W_TAP_BYTES = 64 * 128;                    // one [64][64] bf16 weight block
+  static constexpr int W_BYTES = HALO ? 9 * W_TAP_BYTES : 0;      // resident weights of one client
   static constexpr int A_BYTES = 128 * 128;                       // 128 rows x 64 bf16 (either major)
   static constexpr int B_BYTES = (BM == B_K) ? N_TILE * 128 : (N_TILE / 64) * KC * 128;
-  static constexpr int STAGE_BYTES = A_BYTES + ((B_BYTES + 1023) / 1024) * 1024;
+  static constexpr int HALO_STAGE = (HALO_BYTES + 1023) / 1024 * 1024;
+  static constexpr int STAGE_BYTES = HALO ? HALO_STAGE : (HALOW ? HALO_STAGE + 128 * 128 : A_BYTES + ((B_BYTES + 1023) / 1024) * 1024);
   static constexpr int TMEM_COLS = (2 * N_TILE <= 32) ? 32 : (2 * N_TILE <= 64 ? 64 : (2 * N_TILE <= 128 ? 128 : (2 * N_TILE <= 256 ? 256 : 512)));
   static constexpr int SCRATCH_BYTES = 8 * 3072;                 // per epilogue warp: 32 rows x 64 B staging block + 1 KB bias row
-  static constexpr int SMEM_BYTES = 1024 + NSTAGE * STAGE_BYTES + SCRATCH_BYTES + (int)sizeof(Bars);
+  static constexpr int SMEM_BYTES = 1024 + NSTAGE * STAGE_BYTES + W_BYTES + SCRATCH_BYTES + (int)sizeof(Bars);
+  static_assert(!HALO || N_TILE == 64, "halo form: 64 -> 64 channels");
+  static_assert(!HALOW || N_TILE == 192, "halo weight gradient: up to three 64-column accumulators per buffer");
   static_assert(N_TILE % 32 == 0 && N_TILE <= 256, "epilogue works on 32-column chunks");
   static_assert(BM == B_K || N_TILE % 64 == 0, "MN-major B is loaded in 64-column boxes");
   static_assert(NSTAGE <= 8, "barrier arrays hold 8 stages");
@@ -188,7 +208,7 @@ __device__ __forceinline__ bool decode_work(const Params& p, int wi, TileCoord& 
   t.m0 = t.mt * 128;
   t.n0 = t.nt * N_TILE;
   if (p.active && !p.active[t.bi / p.act_div]) return false;
-  if (AM == A_CONV || p.out_conv) {
+  if (AM == A_CONV || AM == A_HALO || p.out_conv) {
     const int tpi = p.tiles_x * p.tiles_y;
     const int tn = 128 >> (p.tw_log + p.th_log);
     const int ti = t.mt / tpi, rem = t.mt - ti * tpi;
@@ -265,12 +285,14 @@ bgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   using C = Cfg<AM, BM, N_TILE, NSTAGE>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint4* scratch_all = reinterpret_cast<uint4*>(smem + NSTAGE * C::STAGE_BYTES);
-  Bars* bars = reinterpret_cast<Bars*>(smem + NSTAGE * C::STAGE_BYTES + C::SCRATCH_BYTES);
+  uint8_t* w_sm = smem + NSTAGE * C::STAGE_BYTES;                  // A_HALO: nine resident weight blocks
+  uint4* scratch_all = reinterpret_cast<uint4*>(smem + NSTAGE * C::STAGE_BYTES + C::W_BYTES);
+  Bars* bars = reinterpret_cast<Bars*>(smem + NSTAGE * C::STAGE_BYTES + C::W_BYTES + C::SCRATCH_BYTES);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int i = 0; i < NSTAGE; ++i) { mbar_init(&bars->full[i], 1); mbar_init(&bars->empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&bars->tfull[i], 1); mbar_init(&bars->tempty[i], kEpiWarps); }
+    mbar_init(&bars->wfull, 1); mbar_init(&bars->wempty, 1);
     fence_mbar_init();
   }
   if (warp == kMmaWarp) { tmem_alloc(&bars->tmem_base, C::TMEM_COLS); tmem_relinquish(); }
@@ -280,8 +302,205 @@ bgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   fence_after_sync();
   const uint32_t tmem_base = bars->tmem_base;
   const int num_work = p.batches * p.m_tiles * p.n_tiles;
+  // work items of this CTA: strided over the grid, or (A_HALO) one contiguous range so that a CTA changes client — and
+  // reloads the resident weights — at most twice
+  const int wi_begin = C::HALO ? (int)((long long)num_work * blockIdx.x / gridDim.x) : (int)blockIdx.x;
+  const int wi_end = C::HALO ? (int)((long long)num_work * (blockIdx.x + 1) / gridDim.x) : num_work;
+  const int wi_step = C::HALO ? 1 : (int)gridDim.x;
 
-  if (warp == kTmaWarp) {
+  if (warp == kTmaWarp && C::HALOW) {
+    // ================================================================ TMA producer, halo weight gradient
+    const bool leader = elect_one();
+    int stage = 0; uint32_t phase = 0;
+    const int tpi = p.tiles_x * p.tiles_y, ktiles = p.imgs * tpi;
+    for (int wi = blockIdx.x; wi < num_work; wi += gridDim.x) {
+      const int bi = wi >> 1;
+      if (p.active && !p.active[bi / p.act_div]) continue;
+      for (int kt = 0; kt < ktiles; ++kt) {
+        const int img = kt / tpi, rem = kt - img * tpi;
+        const int ty0 = (rem / p.tiles_x) << p.th_log, tx0 = (rem % p.tiles_x) << p.tw_log;
+        mbar_wait(&bars->empty[stage], phase ^ 1);
+        if (leader) {
+          uint8_t* dst = smem + stage * C::STAGE_BYTES;
+          mbar_arrive_expect_tx(&bars->full[stage], C::HALO_BYTES + 128 * 128);
+          tma_load_4d(dst, &tmA, &bars->full[stage], 0, tx0 - 1, ty0 - 1, bi * p.src_cimgs + p.src_img0 + img);   // x halo
+          tma_load_4d(dst + C::HALO_STAGE, &tmB, &bars->full[stage], 0, tx0, ty0, bi * p.imgs + img);             // dY tile
+        }
+        if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == kMmaWarp && C::HALOW) {
+    // ================================================================ MMA issuer, halo weight gradient
+    // M tile mt = weight taps (2mt, 2mt+1) x 64 input channels: tap (kh, kw) is the halo view shifted by kh rows and kw
+    // pixels; the second tap of the pair is reached through the leading-dimension offset of the MN-major descriptor
+    const bool leader = elect_one();
+    constexpr uint32_t IDESC = make_idesc_bf16(128, 64, 1, 1);
+    const uint32_t sbase = smem_u32(smem);
+    uint64_t a_desc[5];
+#pragma unroll
+    for (int mt = 0; mt < 5; ++mt) {
+      const int t0 = 2 * mt, t1 = (2 * mt + 1 < 9) ? 2 * mt + 1 : 2 * mt;
+      const uint32_t o0 = ((t0 / 3) * C::HALO_W + (t0 % 3)) * 128, o1 = ((t1 / 3) * C::HALO_W + (t1 % 3)) * 128;
+      a_desc[mt] = make_smem_desc(sbase + o0, (o1 > o0) ? (o1 - o0) : 128, C::HALO_PITCH, LT_SW128);
+    }
+    const uint64_t b_desc0 = make_smem_desc(sbase + C::HALO_STAGE, KC * 128, 1024, LT_SW128);
+    const int ktiles = p.imgs * p.tiles_x * p.tiles_y;
+    int stage = 0; uint32_t phase = 0; int buf = 0; uint32_t tphase0 = 0, tphase1 = 0;
+    for (int wi = blockIdx.x; wi < num_work; wi += gridDim.x) {
+      const int bi = wi >> 1, set = wi & 1;
+      if (p.active && !p.active[bi / p.act_div]) continue;
+      mbar_wait(&bars->tempty[buf], (buf ? tphase1 : tphase0) ^ 1);
+      fence_after_sync();
+      const uint32_t d_tmem = tmem_base + buf * N_TILE;
+      for (int kt = 0; kt < ktiles; ++kt) {
+        mbar_wait(&bars->full[stage], phase);
+        fence_after_sync();
+        if (leader) {
+          const uint32_t soff = stage * C::STAGE_BYTES;
+          const uint64_t b_s = desc_advance(b_desc0, soff);
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {
+            if (set == 1 && j == 2) break;                       // set 0: M tiles 0,1,2; set 1: M tiles 3,4
+            const uint64_t a_s = desc_advance(set ? a_desc[3 + (j & 1)] : a_desc[j], soff);
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks)                       // K16 = two image rows of the tile (8 pixels each)
+              umma_bf16(d_tmem + j * 64, desc_advance(a_s, ks * 2 * C::HALO_PITCH), desc_advance(b_s, ks * 2048), IDESC,
+                        (kt | ks) ? 1u : 0u);
+          }
+          umma_commit(&bars->empty[stage]);
+        }
+        __syncwarp();
+        if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+      }
+      if (leader) umma_commit(&bars->tfull[buf]);
+      __syncwarp();
+      if (buf) tphase1 ^= 1; else tphase0 ^= 1;
+      buf ^= 1;
+    }
+  } else if (warp < 2 * kEpiWarps && C::HALOW) {
+    // ================================================================ epilogue, halo weight gradient: accumulator row =
+    // (tap slot, cin), column = cout -> W[cout][tap][cin]: for a fixed column the 32 lanes of a warp touch 128 contiguous
+    // bytes of the fp32 master, so the update runs on direct coalesced accesses
+    const int group = warp >> 2, q = warp & 3;
+    const int row = 32 * q + lane;
+    uint32_t tphase = 0;
+    int item_n = 0;
+    for (int wi = blockIdx.x; wi < num_work; wi += gridDim.x) {
+      const int bi = wi >> 1, set = wi & 1;
+      if (p.active && !p.active[bi / p.act_div]) continue;
+      if ((item_n++ & 1) != group) continue;
+      const int buf = group;
+      mbar_wait(&bars->tfull[buf], tphase);
+      fence_after_sync();
+      const int nmt = set ? 2 : 3;
+      for (int j = 0; j < nmt; ++j) {
+        const int tap = 2 * (set * 3 + j) + (row >> 6), cin = row & 63;
+        const bool valid = tap < 9;
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(32 * q) << 16) + buf * N_TILE + j * 64;
+#pragma unroll 1
+        for (int c0 = 0; c0 < 64; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(taddr + c0, v);
+          tmem_ld_wait();
+          if (!valid) continue;
+          const size_t idx0 = (size_t)c0 * p.w_ld + tap * 64 + cin;       // + i * w_ld per output channel
+          if (p.grad_out) {
+            float* gp = p.grad_out + (size_t)bi * p.g_bs + idx0;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) gp[(size_t)i * p.w_ld] = __uint_as_float(v[i]);
+          } else {
+            float* wp = p.w_master + (size_t)bi * p.w_bs + idx0;
+            __nv_bfloat16* bp = p.w_bf16 + (size_t)bi * p.wb_bs + idx0;
+            float w[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) w[i] = wp[(size_t)i * p.w_ld];    // all loads before any store
+            if (p.w_global) {
+              const float* ap = p.w_global + idx0;
+#pragma unroll
+              for (int i = 0; i < 32; ++i) w[i] -= p.lr * (__uint_as_float(v[i]) + p.mu * (w[i] - __ldg(ap + (size_t)i * p.w_ld)));
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) w[i] -= p.lr * __uint_as_float(v[i]);
+            }
+#pragma unroll
+            for (int i = 0; i < 32; ++i) { wp[(size_t)i * p.w_ld] = w[i]; bp[(size_t)i * p.w_ld] = __float2bfloat16_rn(w[i]); }
+          }
+        }
+      }
+      fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->tempty[buf]);
+      tphase ^= 1;
+    }
+  } else if (warp == kTmaWarp && C::HALO) {
+    // ================================================================ TMA producer, halo form
+    const bool leader = elect_one();
+    int stage = 0; uint32_t phase = 0, wphase = 0; int cur_bi = -1;
+    for (int wi = wi_begin; wi < wi_end; ++wi) {
+      TileCoord t;
+      if (!decode_work<AM, N_TILE>(p, wi, t)) continue;
+      if (t.bi != cur_bi) {
+        if (cur_bi >= 0) { mbar_wait(&bars->wempty, wphase); wphase ^= 1; }
+        cur_bi = t.bi;
+        if (leader) {
+          mbar_arrive_expect_tx(&bars->wfull, C::W_BYTES);
+#pragma unroll 1
+          for (int tap = 0; tap < 9; ++tap) {
+            // the [cout][cin] block of weight tap tap_w: K-major B of the forward conv, MN-major B of the data gradient
+            if (BM == B_K) tma_load_3d(w_sm + tap * C::W_TAP_BYTES, &tmB, &bars->wfull, p.tap_w[tap] * p.ktap, 0, t.bi);
+            else tma_load_4d(w_sm + tap * C::W_TAP_BYTES, &tmB, &bars->wfull, 0, p.tap_w[tap], 0, t.bi);
+          }
+        }
+      }
+      mbar_wait(&bars->empty[stage], phase ^ 1);
+      if (leader) {
+        mbar_arrive_expect_tx(&bars->full[stage], C::HALO_BYTES);
+        tma_load_4d(smem + stage * C::STAGE_BYTES, &tmA, &bars->full[stage], 0, t.tx0 - 1, t.ty0 - 1,
+                    t.bi * p.src_cimgs + p.src_img0 + t.img0);
+      }
+      if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+    }
+  } else if (warp == kMmaWarp && C::HALO) {
+    // ================================================================ MMA issuer, halo form: 9 taps x 4 k-steps per tile
+    const bool leader = elect_one();
+    constexpr uint32_t IDESC = make_idesc_bf16(128, N_TILE, 0, BM == B_K ? 0 : 1);
+    const uint32_t sbase = smem_u32(smem);
+    const uint64_t a_desc0 = make_smem_desc(sbase, 16, C::HALO_PITCH, LT_SW128);      // 8-pixel groups at the box pitch
+    const uint64_t b_desc0 = (BM != B_K) ? make_smem_desc(smem_u32(w_sm), KC * 128, 1024, LT_SW128)
+                                         : make_smem_desc(smem_u32(w_sm), 16, 1024, LT_SW128);
+    constexpr uint32_t B_STEP = (BM != B_K) ? 2048 : 32;
+    uint32_t aoff[9];
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) aoff[tap] = ((p.tap_dy[tap] + 1) * C::HALO_W + (p.tap_dx[tap] + 1)) * 128;
+    const int tpc = p.m_tiles * p.n_tiles;
+    int stage = 0; uint32_t phase = 0, wphase = 0; int buf = 0; uint32_t tphase0 = 0, tphase1 = 0; int cur_bi = -1;
+    for (int wi = wi_begin; wi < wi_end; ++wi) {
+      TileCoord t;
+      if (!decode_work<AM, N_TILE>(p, wi, t)) continue;
+      if (t.bi != cur_bi) { mbar_wait(&bars->wfull, wphase); wphase ^= 1; cur_bi = t.bi; }
+      mbar_wait(&bars->tempty[buf], (buf ? tphase1 : tphase0) ^ 1);
+      mbar_wait(&bars->full[stage], phase);
+      fence_after_sync();
+      if (leader) {
+        const uint32_t d_tmem = tmem_base + buf * N_TILE;
+        const uint64_t a_s = desc_advance(a_desc0, stage * C::STAGE_BYTES);
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+          const uint64_t b_t = desc_advance(b_desc0, tap * C::W_TAP_BYTES);
+#pragma unroll
+          for (int ks = 0; ks < KC / 16; ++ks)
+            umma_bf16(d_tmem, desc_advance(a_s, aoff[tap] + ks * 32), desc_advance(b_t, ks * B_STEP), IDESC, (tap | ks) ? 1u : 0u);
+        }
+        umma_commit(&bars->empty[stage]);
+        umma_commit(&bars->tfull[buf]);
+        if (wi + 1 >= wi_end || (wi + 1) / tpc != t.bi) umma_commit(&bars->wempty);   // last tile of this client here
+      }
+      __syncwarp();
+      if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+      if (buf) tphase1 ^= 1; else tphase0 ^= 1;
+      buf ^= 1;
+    }
+  } else if (warp == kTmaWarp) {
     // ================================================================ TMA producer
     const bool leader = elect_one();
     int stage = 0; uint32_t phase = 0;
@@ -299,7 +518,7 @@ bgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       }
     };
     for (int i = 0; i < pf_ahead; ++i) pf_step();
-    for (int wi = blockIdx.x; wi < num_work; wi += gridDim.x) {
+    for (int wi = wi_begin; wi < wi_end; wi += wi_step) {
       TileCoord t;
       if (!decode_work<AM, N_TILE>(p, wi, t)) continue;
       for (int kc = 0; kc < p.k_chunks; ++kc) {
@@ -325,7 +544,7 @@ bgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                                          : make_smem_desc(sbase + C::A_BYTES, 16, 1024, LT_SW128);
     constexpr uint32_t A_STEP = (AM == A_MN) ? 2048 : 32, B_STEP = (BM != B_K) ? 2048 : 32;
     int stage = 0; uint32_t phase = 0; int buf = 0; uint32_t tphase0 = 0, tphase1 = 0;
-    for (int wi = blockIdx.x; wi < num_work; wi += gridDim.x) {
+    for (int wi = wi_begin; wi < wi_end; wi += wi_step) {
       TileCoord t;
       if (!decode_work<AM, N_TILE>(p, wi, t)) continue;
       mbar_wait(&bars->tempty[buf], (buf ? tphase1 : tphase0) ^ 1);
@@ -360,7 +579,7 @@ bgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     float* sbias = reinterpret_cast<float*>(scratch + 128);
     uint32_t tphase = 0;
     int tile_n = 0;
-    for (int wi = blockIdx.x; wi < num_work; wi += gridDim.x) {
+    for (int wi = wi_begin; wi < wi_end; wi += wi_step) {
       TileCoord t;
       if (!decode_work<AM, N_TILE>(p, wi, t)) continue;
       if ((tile_n++ & 1) != group) continue;

@@ -38,6 +38,14 @@ def enabled(world: int) -> bool:
     return world > 1 and os.environ.get(ENV, "auto").lower() not in ("0", "off", "false", "no")
 
 
+def min_bytes() -> int:
+    """Slabs smaller than this stay on the CUDA-IPC path (``OLSB_NVLS_MIN_BYTES``, default 4 MiB; ``OLSB_NVLS=1`` forces
+    multicast for every size)."""
+    if os.environ.get(ENV, "auto") == "1":
+        return 0
+    return int(os.environ.get("OLSB_NVLS_MIN_BYTES", 4 << 20))
+
+
 def last_error() -> Optional[str]:
     return _last_error
 

@@ -62,7 +62,8 @@ upd = torch.randn(ws.C, P, device=nat.device) * 1e-2
 base = ws.get_global().clone()
 ws.master.copy_(base[None, :] + upd)
 w = torch.rand(ws.C, device=nat.device) + 0.5
-w[0] = 0.0                                                      # one masked client per rank
+if ws.C > 1:
+    w[0] = 0.0                                                  # one masked client per rank
 ws.reset_round_stats()
 ws.reduce_and_update(w, opt="avg", server_lr=1.0)
 got = ws.get_global()
