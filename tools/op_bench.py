@@ -39,6 +39,7 @@ def main():
     ap.add_argument("--clients", type=int, default=64)
     ap.add_argument("--reps", type=int, default=10)
     ap.add_argument("--once", action="store_true")
+    ap.add_argument("--nowarm", action="store_true", help="profiler mode: every op exactly once, no warm-up")
     ap.add_argument("--only", default="")
     ap.add_argument("--json", default="")
     a = ap.parse_args()
@@ -109,6 +110,9 @@ def main():
     # ------------------------------------------------------------------ run
     rows = []
     for name, fn, flops, nbytes in ops:
+        if a.nowarm:
+            fn(); torch.cuda.synchronize()
+            continue
         fn(); fn()
         torch.cuda.synchronize()
         if a.once:
