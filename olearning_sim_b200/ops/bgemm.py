@@ -25,7 +25,7 @@ import torch
 
 from . import native
 
-A_K, A_MN, A_CONV, A_HALO, A_HALOW = 0, 1, 2, 3, 4
+A_K, A_MN, A_CONV, A_HALO, A_HALOW, A_CONVX = 0, 1, 2, 3, 4, 5
 B_K, B_MN, B_CONVX, B_WT = 0, 1, 2, 3
 E_STORE, E_GNSTAT, E_SOFTMAX, E_DSOFT, E_SGD, E_SGD_T = 0, 1, 2, 3, 4, 5
 ACT_NONE, ACT_RELU, ACT_GELU, ACT_GELU_BWD = 0, 1, 2, 3
@@ -355,6 +355,7 @@ HALO = __import__("os").environ.get("OLSB_HALO", "1") != "0"      # halo-box for
 
 
 HALO_WGRAD = __import__("os").environ.get("OLSB_HALO_WGRAD", "1") != "0"
+WGRAD_T = __import__("os").environ.get("OLSB_WGRAD_T", "1") != "0"      # weight gradients with rows = (tap, cin), columns = cout
 
 
 def _halo_ok(H: int, Cin: int, Cout: int, ksize: int, stride: int) -> bool:
@@ -476,16 +477,28 @@ def conv_wgrad(C_: int, imgs: int, H: int, Cin: int, Cout: int, ksize: int, stri
     kb_h, kb_n = (64 // OH, 1) if OH * OH >= 64 else (OH, 64 // (OH * OH))
     cpi = max(OH * OH // 64, 1)
     g = Bgemm()
-    g.am, g.bm, g.n_tile, g.epi = A_MN, B_CONVX, 192, E_SGD
+    # measured (64 clients): 4x4x512 393 vs 600 us, 8x8x256 160 vs 212 us; with 128 output channels the 128-column tile
+    # needs more operand bytes per MAC than the 192-column form below (206 vs 174 us) and stays on it
+    transposed = WGRAD_T and Cout % 256 == 0 and Cin % 64 == 0
     npix = imgs * OH * OH
-    g.a = tmap(dy, 0, (Cout, npix, C_), (Cout, npix * Cout), (64, 64, 1))
     nimg = x.numel() // (H * H * Cin)
-    g.b = tmap(x, 0, (Cin, H, H, nimg), (Cin, H * Cin, H * H * Cin), (64, OH * stride, kb_h * stride, kb_n), (1, stride, stride, 1))
+    t_dy = tmap(dy, 0, (Cout, npix, C_), (Cout, npix * Cout), (64, 64, 1))
+    t_x = tmap(x, 0, (Cin, H, H, nimg), (Cin, H * Cin, H * H * Cin), (64, OH * stride, kb_h * stride, kb_n), (1, stride, stride, 1))
     p = g.p
     p.cchunks = (Cin + 63) // 64
     p.nblocks, p.cin, p.ntaps = ktaps * p.cchunks, Cin, ktaps
-    p.batches, p.M, p.N = C_, Cout, ktot
-    p.m_tiles, p.n_tiles, p.k_chunks = (Cout + 127) // 128, (p.nblocks + 2) // 3, npix // 64
+    if transposed:
+        # D[(tap, cin)][cout]: the update walks W[cout][tap][cin] with the lanes of a warp on contiguous addresses
+        nt = 256
+        g.am, g.bm, g.n_tile, g.epi = A_CONVX, B_MN, nt, E_SGD_T
+        g.a, g.b = t_x, t_dy
+        p.batches, p.M, p.N = C_, p.nblocks * 64, Cout
+        p.m_tiles, p.n_tiles, p.k_chunks = (p.nblocks + 1) // 2, Cout // nt, npix // 64
+    else:
+        g.am, g.bm, g.n_tile, g.epi = A_MN, B_CONVX, 192, E_SGD
+        g.a, g.b = t_dy, t_x
+        p.batches, p.M, p.N = C_, Cout, ktot
+        p.m_tiles, p.n_tiles, p.k_chunks = (Cout + 127) // 128, (p.nblocks + 2) // 3, npix // 64
     for kh in range(ksize):
         for kw in range(ksize):
             t = kh * ksize + kw

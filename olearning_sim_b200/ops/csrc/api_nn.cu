@@ -144,6 +144,8 @@ int olsb_bgemm(const OlsbBgemm* g, void* stream) {
     // ---- halo-box form (3x3, stride 1, 64 -> 64 channels): resident weights, one box per tile
     case A_HALO * 1000000 + B_K * 100000 + 64 * 100 + E_GNSTAT: return launch<A_HALO, B_K, 64, E_GNSTAT, 5>(g, st);
     case A_HALO * 1000000 + B_WT * 100000 + 64 * 100 + E_STORE: return launch<A_HALO, B_WT, 64, E_STORE, 5>(g, st);
+    case A_CONVX * 1000000 + B_MN * 100000 + 128 * 100 + E_SGD_T: return launch<A_CONVX, B_MN, 128, E_SGD_T, 6>(g, st);
+    case A_CONVX * 1000000 + B_MN * 100000 + 256 * 100 + E_SGD_T: return launch<A_CONVX, B_MN, 256, E_SGD_T, 4>(g, st);
     case A_HALOW * 1000000 + B_MN * 100000 + 192 * 100 + E_SGD_T: return launch<A_HALOW, B_MN, 192, E_SGD_T, 5>(g, st);
     case A_MN * 1000000 + B_CONVX * 100000 + 192 * 100 + E_SGD: return launch<A_MN, B_CONVX, 192, E_SGD, 5>(g, st);
     default:

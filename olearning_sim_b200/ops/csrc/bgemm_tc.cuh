@@ -13,6 +13,9 @@
 //                            is a start-address shift of the same K-major view, and the client's nine 64 x 64 weight
 //                            blocks stay resident in shared memory while a CTA walks a contiguous range of tiles
 //                            (6x less L2 -> SM operand traffic than one box per tap: that feed bounds the N = 64 tiles)
+//                    A_CONVX MN-major 64-pixel window of the conv input, two (tap, 64-channel chunk) blocks per M tile: the
+//                            weight gradient with rows = (tap, cin) and columns = cout (B_MN over dY), so that the fused
+//                            SGD epilogue E_SGD_T walks the fp32 master with the 32 lanes of a warp on contiguous bytes
 //                    A_HALOW the weight gradient of the same layer: the halo box is the MN-major A operand (M = 2 taps x
 //                            64 input channels, the second tap = the descriptor's leading-dimension offset), B = the
 //                            16 x 8-pixel dY tile (MN-major), K = pixels; a work item is (client, set of M tiles) and
@@ -39,7 +42,7 @@ constexpr int kThreads = 320;          // warps 0-7 epilogue (group g = warp / 4
 constexpr int kEpiWarps = 4;          // warps per epilogue group = TMEM lane quadrants
 constexpr int kTmaWarp = 8, kMmaWarp = 9;
 constexpr int KC = 64;                 // K elements per pipeline stage (one 128-byte swizzle row)
-enum { A_K = 0, A_MN = 1, A_CONV = 2, A_HALO = 3, A_HALOW = 4 };
+enum { A_K = 0, A_MN = 1, A_CONV = 2, A_HALO = 3, A_HALOW = 4, A_CONVX = 5 };
 enum { B_K = 0, B_MN = 1, B_CONVX = 2, B_WT = 3 };
 enum { E_STORE = 0, E_GNSTAT = 1, E_SOFTMAX = 2, E_DSOFT = 3, E_SGD = 4, E_SGD_T = 5 };
 enum { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2, ACT_GELU_BWD = 3 };
@@ -240,6 +243,17 @@ __device__ __forceinline__ void issue_chunk(const Params& p, const CUtensorMap* 
   if (AM == A_K) {
     if (p.a_bdiv) op4(a_dst, tmA, kc * KC, t.m0, t.bi % p.a_bdiv, t.bi / p.a_bdiv);
     else op3(a_dst, tmA, kc * KC, t.m0, t.bi);
+  } else if (AM == A_CONVX) {
+    const int ci = kc / p.kb_cpi;
+    const int img = ci * p.kb_n, y0 = (kc - ci * p.kb_cpi) * p.kb_h;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int blk = t.mt * 2 + j;
+      int tp = blk / p.cchunks;
+      int c0 = (blk - tp * p.cchunks) * 64;
+      if (blk >= p.nblocks) { tp = 0; c0 = p.cin + 64; }           // padding block: out of bounds -> zeros
+      op4(a_dst + j * KC * 128, tmA, c0, p.tap_dx[tp], y0 * p.src_stride + p.tap_dy[tp], t.bi * p.src_cimgs + p.src_img0 + img);
+    }
   } else if (AM == A_MN) {
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
@@ -537,12 +551,13 @@ bgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   } else if (warp == kMmaWarp) {
     // ================================================================ MMA issuer
     const bool leader = elect_one();
-    constexpr uint32_t IDESC = make_idesc_bf16(128, N_TILE, AM == A_MN ? 1 : 0, BM == B_K ? 0 : 1);
+    constexpr bool A_IS_MN = (AM == A_MN || AM == A_CONVX);
+    constexpr uint32_t IDESC = make_idesc_bf16(128, N_TILE, A_IS_MN ? 1 : 0, BM == B_K ? 0 : 1);
     const uint32_t sbase = smem_u32(smem);
-    const uint64_t a_desc0 = (AM == A_MN) ? make_smem_desc(sbase, KC * 128, 1024, LT_SW128) : make_smem_desc(sbase, 16, 1024, LT_SW128);
+    const uint64_t a_desc0 = A_IS_MN ? make_smem_desc(sbase, KC * 128, 1024, LT_SW128) : make_smem_desc(sbase, 16, 1024, LT_SW128);
     const uint64_t b_desc0 = (BM != B_K) ? make_smem_desc(sbase + C::A_BYTES, KC * 128, 1024, LT_SW128)
                                          : make_smem_desc(sbase + C::A_BYTES, 16, 1024, LT_SW128);
-    constexpr uint32_t A_STEP = (AM == A_MN) ? 2048 : 32, B_STEP = (BM != B_K) ? 2048 : 32;
+    constexpr uint32_t A_STEP = A_IS_MN ? 2048 : 32, B_STEP = (BM != B_K) ? 2048 : 32;
     int stage = 0; uint32_t phase = 0; int buf = 0; uint32_t tphase0 = 0, tphase1 = 0;
     for (int wi = wi_begin; wi < wi_end; wi += wi_step) {
       TileCoord t;
@@ -642,6 +657,14 @@ bgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         uint32_t v[32];
         tmem_ld32(taddr, v);
         const int nchunks = min(N_TILE / 32, (p.N - t.n0 + 31) / 32);          // warp-uniform
+        // second epilogue operand of this row (GELU-backward pre-activation, else the residual addend): the next chunk's 64
+        // bytes are requested one chunk ahead — a dependent load per chunk exposed a full memory latency 8 times per tile
+        const __nv_bfloat16* pre = (EPI == E_STORE) ? (p.act == ACT_GELU_BWD ? p.aux_in : p.addend) : nullptr;
+        uint4 an[4];
+        if (EPI == E_STORE && pre && rvalid) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) an[i] = reinterpret_cast<const uint4*>(pre + obase + t.n0)[i];
+        }
 #pragma unroll 1
         for (int j = 0; j < nchunks; ++j) {
           const int nb = t.n0 + j * 32;
@@ -650,6 +673,15 @@ bgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 #pragma unroll
           for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
           if (j + 1 < nchunks) tmem_ld32(taddr + (j + 1) * 32, v);           // next chunk in flight
+          uint4 ac[4];
+          if (EPI == E_STORE && pre) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) ac[i] = an[i];
+            if (j + 1 < nchunks && rvalid) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) an[i] = reinterpret_cast<const uint4*>(pre + obase + nb + 32)[i];
+            }
+          }
           if (EPI == E_GNSTAT) {
             const int g = nb / p.gn_cpg;
             if (g != gcur) { if (gcur >= 0) flush(gcur); gcur = g; }
@@ -665,10 +697,20 @@ bgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               for (int i = 0; i < 8; ++i) { const float4 b = bp[i]; f[4 * i] += b.x; f[4 * i + 1] += b.y; f[4 * i + 2] += b.z; f[4 * i + 3] += b.w; }
             }
             if (p.addend && rvalid) {
-              float a[32];
-              load32(p.addend + obase + nb, a);
+              if (p.act == ACT_GELU_BWD) {                     // both operands: the addend is the un-pipelined one
+                float a2[32];
+                load32(p.addend + obase + nb, a2);
 #pragma unroll
-              for (int i = 0; i < 32; ++i) f[i] += a[i];
+                for (int i = 0; i < 32; ++i) f[i] += a2[i];
+              } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  float a8[8];
+                  unpack8(ac[i], a8);
+#pragma unroll
+                  for (int k = 0; k < 8; ++k) f[8 * i + k] += a8[k];
+                }
+              }
             }
             if (p.act == ACT_RELU) {
 #pragma unroll
@@ -681,10 +723,13 @@ bgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 #pragma unroll
               for (int i = 0; i < 32; ++i) f[i] = gelu_f(f[i]);
             } else if (p.act == ACT_GELU_BWD) {
-              float a[32];
-              if (rvalid) load32(p.aux_in + obase + nb, a);
 #pragma unroll
-              for (int i = 0; i < 32; ++i) f[i] = rvalid ? f[i] * gelu_grad_f(a[i]) : 0.f;
+              for (int i = 0; i < 4; ++i) {
+                float a8[8];
+                unpack8(ac[i], a8);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) f[8 * i + k] = rvalid ? f[8 * i + k] * gelu_grad_f(a8[k]) : 0.f;
+              }
             }
           }
           // 32 rows x 64 bytes of the warp, written as full sectors (8 rows x 64 contiguous bytes per instruction)
@@ -750,6 +795,45 @@ bgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           uint4 pk[4];
           pack32(f, pk);
           stage_rows_out<4>(scratch, lane, pk, reinterpret_cast<char*>(p.out), (obase + t.n0 + j * 32) * 2, rvalid);
+        }
+      } else if (EPI == E_SGD_T) {
+        // rows = (tap, cin) blocks of the weight, columns = output channels: W[b][cout][kidx].  For a fixed column the 32
+        // lanes of a warp (consecutive cin) touch 128 contiguous bytes of the fp32 master and 64 of the bf16 copy, so the
+        // read-modify-write runs on fully coalesced accesses with 32 independent loads in flight per thread
+        const int blk = t.mt * 2 + (row >> 6), ch = row & 63;
+        const int tp = blk / p.cchunks, c0 = (blk - tp * p.cchunks) * 64;
+        const bool kvalid = blk < p.nblocks && c0 + ch < p.cin;
+        const size_t kidx = (size_t)tp * p.cin + c0 + ch;
+#pragma unroll 1
+        for (int j = 0; j < N_TILE / 32; ++j) {
+          const int nb = t.n0 + j * 32;
+          if (nb >= p.N) break;
+          uint32_t v[32];
+          tmem_ld32(taddr + j * 32, v);
+          tmem_ld_wait();
+          if (!kvalid) continue;
+          const size_t idx0 = (size_t)nb * p.w_ld + kidx;                  // + i * w_ld per output channel
+          if (p.grad_out) {
+            float* gp = p.grad_out + (size_t)t.bi * p.g_bs + idx0;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) gp[(size_t)i * p.w_ld] = __uint_as_float(v[i]);
+          } else {
+            float* wp = p.w_master + (size_t)t.bi * p.w_bs + idx0;
+            __nv_bfloat16* bp = p.w_bf16 + (size_t)t.bi * p.wb_bs + idx0;
+            float w[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) w[i] = wp[(size_t)i * p.w_ld];    // all loads before any store
+            if (p.w_global) {
+              const float* ap = p.w_global + idx0;
+#pragma unroll
+              for (int i = 0; i < 32; ++i) w[i] -= p.lr * (__uint_as_float(v[i]) + p.mu * (w[i] - __ldg(ap + (size_t)i * p.w_ld)));
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) w[i] -= p.lr * __uint_as_float(v[i]);
+            }
+#pragma unroll
+            for (int i = 0; i < 32; ++i) { wp[(size_t)i * p.w_ld] = w[i]; bp[(size_t)i * p.w_ld] = __float2bfloat16_rn(w[i]); }
+          }
         }
       } else {  // E_SGD: W[b][m][n] -= lr * (g + mu (w - w_global)), bf16 operand copy refreshed in the same pass
         uint32_t vn[32];
