@@ -773,25 +773,55 @@ bgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         }
       } else if (EPI == E_DSOFT) {
         float dot = 0.f;
-#pragma unroll 1
-        for (int j = 0; j < N_TILE / 32; ++j) {
-          uint32_t v[32];
-          tmem_ld32(taddr + j * 32, v);
-          tmem_ld_wait();
-          float a[32];
-          if (rvalid) load32(p.aux_in + obase + t.n0 + j * 32, a);
+        // the probabilities of this row are requested one 64-byte chunk ahead of their use in both passes (the second
+        // pass hits L1/L2): a dependent load per chunk exposed the memory latency eight times per tile
+        const uint4* prow = reinterpret_cast<const uint4*>(p.aux_in + obase + t.n0);
+        uint4 an[4];
+        if (rvalid) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) dot += rvalid ? __uint_as_float(v[i]) * a[i] : 0.f;
+          for (int i = 0; i < 4; ++i) an[i] = prow[i];
         }
 #pragma unroll 1
         for (int j = 0; j < N_TILE / 32; ++j) {
           uint32_t v[32];
           tmem_ld32(taddr + j * 32, v);
-          tmem_ld_wait();
-          float a[32], f[32];
-          if (rvalid) load32(p.aux_in + obase + t.n0 + j * 32, a);
+          uint4 ac[4];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) f[i] = rvalid ? a[i] * (__uint_as_float(v[i]) - dot) * p.scale : 0.f;
+          for (int i = 0; i < 4; ++i) ac[i] = an[i];
+          if (rvalid) {
+            const int jn = (j + 1 < N_TILE / 32) ? j + 1 : 0;          // last chunk: start the second pass
+#pragma unroll
+            for (int i = 0; i < 4; ++i) an[i] = prow[jn * 4 + i];
+          }
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            float a8[8];
+            unpack8(ac[i], a8);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) dot += rvalid ? __uint_as_float(v[8 * i + k]) * a8[k] : 0.f;
+          }
+        }
+#pragma unroll 1
+        for (int j = 0; j < N_TILE / 32; ++j) {
+          uint32_t v[32];
+          tmem_ld32(taddr + j * 32, v);
+          uint4 ac[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) ac[i] = an[i];
+          if (rvalid && j + 1 < N_TILE / 32) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) an[i] = prow[(j + 1) * 4 + i];
+          }
+          tmem_ld_wait();
+          float f[32];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            float a8[8];
+            unpack8(ac[i], a8);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) f[8 * i + k] = rvalid ? a8[k] * (__uint_as_float(v[8 * i + k]) - dot) * p.scale : 0.f;
+          }
           uint4 pk[4];
           pack32(f, pk);
           stage_rows_out<4>(scratch, lane, pk, reinterpret_cast<char*>(p.out), (obase + t.n0 + j * 32) * 2, rvalid);
