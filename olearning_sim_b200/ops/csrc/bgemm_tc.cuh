@@ -660,7 +660,7 @@ bgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         // second epilogue operand of this row (GELU-backward pre-activation, else the residual addend): the next chunk's 64
         // bytes are requested one chunk ahead — a dependent load per chunk exposed a full memory latency 8 times per tile
         const __nv_bfloat16* pre = (EPI == E_STORE) ? (p.act == ACT_GELU_BWD ? p.aux_in : p.addend) : nullptr;
-        uint4 an[4];
+        uint4 an[4] = {};
         if (EPI == E_STORE && pre && rvalid) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) an[i] = reinterpret_cast<const uint4*>(pre + obase + t.n0)[i];
@@ -728,7 +728,8 @@ bgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                 float a8[8];
                 unpack8(ac[i], a8);
 #pragma unroll
-                for (int k = 0; k < 8; ++k) f[8 * i + k] = rvalid ? f[8 * i + k] * gelu_grad_f(a8[k]) : 0.f;
+                for (int k = 0; k < 8; ++k) f[8 * i + k] *= gelu_grad_f(a8[k]);   // rows beyond M are never stored: no per-element select
+                                                                                  // (it compiled to a branch around every MUFU sequence)
               }
             }
           }
@@ -776,7 +777,7 @@ bgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         // the probabilities of this row are requested one 64-byte chunk ahead of their use in both passes (the second
         // pass hits L1/L2): a dependent load per chunk exposed the memory latency eight times per tile
         const uint4* prow = reinterpret_cast<const uint4*>(p.aux_in + obase + t.n0);
-        uint4 an[4];
+        uint4 an[4] = {};
         if (rvalid) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) an[i] = prow[i];
@@ -799,7 +800,7 @@ bgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             float a8[8];
             unpack8(ac[i], a8);
 #pragma unroll
-            for (int k = 0; k < 8; ++k) dot += rvalid ? __uint_as_float(v[8 * i + k]) * a8[k] : 0.f;
+            for (int k = 0; k < 8; ++k) dot = fmaf(__uint_as_float(v[8 * i + k]), a8[k], dot);
           }
         }
 #pragma unroll 1
@@ -820,7 +821,7 @@ bgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             float a8[8];
             unpack8(ac[i], a8);
 #pragma unroll
-            for (int k = 0; k < 8; ++k) f[8 * i + k] = rvalid ? a8[k] * (__uint_as_float(v[8 * i + k]) - dot) * p.scale : 0.f;
+            for (int k = 0; k < 8; ++k) f[8 * i + k] = a8[k] * (__uint_as_float(v[8 * i + k]) - dot) * p.scale;
           }
           uint4 pk[4];
           pack32(f, pk);
