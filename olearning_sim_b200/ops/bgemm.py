@@ -529,8 +529,16 @@ def gn_apply(p: GnApplyParams) -> None:
     _ck(_lib().olsb_gn_apply(C.byref(p), native._stream())); _count()
 
 
+GN_FUSED = __import__("os").environ.get("OLSB_GN_FUSED", "1") != "0"     # one-kernel GroupNorm backward (gradient parked in smem)
+_gn_mode_set = False
+
+
 def gn_bwd(p: GnBwdParams) -> None:
-    _ck(_lib().olsb_gn_bwd(C.byref(p), native._stream())); _count(2)
+    global _gn_mode_set
+    if not _gn_mode_set:
+        _lib().olsb_gn_set_fused(C.c_int(1 if GN_FUSED else 0))
+        _gn_mode_set = True
+    _ck(_lib().olsb_gn_bwd(C.byref(p), native._stream())); _count(1 if GN_FUSED else 2)
 
 
 def pool_head(p: PoolHeadParams) -> None:

@@ -174,9 +174,25 @@ int olsb_gn_apply(const nnk::GnApplyParams* p, void* stream) {
 }
 
 // GroupNorm backward: reduce pass (per-image sums, dgamma / dbeta) then apply pass (dx, optional dres)
+static int g_gn_fused = 1;
+int olsb_gn_set_fused(int v) { const int o = g_gn_fused; g_gn_fused = v; return o; }
+
 int olsb_gn_bwd(const nnk::GnBwdParams* p, void* stream) {
   if (int r = ensure_init()) return r;
   if (p->groups > 8 || p->Ch > 512 || (256 % (p->Ch / 8))) { snprintf(g_err, sizeof(g_err), "gn_bwd: channels in {64,128,256,512}, groups <= 8"); return -6; }
+  if (g_gn_fused) {
+    // one kernel, masked gradient parked in shared memory between the reduction and the apply pass
+    const int smem = p->HW * p->Ch * 2;
+    static int attr = 0;
+    if (smem > attr) { CK(cudaFuncSetAttribute(nnk::gn_bwd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr = smem; }
+    if (smem <= 200 * 1024 && (256 % (p->Ch / 8)) == 0) {
+      // 128 KB images (one CTA per SM): 512 threads for bytes in flight; smaller images: 256 threads, several CTAs per SM
+      const int th = smem > 64 * 1024 ? 512 : 256;
+      nnk::gn_bwd_fused_kernel<<<dim3(p->imgs, p->C), th, smem, (cudaStream_t)stream>>>(*p);
+      CK(cudaGetLastError());
+      return 0;
+    }
+  }
   nnk::gn_bwd_reduce_kernel<<<dim3(p->imgs, p->C), 256, 0, (cudaStream_t)stream>>>(*p);
   CK(cudaGetLastError());
   const int vpi = p->HW * p->Ch / 8;

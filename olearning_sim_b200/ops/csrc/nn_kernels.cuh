@@ -188,6 +188,93 @@ __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(const GnBwdParams p)
   }
 }
 
+// Both passes in one kernel, one CTA per image: the masked gradient is parked in shared memory (bf16, HW x Ch) during the
+// reduction and the second pass re-reads only `raw` — from L2, the image was streamed through it microseconds earlier and
+// at most one or two images per SM are in flight.  HBM traffic 3 reads + 2 writes instead of 6 + 2.
+__global__ void __launch_bounds__(512) gn_bwd_fused_kernel(const GnBwdParams p) {
+  extern __shared__ uint4 s_d[];                 // [HW * Ch / 8] masked gradient
+  const int c = blockIdx.y, b = blockIdx.x;
+  if (p.active && !p.active[c]) return;
+  __shared__ float s_mu[8], s_rs[8], s_S[8][2];
+  __shared__ float s_dg[512], s_db[512];
+  const int cpg = p.Ch / p.groups;
+  const float inv_n = 1.f / (float)(p.HW * cpg);
+  for (int i = threadIdx.x; i < p.Ch; i += blockDim.x) { s_dg[i] = 0.f; s_db[i] = 0.f; }
+  if (threadIdx.x < p.groups) {
+    const float* st = p.stats + ((size_t)(c * p.imgs + b) * p.groups + threadIdx.x) * 2;
+    const float mu = st[0] * inv_n;
+    s_mu[threadIdx.x] = mu; s_rs[threadIdx.x] = rsqrtf(fmaxf(st[1] * inv_n - mu * mu, 0.f) + kGnEps);
+    s_S[threadIdx.x][0] = 0.f; s_S[threadIdx.x][1] = 0.f;
+  }
+  __syncthreads();
+  const int vpc = p.Ch / 8;
+  const int cv = threadIdx.x % vpc, pl = threadIdx.x / vpc, npl = blockDim.x / vpc;
+  const int ch = cv * 8, g = ch / cpg;
+  const size_t base = (size_t)(c * p.imgs + b) * p.HW * p.Ch;
+  float ga[8], dg[8], db[8], S1 = 0.f, S2 = 0.f;
+  load_f8(p.master + (size_t)c * p.P + p.gamma_off + ch, ga);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) dg[i] = db[i] = 0.f;
+  const float mu = s_mu[g], rs = s_rs[g];
+  for (int pix = pl; pix < p.HW; pix += 2 * npl) {
+    // two pixels per iteration: twice the bytes in flight per thread
+    const int pix2 = pix + npl;
+    const bool has2 = pix2 < p.HW;
+    const size_t o = base + (size_t)pix * p.Ch + ch, o2 = base + (size_t)pix2 * p.Ch + ch;
+    uint4 qd = *reinterpret_cast<const uint4*>(p.dy + o), qx = *reinterpret_cast<const uint4*>(p.raw + o), qm = make_uint4(0, 0, 0, 0);
+    uint4 qd2 = make_uint4(0, 0, 0, 0), qx2 = qd2, qm2 = qd2;
+    if (p.mask) qm = *reinterpret_cast<const uint4*>(p.mask + o);
+    if (has2) {
+      qd2 = *reinterpret_cast<const uint4*>(p.dy + o2); qx2 = *reinterpret_cast<const uint4*>(p.raw + o2);
+      if (p.mask) qm2 = *reinterpret_cast<const uint4*>(p.mask + o2);
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      if (h == 1 && !has2) break;
+      float d[8], x[8], m[8];
+      unpack8(h ? qd2 : qd, d); unpack8(h ? qx2 : qx, x);
+      if (p.mask) {
+        unpack8(h ? qm2 : qm, m);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) d[i] = m[i] > 0.f ? d[i] : 0.f;
+      }
+      s_d[(size_t)(h ? pix2 : pix) * vpc + cv] = pack8(d);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float xh = (x[i] - mu) * rs;
+        dg[i] += d[i] * xh; db[i] += d[i];
+        const float gg = d[i] * ga[i];
+        S1 += gg; S2 += gg * xh;
+      }
+    }
+  }
+  atomicAdd(&s_S[g][0], S1); atomicAdd(&s_S[g][1], S2);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { atomicAdd(&s_dg[ch + i], dg[i]); atomicAdd(&s_db[ch + i], db[i]); }
+  __syncthreads();
+  float* gr = p.gsmall + (size_t)c * p.gs_stride;
+  for (int i = threadIdx.x; i < p.Ch; i += blockDim.x) {
+    atomicAdd(gr + p.g_gamma_off + i, s_dg[i]);
+    atomicAdd(gr + p.g_beta_off + i, s_db[i]);
+  }
+  // ---- pass 2 (same thread -> same (pixel, channel vector) pairs as above: each thread re-reads what it wrote)
+  const float m1 = s_S[g][0] * inv_n, m2 = s_S[g][1] * inv_n;
+  for (int pix = pl; pix < p.HW; pix += npl) {
+    const size_t o = base + (size_t)pix * p.Ch + ch;
+    float d[8], x[8], r[8];
+    const uint4 qd = s_d[(size_t)pix * vpc + cv];
+    unpack8(qd, d);
+    unpack8(*reinterpret_cast<const uint4*>(p.raw + o), x);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float xh = (x[i] - mu) * rs;
+      r[i] = rs * (d[i] * ga[i] - m1 - xh * m2);
+    }
+    *reinterpret_cast<uint4*>(p.dx + o) = pack8(r);
+    if (p.dres) *reinterpret_cast<uint4*>(p.dres + o) = qd;
+  }
+}
+
 // pass 2:  dx = rstd * (g * gamma - m1 - xhat * m2),  optionally dres = g
 __global__ void gn_bwd_apply_kernel(const GnBwdParams p) {
   const int c = blockIdx.z, b = blockIdx.y;
