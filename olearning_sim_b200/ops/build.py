@@ -53,13 +53,16 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         if LIB.exists():
             return LIB  # stale-but-present beats nothing on a box without a toolkit
         raise RuntimeError("nvcc not found and no prebuilt _olsb200_kernels.so present")
-    cmd = [nvcc, *NVCC_FLAGS, "-o", str(LIB)] + [str(CSRC / s) for s in SOURCES] + ["-lcudart"]
+    tmp = LIB.with_suffix(".so.tmp%d" % os.getpid())          # link into a scratch name, publish atomically
+    cmd = [nvcc, *NVCC_FLAGS, "-o", str(tmp)] + [str(CSRC / s) for s in SOURCES] + ["-lcudart"]
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
+        tmp.unlink(missing_ok=True)
         raise RuntimeError(f"nvcc failed:\n{res.stdout}\n{res.stderr}")
+    os.replace(tmp, LIB)
     STAMP.write_text(source_hash())
     if verbose:
         print(res.stderr)

@@ -7,7 +7,7 @@ lib = os.path.join(root, "olearning_sim_b200/ops/_olsb200_kernels.so")
 tag = sys.argv[1] if len(sys.argv) > 1 else "r1"
 out = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
 pats = {"UTCHMMA": r"\bUTCHMMA", "….WS": r"UTCHMMA\.WS", "….2CTA": r"UTCHMMA\.2CTA", "UTMALDG": r"\bUTMALDG", "UTMAPF": r"UTMAPF|UTMACCTL", "LDTM": r"\bLDTM",
-        "UTCBAR": r"\bUTCBAR", "SYNCS": r"\bSYNCS", "UBLKPF": r"UBLKPF|UBLKCP", "HMMA(legacy)": r"\bHMMA", "SHFL": r"\bSHFL"}
+        "UTCBAR": r"\bUTCBAR", "SYNCS": r"\bSYNCS", "UBLKPF": r"UBLKPF|UBLKCP", "HMMA(legacy)": r"\bHMMA", "SHFL": r"\bSHFL", "LDGMC/STGMC": r"\b(LDGMC|STGMC)"}
 per, cur = collections.OrderedDict(), None
 for line in out.splitlines():
     m = re.search(r"Function : (\S+)", line)
@@ -22,7 +22,7 @@ for line in out.splitlines():
                 per[cur][k] += 1
 lines = ["SASS evidence for the sm_100a build (cuobjdump -sass olearning_sim_b200/ops/_olsb200_kernels.so)", "",
          "UTCHMMA = tcgen05.mma (.WS = weight-stationary form, .2CTA = cta_group::2 pair MMA), UTMALDG = TMA tensor load, LDTM = tcgen05.ld (TMEM -> registers), UTCBAR = tcgen05.commit,",
-         "SYNCS = mbarrier ops, UBLK* = bulk L2 prefetch.  No legacy HMMA (mma.sync) anywhere.", "",
+         "SYNCS = mbarrier ops, UBLK* = bulk L2 prefetch, LDGMC / STGMC = multimem.ld_reduce / multimem.st (NVSwitch multicast).  No legacy HMMA (mma.sync) anywhere.", "",
          f"{'kernel':<112} " + " ".join(f"{k:>8}" for k in pats)]
 for k, c in per.items():
     lines.append(f"{k:<112} " + " ".join(f"{c[p]:>8}" for p in pats))
