@@ -529,7 +529,10 @@ def gn_apply(p: GnApplyParams) -> None:
     _ck(_lib().olsb_gn_apply(C.byref(p), native._stream())); _count()
 
 
-GN_FUSED = __import__("os").environ.get("OLSB_GN_FUSED", "1") != "0"     # one-kernel GroupNorm backward (gradient parked in smem)
+# one-kernel GroupNorm backward (gradient parked in smem).  Measured slower than the two-pass form on the ResNet-18 step
+# (134 vs 123 us per layer at 64 clients: the 128 KB images of stage 1 leave one 512-thread CTA per SM, too few bytes in
+# flight), so it is opt-in
+GN_FUSED = __import__("os").environ.get("OLSB_GN_FUSED", "0") == "1"
 _gn_mode_set = False
 
 

@@ -665,7 +665,7 @@ bgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 #pragma unroll
           for (int i = 0; i < 4; ++i) an[i] = reinterpret_cast<const uint4*>(pre + obase + t.n0)[i];
         }
-#pragma unroll 2
+#pragma unroll 1
         for (int j = 0; j < nchunks; ++j) {
           const int nb = t.n0 + j * 32;
           tmem_ld_wait();
