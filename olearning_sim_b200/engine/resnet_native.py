@@ -217,8 +217,9 @@ class ResNetWorkspace(FlatWorkspace):
         def cf(x, name, H, cin, cout, k, s, raw, li, **kw):
             bgm.conv_fwd(n, B, H, cin, cout, k, s, x, wb, L.conv[name][0], Pb, raw, self.stats[li], G, act, **kw)
 
-        def cd(dy, name, H, cin, cout, k, s, dx, addend=None):
-            bgm.conv_dgrad(n, B, H, cin, cout, k, s, dy, wb, L.conv[name][0], Pb, dx, addend, act)
+        def cd(dy, name, H, cin, cout, k, s, dx, addend=None, relu_mask=None, mask_even=True):
+            bgm.conv_dgrad(n, B, H, cin, cout, k, s, dy, wb, L.conv[name][0], Pb, dx, addend, act, relu_mask=relu_mask,
+                           mask_even=mask_even)
 
         def cw(dy, x, name, H, cin, cout, k, s, **kw):
             bgm.conv_wgrad(n, B, H, cin, cout, k, s, dy, x, m, wb, L.conv[name][0], P, Pb, lr, mu, gw, act, **kw)
@@ -257,7 +258,11 @@ class ResNetWorkspace(FlatWorkspace):
         hp.loss_sum, hp.nonfinite = bgm._ptr(self.loss_sum[w0:w1]), bgm._ptr(self.nonfinite[w0:w1])
         hp.apply_update = 1
         bgm.pool_head(hp)
-        # ------------------------------------------------------------------ backward (X holds d hout of the block)
+        # ------------------------------------------------------------------ backward
+        # `cur` holds d hout of the block.  Every data-gradient epilogue gates its output with the ReLU of the activation it
+        # belongs to (relu_mask), so the GroupNorm backward passes read (dy, raw) only; the head's gradient is the one
+        # ungated input (gated inside the first GroupNorm backward, which then also writes the gated copy for the shortcut).
+        cur, spare, gated = X, Z, False
         for bi in range(len(L.blocks) - 1, -1, -1):
             name, s, down, cin, cout = L.blocks[bi]
             t = self.blk[bi]
@@ -265,22 +270,28 @@ class ResNetWorkspace(FlatWorkspace):
             ro = res
             rin = ro * s
             hin = self.blk[bi - 1]["hout"] if bi > 0 else self.a0
-            # GN2 (+ ReLU gate of the block output): Y = d raw2, Z = gated d hout (gradient of the shortcut branch)
-            self._gn_bwd(n, act, l2, X, t["hout"], t["raw2"], f"{name}.g2", Y, ro, cout, dres=Z)
-            cd(Y, f"{name}.c2.weight", ro, cout, cout, 3, 1, X)                   # X = d y1
+            if gated:      # R = gated d hout (also the gradient of the shortcut branch), T = free buffer
+                self._gn_bwd(n, act, l2, cur, None, t["raw2"], f"{name}.g2", Y, ro, cout)
+                R, T = cur, spare
+            else:
+                self._gn_bwd(n, act, l2, cur, t["hout"], t["raw2"], f"{name}.g2", Y, ro, cout, dres=spare)
+                R, T = spare, cur
+            cd(Y, f"{name}.c2.weight", ro, cout, cout, 3, 1, T, relu_mask=t["y1"])      # T = gated d y1
             cw(Y, t["y1"], f"{name}.c2.weight", ro, cout, cout, 3, 1)
-            self._gn_bwd(n, act, l1, X, t["y1"], t["raw1"], f"{name}.g1", Y, ro, cout)     # Y = d raw1
+            self._gn_bwd(n, act, l1, T, None, t["raw1"], f"{name}.g1", Y, ro, cout)         # Y = d raw1
             if down:
-                cd(Y, f"{name}.c1.weight", rin, cin, cout, 3, s, X)               # X = d hin (conv path), all four parities
+                # conv path into all four pixel parities; the (even, even) class stays ungated until the shortcut is added
+                cd(Y, f"{name}.c1.weight", rin, cin, cout, 3, s, T, relu_mask=hin, mask_even=False)
                 cw(Y, hin, f"{name}.c1.weight", rin, cin, cout, 3, s)
-                self._gn_bwd(n, act, ld, Z, None, t["rawd"], f"{name}.dg", Y, ro, cout)    # Y = d rawd
-                cd(Y, f"{name}.ds.weight", rin, cin, cout, 1, s, X, addend=X)     # += shortcut conv (even pixels)
+                self._gn_bwd(n, act, ld, R, None, t["rawd"], f"{name}.dg", Y, ro, cout)     # Y = d rawd
+                cd(Y, f"{name}.ds.weight", rin, cin, cout, 1, s, T, addend=T, relu_mask=hin)   # += shortcut conv, gate
                 cw(Y, hin, f"{name}.ds.weight", rin, cin, cout, 1, s)
             else:
-                cd(Y, f"{name}.c1.weight", rin, cin, cout, 3, 1, X, addend=Z)     # X = d hin = conv path + identity
+                cd(Y, f"{name}.c1.weight", rin, cin, cout, 3, 1, T, addend=R, relu_mask=hin)   # conv path + identity, gated
                 cw(Y, hin, f"{name}.c1.weight", rin, cin, cout, 3, 1)
+            cur, spare, gated = T, R, True
             res = rin
-        self._gn_bwd(n, act, 0, X, self.a0, self.raw0, "stem.gn", Y, 32, W)
+        self._gn_bwd(n, act, 0, cur, None, self.raw0, "stem.gn", Y, 32, W)
         cw(Y, xcol, "stem.weight", 32, 32, W, 1, 1, x_cimgs=self.shard, x_img0=off)
         # ------------------------------------------------------------------ GN parameters: one fused SGD launch
         gn_n = L.small["fc.weight"][0] - L.small_off        # fc was updated by the head kernel

@@ -28,7 +28,7 @@ from . import native
 A_K, A_MN, A_CONV, A_HALO, A_HALOW, A_CONVX = 0, 1, 2, 3, 4, 5
 B_K, B_MN, B_CONVX, B_WT = 0, 1, 2, 3
 E_STORE, E_GNSTAT, E_SOFTMAX, E_DSOFT, E_SGD, E_SGD_T = 0, 1, 2, 3, 4, 5
-ACT_NONE, ACT_RELU, ACT_GELU, ACT_GELU_BWD = 0, 1, 2, 3
+ACT_NONE, ACT_RELU, ACT_GELU, ACT_GELU_BWD, ACT_RELU_BWD = 0, 1, 2, 3, 4
 
 I9 = C.c_int * 9
 
@@ -402,9 +402,13 @@ def conv_fwd(C_: int, imgs: int, H: int, Cin: int, Cout: int, ksize: int, stride
 
 
 def conv_dgrad(C_: int, imgs: int, H: int, Cin: int, Cout: int, ksize: int, stride: int, dy: torch.Tensor, wb: torch.Tensor,
-               w_off: int, wb_stride: int, dx: torch.Tensor, addend: Optional[torch.Tensor] = None, active=None) -> None:
+               w_off: int, wb_stride: int, dx: torch.Tensor, addend: Optional[torch.Tensor] = None, active=None,
+               relu_mask: Optional[torch.Tensor] = None, mask_even: bool = True) -> None:
     """dx[c,b,y,x,:Cin] = sum over taps of dy (.) W^T.  ``H`` is the INPUT (dx) resolution; stride 2 runs one launch per
-    output-pixel parity class (each class is a stride-1 correlation of dy with a subset of the taps)."""
+    output-pixel parity class (each class is a stride-1 correlation of dy with a subset of the taps).
+    ``relu_mask``: the forward activation this gradient belongs to (same shape as dx); the epilogue zeroes the gradient
+    where it is not positive (ReLU backward), after the addend.  ``mask_even=False`` leaves the (even, even) pixel class
+    of a stride-2 layer ungated — a following 1x1 stride-2 shortcut gradient adds to exactly those pixels and gates them."""
     OH = H // stride
     pad = ksize // 2
     twl, thl, tn = _tile_geom(OH, OH)
@@ -443,6 +447,8 @@ def conv_dgrad(C_: int, imgs: int, H: int, Cin: int, Cout: int, ksize: int, stri
         p.out, p.ld, p.out_conv, p.os, p.py, p.px, p.OW, p.OH = _ptr(dx), Cin, 1, stride, py, px, H, H
         p.o_bdiv, p.scale = 1, 1.0
         p.addend = _ptr(addend)
+        if relu_mask is not None and (mask_even or (py, px) != (0, 0)):
+            p.act, p.aux_in = ACT_RELU_BWD, _ptr(relu_mask)
         launch(g)
 
 

@@ -45,7 +45,7 @@ constexpr int KC = 64;                 // K elements per pipeline stage (one 128
 enum { A_K = 0, A_MN = 1, A_CONV = 2, A_HALO = 3, A_HALOW = 4, A_CONVX = 5 };
 enum { B_K = 0, B_MN = 1, B_CONVX = 2, B_WT = 3 };
 enum { E_STORE = 0, E_GNSTAT = 1, E_SOFTMAX = 2, E_DSOFT = 3, E_SGD = 4, E_SGD_T = 5 };
-enum { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2, ACT_GELU_BWD = 3 };
+enum { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2, ACT_GELU_BWD = 3, ACT_RELU_BWD = 4 };   // *_BWD gate / scale by aux_in
 
 struct Bars {
   uint64_t full[8];
@@ -659,7 +659,8 @@ bgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         const int nchunks = min(N_TILE / 32, (p.N - t.n0 + 31) / 32);          // warp-uniform
         // second epilogue operand of this row (GELU-backward pre-activation, else the residual addend): the next chunk's 64
         // bytes are requested one chunk ahead — a dependent load per chunk exposed a full memory latency 8 times per tile
-        const __nv_bfloat16* pre = (EPI == E_STORE) ? (p.act == ACT_GELU_BWD ? p.aux_in : p.addend) : nullptr;
+        const bool act_bwd = p.act == ACT_GELU_BWD || p.act == ACT_RELU_BWD;
+        const __nv_bfloat16* pre = (EPI == E_STORE) ? (act_bwd ? p.aux_in : p.addend) : nullptr;
         uint4 an[4] = {};
         if (EPI == E_STORE && pre && rvalid) {
 #pragma unroll
@@ -697,7 +698,7 @@ bgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               for (int i = 0; i < 8; ++i) { const float4 b = bp[i]; f[4 * i] += b.x; f[4 * i + 1] += b.y; f[4 * i + 2] += b.z; f[4 * i + 3] += b.w; }
             }
             if (p.addend && rvalid) {
-              if (p.act == ACT_GELU_BWD) {                     // both operands: the addend is the un-pipelined one
+              if (act_bwd) {                                   // both operands: the addend is the un-pipelined one
                 float a2[32];
                 load32(p.addend + obase + nb, a2);
 #pragma unroll
@@ -722,6 +723,16 @@ bgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               }
 #pragma unroll
               for (int i = 0; i < 32; ++i) f[i] = gelu_f(f[i]);
+            } else if (p.act == ACT_RELU_BWD) {
+              // gradient gate of the ReLU that produced aux_in (the layer input this gradient belongs to): the consumer
+              // (GroupNorm backward) then needs no mask pass of its own
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                float a8[8];
+                unpack8(ac[i], a8);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) f[8 * i + k] = a8[k] > 0.f ? f[8 * i + k] : 0.f;
+              }
             } else if (p.act == ACT_GELU_BWD) {
 #pragma unroll
               for (int i = 0; i < 4; ++i) {

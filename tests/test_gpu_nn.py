@@ -157,6 +157,11 @@ def test_conv_fwd_dgrad_wgrad(bgm, H, Cin, Cout, k, s):
         if s == 1 or k == 1:
             want = want + add.float()
         assert rel(dx, want) < 8e-3
+        if k == 3:
+            # ReLU-backward gate fused into the epilogue (after the addend); stride 2: every pixel parity class gated
+            dxm = torch.full_like(dx, 7.0)
+            bgm.conv_dgrad(C, imgs, H, Cin, Cout, k, s, dy, wb, 8, Pb, dxm, addend=add if s == 1 else None, relu_mask=x)
+            assert rel(dxm, want * (x.float() > 0)) < 8e-3
     else:
         dy = rb(C * imgs, OH, OH, Cout, scale=0.1)
         ys.backward(dy.float().reshape(C, imgs, OH, OH, Cout).permute(0, 1, 4, 2, 3))

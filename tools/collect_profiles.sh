@@ -8,7 +8,7 @@ for n in 2 4 8; do [ -f gpurun_out/bench_c2_n$n.json ] && grep -h '^{"metric"' g
 for f in gpurun_out/final_launches_c*.csv; do [ -f "$f" ] && python tools/ncu_launch_summary.py "$f" > profiles/r2_launches_$(basename $f .csv | sed 's/final_launches_//').txt; done
 [ -f gpurun_out/gpu_tests_final.log ] && cp gpurun_out/gpu_tests_final.log profiles/r2_gpu_tests.log
 for n in 2 4 8; do [ -f gpurun_out/mgpu_oracle_n$n.jsonl ] && cp gpurun_out/mgpu_oracle_n$n.jsonl profiles/r2_mgpu_oracle_n$n.jsonl; [ -f gpurun_out/peer_loss_n$n.jsonl ] && cp gpurun_out/peer_loss_n$n.jsonl profiles/r2_peer_loss_n$n.jsonl; done
-if ls gpurun_out/ncuF_*.ncu-rep > /dev/null 2>&1; then python tools/ncu_export.py r2 gpurun_out/ncuF_*.ncu-rep > /dev/null; python tools/ncu_table.py r2 > /dev/null; fi
+if ls gpurun_out/ncu_csv/r2_ncu_* > /dev/null 2>&1; then cp gpurun_out/ncu_csv/r2_ncu_* profiles/; python tools/ncu_table.py r2 > /dev/null; fi
 [ -f gpurun_out/final_sanitize_nn.log ] && { echo "compute-sanitizer over the round-2 kernels (tools/sanitize_nn.sh; per-run logs stay in gpurun_out/)"; cat gpurun_out/final_sanitize_nn.log; echo; echo "racecheck layernorm: the 2 reported hazards are inside at::native::layer_norm_grad_input_kernel_vectorized (PyTorch's own kernel, used by the oracle of the test), not in this repo's kernels."; } > profiles/r2_sanitizer.txt
 python tools/sass_evidence.py r2 > /dev/null 2>&1
 python tools/make_results_md.py > /dev/null

@@ -22,7 +22,8 @@ KEEP = re.compile(r"^(gpu__time_duration\.sum|sm__pipe_tensor_cycles_active\.avg
                   r"smsp__inst_executed\.sum|sm__cycles_elapsed\.max)$")
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tag, reps = sys.argv[1], sys.argv[2:]
-os.makedirs(os.path.join(root, "profiles"), exist_ok=True)
+outdir = os.environ.get("OLSB_PROFILE_DIR") or os.path.join(root, "profiles")      # on the GPU box: export into gpurun_out/
+os.makedirs(outdir, exist_ok=True)
 for rep in reps:
     name = re.sub(r"^ncu_", "", os.path.splitext(os.path.basename(rep))[0])
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
@@ -31,7 +32,7 @@ for rep in reps:
         print("skip", rep)
         continue
     hdr, units = rows[0], rows[1]
-    out = os.path.join(root, "profiles", f"{tag}_ncu_{name}.csv")
+    out = os.path.join(outdir, f"{tag}_ncu_{name}.csv")
     with open(out, "w", newline="") as f:
         w = csv.writer(f)
         w.writerow(["kernel", "metric", "unit", "value"])
@@ -51,18 +52,34 @@ for rep in reps:
                 w.writerow([kn, h, u, v])
     src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
     srows = list(csv.reader([l for l in src.splitlines() if not l.startswith("==")]))
-    if srows:
-        h = srows[0]
+    # source page: one section per kernel ("Kernel Name" row, header row, one row per SASS instruction)
+    secs, cur, hdr_next = [], None, False
+    for r in srows:
+        if r and r[0] == "Kernel Name":
+            cur = {"kernel": r[1] if len(r) > 1 else "?", "hdr": None, "rows": []}
+            secs.append(cur)
+            hdr_next = True
+        elif cur is not None and hdr_next:
+            cur["hdr"], hdr_next = r, False
+        elif cur is not None:
+            cur["rows"].append(r)
+    lines = []
+    for sec in secs:
+        h = sec["hdr"] or []
         try:
-            si = next(i for i, x in enumerate(h) if x.strip() in ("# Samples", "Warp Stall Sampling (All Samples)", "Samples"))
+            si = next(i for i, x in enumerate(h) if x.strip() in ("# Samples", "Samples"))
             ci = next(i for i, x in enumerate(h) if x.strip() == "Source")
-            best = sorted((r for r in srows[1:] if len(r) > max(si, ci) and r[si].replace(",", "").isdigit()),
-                          key=lambda r: -int(r[si].replace(",", "")))[:12]
-            with open(os.path.join(root, "profiles", f"{tag}_ncu_{name}_stalls.txt"), "w") as f:
-                tot = sum(int(r[si].replace(",", "")) for r in srows[1:] if len(r) > si and r[si].replace(",", "").isdigit())
-                f.write(f"top stall-sample lines of {name} (total samples {tot})\n")
-                for r in best:
-                    f.write(f"{int(r[si].replace(',', '')):8d}  {r[ci].strip()[:150]}\n")
         except StopIteration:
-            pass
+            continue
+        ok = [r for r in sec["rows"] if len(r) > max(si, ci) and r[si].replace(",", "").isdigit()]
+        tot = sum(int(r[si].replace(",", "")) for r in ok)
+        if not tot:
+            continue
+        lines.append(f"== {sec['kernel'][:110]}  (total warp-stall samples {tot})")
+        for r in sorted(ok, key=lambda r: -int(r[si].replace(",", "")))[:10]:
+            n = int(r[si].replace(",", ""))
+            lines.append(f"{n:8d} {100.0 * n / tot:5.1f}%  {r[ci].strip()[:140]}")
+    if lines:
+        with open(os.path.join(outdir, f"{tag}_ncu_{name}_stalls.txt"), "w") as f:
+            f.write(f"SASS instructions with the most warp-stall samples, per kernel of report {name}\n" + "\n".join(lines) + "\n")
     print(out)
