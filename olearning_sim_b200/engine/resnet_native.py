@@ -34,6 +34,10 @@ def _al(n: int, a: int = 8) -> int:
     return (n + a - 1) // a * a
 
 
+# ReLU-backward gates in the data-gradient epilogues (GroupNorm backward then reads no mask); OLSB_RELU_FUSE=0: gate inside
+# the GroupNorm backward passes
+FUSE_RELU_GATE = __import__("os").environ.get("OLSB_RELU_FUSE", "1") != "0"
+
 class ResNetLayout:
     """Offsets of every parameter of the zoo's ``resnet18`` spec inside the packed row + pack / unpack."""
 
@@ -262,6 +266,7 @@ class ResNetWorkspace(FlatWorkspace):
         # `cur` holds d hout of the block.  Every data-gradient epilogue gates its output with the ReLU of the activation it
         # belongs to (relu_mask), so the GroupNorm backward passes read (dy, raw) only; the head's gradient is the one
         # ungated input (gated inside the first GroupNorm backward, which then also writes the gated copy for the shortcut).
+        fuse = FUSE_RELU_GATE
         cur, spare, gated = X, Z, False
         for bi in range(len(L.blocks) - 1, -1, -1):
             name, s, down, cin, cout = L.blocks[bi]
@@ -276,22 +281,22 @@ class ResNetWorkspace(FlatWorkspace):
             else:
                 self._gn_bwd(n, act, l2, cur, t["hout"], t["raw2"], f"{name}.g2", Y, ro, cout, dres=spare)
                 R, T = spare, cur
-            cd(Y, f"{name}.c2.weight", ro, cout, cout, 3, 1, T, relu_mask=t["y1"])      # T = gated d y1
+            cd(Y, f"{name}.c2.weight", ro, cout, cout, 3, 1, T, relu_mask=t["y1"] if fuse else None)      # T = gated d y1
             cw(Y, t["y1"], f"{name}.c2.weight", ro, cout, cout, 3, 1)
-            self._gn_bwd(n, act, l1, T, None, t["raw1"], f"{name}.g1", Y, ro, cout)         # Y = d raw1
+            self._gn_bwd(n, act, l1, T, None if fuse else t["y1"], t["raw1"], f"{name}.g1", Y, ro, cout)         # Y = d raw1
             if down:
                 # conv path into all four pixel parities; the (even, even) class stays ungated until the shortcut is added
-                cd(Y, f"{name}.c1.weight", rin, cin, cout, 3, s, T, relu_mask=hin, mask_even=False)
+                cd(Y, f"{name}.c1.weight", rin, cin, cout, 3, s, T, relu_mask=hin if fuse else None, mask_even=False)
                 cw(Y, hin, f"{name}.c1.weight", rin, cin, cout, 3, s)
                 self._gn_bwd(n, act, ld, R, None, t["rawd"], f"{name}.dg", Y, ro, cout)     # Y = d rawd
-                cd(Y, f"{name}.ds.weight", rin, cin, cout, 1, s, T, addend=T, relu_mask=hin)   # += shortcut conv, gate
+                cd(Y, f"{name}.ds.weight", rin, cin, cout, 1, s, T, addend=T, relu_mask=hin if fuse else None)   # += shortcut conv, gate
                 cw(Y, hin, f"{name}.ds.weight", rin, cin, cout, 1, s)
             else:
-                cd(Y, f"{name}.c1.weight", rin, cin, cout, 3, 1, T, addend=R, relu_mask=hin)   # conv path + identity, gated
+                cd(Y, f"{name}.c1.weight", rin, cin, cout, 3, 1, T, addend=R, relu_mask=hin if fuse else None)   # conv path + identity, gated
                 cw(Y, hin, f"{name}.c1.weight", rin, cin, cout, 3, 1)
-            cur, spare, gated = T, R, True
+            cur, spare, gated = T, R, fuse
             res = rin
-        self._gn_bwd(n, act, 0, cur, None, self.raw0, "stem.gn", Y, 32, W)
+        self._gn_bwd(n, act, 0, cur, None if gated else self.a0, self.raw0, "stem.gn", Y, 32, W)
         cw(Y, xcol, "stem.weight", 32, 32, W, 1, 1, x_cimgs=self.shard, x_img0=off)
         # ------------------------------------------------------------------ GN parameters: one fused SGD launch
         gn_n = L.small["fc.weight"][0] - L.small_off        # fc was updated by the head kernel

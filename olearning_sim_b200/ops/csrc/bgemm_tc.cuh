@@ -661,10 +661,17 @@ bgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         // bytes are requested one chunk ahead — a dependent load per chunk exposed a full memory latency 8 times per tile
         const bool act_bwd = p.act == ACT_GELU_BWD || p.act == ACT_RELU_BWD;
         const __nv_bfloat16* pre = (EPI == E_STORE) ? (act_bwd ? p.aux_in : p.addend) : nullptr;
-        uint4 an[4] = {};
+        // a gated data gradient with a residual has both: the addend is then the second pipelined operand
+        constexpr bool TWO_OPS = (BM == B_WT);         // only the conv data gradients combine a gate with a residual
+        const __nv_bfloat16* pre2 = (EPI == E_STORE && TWO_OPS && act_bwd) ? p.addend : nullptr;
+        uint4 an[4] = {}, bn[4] = {};
         if (EPI == E_STORE && pre && rvalid) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) an[i] = reinterpret_cast<const uint4*>(pre + obase + t.n0)[i];
+        }
+        if (EPI == E_STORE && TWO_OPS && pre2 && rvalid) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) bn[i] = reinterpret_cast<const uint4*>(pre2 + obase + t.n0)[i];
         }
 #pragma unroll 1
         for (int j = 0; j < nchunks; ++j) {
@@ -674,13 +681,21 @@ bgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 #pragma unroll
           for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
           if (j + 1 < nchunks) tmem_ld32(taddr + (j + 1) * 32, v);           // next chunk in flight
-          uint4 ac[4];
+          uint4 ac[4], bc[4];
           if (EPI == E_STORE && pre) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) ac[i] = an[i];
             if (j + 1 < nchunks && rvalid) {
 #pragma unroll
               for (int i = 0; i < 4; ++i) an[i] = reinterpret_cast<const uint4*>(pre + obase + nb + 32)[i];
+            }
+          }
+          if (EPI == E_STORE && TWO_OPS && pre2) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) bc[i] = bn[i];
+            if (j + 1 < nchunks && rvalid) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) bn[i] = reinterpret_cast<const uint4*>(pre2 + obase + nb + 32)[i];
             }
           }
           if (EPI == E_GNSTAT) {
@@ -698,7 +713,15 @@ bgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               for (int i = 0; i < 8; ++i) { const float4 b = bp[i]; f[4 * i] += b.x; f[4 * i + 1] += b.y; f[4 * i + 2] += b.z; f[4 * i + 3] += b.w; }
             }
             if (p.addend && rvalid) {
-              if (act_bwd) {                                   // both operands: the addend is the un-pipelined one
+              if (act_bwd && TWO_OPS) {                        // both operands: the addend travels in the second buffer
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  float a8[8];
+                  unpack8(bc[i], a8);
+#pragma unroll
+                  for (int k = 0; k < 8; ++k) f[8 * i + k] += a8[k];
+                }
+              } else if (act_bwd) {
                 float a2[32];
                 load32(p.addend + obase + nb, a2);
 #pragma unroll
