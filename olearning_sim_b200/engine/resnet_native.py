@@ -275,26 +275,30 @@ class ResNetWorkspace(FlatWorkspace):
             ro = res
             rin = ro * s
             hin = self.blk[bi - 1]["hout"] if bi > 0 else self.a0
+            # gate in the epilogue only where the data gradient is compute-bound (>= 128 channels): at 64 channels it is
+            # close to HBM-bound and a third operand stream costs what the GroupNorm passes save (measured)
+            f2 = fuse and cout >= 128          # d y1  gated by conv2's data gradient
+            f1 = fuse and cin >= 128           # d hin gated by conv1's (and the shortcut's) data gradient
             if gated:      # R = gated d hout (also the gradient of the shortcut branch), T = free buffer
                 self._gn_bwd(n, act, l2, cur, None, t["raw2"], f"{name}.g2", Y, ro, cout)
                 R, T = cur, spare
             else:
                 self._gn_bwd(n, act, l2, cur, t["hout"], t["raw2"], f"{name}.g2", Y, ro, cout, dres=spare)
                 R, T = spare, cur
-            cd(Y, f"{name}.c2.weight", ro, cout, cout, 3, 1, T, relu_mask=t["y1"] if fuse else None)      # T = gated d y1
+            cd(Y, f"{name}.c2.weight", ro, cout, cout, 3, 1, T, relu_mask=t["y1"] if f2 else None)      # T = d y1
             cw(Y, t["y1"], f"{name}.c2.weight", ro, cout, cout, 3, 1)
-            self._gn_bwd(n, act, l1, T, None if fuse else t["y1"], t["raw1"], f"{name}.g1", Y, ro, cout)         # Y = d raw1
+            self._gn_bwd(n, act, l1, T, None if f2 else t["y1"], t["raw1"], f"{name}.g1", Y, ro, cout)   # Y = d raw1
             if down:
                 # conv path into all four pixel parities; the (even, even) class stays ungated until the shortcut is added
-                cd(Y, f"{name}.c1.weight", rin, cin, cout, 3, s, T, relu_mask=hin if fuse else None, mask_even=False)
+                cd(Y, f"{name}.c1.weight", rin, cin, cout, 3, s, T, relu_mask=hin if f1 else None, mask_even=False)
                 cw(Y, hin, f"{name}.c1.weight", rin, cin, cout, 3, s)
                 self._gn_bwd(n, act, ld, R, None, t["rawd"], f"{name}.dg", Y, ro, cout)     # Y = d rawd
-                cd(Y, f"{name}.ds.weight", rin, cin, cout, 1, s, T, addend=T, relu_mask=hin if fuse else None)   # += shortcut conv, gate
+                cd(Y, f"{name}.ds.weight", rin, cin, cout, 1, s, T, addend=T, relu_mask=hin if f1 else None)   # += shortcut
                 cw(Y, hin, f"{name}.ds.weight", rin, cin, cout, 1, s)
             else:
-                cd(Y, f"{name}.c1.weight", rin, cin, cout, 3, 1, T, addend=R, relu_mask=hin if fuse else None)   # conv path + identity, gated
+                cd(Y, f"{name}.c1.weight", rin, cin, cout, 3, 1, T, addend=R, relu_mask=hin if f1 else None)   # + identity
                 cw(Y, hin, f"{name}.c1.weight", rin, cin, cout, 3, 1)
-            cur, spare, gated = T, R, fuse
+            cur, spare, gated = T, R, f1
             res = rin
         self._gn_bwd(n, act, 0, cur, None if gated else self.a0, self.raw0, "stem.gn", Y, 32, W)
         cw(Y, xcol, "stem.weight", 32, 32, W, 1, 1, x_cimgs=self.shard, x_img0=off)

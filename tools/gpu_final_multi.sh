@@ -18,9 +18,9 @@ for spec in "cnn2 avg" "bert_mini avg"; do
 done
 cat gpurun_out/mgpu_oracle_n$N.jsonl | cut -c1-600
 fi
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29613 tools/peer_loss_check.py 2>gpurun_out/peer_loss_n$N.err | grep -E "^\{" > gpurun_out/peer_loss_n$N.jsonl; cat gpurun_out/peer_loss_n$N.jsonl
+[ -z "$SKIP_PEER" ] && timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29613 tools/peer_loss_check.py 2>gpurun_out/peer_loss_n$N.err | grep -E "^\{" > gpurun_out/peer_loss_n$N.jsonl; cat gpurun_out/peer_loss_n$N.jsonl
 for c in ${CONFIGS:-2}; do
-  timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 2962$N bench.py --gpus $N --config $c --steps ${STEPS:-10} --warmup 3 --phases > gpurun_out/bench_c${c}_n$N.json 2>gpurun_out/bench_c${c}_n$N.err
+  timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 2962$N bench.py --gpus $N --config $c --steps ${STEPS:-10} --warmup 3 --phases ${BENCH_FLAGS:-} > gpurun_out/bench_c${c}_n$N.json 2>gpurun_out/bench_c${c}_n$N.err
   tail -2 gpurun_out/bench_c${c}_n$N.err; grep -h '^{"metric"' gpurun_out/bench_c${c}_n$N.json | python -c "
 import json,sys
 d=json.loads(sys.stdin.read()); b=d.get('baseline') or {}
