@@ -337,7 +337,9 @@ def main() -> int:
     base = None
     if not args.no_baseline:
         try:
-            base = run_library(ctx, args, model, pre, max(args.baseline_steps, 3), 3, not args.no_e2e, args.baseline_dtype)
+            # a participation trace is a function of the round index: then both arms time the same rounds
+            kb = K if pre.get("online_trace") else max(args.baseline_steps, 3)
+            base = run_library(ctx, args, model, pre, kb, W, not args.no_e2e, args.baseline_dtype)
         except Exception as e:  # noqa: BLE001 - the headline must survive a baseline failure
             base = {"error": f"{type(e).__name__}: {e}"[:300]}
     if rank == 0:
