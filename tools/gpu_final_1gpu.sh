@@ -17,6 +17,6 @@ timeout 900 python bench.py --impl nccl_torch --baseline-dtype tf32 --steps 5 --
 timeout 900 python tools/op_bench.py --clients 64 --json gpurun_out/final_op_bench.json > gpurun_out/final_op_bench.txt 2>&1; tail -30 gpurun_out/final_op_bench.txt
 # launch lists (shares) at the two client counts of the scaling run, and for the ResNet / BERT steps
 for spec in "2 1024" "2 128" "3 96" "5 96"; do set -- $spec
-  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 300 -c 700 --csv --log-file gpurun_out/final_launches_c$1_$2.csv python bench.py --config $1 --steps 1 --warmup 3 --no-e2e --no-baseline --clients $2 > /dev/null 2>&1
+  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s ${SKIP:-120} -c 700 --csv --log-file gpurun_out/final_launches_c$1_$2.csv python bench.py --config $1 --steps 1 --warmup 3 --no-e2e --no-baseline --clients $2 > /dev/null 2>&1
   echo "== launches config $1, $2 clients"; python tools/ncu_launch_summary.py gpurun_out/final_launches_c$1_$2.csv | head -14
 done
