@@ -21,7 +21,7 @@ for line in txt.splitlines():
         funcs[cur] = []
     elif cur and re.search(r"/\*[0-9a-f]{4}\*/", line):
         funcs[cur].append(line)
-KEY = re.compile(r"UTCHMMA|UTMALDG|UTMASTG|UBLKCP|UBLKPF|LDTM|STTM|UTCBAR|UTCATOMSWS|SYNCS|multimem|LD\.E.*SYS|ST\.E.*SYS|R2UR|ELECT")
+KEY = re.compile(r"LDGMC|STGMC|UTCHMMA|UTMALDG|UTMASTG|UBLKCP|UBLKPF|LDTM|STTM|UTCBAR|UTCATOMSWS|SYNCS|multimem|LD\.E.*SYS|ST\.E.*SYS|R2UR|ELECT")
 for pat in pats:
     for name, lines in funcs.items():
         if pat not in name:
