@@ -10,7 +10,7 @@ run memcheck "conv and 4-512-512" conv4
 run memcheck "conv and 16-128-256-3-2" conv_s2
 run memcheck "conv and 32-64-64-3-1" conv_halo
 run memcheck "conv and 8-256-256-3-1" conv_wgrad_t
-run memcheck "groupnorm and 32-64" groupnorm_fused
+run memcheck "groupnorm and 32-64" groupnorm_32x32
 run memcheck "groupnorm and 4-512" groupnorm
 run memcheck "layernorm" layernorm
 run memcheck "flow_ticks" flow
@@ -18,4 +18,4 @@ run racecheck "groupnorm and 4-512" groupnorm
 run racecheck "layernorm" layernorm
 run synccheck "linear and 128-256-256" linear
 run synccheck "conv and 32-64-64-3-1" conv_halo
-run racecheck "groupnorm and 32-64" groupnorm_fused
+run racecheck "groupnorm and 32-64" groupnorm_32x32
