@@ -2,7 +2,7 @@
 # gpurun_out/ (scratch) -> profiles/r2_* (tracked): bench lines, op table, launch lists, ncu exports, SASS, sanitizer, multi-GPU logs
 cd "$(dirname "$0")/.."
 for c in 2 3 4 5; do [ -f gpurun_out/final_c${c}_n1.json ] && grep -h '^{"metric"' gpurun_out/final_c${c}_n1.json > profiles/r2_bench_c${c}_n1.json; done
-for n in 2 4 8; do [ -f gpurun_out/bench_c2_n$n.json ] && grep -h '^{"metric"' gpurun_out/bench_c2_n$n.json > profiles/r2_bench_c2_n$n.json; done
+for c in 2 3 4 5; do for n in 2 4 8; do [ -s gpurun_out/bench_c${c}_n$n.json ] && grep -q '^{"metric"' gpurun_out/bench_c${c}_n$n.json && grep -h '^{"metric"' gpurun_out/bench_c${c}_n$n.json > profiles/r2_bench_c${c}_n$n.json; done; done
 [ -f gpurun_out/final_lib_c2_tf32.json ] && grep -h '^{"metric"' gpurun_out/final_lib_c2_tf32.json > profiles/r2_lib_c2_tf32.json
 [ -f gpurun_out/final_op_bench.json ] && cp gpurun_out/final_op_bench.json profiles/r2_op_bench.json
 for f in gpurun_out/final_launches_c*.csv; do [ -f "$f" ] && python tools/ncu_launch_summary.py "$f" > profiles/r2_launches_$(basename $f .csv | sed 's/final_launches_//').txt; done
