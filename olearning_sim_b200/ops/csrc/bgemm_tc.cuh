@@ -2,8 +2,8 @@
 //
 //     D_b[M, N] = sum_k A_b[M, k] * B_b[N, k]          b = client, or (client, sample, head) for attention
 //
-// One persistent warp-specialised kernel (TMA warp, MMA warp, 4 epilogue warps, TMEM double buffering, NSTAGE-deep
-// shared-memory ring) is instantiated over
+// One persistent warp-specialised kernel (TMA warp, MMA warp, two groups of 4 epilogue warps — one per TMEM accumulator
+// buffer —, NSTAGE-deep shared-memory ring) is instantiated over
 //   * the A loader:  A_K     K-major rows straight from a row-major tensor                      (activations, dY)
 //                    A_MN    MN-major (the tensor is read "transposed" by the tensor core)      (dY^T, P^T, dS^T)
 //                    A_CONV  K-major 128-pixel window of an NHWC activation tensor, one TMA box per (tap, 64-channel
@@ -29,7 +29,8 @@
 //                    E_GNSTAT   store + GroupNorm statistics (sum, sum of squares per image and group, fp32 atomics)
 //                    E_SOFTMAX  row softmax of the 128-wide score tile (a thread owns a whole accumulator row)
 //                    E_DSOFT    softmax backward  dS = P o (dP - rowsum(dP o P)) * scale
-//                    E_SGD      weight gradient -> SGD / FedProx step on the fp32 master + bf16 operand copy
+//                    E_SGD      weight gradient -> SGD / FedProx step on the fp32 master + bf16 operand copy (rows = cout)
+//                    E_SGD_T    the same with rows = (tap, cin), columns = cout: lanes of a warp on contiguous master bytes
 // This is the per-client training step of the ResNet-18 and BERT-mini families (BASELINE configs 3 and 5): the role
 // of the reference's per-phone subprocess (ols_core/taskMgr/utils/utils_run_task.py:481-514).
 #pragma once
