@@ -670,3 +670,48 @@ def test_mysql_repos_translate_dialect_and_reconnect_once():
                 srv.drop_next = True
                 return c
         MySqlConnection(connect=Twice(), operational_errors=(FakeMySql.OperationalError,)).execute('SELECT 1')
+
+
+# ---------------------------------------------------------------------------------------------------------
+# communication runtime: multicast policy and the peer-loss error (host-side logic; the device paths are GPU tests)
+# ---------------------------------------------------------------------------------------------------------
+def test_multicast_policy_and_peer_lost_error(monkeypatch):
+    from olearning_sim_b200.parallel import nvls
+    from olearning_sim_b200.parallel.comm import PeerLostError
+    monkeypatch.delenv("OLSB_NVLS", raising=False)
+    monkeypatch.delenv("OLSB_NVLS_MIN_BYTES", raising=False)
+    assert not nvls.enabled(1) and nvls.enabled(8)                     # never for a single rank
+    assert nvls.min_bytes() == 4 << 20                                 # small (latency-bound) slabs stay on CUDA IPC
+    monkeypatch.setenv("OLSB_NVLS_MIN_BYTES", "1024")
+    assert nvls.min_bytes() == 1024
+    monkeypatch.setenv("OLSB_NVLS", "1")
+    assert nvls.min_bytes() == 0 and nvls.enabled(2)                   # forced on: every size
+    monkeypatch.setenv("OLSB_NVLS", "0")
+    assert not nvls.enabled(8)
+    e = PeerLostError(3, 17)
+    assert e.peer == 3 and e.round_idx == 17 and PeerLostError.exit_code == 75 and "rank 3" in str(e)
+
+
+def test_results_tables_are_generated_from_raw_lines(tmp_path):
+    """tools/make_results_md.py must only format what the JSON lines say (efficiency = value(N) / (N value(1)))."""
+    import importlib.util
+    import json
+    import shutil
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("mk", os.path.join(root, "tools", "make_results_md.py"))
+    mk = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mk)
+    prof = tmp_path / "profiles"
+    prof.mkdir()
+    for n, v in ((1, 100.0), (8, 640.0)):
+        line = {"metric": "fl_client_local_steps_per_sec", "value": v, "ms_per_step": 1000.0 / v, "n_gpus": n,
+                "config": {"id": 2, "model": "cnn2 (x)"}, "e2e": {"value": v * 0.9}, "vs_baseline": 10.0,
+                "baseline": {"value": v / 10, "ms_per_step": 1.0, "e2e": {"value": v / 11}, "e2e_ratio": 9.9}, "clocks": {"sm_mhz": 1900}}
+        (prof / f"r2_bench_c2_n{n}.json").write_text(json.dumps(line) + "\n")
+    shutil.copy(os.path.join(root, "BASELINE.md"), tmp_path / "BASELINE.md")
+    shutil.copy(os.path.join(root, "README.md"), tmp_path / "README.md")
+    mk.ROOT, mk.P = str(tmp_path), str(prof)
+    mk.main()
+    txt = (prof / "r2_results.md").read_text()
+    assert "| 2 | cnn2 | 8 | 640 |" in txt and "0.800" in txt             # 640 / (8 * 100)
+    assert "640" in (tmp_path / "README.md").read_text() and "640" in (tmp_path / "BASELINE.md").read_text()
