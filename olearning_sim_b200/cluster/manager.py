@@ -234,23 +234,101 @@ class LocalClusterApi:
             return self._items.pop((k8s_namespace, name), None) is not None
 
 
+class KubeRestCustomObjects:
+    """Dependency-free client for the custom-objects endpoints of a Kubernetes API server (the five verbs of
+    ``kubernetes.client.CustomObjectsApi`` that KubeClusterApi uses), over ``requests``:
+
+        POST / GET(list)   /apis/{group}/{version}/namespaces/{ns}/{plural}
+        GET / PATCH / DELETE  .../{plural}/{name}          (PATCH as application/merge-patch+json)
+
+    ``from_env()`` picks up the in-cluster service account (token + CA under /var/run/secrets/kubernetes.io/serviceaccount,
+    KUBERNETES_SERVICE_HOST/PORT) or ``KUBE_API_URL`` [+ ``KUBE_TOKEN``, ``KUBE_CA_FILE``].  Non-2xx answers raise
+    ``KubeApiError`` (status + the server's Status message) — KubeClusterApi turns them into logged failures, like the
+    reference does with ``ApiException`` (kuberay_cluster_api.py:60-75)."""
+
+    SA_DIR = "/var/run/secrets/kubernetes.io/serviceaccount"
+
+    def __init__(self, base_url: str, token: Optional[str] = None, verify: Any = True, timeout: float = 10.0):
+        import requests
+        self.base, self.timeout = base_url.rstrip("/"), timeout
+        self.s = requests.Session()
+        self.s.verify = verify
+        if token:
+            self.s.headers["Authorization"] = f"Bearer {token}"
+
+    @classmethod
+    def from_env(cls) -> "KubeRestCustomObjects":
+        import os
+        url = os.environ.get("KUBE_API_URL")
+        token, ca = os.environ.get("KUBE_TOKEN"), os.environ.get("KUBE_CA_FILE")
+        if not url and os.environ.get("KUBERNETES_SERVICE_HOST"):
+            url = f"https://{os.environ['KUBERNETES_SERVICE_HOST']}:{os.environ.get('KUBERNETES_SERVICE_PORT', '443')}"
+            try:
+                with open(os.path.join(cls.SA_DIR, "token")) as f:
+                    token = token or f.read().strip()
+            except OSError:
+                pass
+            ca = ca or (os.path.join(cls.SA_DIR, "ca.crt") if os.path.exists(os.path.join(cls.SA_DIR, "ca.crt")) else None)
+        if not url:
+            raise RuntimeError("no Kubernetes API server: set KUBE_API_URL (and KUBE_TOKEN) or run inside a pod")
+        return cls(url, token, ca if ca else True)
+
+    def _url(self, group, version, namespace, plural, name=None) -> str:
+        u = f"{self.base}/apis/{group}/{version}/namespaces/{namespace}/{plural}"
+        return f"{u}/{name}" if name else u
+
+    def _do(self, method: str, url: str, **kw) -> Dict[str, Any]:
+        r = self.s.request(method, url, timeout=self.timeout, **kw)
+        if r.status_code // 100 != 2:
+            try:
+                msg = r.json().get("message", r.text)
+            except ValueError:
+                msg = r.text
+            raise KubeApiError(r.status_code, msg)
+        return r.json() if r.content else {}
+
+    def create_namespaced_custom_object(self, group, version, namespace, plural, body):
+        return self._do("POST", self._url(group, version, namespace, plural), json=body)
+
+    def get_namespaced_custom_object(self, group, version, namespace, plural, name):
+        return self._do("GET", self._url(group, version, namespace, plural, name))
+
+    def list_namespaced_custom_object(self, group, version, namespace, plural, label_selector=""):
+        return self._do("GET", self._url(group, version, namespace, plural),
+                        params={"labelSelector": label_selector} if label_selector else None)
+
+    def patch_namespaced_custom_object(self, group, version, namespace, plural, name, body):
+        return self._do("PATCH", self._url(group, version, namespace, plural, name), data=json.dumps(body),
+                        headers={"Content-Type": "application/merge-patch+json"})
+
+    def delete_namespaced_custom_object(self, group, version, namespace, plural, name):
+        return self._do("DELETE", self._url(group, version, namespace, plural, name))
+
+
+class KubeApiError(RuntimeError):
+    def __init__(self, status: int, message: str):
+        super().__init__(f"{status}: {message}")
+        self.status = status
+
+
 class KubeClusterApi:
     """The same five calls against a Kubernetes API server (custom objects of ``GROUP/VERSION``, plural ``PLURAL``) — the
-    counterpart of the reference's KubeRay client (kuberay_cluster_api.py:37-304).  The ``kubernetes`` client is not part
-    of this image, so the class is gated: constructing it without the package raises a clear error and everything else
-    keeps working on ``LocalClusterApi``.  ``api`` may be injected (tests use a fake ``CustomObjectsApi``)."""
+    counterpart of the reference's KubeRay client (kuberay_cluster_api.py:37-304).  Transport: the official ``kubernetes``
+    client when it is installed, otherwise the built-in REST client ``KubeRestCustomObjects`` (same verbs over
+    ``requests``); ``api`` may also be injected.  Tested end to end against an in-process HTTP API server
+    (tests/test_infra.py)."""
 
     def __init__(self, api: Optional[Any] = None, group: str = GROUP, version: str = VERSION, plural: str = PLURAL):
         if api is None:
             try:
                 from kubernetes import client, config          # type: ignore
-            except ImportError as e:  # pragma: no cover - depends on the deployment image
-                raise RuntimeError("KubeClusterApi needs the 'kubernetes' package; use LocalClusterApi on a single box") from e
-            try:
-                config.load_incluster_config()
-            except Exception:  # noqa: BLE001 - outside a pod: fall back to the user's kubeconfig
-                config.load_kube_config()
-            api = client.CustomObjectsApi()
+                try:
+                    config.load_incluster_config()
+                except Exception:  # noqa: BLE001 - outside a pod: fall back to the user's kubeconfig
+                    config.load_kube_config()
+                api = client.CustomObjectsApi()
+            except ImportError:
+                api = KubeRestCustomObjects.from_env()
         self.api, self.group, self.version, self.plural = api, group, version, plural
 
     def _call(self, fn, *a, **kw):

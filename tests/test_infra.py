@@ -372,3 +372,96 @@ def test_optimizer_state_reshards_across_world_sizes():
     sl3, s3 = shards(3)                      # elastic shrink 4 -> 3 ranks
     assert torch.equal(merge_opt_shards(s3, P), full) and s3[1][0] == sl3
     assert torch.equal(take_opt_shard(merge_opt_shards(s4, P), 0, 24, 24)[:P], full)       # ... -> 1 rank
+
+
+def test_kube_cluster_api_over_http_against_an_api_server():
+    """KubeClusterApi with its built-in REST transport against an in-process HTTP server that implements the custom-objects
+    endpoints of a Kubernetes API server (create 201 / duplicate 409 / get / list with labelSelector / merge-patch / delete /
+    404), including bearer-token auth — the whole GpuClusterManager CRUD cycle goes over real HTTP"""
+    import http.server
+    import threading
+    import urllib.parse
+    from olearning_sim_b200.cluster.manager import GROUP, PLURAL, VERSION, GpuClusterManager, KubeClusterApi, KubeRestCustomObjects
+
+    store, seen = {}, {"auth": set(), "ctype": set()}
+
+    class H(http.server.BaseHTTPRequestHandler):
+        def log_message(self, *a): pass
+
+        def _send(self, code, obj):
+            b = json.dumps(obj).encode()
+            self.send_response(code); self.send_header("Content-Type", "application/json")
+            self.send_header("Content-Length", str(len(b))); self.end_headers(); self.wfile.write(b)
+
+        def _route(self):
+            u = urllib.parse.urlparse(self.path)
+            parts = u.path.strip("/").split("/")
+            if parts[:3] != ["apis", GROUP, VERSION] or parts[3] != "namespaces" or parts[5] != PLURAL:
+                return None
+            return parts[4], (parts[6] if len(parts) > 6 else None), urllib.parse.parse_qs(u.query)
+
+        def _handle(self, method):
+            seen["auth"].add(self.headers.get("Authorization"))
+            if self.headers.get("Authorization") != "Bearer sekrit":
+                return self._send(401, {"kind": "Status", "message": "Unauthorized"})
+            r = self._route()
+            if r is None:
+                return self._send(404, {"kind": "Status", "message": "no such resource"})
+            ns, name, q = r
+            n = int(self.headers.get("Content-Length") or 0)
+            body = json.loads(self.rfile.read(n)) if n else None
+            if method == "POST":
+                key = (ns, body["metadata"]["name"])
+                if key in store:
+                    return self._send(409, {"kind": "Status", "message": f"{PLURAL} {key[1]!r} already exists"})
+                store[key] = body
+                return self._send(201, body)
+            if method == "GET" and name is None:
+                sel = dict(kv.split("=") for kv in q.get("labelSelector", [""])[0].split(",") if kv)
+                items = [o for (n_, _), o in store.items() if n_ == ns and all(o["metadata"].get("labels", {}).get(k) == v for k, v in sel.items())]
+                return self._send(200, {"kind": "List", "items": items})
+            if (ns, name) not in store:
+                return self._send(404, {"kind": "Status", "message": f"{PLURAL} {name!r} not found"})
+            if method == "GET":
+                return self._send(200, store[(ns, name)])
+            if method == "PATCH":
+                seen["ctype"].add(self.headers.get("Content-Type"))
+                def merge(a, b):
+                    for k, v in b.items():
+                        if isinstance(v, dict) and isinstance(a.get(k), dict): merge(a[k], v)
+                        else: a[k] = v
+                merge(store[(ns, name)], body)
+                return self._send(200, store[(ns, name)])
+            if method == "DELETE":
+                return self._send(200, {"kind": "Status", "status": "Success", "details": {"name": store.pop((ns, name))["metadata"]["name"]}})
+
+        def do_GET(self): self._handle("GET")
+        def do_POST(self): self._handle("POST")
+        def do_PATCH(self): self._handle("PATCH")
+        def do_DELETE(self): self._handle("DELETE")
+
+    srv = http.server.ThreadingHTTPServer(("127.0.0.1", 0), H)
+    threading.Thread(target=srv.serve_forever, daemon=True).start()
+    try:
+        url = f"http://127.0.0.1:{srv.server_address[1]}"
+        api = KubeClusterApi(api=KubeRestCustomObjects(url, token="sekrit"))
+        mgr = GpuClusterManager(api=api)
+        d = mgr._d
+        assert mgr.createRayCluster({})["ok"] and (d.k8s_namespace, d.ray_name) in store
+        assert not mgr.createRayCluster({})["ok"]                                    # 409 from the server -> reported failure
+        got = api.get_ray_cluster(d.ray_name, d.k8s_namespace)
+        assert got["kind"] and got["spec"]["workerGroupSpecs"][0]["replicas"] == d.worker_replicas
+        assert len(api.list_ray_clusters(d.k8s_namespace)["items"]) == 1
+        assert api.list_ray_clusters(d.k8s_namespace, label_selector="no=match")["items"] == []
+        assert mgr.modifyRayCluster({"k8s_namespace": d.k8s_namespace, "ray_name": d.ray_name, "ray_label": d.ray_label,
+                                     "worker_min_replicas": 1, "worker_replicas": 2, "worker_max_replicas": 4})["ok"]
+        assert store[(d.k8s_namespace, d.ray_name)]["spec"]["workerGroupSpecs"][0]["replicas"] == 2
+        assert seen["ctype"] == {"application/merge-patch+json"}
+        assert api.get_ray_cluster("nope", d.k8s_namespace) is None                  # 404 -> None, not an exception
+        assert mgr.deleteRayCluster({"k8s_namespace": d.k8s_namespace, "ray_name": d.ray_name})["ok"] and not store
+        assert api.delete_ray_cluster(d.ray_name, d.k8s_namespace) is False
+        bad = KubeClusterApi(api=KubeRestCustomObjects(url, token="wrong"))
+        assert bad.get_ray_cluster("x") is None and bad.list_ray_clusters()["items"] == []       # 401 -> failure, no raise
+        assert seen["auth"] == {"Bearer sekrit", "Bearer wrong"}
+    finally:
+        srv.shutdown()
