@@ -239,3 +239,34 @@ def test_restart_recovery_rebuilds_registry_flows_and_dispatchers(tmp_path):
     svc2.pump()
     assert sorted(drain(out)) == ["update-0", "update-1", "update-2"]
     assert svc2.CheckDeviceflowDispatchFinished("t")
+
+
+def test_websocket_producer_against_a_live_websocket_server():
+    """the WebSocket outbound path end to end: a real ``websockets`` server on localhost receives what the dispatcher's
+    producer sends, in the Pulsar-WebSocket envelope {"payload": base64(message)}"""
+    import base64
+    import json as _json
+    import threading
+    from websockets.sync.server import serve
+
+    got, done = [], threading.Event()
+
+    def handler(ws):
+        for msg in ws:
+            got.append(_json.loads(msg))
+            if len(got) == 3:
+                done.set()
+
+    with serve(handler, "127.0.0.1", 0) as server:
+        t = threading.Thread(target=server.serve_forever, daemon=True)
+        t.start()
+        port = server.socket.getsockname()[1]
+        wp = WebsocketProducer()
+        wp.get_producer({"url": f"ws://127.0.0.1:{port}/ws/v2/producer/persistent/public/default/out"})
+        for i in range(3):
+            wp.send(make_message(f"t1_train_0_dev{i}", "logical_simulation", f"update {i}"))
+        assert done.wait(5.0)
+        wp.close()
+        server.shutdown()
+    bodies = [base64.b64decode(g["payload"]) for g in got]
+    assert all(b"dev" in b for b in bodies) and len({bytes(b) for b in bodies}) == 3
