@@ -715,3 +715,26 @@ def test_results_tables_are_generated_from_raw_lines(tmp_path):
     txt = (prof / "r2_results.md").read_text()
     assert "| 2 | cnn2 | 8 | 640 |" in txt and "0.800" in txt             # 640 / (8 * 100)
     assert "640" in (tmp_path / "README.md").read_text() and "640" in (tmp_path / "BASELINE.md").read_text()
+
+
+@pytest.mark.parametrize("name", ["task_mlp_cpu.json", "task_cnn2_gpu.json", "task_resnet18_gpu.json", "task_bert_mini_gpu.json"])
+def test_example_tasks_pass_the_reference_validators_and_the_wire(name):
+    """every shipped example is a valid reference-schema task: validators accept it, it survives the protobuf round trip, and
+    its DeviceFlow strategy (when it has one) passes the strategy validator"""
+    from olearning_sim_b200.api.validate import ValidateParameters
+    from olearning_sim_b200.deviceflow.validate import ValidateParameters as DfValidate
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    task = json.load(open(os.path.join(root, "examples", name)))
+    from olearning_sim_b200.api.schema import json2taskconfig
+    ok, msg = ValidateParameters().validate_task_parameters(json2taskconfig(task))
+    assert ok, msg
+    back = wire.task_pb_to_json(wire.task_json_to_pb(task))
+    assert back["task_id"] == task["task_id"] and len(back["operatorflow"]["operators"]) == len(task["operatorflow"]["operators"])
+    for op in task["operatorflow"]["operators"]:
+        obc = op.get("operation_behavior_controller") or {}
+        if obc.get("use_gradient_house") and obc.get("strategy_gradient_house"):
+            ok, msg = DfValidate().check_strategy(json.loads(obc["strategy_gradient_house"]))
+            assert ok, msg
+        params = op["logical_simulation"].get("operator_params")
+        if params:
+            assert isinstance(json.loads(params), dict)
