@@ -42,14 +42,16 @@ def test_engine_round_native_vs_torch_backend():
     b.set_global_model(spec.flatten(CNN2.unpack(g0)))
     ra, rb = a.run_round(0), b.run_round(0)
     assert (ra.participants, ra.dropped, ra.arrived, ra.client_steps) == (rb.participants, rb.dropped, rb.arrived, rb.client_steps)
-    assert abs(ra.loss - rb.loss) < 2e-2 * max(1.0, abs(rb.loss)), (ra, rb)
+    # bf16 tensor-core operands vs the fp32 oracle: measured (tools/tol_probe.py, three seeds) loss 2-3e-4, per-tensor model
+    # delta <= 1.7e-2 (conv1.weight); the bounds leave < 2x head-room
+    assert abs(ra.loss - rb.loss) < 2e-3 * max(1.0, abs(rb.loss)), (ra, rb)
     ga = CNN2.unpack(a.global_model())
     gb = spec.unflatten(b.global_model().cpu())
     for k in ga:
         da = ga[k] - CNN2.unpack(g0)[k]
         db = gb[k].cpu() - CNN2.unpack(g0)[k]
         rel = (da - db).norm() / (db.norm() + 1e-12)
-        assert rel < 8e-2, (k, float(rel))
+        assert rel < 3e-2, (k, float(rel))
     a.close()
 
 
@@ -64,11 +66,11 @@ def test_engine_mlp_native_vs_torch_backend():
     ra, rb = a.run_round(0), b.run_round(0)
     assert a.kernel_launches() == 1 + 1 + 2 * 6 + 3          # mask, broadcast, 2 steps x 6, accounting + reduce + finish
     assert (ra.participants, ra.dropped, ra.arrived, ra.client_steps) == (rb.participants, rb.dropped, rb.arrived, rb.client_steps)
-    assert abs(ra.loss - rb.loss) < 3e-2 * max(1.0, abs(rb.loss)), (ra, rb)
+    assert abs(ra.loss - rb.loss) < 3e-3 * max(1.0, abs(rb.loss)), (ra, rb)          # measured 2-5e-4 (tools/tol_probe.py)
     ga, gb = a.spec_flat_global().cpu(), b.spec_flat_global().cpu()
     g0 = a.spec.init(5)
     rel = ((ga - g0) - (gb - g0)).norm() / (gb - g0).norm()
-    assert rel < 8e-2, float(rel)
+    assert rel < 3.5e-2, float(rel)                                                     # measured 1.1-2.1e-2 (bf16 operands)
     a.close()
 
 
@@ -115,11 +117,11 @@ def test_engine_deep_mlp_native_vs_torch_backend():
     ra, rb = a.run_round(0), b.run_round(0)
     assert a.kernel_launches() == 1 + 1 + 2 * 12 + 3
     assert (ra.participants, ra.client_steps) == (rb.participants, rb.client_steps)
-    assert abs(ra.loss - rb.loss) < 3e-2 * max(1.0, abs(rb.loss)), (ra, rb)
+    assert abs(ra.loss - rb.loss) < 1e-3 * max(1.0, abs(rb.loss)), (ra, rb)          # measured 3-8e-5
     ga, gb = a.spec_flat_global().cpu(), b.spec_flat_global().cpu()
     g0 = a.spec.init(5)
     rel = ((ga - g0) - (gb - g0)).norm() / (gb - g0).norm()
-    assert rel < 8e-2, float(rel)
+    assert rel < 6e-2, float(rel)                       # measured 2.4-3.9e-2: bf16 rounding through four layers, both passes
     a.close()
 
 
