@@ -50,7 +50,8 @@ ga = nat.spec_flat_global().cpu()[: nat.spec.num_params]
 gb = ora.global_model().cpu()[: nat.spec.num_params]
 d0 = g0[: nat.spec.num_params]
 rel = float((ga - gb).norm() / (gb - d0).norm().clamp_min(1e-20))
-tol = {"cnn2": 6e-2, "mlp2": 3e-2, "resnet18": 8e-2, "bert_mini": 3e-2}[MODEL] * (4 if OPT == "adam" else 1)
+# measured at 2 and 8 ranks (profiles/r2_mgpu_oracle_n*.jsonl): cnn2 3.4e-3, mlp2 1.1e-2, resnet18 3.3e-2, bert_mini 4.4e-3
+tol = {"cnn2": 1.5e-2, "mlp2": 2.5e-2, "resnet18": 6e-2, "bert_mini": 1.5e-2}[MODEL] * (2 if OPT == "adam" else 1)
 ok = ok and rel < tol
 
 # ---- communication kernels alone vs NCCL all_reduce (fp32)
