@@ -114,18 +114,20 @@ class HttpFileRepo(FileRepo):
 
 
 class S3FileRepo(FileRepo):
-    """S3-compatible object store through a boto3 client (ofl_commons/.../s3_file_repo.py:1-64).  ``client`` injects a
-    ready client (tests use an in-memory fake with the boto3 method names); otherwise ``boto3`` is imported lazily."""
+    """S3-compatible object store (ofl_commons/.../s3_file_repo.py:1-64).  Transport: an injected ``client``, else ``boto3``
+    when it is installed, else the built-in Signature-V4 REST client (utils/s3_rest.py) — the same five calls either way."""
 
     def __init__(self, endpoint_url: str = "", access_key: str = "", secret_key: str = "", bucket: str = "",
                  region: Optional[str] = None, client: Any = None):
         if client is None:
             try:
                 import boto3  # type: ignore
-            except ImportError as e:
-                raise RuntimeError("S3 transfer needs the boto3 client, which is not installed on this box") from e
-            client = boto3.client("s3", endpoint_url=endpoint_url, aws_access_key_id=access_key,
-                                  aws_secret_access_key=secret_key, region_name=region)
+                client = boto3.client("s3", endpoint_url=endpoint_url, aws_access_key_id=access_key,
+                                      aws_secret_access_key=secret_key, region_name=region)
+            except ImportError:
+                from .s3_rest import S3RestClient
+                client = S3RestClient(endpoint_url or f"https://s3.{region or 'us-east-1'}.amazonaws.com", access_key, secret_key,
+                                      region or "us-east-1")
         self._s3, self._bucket = client, bucket
 
     def upload_file(self, local_path, object_name) -> bool:
@@ -172,16 +174,19 @@ class S3FileRepo(FileRepo):
 
 
 class MinioFileRepo(FileRepo):
-    """MinIO through the ``minio`` client (ofl_commons/.../minio_file_repo.py:1-89); ``client`` as for S3."""
+    """MinIO (ofl_commons/.../minio_file_repo.py:1-89): an injected ``client``, else the ``minio`` package, else the built-in
+    Signature-V4 REST client (MinIO speaks the S3 protocol)."""
 
     def __init__(self, endpoint: str = "", access_key: str = "", secret_key: str = "", bucket: str = "",
                  secure: bool = False, client: Any = None):
         if client is None:
             try:
                 from minio import Minio  # type: ignore
-            except ImportError as e:
-                raise RuntimeError("MINIO transfer needs the minio client, which is not installed on this box") from e
-            client = Minio(endpoint, access_key=access_key, secret_key=secret_key, secure=secure)
+                client = Minio(endpoint, access_key=access_key, secret_key=secret_key, secure=secure)
+            except ImportError:
+                from .s3_rest import S3RestClient
+                url = endpoint if "://" in endpoint else ("https://" if secure else "http://") + endpoint
+                client = S3RestClient(url, access_key, secret_key)
         self._c, self._bucket = client, bucket
 
     def upload_file(self, local_path, object_name) -> bool:
