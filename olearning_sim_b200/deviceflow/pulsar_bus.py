@@ -10,8 +10,10 @@ puts the inbound room, the per-flow shelves and the dispatchers on a real broker
 
 Subscriptions are ``Shared`` like the reference's, receive timeouts map to ``BusTimeout``; un-acked messages are
 redelivered by the broker after a restart, which is what the service's restart recovery relies on.  The ``pulsar`` client
-is imported lazily (it is not installable offline); ``client=`` injects any object with the ``pulsar.Client`` surface —
-the tests drive the whole sorter -> shelf -> dispatcher path through an in-memory fake of it.
+is imported lazily (it is not installable offline).  ``PulsarBus("ws://host:8080")`` needs no wheel at all: it talks to
+the broker's WebSocket API through ``deviceflow/pulsar_ws.py``; ``client=`` injects any object with the ``pulsar.Client``
+surface.  The tests drive the whole sorter -> shelf -> dispatcher path both through an in-memory fake client and through
+the WebSocket client against an in-process broker emulation.
 """
 from __future__ import annotations
 
@@ -86,12 +88,17 @@ class PulsarBus:
     virtual_time = False
 
     def __init__(self, service_url: str = "pulsar://127.0.0.1:6650", client: Any = None, tenant_prefix: str = "persistent://public/"):
-        if client is None:
+        if client is None and service_url.startswith(("ws://", "wss://")):
+            # the broker's WebSocket API (deviceflow/pulsar_ws.py): no pulsar-client wheel needed
+            from .pulsar_ws import PulsarWsClient
+            client = PulsarWsClient(service_url)
+            self._shared = PulsarWsClient.ConsumerType.Shared
+        elif client is None:
             try:
                 import pulsar  # type: ignore
             except ImportError as e:
-                raise RuntimeError("the Pulsar transport needs the pulsar-client package, which is not installed on this box; "
-                                   "use InMemoryBus (optionally with journal_path) or inject a client") from e
+                raise RuntimeError("pulsar:// URLs need the pulsar-client package, which is not installed on this box; use the "
+                                   "broker's WebSocket service (ws://host:8080), InMemoryBus, or inject a client") from e
             client = pulsar.Client(service_url)
             self._shared = pulsar.ConsumerType.Shared
         else:

@@ -738,3 +738,124 @@ def test_example_tasks_pass_the_reference_validators_and_the_wire(name):
         params = op["logical_simulation"].get("operator_params")
         if params:
             assert isinstance(json.loads(params), dict)
+
+
+class WsPulsarBroker:
+    """In-process emulation of the two Pulsar WebSocket endpoints (producer / consumer) on a real ``websockets`` server: a
+    topic is a log, a subscription a cursor plus the set of delivered-but-unacknowledged ids, which are redelivered to the
+    next consumer that attaches (what a broker does after a consumer disconnects)."""
+
+    def __init__(self):
+        import threading
+        from websockets.sync.server import serve
+        self.lock = threading.Lock()
+        self.topics, self.subs, self.n = {}, {}, 0                   # topic -> [(id, b64)], (topic, sub) -> {"cursor", "unacked"}
+        self.server = serve(self._handle, "127.0.0.1", 0)
+        self.port = self.server.socket.getsockname()[1]
+        threading.Thread(target=self.server.serve_forever, daemon=True).start()
+
+    def _handle(self, ws):
+        import urllib.parse
+        u = urllib.parse.urlparse(ws.request.path)
+        parts = u.path.strip("/").split("/")                         # ws v2 producer|consumer persistent tenant ns topic [sub]
+        kind, topic = parts[2], "/".join(parts[3:7])
+        if kind == "producer":
+            for frame in ws:
+                m = json.loads(frame)
+                with self.lock:
+                    self.n += 1
+                    mid = f"{self.n}:0"
+                    self.topics.setdefault(topic, []).append((mid, m["payload"]))
+                ws.send(json.dumps({"result": "ok", "messageId": mid, "context": m.get("context")}))
+            return
+        sub = self.subs.setdefault((topic, parts[7]), {"cursor": 0, "unacked": {}})
+        assert "subscriptionType=Shared" in u.query
+        with self.lock:
+            redeliver = list(sub["unacked"].items())
+        for mid, payload in redeliver:                                # unacknowledged from a previous connection first
+            ws.send(json.dumps({"messageId": mid, "payload": payload, "properties": {}, "redeliveryCount": 1}))
+        import time
+        while True:
+            with self.lock:
+                log = self.topics.get(topic, [])
+                new = log[sub["cursor"]:]
+                sub["cursor"] = len(log)
+                for mid, payload in new:
+                    sub["unacked"][mid] = payload
+            for mid, payload in new:
+                ws.send(json.dumps({"messageId": mid, "payload": payload, "properties": {}}))
+            try:
+                ack = ws.recv(timeout=0.01)
+                with self.lock:
+                    sub["unacked"].pop(json.loads(ack)["messageId"], None)
+            except TimeoutError:
+                pass
+            except Exception:                                         # connection closed
+                return
+            time.sleep(0.002)
+
+    def close(self):
+        self.server.shutdown()
+
+
+def test_pulsar_websocket_client_against_a_broker_emulation():
+    """PulsarBus("ws://...") = the broker's WebSocket API end to end: publish, Shared subscription, ack, receive timeout,
+    redelivery of unacknowledged messages after a reconnect, and the DeviceFlow sorter -> shelf -> dispatcher -> outbound
+    path with every hop on that transport"""
+    from olearning_sim_b200.control.repo import FlowTableRepo
+    from olearning_sim_b200.deviceflow.bus import BusTimeout, FakeClock
+    from olearning_sim_b200.deviceflow.pulsar_bus import PulsarBus
+    from olearning_sim_b200.deviceflow.rooms import PulsarClientProducer
+    from olearning_sim_b200.deviceflow.service import DeviceFlowService, NotifyRequest
+    broker = WsPulsarBroker()
+    url = f"ws://127.0.0.1:{broker.port}"
+    try:
+        bus = PulsarBus(url)
+        prod = bus.create_producer("jobs")
+        cons = bus.subscribe("jobs", "workers")
+        for i in range(3):
+            prod.send(f"m{i}".encode())
+        got = [cons.receive(timeout_millis=2000) for _ in range(3)]
+        assert [m.data() for m in got] == [b"m0", b"m1", b"m2"]
+        cons.acknowledge(got[0])
+        with pytest.raises(BusTimeout):
+            cons.receive(timeout_millis=50)
+        time.sleep(0.1)                                               # let the ack land before the connection drops
+        cons.close()
+        cons2 = bus.subscribe("jobs", "workers")                      # same subscription: m1, m2 come back, m0 does not
+        again = sorted(cons2.receive(timeout_millis=2000).data() for _ in range(2))
+        assert again == [b"m1", b"m2"]
+        with pytest.raises(BusTimeout):
+            cons2.receive(timeout_millis=50)
+        # ---- DeviceFlow on the WebSocket transport
+        bus.virtual_time = True
+        PulsarClientProducer.buses[url] = bus
+        df = DeviceFlowService(bus=bus, repo=FlowTableRepo(), clock=FakeClock(), seed=1, dispatcher_timeout_millis=200)
+        st = json.dumps({"real_time_dispatch": {"use_strategy": True, "dispatch_batch_sizes": [2], "drop_simulation": {"drop_probability": 0.0}},
+                         "flow_dispatch": {"use_strategy": False}})
+        assert df.RegisterTask("wt", ["logical_simulation"])
+        agg = bus.subscribe("agg", "aggregator")                      # the cloud aggregator's subscription, before anything is sent
+        assert df.NotifyStart(NotifyRequest("wt", "wt_training_0", "logical_simulation", st, {"pulsar_client": {"url": url, "topic": "agg"}}))
+        inbound = bus.create_producer(df.config.source_topic)
+        for i in range(5):
+            inbound.send(json.dumps({"routing_key": "wt_training_0", "compute_resource": "logical_simulation", "message": f"u{i}"}))
+        deadline = time.time() + 5
+        while df.stats()["sorter"]["shelved"] < 5 and time.time() < deadline:
+            df._sorter.drain()
+        assert df.NotifyComplete(NotifyRequest("wt", "wt_training_0", "logical_simulation"))
+        out = []
+        deadline = time.time() + 10
+        while len(out) < 5 and time.time() < deadline:
+            df.pump()
+            try:
+                while True:
+                    m = agg.receive(timeout_millis=100)
+                    out.append(m.data().decode()); agg.acknowledge(m)
+            except BusTimeout:
+                pass
+        assert sorted(out) == [f"u{i}" for i in range(5)]
+        assert df.CheckDeviceflowDispatchFinished("wt")
+        del PulsarClientProducer.buses[url]
+        bus.close()
+    finally:
+        broker.close()
