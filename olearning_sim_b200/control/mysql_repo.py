@@ -2,7 +2,8 @@
 ols_core/taskMgr/utils/utils.py:29-267 ``TaskTableRepo``, ols_core/resourceMgr/utils/utils.py ``ResTableRepo``,
 ols_core/utils/repo_utils.py:19-345 ``SqlDataBase``).
 
-``MySqlConnection`` adapts a DB-API connection (``pymysql`` by default, imported lazily) to the three things
+``MySqlConnection`` adapts a DB-API connection (``pymysql`` when installed, otherwise the in-tree wire-protocol client
+``utils/mysql_wire.py``) to the three things
 ``SqlDataBase`` needs from sqlite: ``execute(sql, params)`` with ``?`` placeholders and ``"identifier"`` quoting (rewritten
 to ``%s`` / backticks), a cursor with ``rowcount`` / ``fetchone`` / ``fetchall`` / ``description``, and autocommit.  Like every
 repo method of the reference (utils.py:85-97, repo_utils.py:89-106) a statement that fails with an operational error
@@ -37,11 +38,13 @@ class MySqlConnection:
         if connect is None:
             try:
                 import pymysql  # type: ignore
-            except ImportError as e:
-                raise RuntimeError("the MySQL backend needs pymysql, which is not installed on this box; the default SQLite "
-                                   "tables (control/repo.py) need no server") from e
-            operational_errors = (pymysql.err.OperationalError, pymysql.err.InterfaceError)
-            connect = lambda: pymysql.connect(autocommit=True, **kw)       # noqa: E731
+                operational_errors = (pymysql.err.OperationalError, pymysql.err.InterfaceError)
+                connect = lambda: pymysql.connect(autocommit=True, **kw)       # noqa: E731
+            except ImportError:
+                # no pymysql: the in-tree wire-protocol client (utils/mysql_wire.py) provides the same DB-API subset
+                from ..utils import mysql_wire
+                operational_errors = (mysql_wire.OperationalError, mysql_wire.InterfaceError)
+                connect = lambda: mysql_wire.connect(autocommit=True, **kw)    # noqa: E731
         self._connect, self._errors = connect, tuple(operational_errors) or (ConnectionError,)
         self._conn = connect()
         self.reconnects = 0

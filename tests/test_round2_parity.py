@@ -859,3 +859,194 @@ def test_pulsar_websocket_client_against_a_broker_emulation():
         bus.close()
     finally:
         broker.close()
+
+
+class WireMySqlServer:
+    """A MySQL server on the wire protocol, over TCP, backed by sqlite: HandshakeV10 with a random salt, verification of the
+    mysql_native_password scramble (recomputed here from the stored password), COM_QUERY -> OK / ERR / text result set with
+    classic EOF framing, COM_PING, COM_QUIT.  ``drop_next`` closes the socket in the middle of the next query."""
+
+    def __init__(self, user="ols", password="pw-1", database="virtually_phone_DB"):
+        import socket
+        import sqlite3
+        import threading
+        self.user, self.password, self.database = user, password, database
+        self.db = sqlite3.connect(":memory:", check_same_thread=False, isolation_level=None)
+        self.lock, self.drop_next, self.connects, self.seen = threading.Lock(), False, 0, []
+        self.sock = socket.socket()
+        self.sock.bind(("127.0.0.1", 0))
+        self.sock.listen(8)
+        self.port = self.sock.getsockname()[1]
+        threading.Thread(target=self._accept, daemon=True).start()
+
+    def _accept(self):
+        import threading
+        while True:
+            try:
+                c, _ = self.sock.accept()
+            except OSError:
+                return
+            threading.Thread(target=self._serve, args=(c,), daemon=True).start()
+
+    @staticmethod
+    def _send(c, seq, payload):
+        c.sendall(len(payload).to_bytes(3, "little") + bytes([seq]) + payload)
+
+    @staticmethod
+    def _recv(c):
+        def exact(n):
+            b = b""
+            while len(b) < n:
+                x = c.recv(n - len(b))
+                if not x:
+                    raise ConnectionError
+                b += x
+            return b
+        h = exact(4)
+        return h[3], exact(int.from_bytes(h[:3], "little"))
+
+    @staticmethod
+    def _lenenc(b):
+        n = len(b)
+        return (bytes([n]) if n < 251 else b"\xfc" + n.to_bytes(2, "little")) + b
+
+    def _ok(self, c, seq, affected=0, last=0):
+        self._send(c, seq, b"\x00" + self._lenenc(b"")[:0] + bytes([affected if affected < 251 else 250, last if last < 251 else 250]) + b"\x02\x00\x00\x00")
+
+    def _err(self, c, seq, code, msg):
+        self._send(c, seq, b"\xff" + code.to_bytes(2, "little") + b"#HY000" + msg.encode())
+
+    def _serve(self, c):
+        import hashlib
+        import os as _os
+        import struct
+        self.connects += 1
+        salt = bytes(33 + b % 90 for b in _os.urandom(20))            # printable, no NULs (like a real server)
+        caps = 0x1 | 0x4 | 0x8 | 0x200 | 0x2000 | 0x8000 | 0x20000 | 0x80000
+        hs = (b"\x0a" + b"8.0.99-fake\0" + struct.pack("<I", self.connects) + salt[:8] + b"\0" + struct.pack("<H", caps & 0xFFFF) +
+              b"\x2d" + struct.pack("<H", 2) + struct.pack("<H", caps >> 16) + bytes([21]) + b"\0" * 10 + salt[8:] + b"\0" + b"mysql_native_password\0")
+        try:
+            self._send(c, 0, hs)
+            seq, resp = self._recv(c)
+            ccaps = struct.unpack_from("<I", resp, 0)[0]
+            pos = 32
+            end = resp.index(b"\0", pos)
+            user = resp[pos:end].decode()
+            pos = end + 1
+            alen = resp[pos]
+            auth = resp[pos + 1:pos + 1 + alen]
+            pos += 1 + alen
+            dbname = ""
+            if ccaps & 0x8:
+                end = resp.index(b"\0", pos)
+                dbname = resp[pos:end].decode()
+            p1 = hashlib.sha1(self.password.encode()).digest()
+            want = bytes(a ^ b for a, b in zip(p1, hashlib.sha1(salt + hashlib.sha1(p1).digest()).digest()))
+            if user != self.user or auth != want:
+                self._err(c, seq + 1, 1045, f"Access denied for user '{user}'")
+                return c.close()
+            if dbname != self.database:
+                self._err(c, seq + 1, 1049, f"Unknown database '{dbname}'")
+                return c.close()
+            self._ok(c, seq + 1)
+            while True:
+                seq, pkt = self._recv(c)
+                if pkt[0] == 0x01:
+                    return c.close()
+                if pkt[0] == 0x0e:
+                    self._ok(c, 1)
+                    continue
+                q = pkt[1:].decode()
+                if self.drop_next:
+                    self.drop_next = False
+                    return c.close()                                  # connection lost mid-query
+                self._query(c, q)
+        except (ConnectionError, OSError):
+            return
+
+    def _query(self, c, q):
+        import sqlite3
+        self.seen.append(q)
+        up = q.strip().upper()
+        if up.startswith("SET ") or up in ("COMMIT", "ROLLBACK"):
+            return self._ok(c, 1)
+        q2 = (q.replace("`", '"').replace("BIGINT PRIMARY KEY AUTO_INCREMENT", "INTEGER PRIMARY KEY AUTOINCREMENT")
+              .replace("LONGTEXT", "TEXT").replace("DOUBLE", "REAL").replace("\\'", "''"))
+        try:
+            with self.lock:
+                cur = self.db.execute(q2)
+                rows = cur.fetchall() if cur.description else None
+                aff, last = max(cur.rowcount, 0), cur.lastrowid or 0
+        except sqlite3.IntegrityError as e:
+            return self._err(c, 1, 1062, f"Duplicate entry: {e}")
+        except sqlite3.Error as e:
+            return self._err(c, 1, 1064, f"You have an error in your SQL syntax: {e}")
+        if rows is None:
+            return self._ok(c, 1, aff, last)
+        ncol = len(cur.description)
+        seq = 1
+        self._send(c, seq, bytes([ncol]))
+        for i, d in enumerate(cur.description):
+            sample = next((r[i] for r in rows if r[i] is not None), "")
+            ctype = 8 if isinstance(sample, int) else (5 if isinstance(sample, float) else 253)
+            name = d[0].encode()
+            col = (self._lenenc(b"def") + self._lenenc(b"db") + self._lenenc(b"t") + self._lenenc(b"t") + self._lenenc(name) + self._lenenc(name) +
+                   b"\x0c" + (63 if ctype != 253 else 45).to_bytes(2, "little") + (1024).to_bytes(4, "little") + bytes([ctype]) + b"\0\0" + b"\0" + b"\0\0")
+            seq += 1
+            self._send(c, seq, col)
+        seq += 1
+        self._send(c, seq, b"\xfe\0\0\x02\0")
+        for r in rows:
+            seq = (seq + 1) & 0xFF
+            self._send(c, seq, b"".join(b"\xfb" if v is None else self._lenenc(str(v).encode()) for v in r))
+        self._send(c, (seq + 1) & 0xFF, b"\xfe\0\0\x02\0")
+
+    def close(self):
+        self.sock.close()
+
+
+def test_mysql_repos_over_the_wire_protocol():
+    """the table repos on the in-tree MySQL client over TCP: handshake + native-password authentication (verified by the
+    server), DDL / DML / SELECT with typed result sets and NULLs, escaping of hostile strings, duplicate keys, a connection
+    that dies mid-query (reconnect once and retry), wrong password, and the ResourceManager running on top"""
+    from olearning_sim_b200.control.mysql_repo import MySqlConnection, MySqlResTableRepo, MySqlTaskTableRepo
+    from olearning_sim_b200.utils import mysql_wire
+    srv = WireMySqlServer()
+    try:
+        kw = dict(host="127.0.0.1", port=srv.port, user="ols", password="pw-1", database="virtually_phone_DB")
+        raw = mysql_wire.connect(**kw)
+        assert raw.ping()
+        cur = raw.cursor()
+        cur.execute("CREATE TABLE `t` (`a` BIGINT PRIMARY KEY AUTO_INCREMENT, `s` LONGTEXT, `x` DOUBLE)")
+        nasty = "it's a \\\\ \"quoted\"\nline; DROP TABLE t; --"
+        cur.execute("INSERT INTO `t` (`s`, `x`) VALUES (%s, %s)", (nasty, 1.5))
+        cur.execute("INSERT INTO `t` (`s`, `x`) VALUES (%s, %s)", (None, None))
+        cur.execute("SELECT `a`, `s`, `x` FROM `t` ORDER BY `a`")
+        rows = cur.fetchall()
+        assert rows[0][0] == 1 and isinstance(rows[0][0], int) and rows[0][2] == 1.5 and rows[1][1:] == (None, None)
+        assert rows[0][1].startswith("it's a ") and "DROP TABLE" in rows[0][1] and [d[0] for d in cur.description] == ["a", "s", "x"]
+        with pytest.raises(mysql_wire.ProgrammingError):
+            cur.execute("SELEC nonsense")
+        with pytest.raises(mysql_wire.ProgrammingError):
+            cur.execute("INSERT INTO `t` (`a`) VALUES (%s)", (1,))           # duplicate key -> 1062
+        raw.close()
+        with pytest.raises(mysql_wire.OperationalError):
+            mysql_wire.connect(**{**kw, "password": "wrong"})                  # 1045 from the server's scramble check
+        with pytest.raises(mysql_wire.OperationalError):
+            mysql_wire.connect(**{**kw, "database": "nope"})
+        # ---- the repos, through MySqlConnection's pymysql-less fallback
+        conn = MySqlConnection(**kw)
+        tasks, res = MySqlTaskTableRepo(conn), MySqlResTableRepo(conn)
+        assert any("AUTO_INCREMENT" in q and "`taskmgr_table`" in q for q in srv.seen)
+        assert tasks.create_task("w1", "u") and not tasks.create_task("w1", "u")
+        assert tasks.set_task_value("w1", "task_status", "QUEUED") and tasks.get_task_value("w1", "task_status") == "QUEUED"
+        before = srv.connects
+        srv.drop_next = True                                              # the server drops the connection mid-query
+        assert tasks.get_task_value("w1", "task_status") == "QUEUED" and conn.reconnects == 1 and srv.connects == before + 1
+        assert res.insert_data("w1", 2.0, 4.0, 1.0) and res.held()[0]["cpu"] == 2.0
+        assert res.delete_by_taskid("w1") and res.held() == []
+        from olearning_sim_b200.control.resource_manager import FakePhoneMgr, ResourceManager
+        rm = ResourceManager(res, totals={"cpu": 4, "mem": 8, "gpu": 0}, phone_mgr=FakePhoneMgr())
+        assert rm.requestClusterResource("x", 3, 1).name == "SUCCESS" and rm.requestClusterResource("y", 3, 1).name == "NOT_ENOUGH_RES"
+    finally:
+        srv.close()
