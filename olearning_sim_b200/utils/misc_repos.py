@@ -57,7 +57,78 @@ class QueueRepo:
             return len(self._mem[name])
 
 
-RedisRepo = QueueRepo
+class RespClient:
+    """Redis over its wire protocol (RESP2) — the handful of commands the queue repo needs (ols_core/utils/redis_repo.py
+    wraps ``redis.StrictRedis`` rpush / lpop / llen); no ``redis`` package required.  One request/response at a time."""
+
+    def __init__(self, host: str = "127.0.0.1", port: int = 6379, password: Optional[str] = None, db: int = 0,
+                 timeout: float = 10.0):
+        import socket
+        self._s = socket.create_connection((host, int(port)), timeout=timeout)
+        self._f = self._s.makefile("rb")
+        self._lock = threading.Lock()
+        if password:
+            self.command("AUTH", password)
+        if db:
+            self.command("SELECT", str(db))
+
+    def _read(self):
+        line = self._f.readline()
+        if not line:
+            raise ConnectionError("redis: connection closed")
+        t, rest = line[:1], line[1:-2]
+        if t == b"+":
+            return rest.decode()
+        if t == b"-":
+            raise RuntimeError("redis: " + rest.decode())
+        if t == b":":
+            return int(rest)
+        if t == b"$":
+            n = int(rest)
+            if n < 0:
+                return None
+            data = self._f.read(n + 2)
+            return data[:-2].decode("utf-8", "replace")
+        if t == b"*":
+            n = int(rest)
+            return None if n < 0 else [self._read() for _ in range(n)]
+        raise RuntimeError(f"redis: unexpected reply {line!r}")
+
+    def command(self, *args: str):
+        parts = [a if isinstance(a, bytes) else str(a).encode() for a in args]
+        with self._lock:
+            self._s.sendall(b"*%d\r\n" % len(parts) + b"".join(b"$%d\r\n%s\r\n" % (len(p), p) for p in parts))
+            return self._read()
+
+    def close(self) -> None:
+        try:
+            self._s.close()
+        except OSError:
+            pass
+
+
+class RedisRepo(QueueRepo):
+    """The queue repo on a Redis server: ``RedisRepo(url="redis://[:password@]host:port/db")``; without ``url`` it is the
+    in-process / SQLite ``QueueRepo`` (what the single-box deployment uses)."""
+
+    def __init__(self, path: Optional[str] = None, url: Optional[str] = None):
+        self._r: Optional[RespClient] = None
+        if url:
+            import urllib.parse
+            u = urllib.parse.urlparse(url)
+            self._r = RespClient(u.hostname or "127.0.0.1", u.port or 6379, u.password, int((u.path or "/0").strip("/") or 0))
+            self._lock = threading.Lock()
+        else:
+            super().__init__(path)
+
+    def rpush(self, name: str, value: str) -> int:
+        return int(self._r.command("RPUSH", name, value)) if self._r else super().rpush(name, value)
+
+    def lpop(self, name: str) -> Optional[str]:
+        return self._r.command("LPOP", name) if self._r else super().lpop(name)
+
+    def llen(self, name: str) -> int:
+        return int(self._r.command("LLEN", name)) if self._r else super().llen(name)
 
 
 @dataclass

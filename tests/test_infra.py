@@ -574,3 +574,68 @@ def test_s3_and_minio_repos_over_http_with_signature_v4(tmp_path):
         assert ei.value.status == 403 and ei.value.code == "SignatureDoesNotMatch"
     finally:
         srv.shutdown()
+
+
+def test_redis_repo_over_the_resp_protocol():
+    """RedisRepo(url=...) against an in-process RESP2 server over TCP: AUTH, SELECT, RPUSH / LPOP / LLEN, nil replies and
+    error replies; without a URL it stays the in-process queue"""
+    import socketserver
+    import threading
+    from olearning_sim_b200.utils.misc_repos import RedisRepo, RespClient
+
+    lists, seen = {}, []
+
+    class H(socketserver.StreamRequestHandler):
+        def handle(self):
+            authed = False
+            while True:
+                line = self.rfile.readline()
+                if not line:
+                    return
+                n = int(line[1:])
+                args = []
+                for _ in range(n):
+                    ln = int(self.rfile.readline()[1:])
+                    args.append(self.rfile.read(ln + 2)[:-2].decode())
+                cmd = args[0].upper()
+                seen.append(cmd)
+                if cmd == "AUTH":
+                    authed = args[1] == "hunter2"
+                    self.wfile.write(b"+OK\r\n" if authed else b"-WRONGPASS invalid password\r\n")
+                elif not authed:
+                    self.wfile.write(b"-NOAUTH Authentication required.\r\n")
+                elif cmd == "SELECT":
+                    self.wfile.write(b"+OK\r\n")
+                elif cmd == "RPUSH":
+                    lists.setdefault(args[1], []).append(args[2])
+                    self.wfile.write(b":%d\r\n" % len(lists[args[1]]))
+                elif cmd == "LPOP":
+                    q = lists.get(args[1]) or []
+                    if q:
+                        v = q.pop(0).encode()
+                        self.wfile.write(b"$%d\r\n%s\r\n" % (len(v), v))
+                    else:
+                        self.wfile.write(b"$-1\r\n")
+                elif cmd == "LLEN":
+                    self.wfile.write(b":%d\r\n" % len(lists.get(args[1], [])))
+                else:
+                    self.wfile.write(b"-ERR unknown command\r\n")
+
+    srv = socketserver.ThreadingTCPServer(("127.0.0.1", 0), H)
+    threading.Thread(target=srv.serve_forever, daemon=True).start()
+    try:
+        port = srv.server_address[1]
+        r = RedisRepo(url=f"redis://:hunter2@127.0.0.1:{port}/2")
+        assert r.rpush("q", "a\r\nwith crlf") == 1 and r.rpush("q", "b") == 2 and r.llen("q") == 2
+        assert r.lpop("q") == "a\r\nwith crlf" and r.lpop("q") == "b" and r.lpop("q") is None and r.llen("q") == 0
+        assert seen[:2] == ["AUTH", "SELECT"]
+        with pytest.raises(RuntimeError):
+            RespClient("127.0.0.1", port, password="wrong")
+        with pytest.raises(RuntimeError):
+            RespClient("127.0.0.1", port).command("LLEN", "q")          # NOAUTH
+        with pytest.raises(RuntimeError):
+            r._r.command("FLUSHALL")                                     # error reply surfaces as an exception
+        local = RedisRepo()
+        assert local.rpush("q", "x") == 1 and local.lpop("q") == "x" and local.lpop("q") is None
+    finally:
+        srv.shutdown()
