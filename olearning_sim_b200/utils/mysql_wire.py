@@ -1,5 +1,4 @@
-"""Minimal MySQL client on the wire protocol (text protocol, ``mysql_native_password`` and the fast path of
-``caching_sha2_password``) — the DB-API subset ``control/mysql_repo.py`` needs, without ``pymysql``.
+"""Minimal MySQL client on the wire protocol (text protocol, ``mysql_native_password`` and ``caching_sha2_password``) — the DB-API subset ``control/mysql_repo.py`` needs, without ``pymysql``.
 
 The reference keeps its task / resource / flow / log tables in MySQL through SQLAlchemy + pymysql
 (ols_core/utils/repo_utils.py:19-345, taskMgr/utils/utils.py:29-267).  Neither is installable here; ``MySqlConnection``
@@ -11,9 +10,8 @@ falls back to this module:
 Protocol (MySQL 5.7 / 8.0 "Client/Server Protocol"): 4-byte packet header (3-byte little-endian length + sequence id),
 HandshakeV10 -> HandshakeResponse41 (+ AuthSwitchRequest), COM_QUERY with OK / ERR / text result sets (with or without
 CLIENT_DEPRECATE_EOF), COM_PING, COM_QUIT.  Parameters are interpolated client side with MySQL string escaping, as pymysql
-does.  Not implemented: TLS, compression, prepared statements, the RSA / TLS full-authentication exchange of
-``caching_sha2_password`` (an account whose password is not in the server's cache must use ``mysql_native_password`` or log
-in once through another client).
+does.  ``caching_sha2_password`` full authentication (the password is not in the server's cache yet) goes through the RSA
+public-key exchange (``cryptography``).  Not implemented: TLS, compression, prepared statements.
 
 tests/test_round2_parity.py runs the table repos over TCP against an in-process server that speaks this protocol.
 """
@@ -64,6 +62,20 @@ def scramble_sha2(password: str, salt: bytes) -> bytes:
     p2 = hashlib.sha256(p1).digest()
     p3 = hashlib.sha256(p2 + salt).digest()
     return bytes(a ^ b for a, b in zip(p1, p3))
+
+
+def rsa_encrypt_password(password: str, salt: bytes, pem: bytes) -> bytes:
+    """caching_sha2_password / sha256_password full authentication over an unencrypted connection: (password + NUL) XOR
+    salt (repeated), encrypted with the server's RSA public key, OAEP / SHA-1 padding (what libmysqlclient does)."""
+    try:
+        from cryptography.hazmat.primitives import hashes, serialization
+        from cryptography.hazmat.primitives.asymmetric import padding
+    except ImportError as e:  # pragma: no cover - the package is part of this image
+        raise OperationalError("(2061) caching_sha2_password full authentication needs the 'cryptography' package") from e
+    pw = password.encode() + b"\0"
+    x = bytes(b ^ salt[i % len(salt)] for i, b in enumerate(pw))
+    pub = serialization.load_pem_public_key(pem)
+    return pub.encrypt(x, padding.OAEP(mgf=padding.MGF1(algorithm=hashes.SHA1()), algorithm=hashes.SHA1(), label=None))
 
 
 def lenenc_int(buf: bytes, pos: int) -> Tuple[Optional[int], int]:
@@ -256,11 +268,16 @@ class Connection:
                 else:
                     raise OperationalError(f"(2059) authentication plugin '{plugin}' is not supported")
                 continue
-            if pkt[0] == 0x01:                              # caching_sha2_password: 0x03 fast-auth ok, 0x04 full auth needed
-                if pkt[1:2] == b"\x03":
+            if pkt[0] == 0x01:                              # AuthMoreData
+                if pkt[1:2] == b"\x03":                     # caching_sha2_password: fast authentication succeeded
                     continue
-                raise OperationalError("(2061) caching_sha2_password full authentication needs TLS or RSA, which this client "
-                                       "does not implement; use a mysql_native_password account or warm the server's cache")
+                if pkt[1:2] == b"\x04":                     # full authentication: password under the server's RSA key
+                    self._write(b"\x02")                    # request the public key
+                    key = self._read()
+                    if key[0] != 0x01:
+                        raise InterfaceError("expected the server's RSA public key")
+                    self._write(rsa_encrypt_password(password, salt, key[1:]))
+                    continue
             raise InterfaceError(f"unexpected packet 0x{pkt[0]:02x} during authentication")
 
     # ---- command phase ---------------------------------------------------------------------------------------------

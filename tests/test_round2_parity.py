@@ -866,11 +866,11 @@ class WireMySqlServer:
     mysql_native_password scramble (recomputed here from the stored password), COM_QUERY -> OK / ERR / text result set with
     classic EOF framing, COM_PING, COM_QUIT.  ``drop_next`` closes the socket in the middle of the next query."""
 
-    def __init__(self, user="ols", password="pw-1", database="virtually_phone_DB"):
+    def __init__(self, user="ols", password="pw-1", database="virtually_phone_DB", auth="native"):
         import socket
         import sqlite3
         import threading
-        self.user, self.password, self.database = user, password, database
+        self.user, self.password, self.database, self.auth = user, password, database, auth      # native | sha2_fast | sha2_full
         self.db = sqlite3.connect(":memory:", check_same_thread=False, isolation_level=None)
         self.lock, self.drop_next, self.connects, self.seen = threading.Lock(), False, 0, []
         self.sock = socket.socket()
@@ -924,7 +924,8 @@ class WireMySqlServer:
         salt = bytes(33 + b % 90 for b in _os.urandom(20))            # printable, no NULs (like a real server)
         caps = 0x1 | 0x4 | 0x8 | 0x200 | 0x2000 | 0x8000 | 0x20000 | 0x80000
         hs = (b"\x0a" + b"8.0.99-fake\0" + struct.pack("<I", self.connects) + salt[:8] + b"\0" + struct.pack("<H", caps & 0xFFFF) +
-              b"\x2d" + struct.pack("<H", 2) + struct.pack("<H", caps >> 16) + bytes([21]) + b"\0" * 10 + salt[8:] + b"\0" + b"mysql_native_password\0")
+              b"\x2d" + struct.pack("<H", 2) + struct.pack("<H", caps >> 16) + bytes([21]) + b"\0" * 10 + salt[8:] + b"\0" +
+              (b"mysql_native_password\0" if self.auth == "native" else b"caching_sha2_password\0"))
         try:
             self._send(c, 0, hs)
             seq, resp = self._recv(c)
@@ -940,9 +941,30 @@ class WireMySqlServer:
             if ccaps & 0x8:
                 end = resp.index(b"\0", pos)
                 dbname = resp[pos:end].decode()
-            p1 = hashlib.sha1(self.password.encode()).digest()
-            want = bytes(a ^ b for a, b in zip(p1, hashlib.sha1(salt + hashlib.sha1(p1).digest()).digest()))
-            if user != self.user or auth != want:
+            if self.auth == "native":
+                p1 = hashlib.sha1(self.password.encode()).digest()
+                want = bytes(a ^ b for a, b in zip(p1, hashlib.sha1(salt + hashlib.sha1(p1).digest()).digest()))
+                good = auth == want
+            elif self.auth == "sha2_fast":                            # the password hash is in the server's cache
+                p1 = hashlib.sha256(self.password.encode()).digest()
+                want = bytes(a ^ b for a, b in zip(p1, hashlib.sha256(hashlib.sha256(p1).digest() + salt).digest()))
+                good = auth == want
+                if good:
+                    seq += 1
+                    self._send(c, seq, b"\x01\x03")
+            else:                                                     # cold cache: full authentication over RSA
+                from cryptography.hazmat.primitives import hashes, serialization
+                from cryptography.hazmat.primitives.asymmetric import padding, rsa
+                key = rsa.generate_private_key(public_exponent=65537, key_size=2048)
+                pem = key.public_key().public_bytes(serialization.Encoding.PEM, serialization.PublicFormat.SubjectPublicKeyInfo)
+                self._send(c, seq + 1, b"\x01\x04")
+                seq, req = self._recv(c)
+                assert req == b"\x02"
+                self._send(c, seq + 1, b"\x01" + pem)
+                seq, enc = self._recv(c)
+                x = key.decrypt(enc, padding.OAEP(mgf=padding.MGF1(algorithm=hashes.SHA1()), algorithm=hashes.SHA1(), label=None))
+                good = bytes(b ^ salt[i % len(salt)] for i, b in enumerate(x)) == self.password.encode() + b"\0"
+            if user != self.user or not good:
                 self._err(c, seq + 1, 1045, f"Access denied for user '{user}'")
                 return c.close()
             if dbname != self.database:
@@ -1048,5 +1070,24 @@ def test_mysql_repos_over_the_wire_protocol():
         from olearning_sim_b200.control.resource_manager import FakePhoneMgr, ResourceManager
         rm = ResourceManager(res, totals={"cpu": 4, "mem": 8, "gpu": 0}, phone_mgr=FakePhoneMgr())
         assert rm.requestClusterResource("x", 3, 1).name == "SUCCESS" and rm.requestClusterResource("y", 3, 1).name == "NOT_ENOUGH_RES"
+    finally:
+        srv.close()
+
+
+@pytest.mark.parametrize("mode", ["sha2_fast", "sha2_full"])
+def test_mysql_wire_caching_sha2_password(mode):
+    """MySQL 8 default accounts: caching_sha2_password — the fast path (hash in the server's cache: SHA-256 scramble) and the
+    full authentication (RSA public-key exchange, OAEP) — against the protocol server; a wrong password is refused in both"""
+    from olearning_sim_b200.utils import mysql_wire
+    srv = WireMySqlServer(auth=mode)
+    try:
+        kw = dict(host="127.0.0.1", port=srv.port, user="ols", password="pw-1", database="virtually_phone_DB")
+        c = mysql_wire.connect(**kw)
+        cur = c.cursor()
+        cur.execute("SELECT 40 + 2")
+        assert cur.fetchone() == (42,) and c.ping()
+        c.close()
+        with pytest.raises(mysql_wire.OperationalError):
+            mysql_wire.connect(**{**kw, "password": "wrong"})
     finally:
         srv.close()
