@@ -73,11 +73,31 @@ class WaitingForGlobalAggregation(OperatorFlowStrategy):
         super().__init__(*a, **k)
         self._previous_round: Optional[int] = None
 
+    def _ask_websocket(self, url: str) -> Optional[int]:
+        """The reference's selection-service exchange (operatorflow.py:186-237): connect to ``service_url``, send one
+        REGISTER_MESSAGE for the task, read the first answer and take ``data.round_idx`` from it."""
+        import json
+        import uuid
+        from websockets.sync.client import connect
+        cid, mid = str(uuid.uuid4()), str(uuid.uuid4())
+        msg = {"header": {"messageId": mid, "messageType": "REGISTER_MESSAGE", "clientId": cid},
+               "data": {"message_id": mid, "client_id": cid, "task_id": self.task_id}}
+        timeout = float(self.gp.get("service_timeout", 5.0))
+        with connect(url, open_timeout=timeout) as ws:
+            ws.send(json.dumps(msg))
+            answer = json.loads(ws.recv(timeout=timeout))
+        r = (answer.get("data") or {}).get("round_idx")
+        return None if r is None else int(r)
+
     def _current_round(self) -> Optional[int]:
-        svc = self.gp.get("selection_service") or self.services.get(self.task_id)
+        """``selection_service``: a callable (in-process aggregator / tests) or the ``ws://`` URL of the selection service
+        (``service_url`` of the reference's selection_config.yaml); also looked up per task in ``services``."""
+        svc = self.gp.get("selection_service") or self.gp.get("service_url") or self.services.get(self.task_id)
         if svc is None:
             return None
         try:
+            if isinstance(svc, str):
+                return self._ask_websocket(svc)
             return int(svc())
         except Exception as e:  # noqa: BLE001
             logger.error(self.task_id, "TaskMgr", "operatorflow", f"[selection service]: {e}")

@@ -233,6 +233,34 @@ def test_gate_waiting_for_global_aggregation_with_fake_clock():
     assert of2.start(0) and not of2.stop(0)                               # aggregator never advances -> timeout
 
 
+def test_gate_waiting_for_global_aggregation_over_a_live_selection_service():
+    """the reference's selection service is a WebSocket endpoint: the gate sends one REGISTER_MESSAGE per poll and reads
+    ``data.round_idx`` from the first answer — here against a real ``websockets`` server whose round advances after the
+    third question"""
+    import threading
+    from websockets.sync.server import serve
+    asked = []
+
+    def handler(ws):
+        msg = json.loads(ws.recv())
+        asked.append(msg)
+        rnd = 4 if len(asked) <= 3 else 5
+        ws.send(json.dumps({"header": {"messageType": "REGISTER_RESPONSE"}, "data": {"task_id": msg["data"]["task_id"], "round_idx": rnd}}))
+
+    with serve(handler, "127.0.0.1", 0) as server:
+        threading.Thread(target=server.serve_forever, daemon=True).start()
+        url = f"ws://127.0.0.1:{server.socket.getsockname()[1]}/channel"
+        p = {"strategy": "waiting_for_global_aggregation", "wait_interval": 1, "total_timeout": 5}
+        of = OperatorFlow("tws", 1, p, p, gate_params={"service_url": url}, sleep=lambda s: None)
+        assert of.start(0) and of.stop(0)                              # 4 at start, 5 (= previous + 1) after two more polls
+        assert len(asked) >= 4 and all(m["header"]["messageType"] == "REGISTER_MESSAGE" and m["data"]["task_id"] == "tws"
+                                       and m["header"]["clientId"] == m["data"]["client_id"] for m in asked)
+        server.shutdown()
+    dead = OperatorFlow("tws", 1, p, {**p, "total_timeout": 1}, gate_params={"service_url": "ws://127.0.0.1:9/none", "service_timeout": 0.2},
+                        sleep=lambda s: None)
+    assert not dead.start(0)                                           # unreachable service -> the gate times out, no exception
+
+
 def test_gate_sample_and_aggregation_markers(tmp_path):
     src = tmp_path / "all_clients"
     src.mkdir()
