@@ -120,6 +120,9 @@ def deviceflow_handler(df: Any, mount_as: Optional[str] = None):
         "UnRegisterTask": lambda r: {"is_success": bool(df.UnRegisterTask(r["task_id"]))},
         "GetTotalComputeResources": lambda r: {"total_compute_resources": df.GetTotalComputeResources(r["task_id"])},
         "CheckDeviceflowDispatchFinished": lambda r: {"is_success": bool(df.CheckDeviceflowDispatchFinished(r["task_id"]))},
+        # extension (JSON codec): the GPU engine reports what its on-device dispatch of a round did
+        "ReportDeviceDispatch": lambda r: {"is_success": bool(df.ReportDeviceDispatch(
+            r["task_id"], r["flow_id"], r.get("compute_resource", "logical_simulation"), r.get("summary", {})))},
     }, mount_as=mount_as)
 
 
@@ -179,6 +182,46 @@ class RemotePhoneMgr:
 
     def getDeviceTaskStatus(self, task_id):
         return self._stub.getDeviceTaskStatus({"task_id": task_id})
+
+
+class RemoteDeviceFlow:
+    """Client-side adapter with ``DeviceFlowService``'s method surface over gRPC — what a job process holds when the service
+    lives in another process (the reference's ``Deviceflow`` wrapper around the generated stub, utils_run_task.py:53-144:
+    ``start`` -> NotifyStart, ``stop`` -> NotifyComplete, inbound endpoint getters)."""
+
+    def __init__(self, address: str):
+        self.address = address
+        self._stub = JsonStub(connect(address), "TaskOperatorOrientedDeviceFlow")
+
+    @staticmethod
+    def _req(req: Any) -> Dict[str, Any]:
+        return {"task_id": req.task_id, "routing_key": req.routing_key, "compute_resource": req.compute_resource,
+                "strategy": getattr(req, "strategy", ""), "outbound_service": getattr(req, "outbound_service", {}) or {}}
+
+    def NotifyStart(self, req: Any) -> bool:                      # noqa: N802 - RPC names of the reference
+        return bool(self._stub.NotifyStart(self._req(req))["is_success"])
+
+    def NotifyComplete(self, req: Any) -> bool:                   # noqa: N802
+        return bool(self._stub.NotifyComplete(self._req(req))["is_success"])
+
+    def RegisterTask(self, task_id: str, total_compute_resources) -> bool:      # noqa: N802
+        return bool(self._stub.RegisterTask({"task_id": task_id, "total_compute_resources": list(total_compute_resources)})["is_success"])
+
+    def UnRegisterTask(self, task_id: str) -> bool:               # noqa: N802
+        return bool(self._stub.UnRegisterTask({"task_id": task_id})["is_success"])
+
+    def GetDeviceflowPulsarClient(self) -> Dict[str, Any]:        # noqa: N802
+        return self._stub.GetDeviceflowPulsarClient({})
+
+    def GetDeviceflowWebsocket(self) -> Dict[str, Any]:           # noqa: N802
+        return self._stub.GetDeviceflowWebsocket({})
+
+    def CheckDeviceflowDispatchFinished(self, task_id: str) -> bool:            # noqa: N802
+        return bool(self._stub.CheckDeviceflowDispatchFinished({"task_id": task_id})["is_success"])
+
+    def ReportDeviceDispatch(self, task_id: str, flow_id: str, compute_resource: str, summary: Dict[str, Any]) -> bool:   # noqa: N802
+        return bool(self._stub.ReportDeviceDispatch({"task_id": task_id, "flow_id": flow_id, "compute_resource": compute_resource,
+                                                     "summary": summary})["is_success"])
 
 
 def performance_mgr_handler(pm: Any):
@@ -247,6 +290,9 @@ class SimulatorSession:
         self.mounted = mounted
         self.port = self.server.add_insecure_port(f"{host}:{port}")
         self.address = f"{host}:{self.port}"
+        if deviceflow is not None and svc in (0, 5) and task_manager is not None and hasattr(task_manager, "set_job_context"):
+            # job processes (SubprocessJobExecutor / torchrun ranks) reach the DeviceFlow service through this address
+            task_manager.set_job_context("deviceflow_address", self.address)
         self._sleep = session_sleep_time
 
     def start(self, block: bool = False) -> "SimulatorSession":

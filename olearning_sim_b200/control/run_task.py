@@ -558,7 +558,12 @@ def main(argv: Optional[List[str]] = None) -> int:
         repo = TaskTableRepo(ctx["repo_path"])
     if a.profile:
         task.setdefault("engine", {})["profile"] = True
-    runner = RoundRunner(task, repo=repo, working_dir=ctx.get("working_dir"), rank=rank, world=world,
+    deviceflow = None
+    if ctx.get("deviceflow_address"):
+        # the DeviceFlow service of the control-plane process, over gRPC (utils_run_task.py:53-144)
+        from ..api.grpc_service import RemoteDeviceFlow
+        deviceflow = RemoteDeviceFlow(ctx["deviceflow_address"])
+    runner = RoundRunner(task, repo=repo, deviceflow=deviceflow, working_dir=ctx.get("working_dir"), rank=rank, world=world,
                          checkpoint_dir=ctx.get("checkpoint_dir"), trace_path=a.profile or ctx.get("trace_path"))
     from ..parallel.comm import PeerLostError
     try:

@@ -107,6 +107,10 @@ class TaskManager:
     # ================================================================================================
     # RPC surface
     # ================================================================================================
+    def set_job_context(self, key: str, value: Any) -> None:
+        """JSON-safe settings handed to every job (e.g. ``deviceflow_address`` once a gRPC session is listening)."""
+        self._job_context[key] = value
+
     def submitTask(self, request: Any) -> bool:
         task = request if isinstance(request, TaskConfig) else json2taskconfig(request)
         ok, msg = ValidateParameters().validate_task_parameters(task)

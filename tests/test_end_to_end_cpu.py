@@ -162,3 +162,37 @@ def test_elastic_restart_after_rank_loss(tmp_path):
     assert os.path.exists(tmp_path / "killed") and "attempt 1, 1 rank(s)" in log
     assert repo.get_task_value("elastic", "logical_round") == 3
     assert sorted(os.listdir(tmp_path / "ckpt"))[-1].startswith("elastic_2_")
+
+
+def test_subprocess_job_reaches_deviceflow_over_grpc(tmp_path):
+    """the product path: the task runs as a 2-rank process group (gloo) while DeviceFlow lives in the control-plane process —
+    the job finds it through ``deviceflow_address`` (set by the gRPC session) and drives NotifyStart / ReportDeviceDispatch /
+    NotifyComplete through ``RemoteDeviceFlow``, so the service closes every (operator, round) flow"""
+    from olearning_sim_b200.api.grpc_service import RemoteDeviceFlow, SimulatorSession
+    db = str(tmp_path / "tasks.sqlite")
+    repo = TaskTableRepo(db)
+    bus = InMemoryBus(virtual_time=True)
+    df = DeviceFlowService(bus=bus, repo=FlowTableRepo(), clock=FakeClock(), seed=0, dispatcher_timeout_millis=0)
+    rm = ResourceManager(ResTableRepo(), totals={"cpu": 8, "mem": 32, "gpu": 0}, phone_mgr=FakePhoneMgr())
+    ex = SubprocessJobExecutor(nproc_per_node=2, workdir=str(tmp_path / "jobs"), repo_path=db, master_port_base=29761)
+    tm = TaskManager(repo=repo, resource_manager=rm, deviceflow=df, executor=ex)
+    sess = SimulatorSession(port=0, task_manager=tm, resource_manager=rm, deviceflow=df).start()
+    try:
+        assert tm._job_context["deviceflow_address"] == sess.address
+        # the adapter alone, over the wire
+        rdf = RemoteDeviceFlow(sess.address)
+        assert rdf.RegisterTask("probe", ["logical_simulation"]) and rdf.GetDeviceflowPulsarClient() == df.GetDeviceflowPulsarClient()
+        assert rdf.UnRegisterTask("probe")
+        tj = make_task_json(task_id="dfsub", rounds=2, nums=(8,), operator_params=MLP, num_request=(2,), use_df=True, strategy=REAL_TIME,
+                            outbound={"pulsar_client": {"url": "mem://local", "topic": "agg"}})
+        assert tm.submitTask(tj)
+        assert tm.schedule_once(inline=True) == "dfsub"
+        st = tm.wait_for("dfsub", 240, poll=0.5)
+        assert st == TaskStatus.SUCCEEDED, ex.get_job_error(repo.get_task_value("dfsub", "job_id"))
+        done = df.stats()["device_dispatched"]
+        assert sorted(done) == ["dfsub_training_0", "dfsub_training_1"] and df.stats()["flows"] == []
+        assert all(v["participants"] == 8 for v in done.values())
+        df.pump(); df.pump()
+        assert df.CheckDeviceflowDispatchFinished("dfsub")
+    finally:
+        sess.stop()
