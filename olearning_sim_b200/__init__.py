@@ -16,6 +16,31 @@ from .api.schema import TaskConfig, TaskStatus, json2taskconfig, taskconfig2json
 from .engine.fed_engine import FedConfig, FedEngine, RoundResult  # noqa: F401
 
 
+def build_task_service(config=None, resmgr_address=None, deviceflow_address=None, phonemgr_address=None, start_threads=False):
+    """The reference's split deployment: a TaskMgr process whose ResourceMgr / phone manager / DeviceFlow live in other
+    processes (``simu_session.py`` with svc 2 / 6 / 5) and are reached over gRPC — addresses from ``[grpc] resmgr`` /
+    ``phonemgr`` and the ``deviceflow`` section unless given."""
+    from .api.grpc_service import RemoteDeviceFlow, RemoteResourceMgr
+    from .control.jobs import InProcessJobExecutor, SubprocessJobExecutor
+    from .control.repo import TaskTableRepo
+    from .control.task_manager import TaskManager, TaskMgrConfig
+    from .utils.config import OlsbConfig
+    cfg = config or OlsbConfig()
+    rm = RemoteResourceMgr(resmgr_address or cfg.grpc.resmgr, phone_address=phonemgr_address or cfg.grpc.phonemgr)
+    d = cfg.deviceflow
+    df_addr = deviceflow_address or f"{d.grpc_service_address}:{d.grpc_service_port}"
+    df = RemoteDeviceFlow(df_addr)
+    ex = (SubprocessJobExecutor(nproc_per_node=max(cfg.cluster.gpus, 1), repo_path=cfg.storage.task_table)
+          if cfg.cluster.job_executor == "subprocess" else InProcessJobExecutor())
+    t = cfg.taskMgr
+    tm = TaskManager(repo=TaskTableRepo(cfg.storage.task_table), resource_manager=rm, deviceflow=df, executor=ex,
+                     config=TaskMgrConfig(t.scheduler_sleep_time, t.release_sleep_time, t.interrupt_sleep_time,
+                                          t.interrupt_queue_time, t.interrupt_running_time),
+                     start_threads=start_threads,
+                     job_context={"checkpoint_dir": cfg.storage.checkpoint_dir or None, "deviceflow_address": df_addr})
+    return tm, rm, df
+
+
 def build_control_plane(config=None, start_threads=False):
     """Wire TaskManager + ResourceManager + DeviceFlow with the given ``OlsbConfig`` (in-process deployment)."""
     from .control.jobs import InProcessJobExecutor, SubprocessJobExecutor

@@ -22,7 +22,13 @@ def _serve(a) -> int:
     from .utils.config import load_config
     from .utils.misc_repos import PerformanceManager
     cfg = load_config([a.config] if a.config else None, overrides=a.set)
-    tm, rm, df = build_control_plane(cfg, start_threads=True)
+    if a.svc == 1 and a.remote:
+        # the reference's split deployment: this process is the TaskMgr only; ResourceMgr / phone manager / DeviceFlow are
+        # other `serve --svc 2|6|5` processes reached over gRPC ([grpc] resmgr / phonemgr, deviceflow.grpc_service_*)
+        from . import build_task_service
+        tm, rm, df = build_task_service(cfg, start_threads=True)
+    else:
+        tm, rm, df = build_control_plane(cfg, start_threads=True)
     from .utils.metrics import Metrics
     metrics = Metrics()
     perf = PerformanceManager(metrics=metrics)
@@ -102,6 +108,7 @@ def main(argv=None) -> int:
     s.add_argument("--config", default=None, help="INI / YAML / JSON config (reference names accepted)")
     s.add_argument("--set", action="append", default=[], metavar="section.key=value")
     s.add_argument("--svc", type=int, default=0, help="0 all, 1 task, 2 resource, 3 cluster, 4 performance, 5 deviceflow, 6 phone manager")
+    s.add_argument("--remote", action="store_true", help="with --svc 1: use the ResourceMgr / DeviceFlow services of other processes (addresses from the config)")
     s.add_argument("--host", default="127.0.0.1")
     s.add_argument("--port", type=int, default=0)
     s.add_argument("--metrics-port", type=int, default=0, help="expose Prometheus metrics on this port (0 = off)")

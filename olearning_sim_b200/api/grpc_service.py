@@ -184,6 +184,33 @@ class RemotePhoneMgr:
         return self._stub.getDeviceTaskStatus({"task_id": task_id})
 
 
+class RemoteResourceMgr:
+    """Client-side adapter with the part of ``ResourceManager`` the task side uses (``getResource`` / ``requestResource`` /
+    ``releaseResource`` and the ``phone_mgr`` handle), over gRPC — the reference's TaskMgr and TaskScheduler hold exactly such
+    stubs to a ResourceMgr in another process (task_scheduler.py:40-75, task_manager.py:36-60; address = ``[grpc] resmgr``)."""
+
+    def __init__(self, address: str, phone_mgr: Any = None, phone_address: Optional[str] = None):
+        self.address = address
+        self._stub = JsonStub(connect(address), "ResourceMgr")
+        self.phone_mgr = phone_mgr if phone_mgr is not None else RemotePhoneMgr(phone_address or address)
+
+    def getResource(self) -> Dict[str, Any]:                      # noqa: N802 - RPC names of the reference
+        return self._stub.getResource({})
+
+    def getClusterAvailableResource(self) -> Dict[str, Any]:      # noqa: N802
+        return self._stub.getClusterAvailableResource({})
+
+    def requestResource(self, task_id: str, user_id: str = "", cpu: float = 0.0, mem: float = 0.0, gpu: float = 0.0,   # noqa: N802
+                        phones: Optional[Dict[str, int]] = None, type: int = 0):                                       # noqa: A002
+        r = self._stub.requestResource({"task_id": task_id, "user_id": user_id, "cpu": cpu, "mem": mem, "gpu": gpu,
+                                        "phones": phones or {}, "type": type})
+        return bool(r["is_success"]), r.get("status", "")
+
+    def releaseResource(self, task_id: str, user_id: str = "", phones: Optional[Dict[str, int]] = None, type: int = 0):   # noqa: N802,A002
+        r = self._stub.releaseResource({"task_id": task_id, "user_id": user_id, "phones": phones or {}, "type": type})
+        return bool(r["is_success"]), r.get("status", "")
+
+
 class RemoteDeviceFlow:
     """Client-side adapter with ``DeviceFlowService``'s method surface over gRPC — what a job process holds when the service
     lives in another process (the reference's ``Deviceflow`` wrapper around the generated stub, utils_run_task.py:53-144:

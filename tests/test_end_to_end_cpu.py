@@ -196,3 +196,36 @@ def test_subprocess_job_reaches_deviceflow_over_grpc(tmp_path):
         assert df.CheckDeviceflowDispatchFinished("dfsub")
     finally:
         sess.stop()
+
+
+def test_split_deployment_task_service_with_remote_resource_manager_and_deviceflow():
+    """the reference's topology: ResourceMgr (+ phone manager) in one server, DeviceFlow in another, the TaskMgr in a third
+    party that only holds gRPC adapters.  A task submitted to the TaskMgr books and releases resources in the remote
+    ledger and registers / closes its flows in the remote DeviceFlow"""
+    from olearning_sim_b200 import build_task_service
+    from olearning_sim_b200.api.grpc_service import SimulatorSession
+    res_repo = ResTableRepo()
+    rm = ResourceManager(res_repo, totals={"cpu": 8, "mem": 32, "gpu": 0}, phone_mgr=FakePhoneMgr())
+    bus = InMemoryBus(virtual_time=True)
+    df = DeviceFlowService(bus=bus, repo=FlowTableRepo(), clock=FakeClock(), seed=0, dispatcher_timeout_millis=0)
+    s_res = SimulatorSession(port=0, resource_manager=rm, phone_manager=rm.phone_mgr, svc=0).start()      # ResourceMgr + phone services
+    s_df = SimulatorSession(port=0, deviceflow=df, svc=5).start()
+    try:
+        assert "ResourceMgr" in s_res.mounted and s_df.mounted == ["TaskOperatorOrientedDeviceFlow"]
+        tm, rrm, rdf = build_task_service(resmgr_address=s_res.address, phonemgr_address=s_res.address, deviceflow_address=s_df.address)
+        assert rrm.getResource()["cluster"]["cpu"] == 8
+        held = []
+        orig = rm.requestClusterResource
+        rm.requestClusterResource = lambda *a, **k: (held.append(a[0]), orig(*a, **k))[1]                   # observe the remote ledger
+        tj = make_task_json(task_id="split", rounds=2, operator_params=MLP, use_df=True, strategy=REAL_TIME,
+                            outbound={"pulsar_client": {"url": "mem://local", "topic": "agg"}})
+        assert tm.submitTask(tj)
+        tm.schedule_once(inline=True)
+        assert tm.wait_for("split", 120) == TaskStatus.SUCCEEDED
+        assert held == ["split"] and res_repo.held()                                  # booked in the remote ledger ...
+        assert sorted(df.stats()["device_dispatched"]) == ["split_training_0", "split_training_1"]
+        df.pump(); df.pump()
+        assert tm.reap_once() == ["split"]
+        assert res_repo.held() == [] and df.stats()["registered"] == []              # ... released and unregistered remotely
+    finally:
+        s_res.stop(); s_df.stop()
