@@ -237,6 +237,9 @@ class RemoteDeviceFlow:
     def UnRegisterTask(self, task_id: str) -> bool:               # noqa: N802
         return bool(self._stub.UnRegisterTask({"task_id": task_id})["is_success"])
 
+    def GetTotalComputeResources(self, task_id: str):            # noqa: N802
+        return self._stub.GetTotalComputeResources({"task_id": task_id})["total_compute_resources"]
+
     def GetDeviceflowPulsarClient(self) -> Dict[str, Any]:        # noqa: N802
         return self._stub.GetDeviceflowPulsarClient({})
 
