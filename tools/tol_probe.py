@@ -1,3 +1,6 @@
+"""GPU probe: measured deviation of the native (bf16 tensor-core) backend from the fp32 torch backend for the engine-level
+tests (per-tensor model delta and loss, three seeds per family) — the tolerances in tests/test_gpu_kernels.py are set from
+its output (profiles/r2_gpu_tests.log)."""
 import sys, os
 sys.path.insert(0, "/root/repo")
 import torch
